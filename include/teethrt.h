@@ -1,0 +1,190 @@
+/* libteethrt — C ABI of the B200-native (sm_100a) hot path of
+ * ahmedmajid92/multimodal-teeth-restoration-selection.
+ *
+ * The reference has no FFI/plugin interface: its boundary is the PyTorch nn.Module surface
+ * (MMJointDualHead, MMNet, MILNet, MMEnsemble, MILEnsemble) plus OpenCV calls.  This header is the NEW boundary that sits
+ * directly under that surface; every entry point names the reference call site it replaces.  The Python package
+ * `teethrt` binds it with ctypes (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned storage unless the name ends in `_host`
+ *   - the callee never allocates, frees or synchronises; work is enqueued on `stream`
+ *   - returns 0 (TRT_OK) or a negative trt_status; the message is in trt_last_error_string() (thread-local)
+ *   - activations are NHWC bf16 ("rows" = N*H*W pixels, "C" channels, C % 8 == 0); parameters/gradients fp32
+ *   - compiled for sm_100a only; there is no CPU or other-arch fallback
+ */
+#ifndef TEETHRT_H
+#define TEETHRT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEETHRT_VERSION 100
+
+typedef struct CUstream_st* trt_stream_t; /* == cudaStream_t */
+
+enum { TRT_OK = 0, TRT_ERR_INVALID = -1, TRT_ERR_CUDA = -2, TRT_ERR_UNSUPPORTED = -3 };
+
+int trt_version(void);
+const char* trt_last_error_string(void);
+/* Select the device, verify it is sm_100, resolve cuTensorMapEncodeTiled. Call once per process/device. */
+int trt_init(int device);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * 1x1 convolutions as tcgen05 GEMMs.
+ * Replaces: conv_pw / conv_pwl / conv_head (+ BatchNormAct2d + residual) of timm's EfficientNet, reached through
+ * `self.backbone(x_img)` experiments/multimodal_v1/train_mm_joint_dualtask.py:154, ui/gradio_app/infer_mm.py:36,
+ * experiments/vision_v2/train_mil_attention_v1.py:143 — and their autograd backward (:248).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define TRT_EPI_SCALE_SHIFT 1 /* y = acc * scale[n] + shift[n]  (eval-mode BN folded) */
+#define TRT_EPI_SILU 2        /* y = silu(y) */
+#define TRT_EPI_RESIDUAL 4    /* y += residual[m, n]  (bf16) */
+#define TRT_EPI_STATS 8       /* stats[0][n] += sum_m y, stats[1][n] += sum_m y^2  (fp64; train-mode BN batch statistics) */
+
+/* C[M,N] (bf16) = epi( A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major) ), fp32 accumulate in TMEM.
+ * block_n_override: 0 = choose. */
+int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
+                  const float* shift, const void* residual, double* stats, int block_n_override, trt_stream_t stream);
+
+/* out[p*so_p + q*so_q] (fp32) += sum_m P[m,p] * Q[m,q]   (P:[M,Cp], Q:[M,Cq] bf16 row-major; weight gradient).
+ * lbo/sbo/kstep_bytes: 0 = canonical MN-major 128B-swizzle descriptor values (bring-up knobs). */
+int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int M, int Cp, int Cq, long long so_p, long long so_q,
+                        int lbo, int sbo, int kstep_bytes, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * On-device input stage (byte-exact vs OpenCV 4.x).
+ * Replaces: src/preprocessing/normalise.py:10-16 `apply_clahe` (cv2.cvtColor BGR2LAB -> createCLAHE(3.0,(8,8)).apply(L)
+ * -> cv2.cvtColor LAB2BGR), src/preprocessing/pipeline.py:23-29 `centre_crop_resize` (cv2.resize INTER_LINEAR), and
+ * ToTensor/Normalize/torch.flip of experiments/multimodal_v1/train_mm_joint_dualtask.py:83-84,91-92,328-333.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Packed Lab lookup tables (built on the host by teethrt.lab_tables): byte offsets */
+#define TRT_TAB_GAMMA_OFF 0          /* uint16[256]   sRGBGammaTab_b   */
+#define TRT_TAB_CBRT_OFF 512         /* uint16[3072]  LabCbrtTab_b     */
+#define TRT_TAB_YF_OFF 6656          /* int32[512]    LabToYF_b        */
+#define TRT_TAB_ABXZ_OFF 8704        /* int32[36864]  abToXZ_b         */
+#define TRT_TAB_INVGAMMA_OFF 156160  /* uint8[4096]   sRGBInvGammaTab_b */
+#define TRT_TAB_BYTES 160256
+
+size_t trt_clahe_workspace_bytes(int n);
+/* src/dst: uint8 [n,h,w,3] BGR (HWC). clip = CLAHE_CLIP (3.0), grid fixed at 8x8 (src/config.py:15-16). */
+int trt_clahe_bgr_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, float clip, const void* tables,
+                     void* workspace, size_t workspace_bytes, trt_stream_t stream);
+/* uint8 [n,h,w,3] -> [n,dh,dw,3]; centre_crop != 0 crops the centred min(h,w) square first (pipeline.py:25-28). */
+int trt_resize_linear_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int centre_crop, int dh, int dw,
+                         trt_stream_t stream);
+/* uint8 BGR [n,h,w,3] -> RGB planar [n,3,h,w] = (u8/255 - mean)/std; flip: 0 none, 1 W-reverse, 2 H-reverse.
+ * out_bf16 != 0 writes bf16, else fp32. */
+int trt_normalize_flip_u8(const uint8_t* src, void* dst, int n, int h, int w, int flip, int out_bf16, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BatchNorm / squeeze-excite / pooling kernels around the GEMMs (NHWC bf16, rows = N*H*W, C % 8 == 0).
+ * Replace timm's BatchNormAct2d, SqueezeExcite and global_pool inside `self.backbone(x_img)`
+ * (experiments/multimodal_v1/train_mm_joint_dualtask.py:154; experiments/vision_v2/train_mil_attention_v1.py:143)
+ * and their autograd backward (:248 / :184).
+ * A "rec" is a per-BatchNorm record float[4][C] = {scale, shift, mean, rstd} with y = x*scale + shift.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* train mode: stats = {sum, sum^2} (fp64[2][C]) over `count` values -> rec; updates running stats (momentum, unbiased var) */
+int trt_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* rec, int C, double count, float eps, float momentum,
+                    trt_stream_t stream);
+/* eval mode: rec from the running statistics */
+int trt_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float* rec,
+                     int C, float eps, trt_stream_t stream);
+/* bstats = {sum dy, sum dy*xhat} -> coef float[3][C] with dx = a*dy + b*x + c; writes dgamma, dbeta */
+int trt_bn_bwd_finalize(const double* bstats, const float* rec, const float* gamma, float* coef, float* dgamma, float* dbeta,
+                        int C, double count, trt_stream_t stream);
+/* out = act(x*scale+shift) (+ residual); act: 0 none, 1 SiLU */
+int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, int rows, int C, int act,
+                 trt_stream_t stream);
+/* pooled_sum[n,c] = sum_hw act(bn(x)) (zeroed here; rec may be NULL = plain sum) — SE squeeze and global average pool */
+int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int N, int HW, int C, int act, trt_stream_t stream);
+/* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 (pre-activation of the reduce conv, [N,rd]) may be NULL */
+int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
+               float* s1, float* gate, int N, int C, int rd, trt_stream_t stream);
+/* out = silu(bn(x)) * gate[n,c] */
+int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C, trt_stream_t stream);
+int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C, trt_stream_t stream);
+/* out = a*dy + b*x + c */
+int trt_affine2(const void* dy, const void* x, const float* coef, void* out, int rows, int C, trt_stream_t stream);
+/* dgate_pre[n,c] = sum_hw dA * silu(bn(x)) (zeroed here) */
+int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int N, int HW, int C,
+                      trt_stream_t stream);
+/* SE MLP backward: ds2 [N,C], ds1 [N,rd], dmean [N,C] scratch/outputs; parameter gradients are WRITTEN (=) */
+int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
+               const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr, float* dWe,
+               float* dbe, int N, int C, int rd, trt_stream_t stream);
+/* g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * (act ? silu'(bn(x)) : 1); bstats += {sum g, sum g*xhat}. dA/gate/dmean may be NULL */
+int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x, const float* rec,
+                void* g_out, double* bstats, int N, int HW, int C, int act, trt_stream_t stream);
+/* fp32 [N,K] -> bf16 [N,K] and (optional) bf16 [K,N] */
+int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N, int K, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Depthwise and stem convolutions (TF 'same' padding), forward + backward.  Replace timm's Conv2dSame / depthwise
+ * conv_dw / conv_stem inside `self.backbone(x_img)` (train_mm_joint_dualtask.py:154) and autograd (:248).
+ * Weights and weight gradients stay in torch layout ([C,1,k,k] / [CS,3,3,3], fp32).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* x: [N,H,W,C]; in_rec != NULL: input = silu(bn(x)) applied on load; out_rec != NULL (eval): out = silu(bn_out(conv)),
+ * pooled_sum[n,c] (optional, zeroed here) += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output. */
+int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec, float* pooled_sum,
+                   double* stats, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
+/* upstream dD = coef ? a*gy + b*y_raw + c : gy.  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1),
+ * bstats += {sum g, sum g*xhat}; dw[C,1,k,k] += correlation of dD with act(x) (act = silu(bn) when x_rec). */
+int trt_dwconv_bwd(const void* gy, const void* y_raw, const float* coef, const float* w, const void* x_raw,
+                   const float* x_rec, void* g_out, double* bstats, float* dw, int N, int H, int W, int C, int k, int s,
+                   trt_stream_t stream);
+/* x: NCHW [N,3,H,W] fp32 or bf16 -> out NHWC bf16 [N,ceil(H/2),ceil(W/2),CS]; CS in {32, 48} */
+int trt_stem_fwd(const void* x, int x_is_bf16, const float* w, void* out, const float* out_rec, double* stats, int N, int H,
+                 int W, int CS, trt_stream_t stream);
+int trt_stem_wgrad(const void* x, int x_is_bf16, const void* ds, float* dw, int N, int H, int W, int CS, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * MIL gated-attention pooling.  Replaces AttentionMIL.forward (experiments/vision_v2/train_mil_attention_v1.py:124-130)
+ * and MILAttention.forward (ui/gradio_app/infer_mil.py:62-68).  H [B,K,D] fp32, V/U [hid,D], w [hid].
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t trt_mil_attn_smem_bytes(int K, int D, int hid, int backward);
+int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub, const float* ww,
+                     const float* wb, float* M, float* A, float* gV, float* gU, int B, int K, int D, int hid,
+                     trt_stream_t stream);
+/* parameter gradients are ACCUMULATED (+=) with atomics: zero them first */
+int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, const float* gV, const float* gU, const float* Vw,
+                     const float* Uw, const float* ww, float* dH, float* dVw, float* dVb, float* dUw, float* dUb, float* dww,
+                     float* dwb, int B, int K, int D, int hid, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tabular MLP + late fusion + dual heads + dual BCE loss.  Replaces MMJointDualHead.tab / fusion / cls_head / reg_head
+ * (experiments/multimodal_v1/train_mm_joint_dualtask.py:140-159) and the loss (:176-179, :244-247).
+ * params_host / grads_host: HOST arrays of 10 DEVICE pointers in the order
+ *   tab.0.weight, tab.0.bias, tab.1.weight, tab.1.bias, tab.4.weight, tab.4.bias, cls_head.weight, cls_head.bias,
+ *   reg_head.weight, reg_head.bias.
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t trt_tab_heads_scratch_floats(int B, int Hd);
+int trt_tab_heads_fwd(const float* feat, const float* xtab, const float* const* params_host, float* bn_rm, float* bn_rv,
+                      long long* bn_nbt, const float* y_hard, const float* y_soft, const float* sample_w, float* logit,
+                      float* reg, float* loss, float* dlogit, float* dreg, float* scratch, int B, int T, int Hd, int F,
+                      int train, float drop_p, float alpha, float beta, unsigned long long seed,
+                      const unsigned long long* step, trt_stream_t stream);
+int trt_tab_heads_bwd(const float* feat, const float* xtab, const float* const* params_host, const float* bn_rm,
+                      const float* bn_rv, const float* dlogit, const float* dreg, float* dfeat, float* const* grads_host,
+                      float* scratch, int B, int T, int Hd, int F, int train, float drop_p, unsigned long long seed,
+                      const unsigned long long* step, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused optimiser over flat fp32 buffers.  Replaces unscale_/clip_grad_norm_/AdamW.step/CosineAnnealingLR.step,
+ * experiments/multimodal_v1/train_mm_joint_dualtask.py:217-220,249-254.
+ * state (device, trt_optim_state_bytes()): {u64 step; f64 lr0, t_max, beta1, beta2; f32 lr, bc1, bc2, pad; f64 reserved}
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t trt_optim_state_bytes(void);
+int trt_optim_advance(void* state, trt_stream_t stream);                       /* ++step, lr(step), bias corrections */
+int trt_grad_sumsq(const float* g, size_t n, double* out, trt_stream_t stream); /* out[0] = sum g^2 */
+/* g_eff = g * grad_scale * min(1, max_norm / (|g*grad_scale| + 1e-6)); AdamW(lr, betas, eps, weight_decay) */
+int trt_adamw_step(float* p, const float* g, float* m, float* v, size_t n, const void* state, const double* normsq,
+                   float* norm_out, float grad_scale, float max_norm, float eps, float weight_decay, trt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEETHRT_H */

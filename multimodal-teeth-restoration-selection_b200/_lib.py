@@ -1,0 +1,114 @@
+"""ctypes binding of libteethrt.so — the only way the Python host side reaches the GPU kernels.
+
+There is NO fallback: if the shared library is missing or fails to load, importing the product path raises.
+Pointers handed to the library are device pointers of torch tensors (torch is plumbing: memory, streams, NCCL).
+"""
+import ctypes as C
+import os
+import re
+
+import torch
+
+from ._build import LIB_PATH
+
+_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "teethrt.h")
+
+
+class TeethRTError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise TeethRTError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). teethrt has no CPU or PyTorch fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+vp, i32, i64, f32, f64, u64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong, C.c_size_t
+
+_SIGS = {
+    "trt_version": (i32, []),
+    "trt_last_error_string": (C.c_char_p, []),
+    "trt_init": (i32, [i32]),
+    "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+    "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, vp]),
+    "trt_clahe_workspace_bytes": (sz, [i32]),
+    "trt_clahe_bgr_u8": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
+    "trt_resize_linear_u8": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "trt_normalize_flip_u8": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "trt_bn_finalize": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f64, f32, f32, vp]),
+    "trt_bn_fold_eval": (i32, [vp, vp, vp, vp, vp, i32, f32, vp]),
+    "trt_bn_bwd_finalize": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, vp]),
+    "trt_bn_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_pool_act": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_se_fwd": (i32, [vp, f32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_gate_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_bn_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "trt_affine2": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "trt_se_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_se_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),
+    "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "trt_stem_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_stem_wgrad": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_mil_attn_smem_bytes": (sz, [i32, i32, i32, i32]),
+    "trt_mil_attn_fwd": (i32, [vp] * 11 + [i32, i32, i32, i32, vp]),
+    "trt_mil_attn_bwd": (i32, [vp] * 15 + [i32, i32, i32, i32, vp]),
+    "trt_tab_heads_scratch_floats": (sz, [i32, i32]),
+    "trt_tab_heads_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32,
+                                f32, f32, u64, vp, vp]),
+    "trt_tab_heads_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, u64, vp, vp]),
+    "trt_optim_state_bytes": (sz, []),
+    "trt_optim_advance": (i32, [vp, vp]),
+    "trt_grad_sumsq": (i32, [vp, sz, vp, vp]),
+    "trt_adamw_step": (i32, [vp, vp, vp, vp, sz, vp, vp, vp, f32, f32, f32, f32, vp]),
+}
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)       # AttributeError here = library/header mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS = 1, 2, 4, 8
+
+
+def header_symbols():
+    """Every function name include/teethrt.h declares (used by the CPU test that checks the .so exports them all)."""
+    txt = open(_HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(trt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc):
+    if rc != 0:
+        raise TeethRTError(f"libteethrt error {rc}: {lib.trt_last_error_string().decode()}")
+
+
+_inited = set()
+
+
+def init(device=None):
+    """trt_init for the current (or given) CUDA device; raises without a B200-class GPU."""
+    if not torch.cuda.is_available():
+        raise TeethRTError("teethrt needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if dev not in _inited:
+        check(lib.trt_init(dev))
+        _inited.add(dev)
+    return dev

@@ -1,0 +1,563 @@
+// Channel-wise NHWC kernels around the GEMMs: BatchNorm statistics finalisation / application / backward,
+// squeeze-excite (pool, MLP, gate) forward and backward, global average pooling.  All HBM-bound: bf16 activations,
+// 16-byte vector accesses, one thread = one 8-channel vector of one pixel row, fp32 math, fp64 channel sums.
+//
+// Replaces the ATen/cuDNN launches behind timm's BatchNormAct2d / SqueezeExcite / global_pool inside
+// `self.backbone(x_img)` (experiments/multimodal_v1/train_mm_joint_dualtask.py:154) and their autograd backward (:248).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ---- thread mapping: rows x (C/8) vectors; a thread keeps a fixed channel vector so it can own channel accumulators
+struct RowMap {
+  int v;       // channel-vector index (channels 8v .. 8v+7)
+  int vl, ry;  // position inside the block
+  int VX, RY;
+  bool active;
+};
+__device__ __forceinline__ RowMap row_map(int V, int VX, int RY, int slab) {
+  RowMap m;
+  m.VX = VX; m.RY = RY;
+  m.ry = threadIdx.x / VX;
+  m.vl = threadIdx.x - m.ry * VX;
+  m.v = slab * VX + m.vl;
+  m.active = (m.ry < RY) && (m.v < V);
+  return m;
+}
+struct Launch { int V, slabs, VX, RY; };
+inline Launch plan(int C) {
+  Launch L;
+  L.V = C / 8;
+  L.slabs = (L.V + TPB - 1) / TPB;
+  L.VX = (L.V + L.slabs - 1) / L.slabs;
+  L.RY = TPB / L.VX;
+  return L;
+}
+inline int row_blocks(int rows, int RY, int slabs, int target_blocks) {
+  int nb = (rows + RY - 1) / RY;
+  int cap = target_blocks / slabs;
+  if (cap < 1) cap = 1;
+  return nb < cap ? nb : cap;
+}
+
+// reduce NV per-thread values (per channel of the thread's vector) over the block's RY row-lanes; result valid for ry==0
+template <int NV>
+__device__ __forceinline__ void block_reduce_rows(float (&acc)[NV], float* s_red, const RowMap& m) {
+  __syncthreads();
+  if (m.ry < m.RY) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_red[(size_t)i * TPB + threadIdx.x] = acc[i];
+  }
+  __syncthreads();
+  if (m.ry == 0 && m.active) {
+    for (int r = 1; r < m.RY; ++r) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += s_red[(size_t)i * TPB + r * m.VX + m.vl];
+    }
+  }
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) { return act ? siluf_(x) : x; }
+
+// ------------------------------------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   long long* nbt, float* __restrict__ rec, int C, double count, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  rec[c] = sc;
+  rec[C + c] = beta[c] - (float)mean * sc;
+  rec[2 * C + c] = (float)mean;
+  rec[3 * C + c] = rstd;
+  if (running_mean) {
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rm, const float* __restrict__ rv, float* __restrict__ rec, int C,
+                               float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rstd = 1.0f / sqrtf(rv[c] + eps);
+  const float sc = gamma[c] * rstd;
+  rec[c] = sc;
+  rec[C + c] = beta[c] - rm[c] * sc;
+  rec[2 * C + c] = rm[c];
+  rec[3 * C + c] = rstd;
+}
+
+// coef[0]=a, [1]=b, [2]=c with dx = a*dy + b*x + c ; also dgamma / dbeta (written, not accumulated)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ bstats, const float* __restrict__ rec,
+                                       const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int C, double count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sdy = bstats[c], sdyx = bstats[C + c];
+  const float mean = rec[2 * C + c], rstd = rec[3 * C + c];
+  const float a = gamma[c] * rstd;
+  const float m1 = (float)(sdy / count), m2 = (float)(sdyx / count);
+  coef[c] = a;
+  coef[C + c] = -a * rstd * m2;
+  coef[2 * C + c] = a * (mean * rstd * m2 - m1);
+  dgamma[c] = (float)sdyx;
+  dbeta[c] = (float)sdy;
+}
+
+// ------------------------------------------------------------------------------------------------ y = act(bn(x)) (+res)
+__global__ void __launch_bounds__(TPB) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
+                                                       const uint4* __restrict__ res, uint4* __restrict__ out, int rows,
+                                                       int C, int V, int VX, int RY, int act) {
+  const RowMap m = row_map(V, VX, RY, blockIdx.y);
+  if (!m.active) return;
+  const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
+  for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
+    const size_t idx = (size_t)r * V + m.v;
+    f8 a = unpack8(__ldg(x + idx));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act);
+    if (res) {
+      const f8 b = unpack8(__ldg(res + idx));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
+    }
+    out[idx] = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooled[n,c] += sum_hw act(bn(x))
+__global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
+                                                       float* __restrict__ pooled, int HW, int C, int V, int VX, int RY,
+                                                       int act) {
+  __shared__ float s_red[8 * TPB];
+  const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  const int n = blockIdx.y;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (m.active) {
+    f8 sc, sh;
+    if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
+      f8 a = unpack8(__ldg(x + ((size_t)n * HW + r) * V + m.v));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += rec ? act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act) : a.v[i];
+    }
+  }
+  block_reduce_rows<8>(acc, s_red, m);
+  if (m.ry == 0 && m.active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(pooled + (size_t)n * C + 8 * m.v + i, acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SE MLP forward (one block per image)
+__global__ void __launch_bounds__(TPB) se_fwd_kernel(const float* __restrict__ pooled, float inv_hw,
+                                                     const float* __restrict__ Wr, const float* __restrict__ br,
+                                                     const float* __restrict__ We, const float* __restrict__ be,
+                                                     float* __restrict__ s1_out, float* __restrict__ gate, int C, int rd) {
+  extern __shared__ float s_mem[];
+  float* s_mean = s_mem;        // [C]
+  float* s_a1 = s_mem + C;      // [rd]
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += TPB) s_mean[c] = pooled[(size_t)n * C + c] * inv_hw;
+  __syncthreads();
+  for (int r = warp; r < rd; r += TPB / 32) {
+    float acc = 0.f;
+    const float* w = Wr + (size_t)r * C;
+    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w + c), s_mean[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float s1 = acc + br[r];
+      if (s1_out) s1_out[(size_t)n * rd + r] = s1;
+      s_a1[r] = siluf_(s1);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float acc = be[c];
+    const float* w = We + (size_t)c * rd;
+    for (int r = 0; r < rd; ++r) acc = fmaf(__ldg(w + r), s_a1[r], acc);
+    gate[(size_t)n * C + c] = sigmoidf_(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ y = act(bn(x)) * gate[n,c]
+__global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
+                                                         const float* __restrict__ gate, uint4* __restrict__ out, int HW,
+                                                         int C, int V, int VX, int RY) {
+  const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  if (!m.active) return;
+  const int n = blockIdx.y;
+  const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v), g = ldf8(gate + (size_t)n * C + 8 * m.v);
+  for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
+    const size_t idx = ((size_t)n * HW + r) * V + m.v;
+    f8 a = unpack8(__ldg(x + idx));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])) * g.v[i];
+    out[idx] = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward: sums
+// bstats[0][c] += sum dy ; bstats[1][c] += sum dy * xhat
+__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                            const float* __restrict__ rec, double* __restrict__ bstats,
+                                                            int rows, int C, int V, int VX, int RY) {
+  __shared__ float s_red[16 * TPB];
+  const RowMap m = row_map(V, VX, RY, blockIdx.y);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (m.active) {
+    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
+    for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
+      const size_t idx = (size_t)r * V + m.v;
+      const f8 d = unpack8(__ldg(dy + idx)), a = unpack8(__ldg(x + idx));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += d.v[i];
+        acc[8 + i] = fmaf(d.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+      }
+    }
+  }
+  block_reduce_rows<16>(acc, s_red, m);
+  if (m.ry == 0 && m.active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(bstats + 8 * m.v + i, (double)acc[i]);
+      atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
+    }
+  }
+}
+
+// out = a*dy + b*x + c (per channel)   [BN backward apply]
+__global__ void __launch_bounds__(TPB) affine2_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                      const float* __restrict__ coef, uint4* __restrict__ out, int rows,
+                                                      int C, int V, int VX, int RY) {
+  const RowMap m = row_map(V, VX, RY, blockIdx.y);
+  if (!m.active) return;
+  const f8 ca = ldf8(coef + 8 * m.v), cb = ldf8(coef + C + 8 * m.v), cc = ldf8(coef + 2 * C + 8 * m.v);
+  for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
+    const size_t idx = (size_t)r * V + m.v;
+    const f8 d = unpack8(__ldg(dy + idx)), a = unpack8(__ldg(x + idx));
+    f8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = fmaf(ca.v[i], d.v[i], fmaf(cb.v[i], a.v[i], cc.v[i]));
+    out[idx] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SE backward, pass 1
+// dgate_pre[n,c] += sum_hw dA * silu(bn(x))
+__global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ x,
+                                                            const float* __restrict__ rec, float* __restrict__ dgate_pre,
+                                                            int HW, int C, int V, int VX, int RY) {
+  __shared__ float s_red[8 * TPB];
+  const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  const int n = blockIdx.y;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (m.active) {
+    const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
+      const size_t idx = ((size_t)n * HW + r) * V + m.v;
+      const f8 d = unpack8(__ldg(dA + idx)), a = unpack8(__ldg(x + idx));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(d.v[i], siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])), acc[i]);
+    }
+  }
+  block_reduce_rows<8>(acc, s_red, m);
+  if (m.ry == 0 && m.active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dgate_pre + (size_t)n * C + 8 * m.v + i, acc[i]);
+  }
+}
+
+// SE MLP backward per image: ds2[n,C], ds1[n,rd], dmean[n,C]
+__global__ void __launch_bounds__(TPB) se_bwd_kernel(const float* __restrict__ dgate_pre, const float* __restrict__ gate,
+                                                     const float* __restrict__ s1, const float* __restrict__ Wr,
+                                                     const float* __restrict__ We, float* __restrict__ ds2_out,
+                                                     float* __restrict__ ds1_out, float* __restrict__ dmean, int C, int rd) {
+  extern __shared__ float s_mem[];
+  float* s_ds2 = s_mem;        // [C]
+  float* s_ds1 = s_mem + C;    // [rd]
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    const float g = gate[(size_t)n * C + c];
+    const float d = dgate_pre[(size_t)n * C + c] * g * (1.f - g);
+    s_ds2[c] = d;
+    ds2_out[(size_t)n * C + c] = d;
+  }
+  __syncthreads();
+  for (int r = warp; r < rd; r += TPB / 32) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(s_ds2[c], __ldg(We + (size_t)c * rd + r), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float d = acc * silu_gradf_(s1[(size_t)n * rd + r]);
+      s_ds1[r] = d;
+      ds1_out[(size_t)n * rd + r] = d;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float acc = 0.f;
+    for (int r = 0; r < rd; ++r) acc = fmaf(s_ds1[r], __ldg(Wr + (size_t)r * C + c), acc);
+    dmean[(size_t)n * C + c] = acc;
+  }
+}
+
+// SE parameter gradients: reduction over the batch (no atomics): one thread per weight element
+__global__ void __launch_bounds__(TPB) se_bwd_w_kernel(const float* __restrict__ ds2, const float* __restrict__ ds1,
+                                                       const float* __restrict__ s1, const float* __restrict__ pooled,
+                                                       float inv_hw, float* __restrict__ dWr, float* __restrict__ dbr,
+                                                       float* __restrict__ dWe, float* __restrict__ dbe, int N, int C,
+                                                       int rd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * rd) return;
+  {  // dWe[c][r] = sum_n ds2[n][c] * silu(s1[n][r])
+    const int c = i / rd, r = i - c * rd;
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = ds2[(size_t)n * C + c];
+      acc = fmaf(d, siluf_(s1[(size_t)n * rd + r]), acc);
+      accb += d;
+    }
+    dWe[i] = acc;
+    if (r == 0) dbe[c] = accb;
+  }
+  {  // dWr[r][c] = sum_n ds1[n][r] * mean[n][c]
+    const int r = i / C, c = i - r * C;
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = ds1[(size_t)n * rd + r];
+      acc = fmaf(d, pooled[(size_t)n * C + c] * inv_hw, acc);
+      accb += d;
+    }
+    dWr[i] = acc;
+    if (c == 0) dbr[r] = accb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ activation backward
+// g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * silu'(bn(x)) ; bstats += (sum g, sum g*xhat).  dA / gate / dmean may be null.
+// act == 0: no SiLU (g = upstream), used for BN layers without activation.
+__global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ dA, const float* __restrict__ gate,
+                                                      const float* __restrict__ dmean, float inv_hw,
+                                                      const uint4* __restrict__ x, const float* __restrict__ rec,
+                                                      uint4* __restrict__ g_out, double* __restrict__ bstats, int HW, int C,
+                                                      int V, int VX, int RY, int act) {
+  __shared__ float s_red[16 * TPB];
+  const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  const int n = blockIdx.y;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (m.active) {
+    const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
+    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
+    f8 gt, dm;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gt.v[i] = 1.f; dm.v[i] = 0.f; }
+    if (gate) gt = ldf8(gate + (size_t)n * C + 8 * m.v);
+    if (dmean) {
+      dm = ldf8(dmean + (size_t)n * C + 8 * m.v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dm.v[i] *= inv_hw;
+    }
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
+      const size_t idx = ((size_t)n * HW + r) * V + m.v;
+      const f8 a = unpack8(__ldg(x + idx));
+      f8 d;
+      if (dA) d = unpack8(__ldg(dA + idx));
+      f8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float up = (dA ? d.v[i] * gt.v[i] : 0.f) + dm.v[i];
+        const float gg = act ? up * silu_gradf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : up;
+        o.v[i] = gg;
+      }
+      const uint4 packed = pack8(o);
+      g_out[idx] = packed;
+      const f8 oq = unpack8(packed);   // statistics over the bf16-rounded values that are stored
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += oq.v[i];
+        acc[8 + i] = fmaf(oq.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+      }
+    }
+  }
+  block_reduce_rows<16>(acc, s_red, m);
+  if (m.ry == 0 && m.active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(bstats + 8 * m.v + i, (double)acc[i]);
+      atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
+    }
+  }
+}
+
+// fp32 [N, K] weight -> bf16 [N, K] and bf16 [K, N] (transposed copy for dgrad)
+__global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, __nv_bfloat16* __restrict__ ot,
+                              int N, int K) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int n = n0 + j, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[(size_t)n * K + k];
+      o[(size_t)n * K + k] = __float2bfloat16_rn(v);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (ot) {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int k = k0 + j, n = n0 + threadIdx.x;
+      if (n < N && k < K) ot[(size_t)k * N + n] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+  }
+}
+
+}  // namespace
+
+#define CHECK_C(C) TRT_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channels must be a positive multiple of 8 (got %d)", __func__, (C))
+
+extern "C" int trt_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, long long* num_batches_tracked, float* rec, int C, double count,
+                               float eps, float momentum, cudaStream_t stream) {
+  TRT_REQUIRE(stats && gamma && beta && rec && C > 0 && count > 0, "trt_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, gamma, beta, running_mean, running_var,
+                                                          num_batches_tracked, rec, C, count, eps, momentum);
+  return trt_check_launch("trt_bn_finalize");
+}
+
+extern "C" int trt_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                float* rec, int C, float eps, cudaStream_t stream) {
+  TRT_REQUIRE(gamma && beta && running_mean && running_var && rec && C > 0, "trt_bn_fold_eval: bad argument");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, rec, C, eps);
+  return trt_check_launch("trt_bn_fold_eval");
+}
+
+extern "C" int trt_bn_bwd_finalize(const double* bstats, const float* rec, const float* gamma, float* coef, float* dgamma,
+                                   float* dbeta, int C, double count, cudaStream_t stream) {
+  TRT_REQUIRE(bstats && rec && gamma && coef && dgamma && dbeta && C > 0, "trt_bn_bwd_finalize: bad argument");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(bstats, rec, gamma, coef, dgamma, dbeta, C, count);
+  return trt_check_launch("trt_bn_bwd_finalize");
+}
+
+extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, int rows, int C, int act,
+                            cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(x && rec && out && rows > 0, "trt_bn_apply: bad argument");
+  const Launch L = plan(C);
+  dim3 grid(row_blocks(rows, L.RY, L.slabs, 16 * trt_num_sms()), L.slabs);
+  bn_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, (const uint4*)residual, (uint4*)out, rows, C, L.V, L.VX,
+                                            L.RY, act);
+  return trt_check_launch("trt_bn_apply");
+}
+
+extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int N, int HW, int C, int act,
+                            cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(x && pooled_sum && N > 0 && HW > 0, "trt_pool_act: bad argument");
+  const Launch L = plan(C);
+  TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
+  int target = 8 * trt_num_sms() / (N * L.slabs);
+  if (target < 1) target = 1;
+  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act);
+  return trt_check_launch("trt_pool_act");
+}
+
+extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We,
+                          const float* be, float* s1, float* gate, int N, int C, int rd, cudaStream_t stream) {
+  TRT_REQUIRE(pooled_sum && Wr && br && We && be && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
+  se_fwd_kernel<<<N, TPB, (size_t)(C + rd) * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, We, be, s1, gate, C, rd);
+  return trt_check_launch("trt_se_fwd");
+}
+
+extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C,
+                              cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(x && rec && gate && out && N > 0 && HW > 0, "trt_gate_apply: bad argument");
+  const Launch L = plan(C);
+  int target = 16 * trt_num_sms() / (N * L.slabs);
+  if (target < 1) target = 1;
+  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  gate_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, gate, (uint4*)out, HW, C, L.V, L.VX, L.RY);
+  return trt_check_launch("trt_gate_apply");
+}
+
+extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C,
+                                 cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(dy && x && rec && bstats && rows > 0, "trt_bn_bwd_reduce: bad argument");
+  const Launch L = plan(C);
+  dim3 grid(row_blocks(rows, L.RY, L.slabs, 8 * trt_num_sms()), L.slabs);
+  bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY);
+  return trt_check_launch("trt_bn_bwd_reduce");
+}
+
+extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, void* out, int rows, int C,
+                           cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(dy && x && coef && out && rows > 0, "trt_affine2: bad argument");
+  const Launch L = plan(C);
+  dim3 grid(row_blocks(rows, L.RY, L.slabs, 16 * trt_num_sms()), L.slabs);
+  affine2_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, coef, (uint4*)out, rows, C, L.V, L.VX, L.RY);
+  return trt_check_launch("trt_affine2");
+}
+
+extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int N, int HW, int C,
+                                 cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(dA && x && rec && dgate_pre && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
+  const Launch L = plan(C);
+  TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
+  int target = 8 * trt_num_sms() / (N * L.slabs);
+  if (target < 1) target = 1;
+  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  se_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, dgate_pre, HW, C, L.V, L.VX, L.RY);
+  return trt_check_launch("trt_se_bwd_reduce");
+}
+
+extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
+                          const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr,
+                          float* dWe, float* dbe, int N, int C, int rd, cudaStream_t stream) {
+  TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
+              "trt_se_bwd: null pointer");
+  se_bwd_kernel<<<N, TPB, (size_t)(C + rd) * sizeof(float), stream>>>(dgate_pre, gate, s1, Wr, We, ds2, ds1, dmean, C, rd);
+  se_bwd_w_kernel<<<(C * rd + TPB - 1) / TPB, TPB, 0, stream>>>(ds2, ds1, s1, pooled_sum, inv_hw, dWr, dbr, dWe, dbe, N, C, rd);
+  return trt_check_launch("trt_se_bwd");
+}
+
+extern "C" int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x,
+                           const float* rec, void* g_out, double* bstats, int N, int HW, int C, int act,
+                           cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(x && rec && g_out && bstats && N > 0 && HW > 0 && (dA || dmean), "trt_act_bwd: bad argument");
+  const Launch L = plan(C);
+  int target = 8 * trt_num_sms() / (N * L.slabs);
+  if (target < 1) target = 1;
+  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  act_bwd_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, (uint4*)g_out,
+                                           bstats, HW, C, L.V, L.VX, L.RY, act);
+  return trt_check_launch("trt_act_bwd");
+}
+
+extern "C" int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N, int K, cudaStream_t stream) {
+  TRT_REQUIRE(w && w_bf16 && N > 0 && K > 0, "trt_pack_w1x1: bad argument");
+  dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
+  pack_w_kernel<<<grid, block, 0, stream>>>(w, (__nv_bfloat16*)w_bf16, (__nv_bfloat16*)wt_bf16, N, K);
+  return trt_check_launch("trt_pack_w1x1");
+}

@@ -1,0 +1,479 @@
+// tcgen05 / TMEM / TMA GEMMs for the 1x1 convolutions of the EfficientNet encoder (SURVEY.md K2, 92 % of the MACs).
+//
+//   trt_gemm_bf16      C[M,N] = epi(A[M,K] . B[N,K]^T)       forward (B = W[Cout,Cin]) and dgrad (B = W^T[Cin,Cout])
+//                      both operands K-major, 128B-swizzled TMA tiles, fp32 accumulators double-buffered in TMEM,
+//                      persistent CTAs (1/SM): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+//                      Epilogue: folded-BN scale/shift, SiLU, residual add, per-channel sum/sum^2 (train-mode BN
+//                      statistics), bf16 tile staged in swizzled shared memory and written with one TMA store per
+//                      64-column chunk.
+//   trt_gemm_wgrad_bf16  O[p,q] += sum_m P[m,p] * Q[m,q]      weight gradient: both operands MN-major (the reduction
+//                      runs over rows), split over m across CTAs, fp32 red.global.add epilogue.
+//
+// Replaces: the cuDNN/cuBLAS dispatch behind `self.backbone(x_img)` (train_mm_joint_dualtask.py:154) and its autograd
+// backward (:248) for every conv_pw / conv_pwl / conv_head of timm's EfficientNet.
+#include "common.cuh"
+#include "../../include/teethrt.h"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (rows of the output tile = TMEM lanes)
+constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int MAX_STAGES = 8;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int CHUNK_BYTES = BM * 128;        // one 64-column chunk of the staged C tile
+
+struct GemmParams {
+  int M, N, K;
+  int block_n, num_m_blocks, num_n_blocks, num_k_blocks;
+  int stages, acc_stride, tmem_cols, flags;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  double* stats;  // [2][N]
+};
+
+struct SmemLayout {
+  uint32_t a_off, b_off, c_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout make_layout(int block_n, int stages) {
+  SmemLayout L;
+  uint32_t b_stage = (uint32_t)block_n * 128u;
+  L.a_off = 0;
+  L.b_off = L.a_off + (uint32_t)stages * A_STAGE_BYTES;
+  L.c_off = L.b_off + (uint32_t)stages * b_stage;
+  uint32_t chunks = (uint32_t)(block_n + 63) / 64;
+  L.bar_off = L.c_off + chunks * CHUNK_BYTES;
+  L.total = L.bar_off + 256;
+  return L;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16B-aligned by the ABI: align up to 1024 for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const SmemLayout L = make_layout(p.block_n, p.stages);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    ptx::prefetch_tmap(&tmap_c);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], EPI_THREADS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / p.num_n_blocks) * BM;
+        const int n0 = (t % p.num_n_blocks) * p.block_n;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + b_stage_bytes);
+          ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d(smem + L.b_off + stage * b_stage_bytes, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::instr_desc_bf16(BM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + L.a_off + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(smem + L.b_off + stage * b_stage_bytes);
+          const int k_rem = p.K - kb * BK;
+          const int nk = k_rem >= BK ? BK / UK : (k_rem + UK - 1) / UK;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = ptx::smem_desc(a_addr + k * (UK * 2), 0, 1024);
+            const uint64_t db = ptx::smem_desc(b_addr + k * (UK * 2), 0, 1024);
+            ptx::umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row_l = q * 32 + lane;              // row inside the 128-row tile
+    const int et = threadIdx.x - 64;              // 0..127
+    const bool leader = (et == 0);
+    uint8_t* cstage = smem + L.c_off;
+    const bool f_ss = p.flags & TRT_EPI_SCALE_SHIFT, f_silu = p.flags & TRT_EPI_SILU;
+    const bool f_res = p.flags & TRT_EPI_RESIDUAL, f_stats = p.flags & TRT_EPI_STATS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    double st_acc[4] = {0, 0, 0, 0};
+    int st_n0 = -1;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / p.num_n_blocks) * BM;
+      const int n0 = (t % p.num_n_blocks) * p.block_n;
+      const int row = m0 + row_l;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        const int col = n0 + c0;
+        if (f_ss) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (col + h * 8 < p.N) {
+              f8 sc = ldf8(p.scale + col + h * 8), sh = ldf8(p.shift + col + h * 8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[h * 8 + i] = fmaf(v[h * 8 + i], sc.v[i], sh.v[i]);
+            }
+          }
+        }
+        if (f_silu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = siluf_(v[i]);
+        }
+        if (f_res && row < p.M) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (col + h * 8 < p.N) {
+              f8 rr = unpack8(ldg16(p.residual + (size_t)row * p.N + col + h * 8));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[h * 8 + i] += rr.v[i];
+            }
+          }
+        }
+        uint8_t* crow = cstage + (c0 >> 6) * CHUNK_BYTES + row_l * 128;
+        const int piece = (c0 & 63) >> 3;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 o;
+          o.x = pack_bf16(v[h * 8 + 0], v[h * 8 + 1]);
+          o.y = pack_bf16(v[h * 8 + 2], v[h * 8 + 3]);
+          o.z = pack_bf16(v[h * 8 + 4], v[h * 8 + 5]);
+          o.w = pack_bf16(v[h * 8 + 6], v[h * 8 + 7]);
+          *reinterpret_cast<uint4*>(crow + (((piece + h) ^ (row_l & 7)) << 4)) = o;
+        }
+      }
+      // TMEM accumulator drained: hand it back to the MMA warp before the stores
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(1, EPI_THREADS);
+      if (leader) {
+        for (int c0 = 0; c0 < p.block_n; c0 += 64)
+          ptx::tma_store_2d(&tmap_c, cstage + (c0 >> 6) * CHUNK_BYTES, n0 + c0, m0);
+        ptx::tma_store_commit();
+      }
+      if (f_stats) {
+        // thread et owns columns (2et, 2et+1) of the tile; sums run over the bf16-rounded values that were stored
+        if (st_n0 != n0) {
+          if (st_n0 >= 0) {
+            const int c = st_n0 + 2 * et;
+            if (2 * et < p.block_n && c < p.N) {
+              atomicAdd(p.stats + c, st_acc[0]); atomicAdd(p.stats + c + 1, st_acc[1]);
+              atomicAdd(p.stats + p.N + c, st_acc[2]); atomicAdd(p.stats + p.N + c + 1, st_acc[3]);
+            }
+          }
+          st_acc[0] = st_acc[1] = st_acc[2] = st_acc[3] = 0;
+          st_n0 = n0;
+        }
+        if (2 * et < p.block_n) {
+          const int cc = 2 * et;
+          const uint8_t* cb = cstage + (cc >> 6) * CHUNK_BYTES;
+          const int piece = (cc & 63) >> 3, within = (cc & 7) * 2;
+          float s0 = 0, s1 = 0, q0 = 0, q1 = 0;
+#pragma unroll 8
+          for (int rr = 0; rr < BM; ++rr) {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(cb + rr * 128 + ((piece ^ (rr & 7)) << 4) + within);
+            float a = bf16_lo(w), b = bf16_hi(w);
+            s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+          }
+          st_acc[0] += s0; st_acc[1] += s1; st_acc[2] += q0; st_acc[3] += q1;
+        }
+      }
+      if (leader) ptx::tma_store_wait_read0();
+      ptx::named_bar_sync(1, EPI_THREADS);   // staging buffer free again
+    }
+    if (f_stats && st_n0 >= 0) {
+      const int c = st_n0 + 2 * et;
+      if (2 * et < p.block_n && c < p.N) {
+        atomicAdd(p.stats + c, st_acc[0]); atomicAdd(p.stats + c + 1, st_acc[1]);
+        atomicAdd(p.stats + p.N + c, st_acc[2]); atomicAdd(p.stats + p.N + c + 1, st_acc[3]);
+      }
+    }
+    if (leader) ptx::tma_store_wait0();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradParams {
+  int M, Cp, Cq;
+  int block_q;              // UMMA N (multiple of 16, <= 256)
+  int num_p_blocks, num_q_blocks, splits, mblocks_per_split, num_mblocks;
+  int stages, tmem_cols;
+  long long so_p, so_q;     // output strides (elements)
+  float* out;
+  // descriptor knobs (defaults follow the canonical MN-major SW128 layout; overridable by the bring-up test)
+  uint32_t lbo, sbo, kstep_bytes;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q,
+                  const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int q_chunks = (p.block_q + 63) / 64;
+  const uint32_t p_stage = 2 * 8192, q_stage = (uint32_t)q_chunks * 8192;
+  uint8_t* sp = smem;
+  uint8_t* sq = smem + (uint32_t)p.stages * p_stage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sq + (uint32_t)p.stages * q_stage);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* done_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int p0 = (tile / p.num_q_blocks) * BM;
+  const int q0 = (tile % p.num_q_blocks) * p.block_q;
+  const int mb_begin = split * p.mblocks_per_split;
+  const int mb_end = min(mb_begin + p.mblocks_per_split, p.num_mblocks);
+  const int nmb = mb_end - mb_begin;   // host guarantees >= 1
+  const int p_boxes = min(2, (p.Cp - p0 + 63) / 64);
+  const int q_boxes = min(q_chunks, (p.Cq - q0 + 63) / 64);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_p);
+    ptx::prefetch_tmap(&tmap_q);
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < nmb; ++i) {
+        const int r0 = (mb_begin + i) * BK;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)(p_boxes + q_boxes) * 8192u);
+        for (int j = 0; j < p_boxes; ++j)
+          ptx::tma_load_2d(sp + stage * p_stage + j * 8192, &tmap_p, &full_bar[stage], p0 + 64 * j, r0);
+        for (int j = 0; j < q_boxes; ++j)
+          ptx::tma_load_2d(sq + stage * q_stage + j * 8192, &tmap_q, &full_bar[stage], q0 + 64 * j, r0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::instr_desc_bf16(BM, p.block_q, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < nmb; ++i) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(sp + stage * p_stage);
+        const uint32_t b_addr = ptx::smem_u32(sq + stage * q_stage);
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k) {
+          const uint64_t da = ptx::smem_desc(a_addr + k * p.kstep_bytes, p.lbo, p.sbo);
+          const uint64_t db = ptx::smem_desc(b_addr + k * p.kstep_bytes, p.lbo, p.sbo);
+          ptx::umma_f16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int pr = p0 + q * 32 + lane;
+    ptx::mbar_wait(done_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.block_q; c0 += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(taddr + c0, r);
+      ptx::tmem_ld_wait();
+      if (pr < p.Cp) {
+        float* o = p.out + (long long)pr * p.so_p;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int qc = q0 + c0 + i;
+          if (qc < p.Cq) atomicAdd(o + (long long)qc * p.so_q, __uint_as_float(r[i]));
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
+}
+
+int pick_block_n(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  int best = 256, best_pad = 1 << 30;
+  const int cand[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    int pad = (N + cand[i] - 1) / cand[i] * cand[i];
+    if (pad < best_pad) { best_pad = pad; best = cand[i]; }
+  }
+  return best;
+}
+
+bool g_attr_set = false;
+}  // namespace
+
+extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
+                             const float* shift, const void* residual, double* stats, int block_n_override,
+                             cudaStream_t stream) {
+  TRT_REQUIRE(A && B && C, "trt_gemm_bf16: null operand");
+  TRT_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "trt_gemm_bf16: M,N,K must be >0 and N,K multiples of 8 (got %d %d %d)", M, N, K);
+  TRT_REQUIRE(!(flags & TRT_EPI_SCALE_SHIFT) || (scale && shift), "trt_gemm_bf16: scale/shift missing");
+  TRT_REQUIRE(!(flags & TRT_EPI_RESIDUAL) || residual, "trt_gemm_bf16: residual missing");
+  TRT_REQUIRE(!(flags & TRT_EPI_STATS) || stats, "trt_gemm_bf16: stats missing");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.block_n = block_n_override > 0 ? block_n_override : pick_block_n(N);
+  TRT_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "trt_gemm_bf16: bad block_n %d", p.block_n);
+  p.num_m_blocks = (M + BM - 1) / BM;
+  p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
+  TRT_REQUIRE(p.num_n_blocks == 1 || p.block_n % 64 == 0, "trt_gemm_bf16: tiled N needs block_n %% 64 == 0");
+  p.num_k_blocks = (K + BK - 1) / BK;
+  p.tmem_cols = pow2_cols(2 * p.block_n);
+  p.acc_stride = p.tmem_cols / 2;
+  p.flags = flags;
+  p.scale = scale; p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.stats = stats;
+  const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
+  const int chunks = (p.block_n + 63) / 64;
+  const int budget = 220 * 1024 - chunks * CHUNK_BYTES - 2048;
+  int stages = budget / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  SmemLayout L = make_layout(p.block_n, p.stages);
+  size_t smem_bytes = (size_t)L.total + 1024;      // slack for the manual 1024B alignment
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // > half an SM's smem: exactly one persistent CTA per SM
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = trt_make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
+  if ((rc = trt_make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)p.block_n, BK))) return rc;
+  if ((rc = trt_make_tmap_2d(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64))) return rc;
+  if (!g_attr_set) {
+    TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
+  gemm_kmajor_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, tc, p);
+  return trt_check_launch("trt_gemm_bf16");
+}
+
+extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int M, int Cp, int Cq, long long so_p,
+                                   long long so_q, int lbo, int sbo, int kstep_bytes, cudaStream_t stream) {
+  TRT_REQUIRE(P && Q && out, "trt_gemm_wgrad_bf16: null operand");
+  TRT_REQUIRE(M > 0 && Cp > 0 && Cq > 0 && (Cp % 8) == 0 && (Cq % 8) == 0, "trt_gemm_wgrad_bf16: bad shape %d %d %d", M, Cp, Cq);
+  WgradParams p;
+  p.M = M; p.Cp = Cp; p.Cq = Cq;
+  p.block_q = Cq <= 256 ? (Cq + 15) / 16 * 16 : pick_block_n(Cq);
+  p.num_p_blocks = (Cp + BM - 1) / BM;
+  p.num_q_blocks = (Cq + p.block_q - 1) / p.block_q;
+  p.num_mblocks = (M + BK - 1) / BK;
+  const int tiles = p.num_p_blocks * p.num_q_blocks;
+  int splits = (2 * trt_num_sms() + tiles - 1) / tiles;
+  if (splits > p.num_mblocks) splits = p.num_mblocks;
+  if (splits < 1) splits = 1;
+  p.mblocks_per_split = (p.num_mblocks + splits - 1) / splits;
+  p.splits = (p.num_mblocks + p.mblocks_per_split - 1) / p.mblocks_per_split;   // no empty split
+  p.tmem_cols = pow2_cols(p.block_q);
+  p.so_p = so_p; p.so_q = so_q; p.out = out;
+  p.lbo = lbo > 0 ? (uint32_t)lbo : 8192u;
+  p.sbo = sbo > 0 ? (uint32_t)sbo : 1024u;
+  p.kstep_bytes = kstep_bytes > 0 ? (uint32_t)kstep_bytes : 2048u;
+  const int q_chunks = (p.block_q + 63) / 64;
+  const int stage_bytes = (2 + q_chunks) * 8192;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.mblocks_per_split + 1) stages = p.mblocks_per_split + 1;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 1024;
+  CUtensorMap tp, tq;
+  int rc;
+  if ((rc = trt_make_tmap_2d(&tp, P, (uint64_t)M, (uint64_t)Cp, (uint64_t)Cp, BK, 64))) return rc;
+  if ((rc = trt_make_tmap_2d(&tq, Q, (uint64_t)M, (uint64_t)Cq, (uint64_t)Cq, BK, 64))) return rc;
+  if (!g_attr_set) {
+    TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_set = true;
+  }
+  gemm_wgrad_kernel<<<tiles * p.splits, GEMM_THREADS, smem_bytes, stream>>>(tp, tq, p);
+  return trt_check_launch("trt_gemm_wgrad_bf16");
+}

@@ -1,0 +1,337 @@
+// On-device input stage: CLAHE in Lab space (byte-exact vs OpenCV), centre-crop + bilinear resize (byte-exact),
+// ToTensor + Normalize + flip.  Integer/byte work, HBM-bound: shared-memory histograms, LUTs staged in shared memory,
+// coalesced 4-byte global accesses.  Arithmetic follows SURVEY.md App. A (OpenCV 4.x color_lab.cpp / clahe.cpp /
+// resize.cpp fixed-point paths).
+//
+// Replaces: src/preprocessing/normalise.py:10-16 (apply_clahe), src/preprocessing/pipeline.py:23-29
+// (centre_crop_resize), and ToTensor/Normalize/flip of experiments/multimodal_v1/train_mm_joint_dualtask.py:83-84,328-333.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GRID = 8;        // CLAHE_TILEGR = (8, 8)  (src/config.py:16)
+constexpr int NT = GRID * GRID;
+
+struct LabTables {             // views into the packed device table buffer (layout in teethrt.h)
+  const uint16_t* gamma;       // [256]
+  const uint16_t* cbrt;        // [3072]
+  const int32_t* yf;           // [512]  (y, ify) interleaved
+  const int32_t* abxz;         // [36864]
+  const uint8_t* invgamma;     // [4096]
+};
+__host__ __device__ inline LabTables table_views(const void* packed) {
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(packed);
+  LabTables t;
+  t.gamma = reinterpret_cast<const uint16_t*>(b + TRT_TAB_GAMMA_OFF);
+  t.cbrt = reinterpret_cast<const uint16_t*>(b + TRT_TAB_CBRT_OFF);
+  t.yf = reinterpret_cast<const int32_t*>(b + TRT_TAB_YF_OFF);
+  t.abxz = reinterpret_cast<const int32_t*>(b + TRT_TAB_ABXZ_OFF);
+  t.invgamma = b + TRT_TAB_INVGAMMA_OFF;
+  return t;
+}
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ int clamp_u8(int v) { return min(max(v, 0), 255); }
+
+// BGR -> (L, a, b), all uint8 (App. A.1).  s_gamma/s_cbrt are shared-memory copies.
+__device__ __forceinline__ void bgr2lab(int b8, int g8, int r8, const uint16_t* s_gamma, const uint16_t* s_cbrt, int& L,
+                                        int& a, int& bb) {
+  const int R = s_gamma[r8], G = s_gamma[g8], B = s_gamma[b8];
+  const int fX = s_cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
+  const int fY = s_cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
+  const int fZ = s_cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
+  L = clamp_u8(descale(296 * fY - 1336934, 15));
+  a = clamp_u8(descale(500 * (fX - fY) + 128 * 32768, 15));
+  bb = clamp_u8(descale(200 * (fY - fZ) + 128 * 32768, 15));
+}
+
+// (L, a, b) -> BGR (App. A.3)
+__device__ __forceinline__ void lab2bgr(int L, int a, int b, const int32_t* s_yf, const int32_t* __restrict__ g_abxz,
+                                        const uint8_t* s_inv, int& ob, int& og, int& orr) {
+  constexpr int BASE = 16384, minAB = -8145;
+  const int y = s_yf[2 * L], ify = s_yf[2 * L + 1];
+  const int adiv = ((5 * a * 53687 + 128) >> 13) - 128 * BASE / 500;
+  const int bdiv = ((b * 41943 + 16) >> 9) - 128 * BASE / 200 + 1;
+  const int X = __ldg(g_abxz + (ify + adiv - minAB));
+  const int Z = __ldg(g_abxz + (ify - bdiv - minAB));
+  const int ro = min(max(descale(12615 * X - 6296 * y - 2223 * Z, 14), 0), 4095);
+  const int go = min(max(descale(-3773 * X + 7684 * y + 185 * Z, 14), 0), 4095);
+  const int bo = min(max(descale(217 * X - 836 * y + 4715 * Z, 14), 0), 4095);
+  ob = s_inv[bo]; og = s_inv[go]; orr = s_inv[ro];
+}
+
+__device__ __forceinline__ int reflect101(int p, int n) { return p < n ? p : 2 * (n - 1) - p; }
+
+// ---------------------------------------------------------------- pass A: per-tile histograms of L over the padded image
+// grid = (NT * bands, N); each block histograms a horizontal band of one tile with per-warp shared sub-histograms.
+__global__ void __launch_bounds__(256) clahe_hist_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ hist,
+                                                         const void* __restrict__ tables, int H, int W, int th, int tw,
+                                                         int bands) {
+  __shared__ uint16_t s_gamma[256];
+  __shared__ uint16_t s_cbrt[3072];
+  __shared__ uint32_t s_hist[8][256];
+  const LabTables T = table_views(tables);
+  for (int i = threadIdx.x; i < 256; i += 256) s_gamma[i] = T.gamma[i];
+  for (int i = threadIdx.x; i < 3072; i += 256) s_cbrt[i] = T.cbrt[i];
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int tile = blockIdx.x / bands, band = blockIdx.x % bands;
+  const int ty = tile / GRID, tx = tile % GRID;
+  const int rows_per_band = (th + bands - 1) / bands;
+  const int y_begin = band * rows_per_band, y_end = min(th, y_begin + rows_per_band);
+  const uint8_t* img = src + (size_t)blockIdx.y * H * W * 3;
+  const int warp = threadIdx.x >> 5;
+  const int npx = (y_end - y_begin) * tw;
+  for (int i = threadIdx.x; i < npx; i += 256) {
+    const int yy = y_begin + i / tw, xx = i % tw;
+    const int y = reflect101(ty * th + yy, H), x = reflect101(tx * tw + xx, W);
+    const uint8_t* px = img + ((size_t)y * W + x) * 3;
+    int L, a, b;
+    bgr2lab(px[0], px[1], px[2], s_gamma, s_cbrt, L, a, b);
+    atomicAdd(&s_hist[warp][L], 1u);
+  }
+  __syncthreads();
+  uint32_t* out = hist + ((size_t)blockIdx.y * NT + tile) * 256;
+  uint32_t v = 0;
+#pragma unroll
+  for (int wv = 0; wv < 8; ++wv) v += s_hist[wv][threadIdx.x];
+  if (v) atomicAdd(out + threadIdx.x, v);
+}
+
+// ---------------------------------------------------------------- pass A2: clip, redistribute, cumulative LUT (App. A.2)
+// grid = (NT, N), 256 threads = one per bin.
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ luts,
+                                                        int clip_limit, float lut_scale) {
+  __shared__ int s_scan[256];
+  __shared__ int s_red[8];
+  const int i = threadIdx.x;
+  const size_t base = ((size_t)blockIdx.y * NT + blockIdx.x) * 256;
+  int h = (int)hist[base + i];
+  int over = max(h - clip_limit, 0);
+  int ws = over;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+  if ((i & 31) == 0) s_red[i >> 5] = ws;
+  __syncthreads();
+  int clipped = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) clipped += s_red[k];
+  h = min(h, clip_limit) + clipped / 256;
+  const int residual = clipped % 256;
+  if (residual) {
+    const int step = max(256 / residual, 1);
+    if (i % step == 0 && i / step < residual) h += 1;
+  }
+  // inclusive scan over 256 bins
+  s_scan[i] = h;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    int add = i >= o ? s_scan[i - o] : 0;
+    __syncthreads();
+    s_scan[i] += add;
+    __syncthreads();
+  }
+  const int v = __float2int_rn(__fmul_rn((float)s_scan[i], lut_scale));
+  luts[base + i] = (uint8_t)clamp_u8(v);
+}
+
+// ---------------------------------------------------------------- pass B: Lab -> CLAHE(L) blend -> BGR
+__device__ __forceinline__ void clahe_pixel(int b8, int g8, int r8, int ty1, int ty2, float ya, float ya1, int tx1, int tx2,
+                                            float xa, float xa1, const uint16_t* s_gamma, const uint16_t* s_cbrt,
+                                            const int32_t* s_yf, const int32_t* g_abxz, const uint8_t* s_inv,
+                                            const uint8_t* s_luts, int& ob, int& og, int& orr) {
+  int L, a, b;
+  bgr2lab(b8, g8, r8, s_gamma, s_cbrt, L, a, b);
+  const float l11 = (float)s_luts[(ty1 * GRID + tx1) * 256 + L], l12 = (float)s_luts[(ty1 * GRID + tx2) * 256 + L];
+  const float l21 = (float)s_luts[(ty2 * GRID + tx1) * 256 + L], l22 = (float)s_luts[(ty2 * GRID + tx2) * 256 + L];
+  // fp32, written order, no FMA contraction (OpenCV CLAHE_Interpolation_Body)
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  const int L2 = clamp_u8(__float2int_rn(res));
+  lab2bgr(L2, a, b, s_yf, g_abxz, s_inv, ob, og, orr);
+}
+
+__device__ __forceinline__ void tile_coord(int p, float inv_t, int& t1, int& t2, float& a, float& a1) {
+  const float tf = __fsub_rn(__fmul_rn((float)p, inv_t), 0.5f);
+  const int f = (int)floorf(tf);
+  a = __fsub_rn(tf, (float)f);
+  a1 = __fsub_rn(1.0f, a);
+  t1 = max(f, 0);
+  t2 = min(f + 1, GRID - 1);
+}
+
+// grid = (ceil(W/ (256*4)) , rows/ROWS_PER_BLOCK, N); each thread handles 4 consecutive pixels of ROWS rows.
+constexpr int APPLY_ROWS = 16;
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                          const uint8_t* __restrict__ luts, const void* __restrict__ tables,
+                                                          int H, int W, float inv_th, float inv_tw, int vec_ok) {
+  __shared__ uint16_t s_gamma[256];
+  __shared__ uint16_t s_cbrt[3072];
+  __shared__ int32_t s_yf[512];
+  __shared__ uint8_t s_inv[4096];
+  __shared__ __align__(16) uint8_t s_luts[NT * 256];
+  const LabTables T = table_views(tables);
+  for (int i = threadIdx.x; i < 256; i += 256) s_gamma[i] = T.gamma[i];
+  for (int i = threadIdx.x; i < 3072; i += 256) s_cbrt[i] = T.cbrt[i];
+  for (int i = threadIdx.x; i < 512; i += 256) s_yf[i] = T.yf[i];
+  for (int i = threadIdx.x; i < 1024; i += 256)
+    reinterpret_cast<uint32_t*>(s_inv)[i] = reinterpret_cast<const uint32_t*>(T.invgamma)[i];
+  const uint8_t* lut_img = luts + (size_t)blockIdx.z * NT * 256;
+  for (int i = threadIdx.x; i < NT * 256 / 16; i += 256)
+    reinterpret_cast<uint4*>(s_luts)[i] = reinterpret_cast<const uint4*>(lut_img)[i];
+  __syncthreads();
+  const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (x0 >= W) return;
+  const size_t img_off = (size_t)blockIdx.z * H * W * 3;
+  int tx1[4], tx2[4];
+  float xa[4], xa1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile_coord(x0 + j, inv_tw, tx1[j], tx2[j], xa[j], xa1[j]);
+  const int y_begin = blockIdx.y * APPLY_ROWS;
+  for (int y = y_begin; y < min(H, y_begin + APPLY_ROWS); ++y) {
+    int ty1, ty2;
+    float ya, ya1;
+    tile_coord(y, inv_th, ty1, ty2, ya, ya1);
+    const size_t off = img_off + ((size_t)y * W + x0) * 3;
+    if (vec_ok && x0 + 4 <= W) {
+      const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + off);
+      const uint32_t w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2);
+      uint8_t in[12], out[12];
+      *reinterpret_cast<uint32_t*>(in) = w0;
+      *reinterpret_cast<uint32_t*>(in + 4) = w1;
+      *reinterpret_cast<uint32_t*>(in + 8) = w2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int ob, og, orr;
+        clahe_pixel(in[3 * j], in[3 * j + 1], in[3 * j + 2], ty1, ty2, ya, ya1, tx1[j], tx2[j], xa[j], xa1[j], s_gamma,
+                    s_cbrt, s_yf, T.abxz, s_inv, s_luts, ob, og, orr);
+        out[3 * j] = (uint8_t)ob; out[3 * j + 1] = (uint8_t)og; out[3 * j + 2] = (uint8_t)orr;
+      }
+      uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + off);
+      d4[0] = *reinterpret_cast<uint32_t*>(out);
+      d4[1] = *reinterpret_cast<uint32_t*>(out + 4);
+      d4[2] = *reinterpret_cast<uint32_t*>(out + 8);
+    } else {
+      for (int j = 0; j < 4 && x0 + j < W; ++j) {
+        const uint8_t* px = src + off + 3 * j;
+        int ob, og, orr;
+        clahe_pixel(px[0], px[1], px[2], ty1, ty2, ya, ya1, tx1[j], tx2[j], xa[j], xa1[j], s_gamma, s_cbrt, s_yf, T.abxz,
+                    s_inv, s_luts, ob, og, orr);
+        uint8_t* q = dst + off + 3 * j;
+        q[0] = (uint8_t)ob; q[1] = (uint8_t)og; q[2] = (uint8_t)orr;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- centre crop + cv2.resize(INTER_LINEAR) (App. A.4)
+__device__ __forceinline__ void axis_coef(int d, double scale, int ssize, bool zero_edges, int& s, int& w0, int& w1) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int si = (int)floorf(f);
+  f = __fsub_rn(f, (float)si);
+  if (zero_edges) {
+    if (si < 0) { f = 0.f; si = 0; }
+    if (si >= ssize - 1) { f = 0.f; si = ssize - 1; }
+  }
+  s = si;
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.f));
+}
+
+__global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
+                                                            int W, int y_off, int x_off, int sh, int sw, int dh, int dw) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+  if (dx >= dw) return;
+  const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
+  int sx, wx0, wx1, sy, wy0, wy1;
+  axis_coef(dx, scale_x, sw, true, sx, wx0, wx1);
+  axis_coef(dy, scale_y, sh, false, sy, wy0, wy1);
+  const int sx1 = min(sx + 1, sw - 1);
+  const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
+  const uint8_t* img = src + (size_t)blockIdx.z * H * W * 3;
+  const uint8_t* r0 = img + ((size_t)(y0 + y_off) * W + x_off) * 3;
+  const uint8_t* r1 = img + ((size_t)(y1 + y_off) * W + x_off) * 3;
+  uint8_t* o = dst + (((size_t)blockIdx.z * dh + dy) * dw + dx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int a0 = r0[sx * 3 + c] * wx0 + r0[sx1 * 3 + c] * wx1;
+    const int a1 = r1[sx * 3 + c] * wx0 + r1[sx1 * 3 + c] * wx1;
+    const int v = (((wy0 * (a0 >> 4)) >> 16) + ((wy1 * (a1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)clamp_u8(v);
+  }
+}
+
+// ---------------------------------------------------------------- ToTensor + Normalize + flip: u8 HWC BGR -> CHW RGB
+template <typename OutT>
+__global__ void __launch_bounds__(256) normalize_flip_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst, int H,
+                                                             int W, int flip) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int sy = flip == 2 ? H - 1 - y : y, sx = flip == 1 ? W - 1 - x : x;
+  const uint8_t* px = src + (((size_t)blockIdx.z * H + sy) * W + sx) * 3;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  OutT* o = dst + (size_t)blockIdx.z * 3 * H * W + (size_t)y * W + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[2 - c], 255.f), mean[c]), stdv[c]);
+    if constexpr (sizeof(OutT) == 2) o[(size_t)c * H * W] = __float2bfloat16_rn(v);
+    else o[(size_t)c * H * W] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t trt_clahe_workspace_bytes(int n) { return (size_t)n * NT * 256 * (sizeof(uint32_t) + 1); }
+
+extern "C" int trt_clahe_bgr_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, float clip, const void* tables,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  TRT_REQUIRE(src && dst && tables && workspace, "trt_clahe_bgr_u8: null pointer");
+  TRT_REQUIRE(n > 0 && h >= GRID && w >= GRID, "trt_clahe_bgr_u8: bad shape n=%d h=%d w=%d", n, h, w);
+  TRT_REQUIRE(workspace_bytes >= trt_clahe_workspace_bytes(n), "trt_clahe_bgr_u8: workspace too small");
+  // OpenCV pads to a multiple of the grid with a FULL extra tile-size step when only one axis is off (App. A.2)
+  int hp = h, wp = w;
+  if (h % GRID || w % GRID) { hp = h + (GRID - h % GRID); wp = w + (GRID - w % GRID); }
+  const int th = hp / GRID, tw = wp / GRID;
+  TRT_REQUIRE(hp - h < h && wp - w < w, "trt_clahe_bgr_u8: image too small for reflect-101 padding");
+  const int area = th * tw;
+  int clip_limit = (int)((double)clip * (double)area / 256.0);
+  if (clip_limit < 1) clip_limit = 1;
+  const float lut_scale = 255.0f / (float)area;
+  const float inv_th = 1.0f / (float)th, inv_tw = 1.0f / (float)tw;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
+  uint8_t* luts = reinterpret_cast<uint8_t*>(workspace) + (size_t)n * NT * 256 * sizeof(uint32_t);
+  TRT_CUDA(cudaMemsetAsync(hist, 0, (size_t)n * NT * 256 * sizeof(uint32_t), stream));
+  int bands = 1;
+  while (bands < 8 && n * NT * bands < 4 * trt_num_sms() && th / (bands * 2) >= 8) bands *= 2;
+  clahe_hist_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
+  clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
+  const int vec_ok = (w % 4 == 0) && (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 3) == 0);
+  dim3 grid((w + 1023) / 1024, (h + APPLY_ROWS - 1) / APPLY_ROWS, n);
+  clahe_apply_kernel<<<grid, 256, 0, stream>>>(src, dst, luts, tables, h, w, inv_th, inv_tw, vec_ok);
+  return trt_check_launch("trt_clahe_bgr_u8");
+}
+
+extern "C" int trt_resize_linear_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int centre_crop, int dh, int dw,
+                                    cudaStream_t stream) {
+  TRT_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && dh > 0 && dw > 0, "trt_resize_linear_u8: bad argument");
+  int sh = h, sw = w, y_off = 0, x_off = 0;
+  if (centre_crop) {
+    const int d = h < w ? h : w;
+    y_off = (h - d) / 2; x_off = (w - d) / 2; sh = sw = d;
+  }
+  dim3 grid((dw + 255) / 256, dh, n);
+  resize_linear_kernel<<<grid, 256, 0, stream>>>(src, dst, h, w, y_off, x_off, sh, sw, dh, dw);
+  return trt_check_launch("trt_resize_linear_u8");
+}
+
+extern "C" int trt_normalize_flip_u8(const uint8_t* src, void* dst, int n, int h, int w, int flip, int out_bf16,
+                                     cudaStream_t stream) {
+  TRT_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && flip >= 0 && flip <= 2, "trt_normalize_flip_u8: bad argument");
+  dim3 grid((w + 255) / 256, h, n);
+  if (out_bf16)
+    normalize_flip_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), h, w, flip);
+  else
+    normalize_flip_kernel<float><<<grid, 256, 0, stream>>>(src, reinterpret_cast<float*>(dst), h, w, flip);
+  return trt_check_launch("trt_normalize_flip_u8");
+}

@@ -1,0 +1,484 @@
+// Small fused kernels of the hot path:
+//   * MIL gated-attention pooling forward/backward (one CTA per bag: instance matrix staged once in shared memory with
+//     coalesced float4 reads, warp-shuffle reductions for the gate dot products, the softmax over instances and the
+//     weighted sum).  Replaces AttentionMIL.forward, experiments/vision_v2/train_mil_attention_v1.py:124-130 and
+//     MILAttention.forward, ui/gradio_app/infer_mil.py:62-68.
+//   * tabular MLP + late-fusion dual heads + dual BCE loss forward/backward in ONE CTA (the whole problem is a few
+//     hundred KFLOP; what matters is launch count).  Replaces `self.tab`, `self.fusion`, `cls_head`, `reg_head`
+//     (experiments/multimodal_v1/train_mm_joint_dualtask.py:140-159) and the loss (:176-179, :244-247).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int KC = 16;   // instances processed per register chunk
+
+// ================================================================================================= MIL attention
+__global__ void __launch_bounds__(TPB) mil_attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Vw,
+                                                           const float* __restrict__ Vb, const float* __restrict__ Uw,
+                                                           const float* __restrict__ Ub, const float* __restrict__ ww,
+                                                           const float* __restrict__ wb, float* __restrict__ M,
+                                                           float* __restrict__ A, float* __restrict__ gV,
+                                                           float* __restrict__ gU, int K, int D, int hid) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_H = sm;                       // [K][D]
+  float* s_pre = s_H + (size_t)K * D;    // [2*hid][K]  pre-activations (V rows then U rows)
+  float* s_att = s_pre + (size_t)2 * hid * K;   // [K]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* Hg = reinterpret_cast<const float4*>(H + (size_t)b * K * D);
+  const int D4 = D / 4;
+  for (int i = threadIdx.x; i < K * D4; i += TPB) reinterpret_cast<float4*>(s_H)[i] = __ldg(Hg + i);
+  __syncthreads();
+  for (int j = warp; j < 2 * hid; j += TPB / 32) {
+    const float4* wrow = reinterpret_cast<const float4*>((j < hid ? Vw + (size_t)j * D : Uw + (size_t)(j - hid) * D));
+    const float bias = j < hid ? Vb[j] : Ub[j - hid];
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      float acc[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+      for (int d = lane; d < D4; d += 32) {
+        const float4 w4 = __ldg(wrow + d);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          if (k0 + k < K) {
+            const float4 h = reinterpret_cast<const float4*>(s_H + (size_t)(k0 + k) * D)[d];
+            acc[k] = fmaf(w4.x, h.x, fmaf(w4.y, h.y, fmaf(w4.z, h.z, fmaf(w4.w, h.w, acc[k]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0 && k0 + k < K) s_pre[(size_t)j * K + k0 + k] = s + bias;
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += TPB / 32) {
+    float acc = 0.f;
+    for (int j = lane; j < hid; j += 32) {
+      const float tv = tanhf(s_pre[(size_t)j * K + k]);
+      const float su = 1.0f / (1.0f + expf(-s_pre[(size_t)(hid + j) * K + k]));
+      if (gV) { gV[((size_t)b * K + k) * hid + j] = tv; gU[((size_t)b * K + k) * hid + j] = su; }
+      acc = fmaf(ww[j], tv * su, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_att[k] = acc + wb[0];
+  }
+  __syncthreads();
+  if (warp == 0) {   // softmax over the K instances (dim=1 of [B,K]; dim=0 of the twin's single bag)
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, s_att[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < K; k += 32) sum += expf(s_att[k] - mx);
+    sum = warp_sum(sum);
+    for (int k = lane; k < K; k += 32) {
+      const float a = expf(s_att[k] - mx) / sum;
+      s_att[k] = a;
+      A[(size_t)b * K + k] = a;
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += TPB) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(s_att[k], s_H[(size_t)k * D + d], acc);
+    M[(size_t)b * D + d] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) mil_attn_bwd_kernel(const float* __restrict__ dM, const float* __restrict__ H,
+                                                           const float* __restrict__ A, const float* __restrict__ gV,
+                                                           const float* __restrict__ gU, const float* __restrict__ Vw,
+                                                           const float* __restrict__ Uw, const float* __restrict__ ww,
+                                                           float* __restrict__ dH, float* __restrict__ dVw,
+                                                           float* __restrict__ dVb, float* __restrict__ dUw,
+                                                           float* __restrict__ dUb, float* __restrict__ dww,
+                                                           float* __restrict__ dwb, int K, int D, int hid) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_H = sm;                          // [K][D]
+  float* s_dM = s_H + (size_t)K * D;        // [D]
+  float* s_dv = s_dM + D;                   // [K][hid]
+  float* s_du = s_dv + (size_t)K * hid;     // [K][hid]
+  float* s_da = s_du + (size_t)K * hid;     // [K]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D4 = D / 4;
+  const float4* Hg = reinterpret_cast<const float4*>(H + (size_t)b * K * D);
+  for (int i = threadIdx.x; i < K * D4; i += TPB) reinterpret_cast<float4*>(s_H)[i] = __ldg(Hg + i);
+  for (int i = threadIdx.x; i < D; i += TPB) s_dM[i] = dM[(size_t)b * D + i];
+  __syncthreads();
+  for (int k = warp; k < K; k += TPB / 32) {   // dalpha_k = <dM, H_k>
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(s_dM[d], s_H[(size_t)k * D + d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_da[k] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {   // softmax backward
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot = fmaf(A[(size_t)b * K + k], s_da[k], dot);
+    dot = warp_sum(dot);
+    float sb = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float da = A[(size_t)b * K + k] * (s_da[k] - dot);
+      s_da[k] = da;
+      sb += da;
+    }
+    sb = warp_sum(sb);
+    if (lane == 0) atomicAdd(dwb, sb);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += TPB) {
+    float aw = 0.f, av = 0.f, au = 0.f;
+    const float wj = ww[j];
+    for (int k = 0; k < K; ++k) {
+      const float tv = gV[((size_t)b * K + k) * hid + j], su = gU[((size_t)b * K + k) * hid + j];
+      const float da = s_da[k];
+      aw = fmaf(da, tv * su, aw);
+      const float dg = da * wj;
+      const float dv = dg * su * (1.f - tv * tv), du = dg * tv * su * (1.f - su);
+      s_dv[(size_t)k * hid + j] = dv;
+      s_du[(size_t)k * hid + j] = du;
+      av += dv; au += du;
+    }
+    atomicAdd(dww + j, aw);
+    atomicAdd(dVb + j, av);
+    atomicAdd(dUb + j, au);
+  }
+  __syncthreads();
+  for (int j = warp; j < 2 * hid; j += TPB / 32) {   // weight gradients: dW[j][:] += sum_k dv[k][j] * H_k
+    const float* sd = j < hid ? s_dv + j : s_du + (j - hid);
+    float* dst = j < hid ? dVw + (size_t)j * D : dUw + (size_t)(j - hid) * D;
+    for (int d = lane; d < D4; d += 32) {
+      float4 acc = make_float4(0, 0, 0, 0);
+      for (int k = 0; k < K; ++k) {
+        const float c = sd[(size_t)k * hid];
+        const float4 h = reinterpret_cast<const float4*>(s_H + (size_t)k * D)[d];
+        acc.x = fmaf(c, h.x, acc.x); acc.y = fmaf(c, h.y, acc.y); acc.z = fmaf(c, h.z, acc.z); acc.w = fmaf(c, h.w, acc.w);
+      }
+      atomicAdd(dst + 4 * d, acc.x); atomicAdd(dst + 4 * d + 1, acc.y);
+      atomicAdd(dst + 4 * d + 2, acc.z); atomicAdd(dst + 4 * d + 3, acc.w);
+    }
+  }
+  // dH[k][d] = alpha_k * dM[d] + sum_j dv[k][j] Vw[j][d] + du[k][j] Uw[j][d]
+  for (int d = threadIdx.x; d < D; d += TPB) {
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      float acc[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+      for (int j = 0; j < hid; ++j) {
+        const float wv = __ldg(Vw + (size_t)j * D + d), wu = __ldg(Uw + (size_t)j * D + d);
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+          if (k0 + k < K) acc[k] = fmaf(s_dv[(size_t)(k0 + k) * hid + j], wv, fmaf(s_du[(size_t)(k0 + k) * hid + j], wu, acc[k]));
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k)
+        if (k0 + k < K) dH[((size_t)b * K + k0 + k) * D + d] = fmaf(A[(size_t)b * K + k0 + k], s_dM[d], acc[k]);
+    }
+  }
+}
+
+// ================================================================================================= tab MLP + heads + loss
+// counter-based uniform in [0,1): splitmix64 of (seed, stream, index)
+__device__ __forceinline__ float urand(unsigned long long seed, unsigned long long stream_id, unsigned long long idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (stream_id * 0x100000001B3ull + idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float keep_scale(float p, unsigned long long seed, unsigned long long stream_id, unsigned long long idx) {
+  if (p <= 0.f) return 1.f;
+  return urand(seed, stream_id, idx) >= p ? 1.f / (1.f - p) : 0.f;
+}
+
+struct TabParams {
+  int B, T, Hd, F;          // batch, tab_in, tab_hidden, image feature dim
+  int train;                // train-mode BN1d (batch statistics) + dropout
+  float drop_p, bn_eps, bn_momentum, alpha, beta;
+  unsigned long long seed;  // dropout seed
+  const unsigned long long* step;   // device step counter mixed into the seed (may be null)
+  // inputs
+  const float* feat;   // [B,F]
+  const float* xtab;   // [B,T]
+  // parameters
+  const float *W0, *b0, *bn_g, *bn_b, *W1, *b1, *cls_w, *cls_b, *reg_w, *reg_b;
+  float *bn_rm, *bn_rv;
+  long long* bn_nbt;
+  // optional loss inputs
+  const float *y_hard, *y_soft, *sample_w;
+  // outputs
+  float *logit, *reg, *loss;        // [B], [B], [1]
+  float *dlogit, *dreg;             // [B] gradient of the loss w.r.t. the two head outputs (written when targets given)
+  // scratch (global, caller provided): z0 [B,Hd], a1 [B,Hd], ft [B,Hd], bnstat [2*Hd]
+  float* scratch;
+};
+
+__global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
+  const int B = p.B, T = p.T, Hd = p.Hd, F = p.F;
+  float* z0 = p.scratch;
+  float* a1 = z0 + (size_t)B * Hd;
+  float* ft = a1 + (size_t)B * Hd;
+  float* bnstat = ft + (size_t)B * Hd;   // mean[Hd], rstd[Hd]
+  __shared__ float s_loss[TPB / 32];
+  const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
+    const int b = i / Hd, j = i % Hd;
+    float acc = p.b0[j];
+    for (int t = 0; t < T; ++t) acc = fmaf(p.xtab[b * T + t], p.W0[j * T + t], acc);
+    z0[i] = acc;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Hd; j += TPB) {
+    float mean, rstd;
+    if (p.train) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += z0[b * Hd + j];
+      mean = s / B;
+      float v = 0.f;
+      for (int b = 0; b < B; ++b) { const float d = z0[b * Hd + j] - mean; v = fmaf(d, d, v); }
+      const float var = v / B;
+      rstd = rsqrtf(var + p.bn_eps);
+      p.bn_rm[j] = (1.f - p.bn_momentum) * p.bn_rm[j] + p.bn_momentum * mean;
+      p.bn_rv[j] = (1.f - p.bn_momentum) * p.bn_rv[j] + p.bn_momentum * (B > 1 ? v / (B - 1) : var);
+      if (j == 0 && p.bn_nbt) *p.bn_nbt += 1;
+    } else {
+      mean = p.bn_rm[j];
+      rstd = rsqrtf(p.bn_rv[j] + p.bn_eps);
+    }
+    bnstat[j] = mean;
+    bnstat[Hd + j] = rstd;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
+    const int j = i % Hd;
+    float v = (z0[i] - bnstat[j]) * bnstat[Hd + j] * p.bn_g[j] + p.bn_b[j];
+    v = fmaxf(v, 0.f);
+    if (p.train) v *= keep_scale(p.drop_p, seed, 1, i);
+    a1[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
+    const int b = i / Hd, j = i % Hd;
+    float acc = p.b1[j];
+    for (int t = 0; t < Hd; ++t) acc = fmaf(a1[b * Hd + t], p.W1[j * Hd + t], acc);
+    ft[i] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  float loss_part = 0.f;
+  for (int b = warp; b < B; b += TPB / 32) {
+    float lc = 0.f, lr = 0.f;
+    for (int i = lane; i < F + Hd; i += 32) {
+      float f = i < F ? p.feat[(size_t)b * F + i] : ft[b * Hd + (i - F)];
+      if (p.train) f *= keep_scale(p.drop_p, seed, 2, (unsigned long long)b * (F + Hd) + i);
+      lc = fmaf(f, p.cls_w[i], lc);
+      lr = fmaf(f, p.reg_w[i], lr);
+    }
+    lc = warp_sum(lc) + p.cls_b[0];
+    lr = warp_sum(lr) + p.reg_b[0];
+    if (lane == 0) {
+      p.logit[b] = lc;
+      p.reg[b] = lr;
+      if (p.y_hard) {
+        const float w = p.sample_w ? p.sample_w[b] : 1.f;
+        const float yh = p.y_hard[b], ys = p.y_soft[b];
+        const float bh = fmaxf(lc, 0.f) - lc * yh + log1pf(expf(-fabsf(lc)));
+        const float bs = fmaxf(lr, 0.f) - lr * ys + log1pf(expf(-fabsf(lr)));
+        loss_part += w * (p.alpha * bh + p.beta * bs) / B;
+        p.dlogit[b] = p.alpha * w * (1.f / (1.f + expf(-lc)) - yh) / B;
+        p.dreg[b] = p.beta * w * (1.f / (1.f + expf(-lr)) - ys) / B;
+      }
+    }
+  }
+  if (p.y_hard) {
+    if (lane == 0) s_loss[warp] = loss_part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < TPB / 32; ++i) s += s_loss[i];
+      p.loss[0] = s;
+    }
+  }
+}
+
+struct TabBwdParams {
+  TabParams f;                 // same forward description (scratch still holds z0, a1, ft, bnstat)
+  const float *dlogit, *dreg;  // [B]
+  float* dfeat;                // [B,F]
+  float *dW0, *db0, *dbn_g, *dbn_b, *dW1, *db1, *dcls_w, *dcls_b, *dreg_w, *dreg_b;   // written (=), not accumulated
+  float* scratch2;             // dz1 [B,Hd], da1 [B,Hd]
+};
+
+__global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q) {
+  const TabParams& p = q.f;
+  const int B = p.B, T = p.T, Hd = p.Hd, F = p.F;
+  const float* z0 = p.scratch;
+  const float* a1 = z0 + (size_t)B * Hd;
+  const float* ft = a1 + (size_t)B * Hd;
+  const float* bnstat = ft + (size_t)B * Hd;
+  float* dz1 = q.scratch2;
+  float* da1 = dz1 + (size_t)B * Hd;
+  const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
+  // head weight gradients + gradient into the fused vector
+  for (int i = threadIdx.x; i < F + Hd; i += TPB) {
+    float gc = 0.f, gr = 0.f;
+    const float wc = p.cls_w[i], wr = p.reg_w[i];
+    for (int b = 0; b < B; ++b) {
+      float f = i < F ? p.feat[(size_t)b * F + i] : ft[b * Hd + (i - F)];
+      const float ks = p.train ? keep_scale(p.drop_p, seed, 2, (unsigned long long)b * (F + Hd) + i) : 1.f;
+      f *= ks;
+      const float dl = q.dlogit[b], dr = q.dreg[b];
+      gc = fmaf(dl, f, gc);
+      gr = fmaf(dr, f, gr);
+      const float df = (dl * wc + dr * wr) * ks;
+      if (i < F) q.dfeat[(size_t)b * F + i] = df;
+      else dz1[b * Hd + (i - F)] = ft[b * Hd + (i - F)] > 0.f ? df : 0.f;   // through the last ReLU
+    }
+    q.dcls_w[i] = gc;
+    q.dreg_w[i] = gr;
+  }
+  if (threadIdx.x == 0) {
+    float sc = 0.f, sr = 0.f;
+    for (int b = 0; b < B; ++b) { sc += q.dlogit[b]; sr += q.dreg[b]; }
+    q.dcls_b[0] = sc;
+    q.dreg_b[0] = sr;
+  }
+  __syncthreads();
+  // second linear: dW1[j][t] = sum_b dz1[b][j] a1[b][t]; db1; da1 = dz1 . W1
+  for (int i = threadIdx.x; i < Hd * Hd; i += TPB) {
+    const int j = i / Hd, t = i % Hd;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(dz1[b * Hd + j], a1[b * Hd + t], acc);
+    q.dW1[i] = acc;
+  }
+  for (int j = threadIdx.x; j < Hd; j += TPB) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dz1[b * Hd + j];
+    q.db1[j] = acc;
+  }
+  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
+    const int b = i / Hd, t = i % Hd;
+    float acc = 0.f;
+    for (int j = 0; j < Hd; ++j) acc = fmaf(dz1[b * Hd + j], p.W1[j * Hd + t], acc);
+    // through dropout and ReLU of the first layer (a1 > 0 <=> kept and positive)
+    const float ks = p.train ? keep_scale(p.drop_p, seed, 1, i) : 1.f;
+    da1[i] = a1[i] > 0.f ? acc * ks : 0.f;
+  }
+  __syncthreads();
+  // BatchNorm1d backward (batch statistics in train mode, plain scaling in eval) -> overwrite da1 with dz0
+  for (int j = threadIdx.x; j < Hd; j += TPB) {
+    const float mean = bnstat[j], rstd = bnstat[Hd + j], gma = p.bn_g[j];
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float d = da1[b * Hd + j], xh = (z0[b * Hd + j] - mean) * rstd;
+      s1 += d; s2 = fmaf(d, xh, s2);
+    }
+    q.dbn_b[j] = s1;
+    q.dbn_g[j] = s2;
+    for (int b = 0; b < B; ++b) {
+      const float d = da1[b * Hd + j], xh = (z0[b * Hd + j] - mean) * rstd;
+      da1[b * Hd + j] = p.train ? gma * rstd * (d - s1 / B - xh * s2 / B) : gma * rstd * d;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Hd * T; i += TPB) {
+    const int j = i / T, t = i % T;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(da1[b * Hd + j], p.xtab[b * T + t], acc);
+    q.dW0[i] = acc;
+  }
+  for (int j = threadIdx.x; j < Hd; j += TPB) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += da1[b * Hd + j];
+    q.db0[j] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t trt_mil_attn_smem_bytes(int K, int D, int hid, int backward) {
+  if (backward) return ((size_t)K * D + D + 2 * (size_t)K * hid + K) * sizeof(float);
+  return ((size_t)K * D + 2 * (size_t)hid * K + K) * sizeof(float);
+}
+
+extern "C" int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub,
+                                const float* ww, const float* wb, float* M, float* A, float* gV, float* gU, int B, int K,
+                                int D, int hid, cudaStream_t stream) {
+  TRT_REQUIRE(H && Vw && Vb && Uw && Ub && ww && wb && M && A, "trt_mil_attn_fwd: null pointer");
+  TRT_REQUIRE(B > 0 && K > 0 && D > 0 && D % 4 == 0 && hid > 0, "trt_mil_attn_fwd: bad shape");
+  TRT_REQUIRE((gV == nullptr) == (gU == nullptr), "trt_mil_attn_fwd: gV and gU must be given together");
+  const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 0);
+  TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_fwd: bag of %d x %d does not fit in shared memory", K, D);
+  static bool attr = false;
+  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  mil_attn_fwd_kernel<<<B, TPB, smem, stream>>>(H, Vw, Vb, Uw, Ub, ww, wb, M, A, gV, gU, K, D, hid);
+  return trt_check_launch("trt_mil_attn_fwd");
+}
+
+extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, const float* gV, const float* gU,
+                                const float* Vw, const float* Uw, const float* ww, float* dH, float* dVw, float* dVb,
+                                float* dUw, float* dUb, float* dww, float* dwb, int B, int K, int D, int hid,
+                                cudaStream_t stream) {
+  TRT_REQUIRE(dM && H && A && gV && gU && Vw && Uw && ww && dH && dVw && dVb && dUw && dUb && dww && dwb,
+              "trt_mil_attn_bwd: null pointer");
+  TRT_REQUIRE(B > 0 && K > 0 && D > 0 && D % 4 == 0 && hid > 0, "trt_mil_attn_bwd: bad shape");
+  const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 1);
+  TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_bwd: bag of %d x %d does not fit in shared memory", K, D);
+  static bool attr = false;
+  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  mil_attn_bwd_kernel<<<B, TPB, smem, stream>>>(dM, H, A, gV, gU, Vw, Uw, ww, dH, dVw, dVb, dUw, dUb, dww, dwb, K, D, hid);
+  return trt_check_launch("trt_mil_attn_bwd");
+}
+
+extern "C" size_t trt_tab_heads_scratch_floats(int B, int Hd) { return (size_t)5 * B * Hd + 2 * Hd; }
+
+extern "C" int trt_tab_heads_fwd(const float* feat, const float* xtab, const float* const* params_host, float* bn_rm,
+                                 float* bn_rv, long long* bn_nbt, const float* y_hard, const float* y_soft,
+                                 const float* sample_w, float* logit, float* reg, float* loss, float* dlogit, float* dreg,
+                                 float* scratch, int B, int T, int Hd, int F, int train, float drop_p, float alpha,
+                                 float beta, unsigned long long seed, const unsigned long long* step, cudaStream_t stream) {
+  TRT_REQUIRE(feat && xtab && params_host && logit && reg && scratch && bn_rm && bn_rv, "trt_tab_heads_fwd: null pointer");
+  TRT_REQUIRE(B > 0 && T > 0 && Hd > 0 && F > 0, "trt_tab_heads_fwd: bad shape");
+  TRT_REQUIRE(!(train && B < 2), "trt_tab_heads_fwd: Expected more than 1 value per channel when training (BatchNorm1d, batch %d)", B);
+  TRT_REQUIRE(!y_hard || (y_soft && loss && dlogit && dreg), "trt_tab_heads_fwd: loss outputs missing");
+  TabParams p;
+  p.B = B; p.T = T; p.Hd = Hd; p.F = F; p.train = train;
+  p.drop_p = drop_p; p.bn_eps = 1e-5f; p.bn_momentum = 0.1f; p.alpha = alpha; p.beta = beta;
+  p.seed = seed; p.step = step;
+  p.feat = feat; p.xtab = xtab;
+  p.W0 = params_host[0]; p.b0 = params_host[1]; p.bn_g = params_host[2]; p.bn_b = params_host[3]; p.W1 = params_host[4]; p.b1 = params_host[5];
+  p.cls_w = params_host[6]; p.cls_b = params_host[7]; p.reg_w = params_host[8]; p.reg_b = params_host[9];
+  p.bn_rm = bn_rm; p.bn_rv = bn_rv; p.bn_nbt = bn_nbt;
+  p.y_hard = y_hard; p.y_soft = y_soft; p.sample_w = sample_w;
+  p.logit = logit; p.reg = reg; p.loss = loss; p.dlogit = dlogit; p.dreg = dreg;
+  p.scratch = scratch;
+  tab_heads_fwd_kernel<<<1, TPB, 0, stream>>>(p);
+  return trt_check_launch("trt_tab_heads_fwd");
+}
+
+extern "C" int trt_tab_heads_bwd(const float* feat, const float* xtab, const float* const* params_host, const float* bn_rm,
+                                 const float* bn_rv, const float* dlogit, const float* dreg, float* dfeat,
+                                 float* const* grads_host, float* scratch, int B, int T, int Hd, int F, int train, float drop_p,
+                                 unsigned long long seed, const unsigned long long* step, cudaStream_t stream) {
+  TRT_REQUIRE(feat && xtab && params_host && dlogit && dreg && dfeat && grads_host && scratch, "trt_tab_heads_bwd: null pointer");
+  TabBwdParams q;
+  TabParams& p = q.f;
+  p.B = B; p.T = T; p.Hd = Hd; p.F = F; p.train = train;
+  p.drop_p = drop_p; p.bn_eps = 1e-5f; p.bn_momentum = 0.1f; p.alpha = 0; p.beta = 0;
+  p.seed = seed; p.step = step;
+  p.feat = feat; p.xtab = xtab;
+  p.W0 = params_host[0]; p.b0 = params_host[1]; p.bn_g = params_host[2]; p.bn_b = params_host[3]; p.W1 = params_host[4]; p.b1 = params_host[5];
+  p.cls_w = params_host[6]; p.cls_b = params_host[7]; p.reg_w = params_host[8]; p.reg_b = params_host[9];
+  p.bn_rm = const_cast<float*>(bn_rm); p.bn_rv = const_cast<float*>(bn_rv); p.bn_nbt = nullptr;
+  p.y_hard = p.y_soft = p.sample_w = nullptr;
+  p.logit = p.reg = p.loss = p.dlogit = p.dreg = nullptr;
+  p.scratch = scratch;
+  q.dlogit = dlogit; q.dreg = dreg; q.dfeat = dfeat;
+  q.dW0 = grads_host[0]; q.db0 = grads_host[1]; q.dbn_g = grads_host[2]; q.dbn_b = grads_host[3]; q.dW1 = grads_host[4]; q.db1 = grads_host[5];
+  q.dcls_w = grads_host[6]; q.dcls_b = grads_host[7]; q.dreg_w = grads_host[8]; q.dreg_b = grads_host[9];
+  q.scratch2 = scratch + (size_t)3 * B * Hd + 2 * Hd;
+  tab_heads_bwd_kernel<<<1, TPB, 0, stream>>>(q);
+  return trt_check_launch("trt_tab_heads_bwd");
+}

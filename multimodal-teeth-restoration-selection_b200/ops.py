@@ -1,0 +1,238 @@
+"""Thin tensor-level wrappers over the C ABI (include/teethrt.h).  Each function only checks dtypes/contiguity, hands
+device pointers + the current CUDA stream to libteethrt and returns the output tensors; all arithmetic is in the kernels.
+Activations: NHWC bf16 viewed as [rows, C]; parameters/gradients fp32."""
+import ctypes as C
+import math
+
+import torch
+
+from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS  # noqa: F401
+
+bf16 = torch.bfloat16
+
+
+def _c(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "teethrt ops need contiguous CUDA tensors"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+def same_out(i, s):
+    return (i + s - 1) // s
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs (tcgen05)
+def gemm(A, B, flags=0, scale=None, shift=None, residual=None, stats=None, out=None, block_n=0):
+    """C[M,N] = epi(A[M,K] @ B[N,K]^T), bf16 in/out, fp32 accumulate in TMEM."""
+    _c(A, bf16), _c(B, bf16)
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=bf16)
+    check(lib.trt_gemm_bf16(ptr(A), ptr(B), ptr(out), M, N, K, flags, ptr(scale), ptr(shift), ptr(residual), ptr(stats),
+                            block_n, stream()))
+    return out
+
+
+def gemm_wgrad(P, Q, out, so_p=None, so_q=None, lbo=0, sbo=0, kstep=0):
+    """out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]  (fp32 accumulate/atomics)."""
+    _c(P, bf16), _c(Q, bf16), _c(out, torch.float32)
+    M, Cp = P.shape
+    Cq = Q.shape[1]
+    assert Q.shape[0] == M
+    if so_p is None:
+        so_p, so_q = Cq, 1
+    check(lib.trt_gemm_wgrad_bf16(ptr(P), ptr(Q), ptr(out), M, Cp, Cq, so_p, so_q, lbo, sbo, kstep, stream()))
+    return out
+
+
+def pack_w1x1(w, w_bf16, wt_bf16=None):
+    N, K = w.shape[0], w.shape[1]
+    check(lib.trt_pack_w1x1(ptr(w), ptr(w_bf16), ptr(wt_bf16), N, K, stream()))
+
+
+# ------------------------------------------------------------------------------------------------ BN / SE / pool
+def bn_finalize(stats, gamma, beta, rm, rv, nbt, rec, count, eps, momentum=0.1):
+    check(lib.trt_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), gamma.numel(),
+                              float(count), eps, momentum, stream()))
+
+
+def bn_fold_eval(gamma, beta, rm, rv, rec, eps):
+    check(lib.trt_bn_fold_eval(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(rec), gamma.numel(), eps, stream()))
+
+
+def bn_bwd_finalize(bstats, rec, gamma, coef, dgamma, dbeta, count):
+    check(lib.trt_bn_bwd_finalize(ptr(bstats), ptr(rec), ptr(gamma), ptr(coef), ptr(dgamma), ptr(dbeta), gamma.numel(),
+                                  float(count), stream()))
+
+
+def bn_apply(x, rec, out, residual=None, act=0):
+    rows, Cc = x.shape
+    check(lib.trt_bn_apply(ptr(x), ptr(rec), ptr(residual), ptr(out), rows, Cc, act, stream()))
+    return out
+
+
+def pool_act(x, rec, pooled, N, HW, act=1):
+    check(lib.trt_pool_act(ptr(x), ptr(rec), ptr(pooled), N, HW, x.shape[-1], act, stream()))
+    return pooled
+
+
+def se_fwd(pooled, inv_hw, Wr, br, We, be, s1, gate):
+    N, Cc = pooled.shape
+    check(lib.trt_se_fwd(ptr(pooled), inv_hw, ptr(Wr), ptr(br), ptr(We), ptr(be), ptr(s1), ptr(gate), N, Cc, Wr.shape[0],
+                         stream()))
+
+
+def gate_apply(x, rec, gate, out, N, HW):
+    check(lib.trt_gate_apply(ptr(x), ptr(rec), ptr(gate), ptr(out), N, HW, x.shape[-1], stream()))
+    return out
+
+
+def bn_bwd_reduce(dy, x, rec, bstats):
+    rows, Cc = x.shape
+    check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), rows, Cc, stream()))
+
+
+def affine2(dy, x, coef, out):
+    rows, Cc = x.shape
+    check(lib.trt_affine2(ptr(dy), ptr(x), ptr(coef), ptr(out), rows, Cc, stream()))
+    return out
+
+
+def se_bwd_reduce(dA, x, rec, dgate_pre, N, HW):
+    check(lib.trt_se_bwd_reduce(ptr(dA), ptr(x), ptr(rec), ptr(dgate_pre), N, HW, x.shape[-1], stream()))
+
+
+def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe):
+    N, Cc = gate.shape
+    check(lib.trt_se_bwd(ptr(dgate_pre), ptr(gate), ptr(s1), ptr(pooled), inv_hw, ptr(Wr), ptr(We), ptr(ds2), ptr(ds1),
+                         ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), N, Cc, Wr.shape[0], stream()))
+
+
+def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1):
+    check(lib.trt_act_bwd(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(g_out), ptr(bstats), N, HW,
+                          x.shape[-1], act, stream()))
+    return g_out
+
+
+# ------------------------------------------------------------------------------------------------ spatial convs
+def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None):
+    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), N, H, W,
+                             x.shape[-1], k, s, stream()))
+    return out
+
+
+def dwconv_bwd(gy, y_raw, coef, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s):
+    check(lib.trt_dwconv_bwd(ptr(gy), ptr(y_raw), ptr(coef), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats),
+                             ptr(dw), N, H, W, x_raw.shape[-1], k, s, stream()))
+
+
+def stem_fwd(x, w, out, out_rec=None, stats=None):
+    N, _, H, W = x.shape
+    assert x.dtype in (torch.float32, bf16)
+    check(lib.trt_stem_fwd(ptr(x), int(x.dtype == bf16), ptr(w), ptr(out), ptr(out_rec), ptr(stats), N, H, W, w.shape[0],
+                           stream()))
+    return out
+
+
+def stem_wgrad(x, ds, dw):
+    N, _, H, W = x.shape
+    check(lib.trt_stem_wgrad(ptr(x), int(x.dtype == bf16), ptr(ds), ptr(dw), N, H, W, dw.shape[0], stream()))
+
+
+# ------------------------------------------------------------------------------------------------ MIL pooling
+def mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False):
+    B, K, D = H.shape
+    hid = Vw.shape[0]
+    M = torch.empty((B, D), device=H.device, dtype=torch.float32)
+    A = torch.empty((B, K), device=H.device, dtype=torch.float32)
+    gV = gU = None
+    if save:
+        gV = torch.empty((B, K, hid), device=H.device, dtype=torch.float32)
+        gU = torch.empty_like(gV)
+    check(lib.trt_mil_attn_fwd(ptr(H), ptr(Vw), ptr(Vb), ptr(Uw), ptr(Ub), ptr(ww), ptr(wb), ptr(M), ptr(A), ptr(gV),
+                               ptr(gU), B, K, D, hid, stream()))
+    return M, A, gV, gU
+
+
+def mil_attn_bwd(dM, H, A, gV, gU, Vw, Uw, ww, dVw, dVb, dUw, dUb, dww, dwb):
+    B, K, D = H.shape
+    dH = torch.empty_like(H)
+    check(lib.trt_mil_attn_bwd(ptr(dM), ptr(H), ptr(A), ptr(gV), ptr(gU), ptr(Vw), ptr(Uw), ptr(ww), ptr(dH), ptr(dVw),
+                               ptr(dVb), ptr(dUw), ptr(dUb), ptr(dww), ptr(dwb), B, K, D, Vw.shape[0], stream()))
+    return dH
+
+
+# ------------------------------------------------------------------------------------------------ tab + heads + loss
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def tab_heads_scratch(B, Hd, device):
+    return torch.empty(lib.trt_tab_heads_scratch_floats(B, Hd), device=device, dtype=torch.float32)
+
+
+def tab_heads_fwd(feat, xtab, params, bn_rm, bn_rv, bn_nbt, scratch, train, drop_p=0.0, targets=None, alpha=1.0, beta=0.3,
+                  seed=0, step=None, out=None):
+    """params: the 10 tensors in the order of teethrt.h.  targets = (y_hard, y_soft, sample_w|None) fuses the loss."""
+    B, F = feat.shape
+    T, Hd = xtab.shape[1], params[0].shape[0]
+    dev = feat.device
+    if out is None:
+        out = {k: torch.empty(B, device=dev, dtype=torch.float32) for k in ("logit", "reg", "dlogit", "dreg")}
+        out["loss"] = torch.zeros(1, device=dev, dtype=torch.float32)
+    yh = ys = sw = None
+    if targets is not None:
+        yh, ys, sw = targets
+    arr = _ptr_array(params)
+    check(lib.trt_tab_heads_fwd(ptr(feat), ptr(xtab), arr, ptr(bn_rm), ptr(bn_rv), ptr(bn_nbt), ptr(yh), ptr(ys), ptr(sw),
+                                ptr(out["logit"]), ptr(out["reg"]), ptr(out["loss"]), ptr(out["dlogit"]), ptr(out["dreg"]),
+                                ptr(scratch), B, T, Hd, F, int(train), drop_p, alpha, beta, seed, ptr(step), stream()))
+    return out
+
+
+def tab_heads_bwd(feat, xtab, params, bn_rm, bn_rv, dlogit, dreg, dfeat, grads, scratch, train, drop_p=0.0, seed=0,
+                  step=None):
+    B, F = feat.shape
+    T, Hd = xtab.shape[1], params[0].shape[0]
+    check(lib.trt_tab_heads_bwd(ptr(feat), ptr(xtab), _ptr_array(params), ptr(bn_rm), ptr(bn_rv), ptr(dlogit), ptr(dreg),
+                                ptr(dfeat), _ptr_array(grads), ptr(scratch), B, T, Hd, F, int(train), drop_p, seed,
+                                ptr(step), stream()))
+    return dfeat
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+class OptimState:
+    """Device-resident {step, lr schedule, bias corrections} (layout: optim.cu OptState)."""
+
+    def __init__(self, device, lr, t_max=0, betas=(0.9, 0.999)):
+        import struct
+        raw = struct.pack("<Qddddffffd", 0, float(lr), float(t_max), betas[0], betas[1], float(lr), 0.0, 0.0, 0.0, 0.0)
+        assert len(raw) == lib.trt_optim_state_bytes()
+        self.buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+    def advance(self):
+        check(lib.trt_optim_advance(ptr(self.buf), stream()))
+
+    def read(self):
+        import struct
+        vals = struct.unpack("<Qddddffffd", bytes(self.buf.cpu().numpy().tobytes()))
+        return dict(step=vals[0], lr0=vals[1], t_max=vals[2], lr=vals[5], bc1=vals[6], bc2=vals[7])
+
+
+def grad_sumsq(g, out):
+    check(lib.trt_grad_sumsq(ptr(g), g.numel(), ptr(out), stream()))
+
+
+def adamw_step(p, g, m, v, state, normsq=None, norm_out=None, grad_scale=1.0, max_norm=1.0, eps=1e-8, weight_decay=1e-4):
+    check(lib.trt_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(state.buf), ptr(normsq), ptr(norm_out),
+                             grad_scale, max_norm, eps, weight_decay, stream()))
+
+
+# ------------------------------------------------------------------------------------------------ input stage
+def same_pad(i, k, s):
+    total = max((math.ceil(i / s) - 1) * s + k - i, 0)
+    return total // 2, total - total // 2
