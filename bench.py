@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its config: mm dual-task TRAIN images/s (tf_efficientnet_b4_ns + tabular MLP,
+synthetic 224x224 images + 9 clinical features, batch 64 per GPU, bf16 compute / fp32 masters, dropout 0.2, dual BCE,
+clip 1.0, AdamW 3e-4 / wd 1e-4, cosine per iteration) and, with --infer, batch-1 inference p50 latency.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N>1, one rank per GPU)
+    python bench.py --impl reference --gpus N ...            # the reference's own CPU path (oracle = reference classes
+                                                             # on the timm shim), rank 0 only
+
+One JSON line on stdout (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same through
+DualTaskTrainer.step() with pinned HOST inputs (H2D inside the timed region) and a D2H read of the loss every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG, BATCH, TAB = 224, 64, 9
+FLOP_PER_IMG_FWD = 3.004e9                       # tf_efficientnet_b4_ns @224
+FLOP_PER_IMG_TRAIN = 3 * FLOP_PER_IMG_FWD        # fwd + dgrad + wgrad
+BYTES_PER_IMG_TRAIN = 245e6                      # layer-fused bf16 lower bound
+BYTES_PER_STEP_OPT = 492e6                       # AdamW: 28 B x 17.56 M params
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(B, seed, device="cpu", pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, IMG, IMG, generator=g)
+    xt = torch.randn(B, TAB, generator=g)
+    yh = (torch.rand(B, generator=g) < 0.6).float()
+    ys = (yh * 0.8 + 0.2 * torch.rand(B, generator=g)).clamp(0, 1)
+    out = [x, xt, yh, ys]
+    if pin:
+        out = [t.pin_memory() for t in out]
+    if device != "cpu":
+        out = [t.to(device) for t in out]
+    return out
+
+
+# ====================================================================================================== reference arm
+def oracle_train_throughput(batch, steps, warmup, threads):
+    """The reference's hot loop (train_mm_joint_dualtask.py:241-256) on its own classes over the timm shim, fp32, CPU."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_models as R
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = R.MMJointDualHead().train()
+    opt, sched = R.make_optimizer(model, t_max=1000)
+    x, xt, yh, ys = synth_batch(batch, 1000)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        R.mm_train_step(model, opt, sched, x, xt, yh, ys)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return batch / med, med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sample_b = 16
+    steps, warmup = min(args.steps, 6), min(args.warmup, 2)
+    ips, med = oracle_train_throughput(sample_b, steps, max(warmup, 1), cores)
+    line = {"impl": "reference", "metric": "mm_dualtask_train_images_per_s", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": max(warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "mm dual-task train step, tf_efficientnet_b4_ns + tab MLP, 224x224, CPU reference path",
+                       "per_step_sample": f"batch {sample_b} (bounded sample of the batch-64 step; images/s is batch-size normalised)"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                             "sample": f"{steps} fp32 train steps of batch {sample_b} through the reference's MMJointDualHead on the oracle timm shim"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ====================================================================================================== our arm
+def time_dominant_kernel(torch, ops, pk):
+    """Roofline of the dominant kernel class (tcgen05 1x1-conv GEMM) on its largest launch of the step: blocks.1.0.conv_pw,
+    A[64*112*112, 24] x W[144, 24]^T with the BN-statistics epilogue.  Algorithmic bytes = read A + W, write C (bf16)."""
+    M, K, N = BATCH * 112 * 112, 24, 144
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    Wt = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)      # > 126 MB L2
+    for _ in range(3):
+        ops.gemm(A, Wt, ops.EPI_STATS, stats=stats, out=C)
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(A, Wt, ops.EPI_STATS, stats=stats, out=C)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.mean(times)
+    alg = (M * K + N * K + M * N) * 2
+    ach = alg / t / 1e9
+    return {"kernel": "gemm_kmajor_kernel (blocks.1.0.conv_pw fwd, M=802816 K=24 N=144, BN-stats epilogue)", "bound": "hbm",
+            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+            "peak_source": pk["src"], "avg_launch_us": t * 1e6, "algorithmic_bytes_per_launch": alg}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import teethrt
+    from teethrt import ops
+    from teethrt._lib import lib
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    teethrt.init(local)
+    pk = peaks()
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    model = MMJointDualHead('tf_efficientnet_b4_ns', tab_in=TAB, tab_hidden=64, drop=0.2).to(dev)
+    total_steps = 2 * (args.steps + args.warmup) + 8
+    tr = DualTaskTrainer(model, lr=3e-4, weight_decay=1e-4, t_max=total_steps, alpha=1.0, beta=0.3, grad_clip=1.0, graph=True,
+                         seed=1234)
+    dev_batches = [synth_batch(BATCH, 1000 + rank * 17 + i, device=dev) for i in range(2)]
+    host_batches = [synth_batch(BATCH, 2000 + rank * 17 + i, pin=True) for i in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: eager steps + graph capture + replays
+    for i in range(max(args.warmup, 3) + tr.graph_warmup):
+        tr.step(*dev_batches[i % 2])
+    barrier()
+    launches_before = lib.trt_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- (1) device-resident inputs
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        tr.step(*dev_batches[i % 2])
+    e1.record()
+    barrier()
+    t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    # ---- (2) end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
+    barrier()
+    losses = []
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        loss = tr.step(*host_batches[i % 2])
+        losses.append(float(loss.item()))
+    e3.record()
+    barrier()
+    t_e2e = torch.tensor([e2.elapsed_time(e3) * 1e-3], device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(t_dev), float(t_e2e)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    imgs = BATCH * world * args.steps
+    value, e2e_value = imgs / t_dev, imgs / t_e2e
+    # kernels per step: replayed graphs hold what the capture pass launched through the C ABI
+    per_step = tr.launches_per_step or 0
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
+    step_flops = FLOP_PER_IMG_TRAIN * BATCH
+    step_bytes = BYTES_PER_IMG_TRAIN * BATCH + BYTES_PER_STEP_OPT
+    ms = t_dev / args.steps * 1e3
+    roof = time_dominant_kernel(torch, ops, pk)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        ips, med = oracle_train_throughput(8, 4, 1, cores)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+               "sample": "4 fp32 train steps of batch 8 (bounded sample of the batch-64 step) through the reference's "
+                         "MMJointDualHead class on the oracle timm shim, all host threads"}
+    line = {"metric": "mm_dualtask_train_images_per_s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3) + tr.graph_warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: mm dual-task train step, tf_efficientnet_b4_ns + tab MLP(9->64->64) + dual heads, "
+                                   "224x224, batch 64 per GPU, dropout 0.2, dual BCE, clip 1.0, AdamW, cosine/iter",
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "l2": "per-step activations (~7 GB) and parameters+moments (281 MB) exceed the 126 MB L2; no flush needed",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": t_e2e / args.steps * 1e3, "last_loss": losses[-1]},
+            "gpu_launches": int(per_step * args.steps * 2) if per_step else int(lib.trt_launch_count() - launches_before),
+            "launches_per_step": per_step,
+            "clocks": clocks,
+            "roofline": roof,
+            "step_roofline": {"tensor_frac_of_measured_sustained": step_flops / (ms * 1e-3) / 1e12 / pk["tf_sust"],
+                              "achieved_tflops": step_flops / (ms * 1e-3) / 1e12,
+                              "hbm_frac_layer_fused_bytes": step_bytes / (ms * 1e-3) / 1e9 / pk["hbm"],
+                              "algorithmic_gb_per_step": step_bytes / 1e9, "gflop_per_step": step_flops / 1e9},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_infer(args):
+    """batch-1 inference p50 latency: (A) one MMNet forward, (B) MMEnsemble semantics = 5 folds x 3 TTA flips."""
+    import torch
+    import teethrt
+    from teethrt.modules import MMNet
+    from teethrt.infer import _GraphedForward
+    torch.cuda.set_device(0)
+    teethrt.init(0)
+    torch.manual_seed(0)
+    folds = [MMNet().cuda().eval() for _ in range(5)]
+    x1, t1 = torch.randn(1, 3, IMG, IMG, device="cuda"), torch.randn(1, TAB, device="cuda")
+    x3, t3 = torch.randn(3, 3, IMG, IMG, device="cuda"), torch.randn(3, TAB, device="cuda")
+    g1 = _GraphedForward(lambda a, b: folds[0](a, b)[0], [x1, t1])
+    g3 = [_GraphedForward(lambda a, b, m=m: m(a, b)[0], [x3, t3]) for m in folds]
+
+    def timeit(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2], ts[int(len(ts) * 0.95)]
+
+    def ens():
+        out = [torch.sigmoid(g(x3, t3).mean() / 2.5) for g in g3]
+        return torch.stack(out).mean()
+
+    p50a, p95a = timeit(lambda: g1(x1, t1), args.steps * 10, 50)
+    p50b, p95b = timeit(ens, args.steps * 5, 20)
+    print(json.dumps({"metric": "mm_batch1_infer_p50_latency", "value": p50a, "unit": "ms", "higher_is_better": False, "n_gpus": 1,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "batch-1 MMNet forward (B4 @224 + tab), CUDA-graph replay"},
+                      "single_forward": {"p50_ms": p50a, "p95_ms": p95a},
+                      "ensemble_5fold_3tta": {"p50_ms": p50b, "p95_ms": p95b}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--infer", action="store_true", help="batch-1 inference latency instead of the train step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.infer:
+        run_infer(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

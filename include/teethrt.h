@@ -32,6 +32,8 @@ int trt_version(void);
 const char* trt_last_error_string(void);
 /* Select the device, verify it is sm_100, resolve cuTensorMapEncodeTiled. Call once per process/device. */
 int trt_init(int device);
+/* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+unsigned long long trt_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 1x1 convolutions as tcgen05 GEMMs.
@@ -104,7 +106,7 @@ int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int N, int 
 /* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 (pre-activation of the reduce conv, [N,rd]) may be NULL */
 int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
                float* s1, float* gate, int N, int C, int rd, trt_stream_t stream);
-/* out = silu(bn(x)) * gate[n,c] */
+/* out = (rec ? silu(bn(x)) : x) * gate[n,c] */
 int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C, trt_stream_t stream);
 int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C, trt_stream_t stream);
 /* out = a*dy + b*x + c */
@@ -119,6 +121,8 @@ int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const
 /* g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * (act ? silu'(bn(x)) : 1); bstats += {sum g, sum g*xhat}. dA/gate/dmean may be NULL */
 int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x, const float* rec,
                 void* g_out, double* bstats, int N, int HW, int C, int act, trt_stream_t stream);
+/* x *= alpha (fp32; turns pooled sums into the global-average-pool features) */
+int trt_scale_f32(float* x, size_t n, float alpha, trt_stream_t stream);
 /* fp32 [N,K] -> bf16 [N,K] and (optional) bf16 [K,N] */
 int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N, int K, trt_stream_t stream);
 
@@ -153,6 +157,15 @@ int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const flo
 int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, const float* gV, const float* gU, const float* Vw,
                      const float* Uw, const float* ww, float* dH, float* dVw, float* dVb, float* dUw, float* dUb, float* dww,
                      float* dwb, int B, int K, int D, int hid, trt_stream_t stream);
+
+/* MIL bag head: logit[b] = <dropout(M[b]), w> + bias (MILNet.drop + MILNet.head, train_mil_attention_v1.py:146-147;
+ * infer_mil.py:95) and its backward (dw, db WRITTEN); BCE-with-logits mean loss + gradient (train_mil_attention_v1.py:183). */
+int trt_linear1_fwd(const float* M, const float* w, const float* bias, float* logit, int B, int D, float drop_p,
+                    unsigned long long seed, const unsigned long long* step, trt_stream_t stream);
+int trt_linear1_bwd(const float* dlogit, const float* M, const float* w, float* dM, float* dw, float* db, int B, int D,
+                    float drop_p, unsigned long long seed, const unsigned long long* step, trt_stream_t stream);
+int trt_bce_logits(const float* logit, const float* y, const float* sample_w, float* loss, float* dlogit, int B,
+                   trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Tabular MLP + late fusion + dual heads + dual BCE loss.  Replaces MMJointDualHead.tab / fusion / cls_head / reg_head

@@ -33,6 +33,7 @@ _SIGS = {
     "trt_version": (i32, []),
     "trt_last_error_string": (C.c_char_p, []),
     "trt_init": (i32, [i32]),
+    "trt_launch_count": (u64, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, vp]),
     "trt_clahe_workspace_bytes": (sz, [i32]),
@@ -51,6 +52,7 @@ _SIGS = {
     "trt_se_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_se_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_scale_f32": (i32, [vp, sz, f32, vp]),
     "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),
     "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
@@ -59,6 +61,9 @@ _SIGS = {
     "trt_mil_attn_smem_bytes": (sz, [i32, i32, i32, i32]),
     "trt_mil_attn_fwd": (i32, [vp] * 11 + [i32, i32, i32, i32, vp]),
     "trt_mil_attn_bwd": (i32, [vp] * 15 + [i32, i32, i32, i32, vp]),
+    "trt_linear1_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, u64, vp, vp]),
+    "trt_linear1_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, vp, vp]),
+    "trt_bce_logits": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "trt_tab_heads_scratch_floats": (sz, [i32, i32]),
     "trt_tab_heads_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32,
                                 f32, f32, u64, vp, vp]),
@@ -107,7 +112,8 @@ def init(device=None):
     """trt_init for the current (or given) CUDA device; raises without a B200-class GPU."""
     if not torch.cuda.is_available():
         raise TeethRTError("teethrt needs a CUDA device (sm_100a); there is no CPU fallback")
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    idx = None if device is None else (device if isinstance(device, int) else torch.device(device).index)
+    dev = torch.cuda.current_device() if idx is None else idx
     if dev not in _inited:
         check(lib.trt_init(dev))
         _inited.add(dev)

@@ -1,0 +1,497 @@
+"""EfficientNet encoder (`tf_efficientnet_b{0,4}_ns`) on libteethrt kernels, with timm's state-dict keys.
+
+This is what `timm.create_model(name, pretrained, num_classes=0, global_pool='avg')` returns in the reference
+(experiments/multimodal_v1/train_mm_joint_dualtask.py:138; ui/gradio_app/infer_mm.py:22;
+experiments/vision_v2/train_mil_attention_v1.py:135; ui/gradio_app/infer_mil.py:75).  Parameters live in ordinary
+torch-layout fp32 `nn.Parameter`s under timm's names (conv_stem, bn1, blocks.S.I.{conv_pw,bn1,conv_dw,bn2,se.conv_reduce,
+se.conv_expand,conv_pwl,bn3}, conv_head, bn2), so reference checkpoints load with strict=True.  All arithmetic runs in the
+CUDA library: activations are NHWC bf16, 1x1 convs are tcgen05 GEMMs with BN statistics / folded BN + SiLU + residual in
+the epilogue, depthwise convs apply the producer's BN+SiLU on load.  No PyTorch compute fallback exists.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import init
+
+bf16 = torch.bfloat16
+BN_EPS, BN_MOM = 1e-3, 0.1
+
+_B0 = [("ds", 1, 3, 1, 1, 16), ("ir", 2, 3, 2, 6, 24), ("ir", 2, 5, 2, 6, 40), ("ir", 3, 3, 2, 6, 80),
+       ("ir", 3, 5, 1, 6, 112), ("ir", 4, 5, 2, 6, 192), ("ir", 1, 3, 1, 6, 320)]
+ARCHS = {"tf_efficientnet_b0_ns": (1.0, 1.0), "tf_efficientnet_b0": (1.0, 1.0), "tf_efficientnet_b0.ns_jft_in1k": (1.0, 1.0),
+         "tf_efficientnet_b4_ns": (1.4, 1.8), "tf_efficientnet_b4": (1.4, 1.8), "tf_efficientnet_b4.ns_jft_in1k": (1.4, 1.8)}
+
+
+def _round_ch(c, mult, div=8):
+    c = c * mult
+    n = max(div, int(c + div / 2) // div * div)
+    return n + div if n < 0.9 * c else n
+
+
+def arch_spec(name):
+    if name not in ARCHS:
+        raise ValueError(f"teethrt: backbone {name!r} is not built (have {sorted(ARCHS)})")
+    wm, dm = ARCHS[name]
+    stem = _round_ch(32, wm)
+    stages, cin = [], stem
+    for typ, r, k, s, e, c in _B0:
+        cout = _round_ch(c, wm)
+        blocks = []
+        for i in range(int(math.ceil(r * dm))):
+            blocks.append(dict(type=typ, k=k, s=s if i == 0 else 1, cin=cin, cout=cout, mid=cin * e,
+                               rd=int(round(cin * 0.25))))
+            cin = cout
+        stages.append(blocks)
+    return stem, stages, _round_ch(1280, wm)
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class _Conv(nn.Module):
+    def __init__(self, cout, cin_g, k, bias=False, fan_out=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin_g, k, k))
+        nn.init.normal_(self.weight, 0.0, math.sqrt(2.0 / (fan_out or k * k * cout)))
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+
+
+class _BN(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _SE(nn.Module):
+    def __init__(self, c, rd):
+        super().__init__()
+        self.conv_reduce = _Conv(rd, c, 1, bias=True)
+        self.conv_expand = _Conv(c, rd, 1, bias=True)
+
+
+class _DSBlock(nn.Module):
+    def __init__(self, b):
+        super().__init__()
+        self.cfg = b
+        self.conv_dw = _Conv(b["cin"], 1, b["k"], fan_out=b["k"] * b["k"])
+        self.bn1 = _BN(b["cin"])
+        self.se = _SE(b["cin"], b["rd"])
+        self.conv_pw = _Conv(b["cout"], b["cin"], 1)
+        self.bn2 = _BN(b["cout"])
+
+
+class _IRBlock(nn.Module):
+    def __init__(self, b):
+        super().__init__()
+        self.cfg = b
+        self.conv_pw = _Conv(b["mid"], b["cin"], 1)
+        self.bn1 = _BN(b["mid"])
+        self.conv_dw = _Conv(b["mid"], 1, b["k"], fan_out=b["k"] * b["k"])
+        self.bn2 = _BN(b["mid"])
+        self.se = _SE(b["mid"], b["rd"])
+        self.conv_pwl = _Conv(b["cout"], b["mid"], 1)
+        self.bn3 = _BN(b["cout"])
+
+
+class _Arena:
+    """Bump allocator over one pre-zeroed tensor (per-BN statistics: one memset per pass instead of one per layer)."""
+
+    def __init__(self, n, dtype, device):
+        self.buf = torch.zeros(n, dtype=dtype, device=device)
+        self.off = 0
+
+    def take(self, n, shape=None):
+        v = self.buf[self.off:self.off + n]
+        self.off += n
+        return v.view(shape) if shape else v
+
+
+class EfficientNet(nn.Module):
+    """timm-compatible EfficientNet feature extractor (num_classes=0)."""
+
+    def __init__(self, name="tf_efficientnet_b4_ns", global_pool="avg"):
+        super().__init__()
+        stem, stages, feat = arch_spec(name)
+        self.arch, self.num_features, self.global_pool_type = name, feat, global_pool
+        self.conv_stem = _Conv(stem, 3, 3)
+        self.bn1 = _BN(stem)
+        self.blocks = nn.Sequential(*[nn.Sequential(*[(_DSBlock if b["type"] == "ds" else _IRBlock)(b) for b in st])
+                                      for st in stages])
+        self.conv_head = _Conv(feat, stages[-1][-1]["cout"], 1)
+        self.bn2 = _BN(feat)
+        self.classifier = nn.Identity()
+        self._eval_cache = None
+        self.grad_sink = None      # optional dict name -> fp32 tensor that receives (accumulates) parameter gradients
+
+    # ---- cache invalidation: anything that can change weights or BN buffers outside a train step
+    def train(self, mode=True):
+        self._eval_cache = None
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self._eval_cache = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._eval_cache = None
+        return super().load_state_dict(*a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._eval_cache = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def block_list(self):
+        return [(f"blocks.{si}.{bi}", blk) for si, st in enumerate(self.blocks) for bi, blk in enumerate(st)]
+
+    def bn_list(self):
+        out = [("bn1", self.bn1)]
+        for name, blk in self.block_list():
+            for bn in ("bn1", "bn2", "bn3"):
+                if hasattr(blk, bn):
+                    out.append((f"{name}.{bn}", getattr(blk, bn)))
+        return out + [("bn2", self.bn2)]
+
+    def conv1x1_list(self):
+        out = []
+        for name, blk in self.block_list():
+            for cv in ("conv_pw", "conv_pwl"):
+                if hasattr(blk, cv):
+                    out.append((f"{name}.{cv}", getattr(blk, cv)))
+        return out + [("conv_head", self.conv_head)]
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, x):
+        feat = encoder_forward(self, x)
+        if self.global_pool_type == "avg":
+            return feat
+        raise NotImplementedError("teethrt EfficientNet: only global_pool='avg' features are produced on the device; "
+                                  "use forward_pooled() (the MIL twin applies its own global average pool)")
+
+    def forward_pooled(self, x):
+        return encoder_forward(self, x)
+
+
+def create_model(model_name, pretrained=False, num_classes=0, global_pool="avg", **kw):
+    """Drop-in for the reference's `timm.create_model(...)` call; `pretrained` needs a network and is ignored (q11)."""
+    if num_classes != 0:
+        raise ValueError("teethrt.create_model: only num_classes=0 (feature extractor) is on the hot path")
+    return EfficientNet(model_name, global_pool=global_pool)
+
+
+# ================================================================================================= runtime
+def _packed_weights(enc, dev, transposed):
+    """bf16 copies of every 1x1 conv weight ([Cout,Cin] and, for training, [Cin,Cout])."""
+    out = {}
+    for name, cv in enc.conv1x1_list():
+        n, k = cv.weight.shape[0], cv.weight.shape[1]
+        wb = torch.empty((n, k), device=dev, dtype=bf16)
+        wt = torch.empty((k, n), device=dev, dtype=bf16) if transposed else None
+        ops.pack_w1x1(cv.weight.detach(), wb, wt)
+        out[name] = (wb, wt)
+    return out
+
+
+def _eval_cache(enc, dev):
+    if enc._eval_cache is None:
+        recs = {}
+        for name, bn in enc.bn_list():
+            rec = torch.empty((4, bn.weight.numel()), device=dev, dtype=torch.float32)
+            ops.bn_fold_eval(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, rec, BN_EPS)
+            recs[name] = rec
+        enc._eval_cache = dict(recs=recs, w=_packed_weights(enc, dev, False))
+    return enc._eval_cache
+
+
+def _check_input(enc, x):
+    if not x.is_cuda:
+        raise RuntimeError("teethrt EfficientNet runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("expected an image batch [N,3,H,W]")
+    if x.dtype not in (torch.float32, bf16):
+        x = x.float()
+    init(x.device)
+    return x.contiguous()
+
+
+def _se_gate(blk, pooled, inv_hw, N, C, dev, save):
+    rd = blk.cfg["rd"]
+    s1 = torch.empty((N, rd), device=dev, dtype=torch.float32) if save else None
+    gate = torch.empty((N, C), device=dev, dtype=torch.float32)
+    se = blk.se
+    ops.se_fwd(pooled, inv_hw, se.conv_reduce.weight.detach(), se.conv_reduce.bias.detach(), se.conv_expand.weight.detach(),
+               se.conv_expand.bias.detach(), s1, gate)
+    return s1, gate
+
+
+def forward_eval(enc, x):
+    """Inference: BN folded from running statistics; 4 launches per MBConv block (+1 for the SE MLP)."""
+    x = _check_input(enc, x)
+    dev = x.device
+    cache = _eval_cache(enc, dev)
+    R, Wp = cache["recs"], cache["w"]
+    N, _, H, W = x.shape
+    h, w = ops.same_out(H, 2), ops.same_out(W, 2)
+    cur = torch.empty((N * h * w, enc.conv_stem.weight.shape[0]), device=dev, dtype=bf16)
+    ops.stem_fwd(x, enc.conv_stem.weight.detach(), cur, out_rec=R["bn1"])
+    for name, blk in enc.block_list():
+        c = blk.cfg
+        k, s = c["k"], c["s"]
+        skip = cur if (s == 1 and c["cin"] == c["cout"]) else None
+        if c["type"] == "ir":
+            rec = R[name + ".bn1"]
+            e = ops.gemm(cur, Wp[name + ".conv_pw"][0], ops.EPI_SCALE_SHIFT | ops.EPI_SILU, rec[0], rec[1])
+            cm, dwrec, pw, outrec = c["mid"], R[name + ".bn2"], Wp[name + ".conv_pwl"][0], R[name + ".bn3"]
+        else:
+            e, cm, dwrec, pw, outrec = cur, c["cin"], R[name + ".bn1"], Wp[name + ".conv_pw"][0], R[name + ".bn2"]
+        oh, ow = ops.same_out(h, s), ops.same_out(w, s)
+        d = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
+        pooled = torch.empty((N, cm), device=dev, dtype=torch.float32)
+        ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled)
+        _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)
+        ops.gate_apply(d, None, gate, d, N, oh * ow)
+        flags = ops.EPI_SCALE_SHIFT | (ops.EPI_RESIDUAL if skip is not None else 0)
+        cur = ops.gemm(d, pw, flags, outrec[0], outrec[1], residual=skip)
+        h, w = oh, ow
+    rec = R["bn2"]
+    hd = ops.gemm(cur, Wp["conv_head"][0], ops.EPI_SCALE_SHIFT | ops.EPI_SILU, rec[0], rec[1])
+    feat = torch.empty((N, enc.num_features), device=dev, dtype=torch.float32)
+    ops.pool_act(hd, None, feat, N, h * w, act=0)
+    ops.scale_f32(feat, 1.0 / (h * w))
+    return feat
+
+
+def forward_train(enc, x, save=True):
+    """Train-mode forward (batch statistics, running-stat update).  Returns (feat [N,F] fp32, ctx for backward)."""
+    x = _check_input(enc, x)
+    dev = x.device
+    N, _, H, W = x.shape
+    Wp = _packed_weights(enc, dev, True)
+    bns = dict(enc.bn_list())
+    total_c = sum(b.weight.numel() for b in bns.values())
+    stats = _Arena(2 * total_c, torch.float64, dev)
+    recs = _Arena(4 * total_c, torch.float32, dev)
+    ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
+
+    def finalize(bn_name, st, count):
+        bn = bns[bn_name]
+        c = bn.weight.numel()
+        rec = recs.take(4 * c, (4, c))
+        ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        rec, count, BN_EPS, BN_MOM)
+        ctx["rec"][bn_name] = rec
+        return rec
+
+    h, w = ops.same_out(H, 2), ops.same_out(W, 2)
+    cs = enc.conv_stem.weight.shape[0]
+    s_raw = torch.empty((N * h * w, cs), device=dev, dtype=bf16)
+    st = stats.take(2 * cs)
+    ops.stem_fwd(x, enc.conv_stem.weight.detach(), s_raw, stats=st)
+    cur, cur_rec = s_raw, finalize("bn1", st, N * h * w)          # lazy: (raw, pending BN+SiLU)
+    ctx["stem"] = dict(raw=s_raw, h=h, w=w)
+    for name, blk in enc.block_list():
+        c = blk.cfg
+        k, s = c["k"], c["s"]
+        has_skip = s == 1 and c["cin"] == c["cout"]
+        sv = dict(name=name, h=h, w=w, in_rec=None)
+        if c["type"] == "ir" or has_skip:
+            if cur_rec is not None:        # materialise the pending activation (GEMM operand / residual need a real tensor)
+                cur = ops.bn_apply(cur, cur_rec, torch.empty_like(cur), act=1)
+                sv["materialised_from"] = True
+                cur_rec = None
+        sv["x"] = cur
+        if c["type"] == "ir":
+            cm = c["mid"]
+            st = stats.take(2 * cm)
+            e_raw = ops.gemm(cur, Wp[name + ".conv_pw"][0], ops.EPI_STATS, stats=st)
+            rec1 = finalize(name + ".bn1", st, N * h * w)
+            dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, rec1, name + ".bn2", name + ".conv_pwl", name + ".bn3"
+            sv["e_raw"] = e_raw
+        else:
+            cm = c["cin"]
+            dw_in, dw_rec, bn_dw, pw_name, bn_out = cur, cur_rec, name + ".bn1", name + ".conv_pw", name + ".bn2"
+            sv["in_rec"] = cur_rec
+        oh, ow = ops.same_out(h, s), ops.same_out(w, s)
+        d_raw = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
+        st = stats.take(2 * cm)
+        ops.dwconv_fwd(dw_in, dw_rec, blk.conv_dw.weight.detach(), d_raw, N, h, w, k, s, stats=st)
+        rec_d = finalize(bn_dw, st, N * oh * ow)
+        pooled = torch.empty((N, cm), device=dev, dtype=torch.float32)
+        ops.pool_act(d_raw, rec_d, pooled, N, oh * ow, act=1)
+        s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
+        a = ops.gate_apply(d_raw, rec_d, gate, torch.empty_like(d_raw), N, oh * ow)
+        st = stats.take(2 * c["cout"])
+        p_raw = ops.gemm(a, Wp[pw_name][0], ops.EPI_STATS, stats=st)
+        rec_o = finalize(bn_out, st, N * oh * ow)
+        y = ops.bn_apply(p_raw, rec_o, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0)
+        sv.update(d_raw=d_raw, pooled=pooled, s1=s1, gate=gate, a=a, p_raw=p_raw, oh=oh, ow=ow, has_skip=has_skip,
+                  bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out)
+        ctx["blocks"].append((blk, sv))
+        cur, cur_rec, h, w = y, None, oh, ow
+    st = stats.take(2 * enc.num_features)
+    hd_raw = ops.gemm(cur, Wp["conv_head"][0], ops.EPI_STATS, stats=st)
+    rec_h = finalize("bn2", st, N * h * w)
+    feat = torch.empty((N, enc.num_features), device=dev, dtype=torch.float32)
+    ops.pool_act(hd_raw, rec_h, feat, N, h * w, act=1)
+    ops.scale_f32(feat, 1.0 / (h * w))
+    ctx.update(head=dict(x=cur, raw=hd_raw, h=h, w=w))
+    return feat, ctx
+
+
+_ones_coef = {}
+
+
+def _add_coef(C, dev):
+    key = (C, dev)
+    if key not in _ones_coef:
+        t = torch.zeros((3, C), device=dev, dtype=torch.float32)
+        t[:2] = 1.0
+        _ones_coef[key] = t
+    return _ones_coef[key]
+
+
+def backward_train(enc, ctx, dfeat, grads):
+    """Backward of forward_train.  `grads`: dict name -> fp32 tensor (torch layout) for every parameter of the encoder;
+    1x1-conv / depthwise / stem weight gradients are ACCUMULATED (+=) — pass zeroed tensors; the others are written."""
+    dev = dfeat.device
+    N, Wp, REC = ctx["N"], ctx["Wp"], ctx["rec"]
+    bns = dict(enc.bn_list())
+    total_c = sum(b.weight.numel() for b in bns.values())
+    bstats = _Arena(2 * total_c, torch.float64, dev)
+    dfeat = dfeat.contiguous().float()
+
+    def bn_back(bn_name, bst, count):
+        bn = bns[bn_name]
+        c = bn.weight.numel()
+        coef = torch.empty((3, c), device=dev, dtype=torch.float32)
+        ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"],
+                            count)
+        return coef
+
+    # ---- head: feat = mean_hw silu(bn2(conv_head(y)))
+    hd = ctx["head"]
+    hw = hd["h"] * hd["w"]
+    F_ = enc.num_features
+    bst = bstats.take(2 * F_)
+    g = ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"], torch.empty_like(hd["raw"]), bst, N, hw, act=1)
+    coef = bn_back("bn2", bst, N * hw)
+    d_raw = ops.affine2(g, hd["raw"], coef, g)
+    dy = ops.gemm(d_raw, Wp["conv_head"][1])
+    ops.gemm_wgrad(d_raw, hd["x"], grads["conv_head.weight"])
+    del g, d_raw
+
+    for blk, sv in reversed(ctx["blocks"]):
+        c, name = blk.cfg, sv["name"]
+        k, s = c["k"], c["s"]
+        h, w, oh, ow = sv["h"], sv["w"], sv["oh"], sv["ow"]
+        ohw = oh * ow
+        cm = sv["d_raw"].shape[1]
+        # project conv + its BN (no activation)
+        bst = bstats.take(2 * c["cout"])
+        ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst)
+        coef = bn_back(sv["bn_out"], bst, N * ohw)
+        dp = ops.affine2(dy, sv["p_raw"], coef, torch.empty_like(dy))
+        dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
+        ops.gemm_wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
+        # squeeze-excite + activation + BN of the depthwise output
+        rec_d = REC[sv["bn_dw"]]
+        dgate_pre = torch.empty((N, cm), device=dev, dtype=torch.float32)
+        ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw)
+        ds2, dmean = torch.empty_like(dgate_pre), torch.empty_like(dgate_pre)
+        ds1 = torch.empty((N, c["rd"]), device=dev, dtype=torch.float32)
+        se = blk.se
+        ops.se_bwd(dgate_pre, sv["gate"], sv["s1"], sv["pooled"], 1.0 / ohw, se.conv_reduce.weight.detach(),
+                   se.conv_expand.weight.detach(), ds2, ds1, dmean, grads[name + ".se.conv_reduce.weight"],
+                   grads[name + ".se.conv_reduce.bias"], grads[name + ".se.conv_expand.weight"],
+                   grads[name + ".se.conv_expand.bias"])
+        bst = bstats.take(2 * cm)
+        g2 = ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, dA, bst, N, ohw, act=1)
+        coef_d = bn_back(sv["bn_dw"], bst, N * ohw)
+        dw_grad = grads[name + ".conv_dw.weight"]
+        if c["type"] == "ir":
+            e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
+            bst = bstats.take(2 * cm)
+            g1 = torch.empty_like(e_raw)
+            ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, dw_grad, N, h, w, k, s)
+            coef1 = bn_back(name + ".bn1", bst, N * h * w)
+            de = ops.affine2(g1, e_raw, coef1, g1)
+            flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
+            dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
+            ops.gemm_wgrad(de, sv["x"], grads[name + ".conv_pw.weight"])
+            dy = dx
+        else:
+            x_in, in_rec = sv["x"], sv["in_rec"]
+            is_first = blk is ctx["blocks"][0][0]
+            if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
+                bst = bstats.take(2 * c["cin"])
+                g_in = torch.empty_like(x_in)
+                ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h,
+                               w, k, s)
+                coef_s = bn_back("bn1", bst, N * h * w)
+                ds = ops.affine2(g_in, x_in, coef_s, g_in)
+                ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+                dy = None
+            else:
+                g_in = torch.empty_like(x_in)
+                ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), x_in, None, g_in, None, dw_grad, N, h,
+                               w, k, s)
+                if sv["has_skip"]:
+                    g_in = ops.affine2(g_in, dy, _add_coef(c["cin"], dev), g_in)
+                dy = g_in
+                if sv.get("materialised_from") and is_first:
+                    # the block input was silu(bn1(stem)) materialised by bn_apply: continue into the stem
+                    st_raw = ctx["stem"]["raw"]
+                    hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
+                    bst = bstats.take(2 * c["cin"])
+                    g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
+                    coef_s = bn_back("bn1", bst, N * hw0)
+                    ds = ops.affine2(g_s, st_raw, coef_s, g_s)
+                    ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+                    dy = None
+        if c["type"] == "ir" and sv.get("materialised_from"):
+            st_raw = ctx["stem"]["raw"]
+            hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
+            bst = bstats.take(2 * st_raw.shape[1])
+            g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
+            coef_s = bn_back("bn1", bst, N * hw0)
+            ds = ops.affine2(g_s, st_raw, coef_s, g_s)
+            ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+            dy = None
+    return grads
+
+
+class _EncoderFn(torch.autograd.Function):
+    """autograd bridge for the reference's own training loop (loss.backward() at train_mm_joint_dualtask.py:248)."""
+
+    @staticmethod
+    def forward(ctx, enc, x, *params):
+        feat, saved = forward_train(enc, x)
+        ctx.enc, ctx.saved = enc, saved
+        ctx.names = [n for n, _ in enc.named_parameters()]
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        enc = ctx.enc
+        named = dict(enc.named_parameters())
+        sink = enc.grad_sink
+        grads = {n: (sink[n] if sink is not None else torch.zeros_like(p)) for n, p in named.items()}
+        backward_train(enc, ctx.saved, dfeat, grads)
+        ctx.saved = None
+        out = tuple(grads[n] if named[n].requires_grad else None for n in ctx.names)
+        return (None, None) + out
+
+
+def encoder_forward(enc, x):
+    if enc.training:
+        params = [p for _, p in enc.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _EncoderFn.apply(enc, x, *params)
+        return forward_train(enc, x)[0]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in enc.parameters()) and x.requires_grad:
+        raise NotImplementedError("teethrt: gradients w.r.t. the input image in eval mode are not on the hot path")
+    return forward_eval(enc, x)

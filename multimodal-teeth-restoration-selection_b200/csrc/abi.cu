@@ -15,7 +15,12 @@ int trt_set_error(int status, const char* fmt, ...) {
   return status;
 }
 
+static unsigned long long g_launches = 0;
+void trt_count_launch(int n) { g_launches += (unsigned long long)n; }
+extern "C" unsigned long long trt_launch_count(void) { return g_launches; }
+
 int trt_check_launch(const char* what) {
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return trt_set_error(TRT_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
   return TRT_OK;

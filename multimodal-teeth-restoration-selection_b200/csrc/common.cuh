@@ -13,7 +13,8 @@
 
 // ---------------------------------------------------------------- status / error plumbing (abi.cu)
 int trt_set_error(int status, const char* fmt, ...);
-int trt_check_launch(const char* what);
+int trt_check_launch(const char* what);   // also counts one kernel launch
+void trt_count_launch(int n);             // extra launches of entry points that enqueue more than one kernel
 #define TRT_REQUIRE(cond, ...) do { if (!(cond)) return trt_set_error(TRT_ERR_INVALID, __VA_ARGS__); } while (0)
 #define TRT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return trt_set_error(TRT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } while (0)

@@ -197,12 +197,14 @@ __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   if (!m.active) return;
   const int n = blockIdx.y;
-  const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v), g = ldf8(gate + (size_t)n * C + 8 * m.v);
+  f8 sc, sh;
+  if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
+  const f8 g = ldf8(gate + (size_t)n * C + 8 * m.v);
   for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
     const size_t idx = ((size_t)n * HW + r) * V + m.v;
     f8 a = unpack8(__ldg(x + idx));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])) * g.v[i];
+    for (int i = 0; i < 8; ++i) a.v[i] = (rec ? siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : a.v[i]) * g.v[i];
     out[idx] = pack8(a);
   }
 }
@@ -428,6 +430,10 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
+__global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float alpha) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= alpha;
+}
+
 }  // namespace
 
 #define CHECK_C(C) TRT_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channels must be a positive multiple of 8 (got %d)", __func__, (C))
@@ -489,7 +495,7 @@ extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr
 extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C,
                               cudaStream_t stream) {
   CHECK_C(C);
-  TRT_REQUIRE(x && rec && gate && out && N > 0 && HW > 0, "trt_gate_apply: bad argument");
+  TRT_REQUIRE(x && gate && out && N > 0 && HW > 0, "trt_gate_apply: bad argument");
   const Launch L = plan(C);
   int target = 16 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
@@ -538,6 +544,7 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
               "trt_se_bwd: null pointer");
   se_bwd_kernel<<<N, TPB, (size_t)(C + rd) * sizeof(float), stream>>>(dgate_pre, gate, s1, Wr, We, ds2, ds1, dmean, C, rd);
   se_bwd_w_kernel<<<(C * rd + TPB - 1) / TPB, TPB, 0, stream>>>(ds2, ds1, s1, pooled_sum, inv_hw, dWr, dbr, dWe, dbe, N, C, rd);
+  trt_count_launch(1);
   return trt_check_launch("trt_se_bwd");
 }
 
@@ -560,4 +567,12 @@ extern "C" int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N,
   dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
   pack_w_kernel<<<grid, block, 0, stream>>>(w, (__nv_bfloat16*)w_bf16, (__nv_bfloat16*)wt_bf16, N, K);
   return trt_check_launch("trt_pack_w1x1");
+}
+
+extern "C" int trt_scale_f32(float* x, size_t n, float alpha, cudaStream_t stream) {
+  TRT_REQUIRE(x && n > 0, "trt_scale_f32: bad argument");
+  int grid = (int)((n + 255) / 256);
+  if (grid > 4 * trt_num_sms()) grid = 4 * trt_num_sms();
+  scale_f32_kernel<<<grid, 256, 0, stream>>>(x, n, alpha);
+  return trt_check_launch("trt_scale_f32");
 }

@@ -309,6 +309,7 @@ extern "C" int trt_clahe_bgr_u8(const uint8_t* src, uint8_t* dst, int n, int h, 
   const int vec_ok = (w % 4 == 0) && (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 3) == 0);
   dim3 grid((w + 1023) / 1024, (h + APPLY_ROWS - 1) / APPLY_ROWS, n);
   clahe_apply_kernel<<<grid, 256, 0, stream>>>(src, dst, luts, tables, h, w, inv_th, inv_tw, vec_ok);
+  trt_count_launch(2);
   return trt_check_launch("trt_clahe_bgr_u8");
 }
 

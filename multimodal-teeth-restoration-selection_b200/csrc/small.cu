@@ -396,6 +396,75 @@ __global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q
   }
 }
 
+
+// ================================================================================================= MIL head + BCE
+// logit[b] = <dropout(M[b]), w> + bias   (MILNet.drop + MILNet.head, train_mil_attention_v1.py:146-147)
+__global__ void __launch_bounds__(TPB) linear1_fwd_kernel(const float* __restrict__ M, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ logit, int D,
+                                                          float drop_p, unsigned long long seed,
+                                                          const unsigned long long* __restrict__ step) {
+  __shared__ float s[TPB / 32];
+  const int b = blockIdx.x;
+  const unsigned long long sd = seed + (step ? *step * 0x9E3779B97F4A7C15ull : 0ull);
+  float acc = 0.f;
+  for (int d = threadIdx.x; d < D; d += TPB)
+    acc = fmaf(M[(size_t)b * D + d] * keep_scale(drop_p, sd, 3, (unsigned long long)b * D + d), w[d], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = bias[0];
+    for (int i = 0; i < TPB / 32; ++i) t += s[i];
+    logit[b] = t;
+  }
+}
+
+// dM[b][d] = dlogit[b]*w[d]*keep ; dw[d] = sum_b dlogit[b]*M[b][d]*keep ; db = sum_b dlogit[b]   (written, single block)
+__global__ void __launch_bounds__(TPB) linear1_bwd_kernel(const float* __restrict__ dlogit, const float* __restrict__ M,
+                                                          const float* __restrict__ w, float* __restrict__ dM,
+                                                          float* __restrict__ dw, float* __restrict__ db, int B, int D,
+                                                          float drop_p, unsigned long long seed,
+                                                          const unsigned long long* __restrict__ step) {
+  const unsigned long long sd = seed + (step ? *step * 0x9E3779B97F4A7C15ull : 0ull);
+  for (int d = blockIdx.x * TPB + threadIdx.x; d < D; d += gridDim.x * TPB) {
+    float acc = 0.f;
+    const float wd = w[d];
+    for (int b = 0; b < B; ++b) {
+      const float ks = keep_scale(drop_p, sd, 3, (unsigned long long)b * D + d);
+      const float dl = dlogit[b];
+      dM[(size_t)b * D + d] = dl * wd * ks;
+      acc = fmaf(dl, M[(size_t)b * D + d] * ks, acc);
+    }
+    dw[d] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += dlogit[b];
+    db[0] = t;
+  }
+}
+
+// loss = mean_b w_b * bce(logit_b, y_b) ; dlogit_b = w_b * (sigmoid(logit_b) - y_b) / B   (train_mil_attention_v1.py:183)
+__global__ void __launch_bounds__(TPB) bce_logits_kernel(const float* __restrict__ logit, const float* __restrict__ y,
+                                                         const float* __restrict__ sw, float* __restrict__ loss,
+                                                         float* __restrict__ dlogit, int B) {
+  __shared__ float s[TPB / 32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += TPB) {
+    const float x = logit[b], t = y[b], w = sw ? sw[b] : 1.f;
+    acc += w * (fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)))) / B;
+    if (dlogit) dlogit[b] = w * (1.f / (1.f + expf(-x)) - t) / B;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < TPB / 32; ++i) t += s[i];
+    loss[0] = t;
+  }
+}
+
 }  // namespace
 
 extern "C" size_t trt_mil_attn_smem_bytes(int K, int D, int hid, int backward) {
@@ -481,4 +550,27 @@ extern "C" int trt_tab_heads_bwd(const float* feat, const float* xtab, const flo
   q.scratch2 = scratch + (size_t)3 * B * Hd + 2 * Hd;
   tab_heads_bwd_kernel<<<1, TPB, 0, stream>>>(q);
   return trt_check_launch("trt_tab_heads_bwd");
+}
+
+
+extern "C" int trt_linear1_fwd(const float* M, const float* w, const float* bias, float* logit, int B, int D, float drop_p,
+                               unsigned long long seed, const unsigned long long* step, cudaStream_t stream) {
+  TRT_REQUIRE(M && w && bias && logit && B > 0 && D > 0, "trt_linear1_fwd: bad argument");
+  linear1_fwd_kernel<<<B, TPB, 0, stream>>>(M, w, bias, logit, D, drop_p, seed, step);
+  return trt_check_launch("trt_linear1_fwd");
+}
+
+extern "C" int trt_linear1_bwd(const float* dlogit, const float* M, const float* w, float* dM, float* dw, float* db, int B,
+                               int D, float drop_p, unsigned long long seed, const unsigned long long* step,
+                               cudaStream_t stream) {
+  TRT_REQUIRE(dlogit && M && w && dM && dw && db && B > 0 && D > 0, "trt_linear1_bwd: bad argument");
+  linear1_bwd_kernel<<<(D + TPB - 1) / TPB, TPB, 0, stream>>>(dlogit, M, w, dM, dw, db, B, D, drop_p, seed, step);
+  return trt_check_launch("trt_linear1_bwd");
+}
+
+extern "C" int trt_bce_logits(const float* logit, const float* y, const float* sample_w, float* loss, float* dlogit, int B,
+                              cudaStream_t stream) {
+  TRT_REQUIRE(logit && y && loss && B > 0, "trt_bce_logits: bad argument");
+  bce_logits_kernel<<<1, TPB, 0, stream>>>(logit, y, sample_w, loss, dlogit, B);
+  return trt_check_launch("trt_bce_logits");
 }

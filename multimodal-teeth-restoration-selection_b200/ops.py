@@ -90,6 +90,11 @@ def gate_apply(x, rec, gate, out, N, HW):
     return out
 
 
+def scale_f32(x, alpha):
+    check(lib.trt_scale_f32(ptr(x), x.numel(), alpha, stream()))
+    return x
+
+
 def bn_bwd_reduce(dy, x, rec, bstats):
     rows, Cc = x.shape
     check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), rows, Cc, stream()))
@@ -163,6 +168,28 @@ def mil_attn_bwd(dM, H, A, gV, gU, Vw, Uw, ww, dVw, dVb, dUw, dUb, dww, dwb):
     check(lib.trt_mil_attn_bwd(ptr(dM), ptr(H), ptr(A), ptr(gV), ptr(gU), ptr(Vw), ptr(Uw), ptr(ww), ptr(dH), ptr(dVw),
                                ptr(dVb), ptr(dUw), ptr(dUb), ptr(dww), ptr(dwb), B, K, D, Vw.shape[0], stream()))
     return dH
+
+
+def linear1_fwd(M, w, b, drop_p=0.0, seed=0, step=None):
+    B, D = M.shape
+    logit = torch.empty(B, device=M.device, dtype=torch.float32)
+    check(lib.trt_linear1_fwd(ptr(M), ptr(w), ptr(b), ptr(logit), B, D, drop_p, seed, ptr(step), stream()))
+    return logit
+
+
+def linear1_bwd(dlogit, M, w, dw, db, drop_p=0.0, seed=0, step=None):
+    B, D = M.shape
+    dM = torch.empty_like(M)
+    check(lib.trt_linear1_bwd(ptr(dlogit), ptr(M), ptr(w), ptr(dM), ptr(dw), ptr(db), B, D, drop_p, seed, ptr(step), stream()))
+    return dM
+
+
+def bce_logits(logit, y, sample_w=None, want_grad=True):
+    B = logit.numel()
+    loss = torch.empty(1, device=logit.device, dtype=torch.float32)
+    dlogit = torch.empty_like(logit) if want_grad else None
+    check(lib.trt_bce_logits(ptr(logit), ptr(y), ptr(sample_w), ptr(loss), ptr(dlogit), B, stream()))
+    return loss, dlogit
 
 
 # ------------------------------------------------------------------------------------------------ tab + heads + loss

@@ -1,0 +1,281 @@
+"""Fused train steps for the two hot loops of the reference, with the same recipe and none of its per-step host work:
+
+    DualTaskTrainer.step(x_img, x_tab, y_h, y_s, w)   <- experiments/multimodal_v1/train_mm_joint_dualtask.py:236-256
+    MILTrainer.step(bags, y)                          <- experiments/vision_v2/train_mil_attention_v1.py:177-189
+
+zero_grad -> forward -> loss -> backward -> clip_grad_norm_(1.0) -> AdamW(lr, wd) -> cosine LR per iteration, all on
+libteethrt kernels over FLAT fp32 parameter/gradient/moment buffers (the nn.Parameters of the model become views of the
+flat buffer, so state_dict()/checkpoints are unchanged).  The whole step is captured once into a CUDA graph and replayed;
+the step counter, LR schedule and dropout seeds live on the device.  Data parallel: one process per GPU, the flat gradient
+is all-reduced over NCCL in reverse-execution buckets launched on a side stream while the rest of backward runs.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .backbone import forward_train, backward_train
+from .modules import TAB_PARAM_KEYS
+
+ALIGN = 8  # floats: every parameter starts on a 32-byte boundary inside the flat buffer
+
+
+class FlatParams:
+    """Re-homes every parameter of `module` into one flat fp32 buffer (forward/registration order)."""
+
+    def __init__(self, module):
+        self.module = module
+        named = list(module.named_parameters())
+        dev = named[0][1].device
+        self.offsets, off = {}, 0
+        for n, p in named:
+            if p.dtype != torch.float32:
+                raise TypeError(f"{n}: fp32 master parameters expected")
+            self.offsets[n] = (off, p.numel(), tuple(p.shape))
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.p = torch.zeros(off, device=dev)
+        self.g = torch.zeros(off, device=dev)
+        self.m = torch.zeros(off, device=dev)
+        self.v = torch.zeros(off, device=dev)
+        with torch.no_grad():
+            for n, p in named:
+                o, k, shp = self.offsets[n]
+                view = self.p[o:o + k].view(shp)
+                view.copy_(p.data)
+                p.data = view
+        self.grads = {n: self.g[o:o + k].view(shp) for n, (o, k, shp) in self.offsets.items()}
+        self.names = [n for n, _ in named]
+
+    def attach_grads(self):
+        """Expose the flat gradient through .grad (for inspection / torch optimisers)."""
+        for n, p in self.module.named_parameters():
+            p.grad = self.grads[n]
+
+
+class _FusedTrainer:
+    def __init__(self, model, lr, weight_decay, t_max, grad_clip, graph, process_group, num_buckets, graph_warmup=2):
+        self.model = model.train()
+        self.flat = FlatParams(model)
+        dev = self.flat.p.device
+        self.dev = dev
+        self.state = ops.OptimState(dev, lr, t_max=t_max)
+        self.wd, self.clip = float(weight_decay), float(grad_clip)
+        self.normsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.grad_norm = torch.zeros(1, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or (dist.is_available() and dist.is_initialized())) else 1
+        if self.world > 1 and self.pg is None:
+            self.pg = dist.group.WORLD
+        self.num_buckets = max(1, num_buckets)
+        self.use_graph = graph
+        self.graph_warmup = graph_warmup
+        self._graphs = None
+        self._nsteps = 0
+        self._static = None
+        self.launches_per_step = None
+        if self.world > 1:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+            self._sync_initial_state()
+
+    # ---- data parallel -----------------------------------------------------------------------------------------------
+    def _sync_initial_state(self):
+        dist.broadcast(self.flat.p, src=0, group=self.pg)
+        for b in self.model.buffers():
+            dist.broadcast(b, src=0, group=self.pg)
+
+    def _bucket_ranges(self, boundaries):
+        """Contiguous ranges of the flat gradient, last-executed parameters first (reverse forward order)."""
+        edges = sorted(set([0, self.flat.numel] + boundaries))
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)][::-1]
+
+    # ---- to be provided by subclasses --------------------------------------------------------------------------------
+    def _make_static(self, *inputs):
+        raise NotImplementedError
+
+    def _segments(self):
+        """List of callables; segment i finishes the gradients of bucket i (reverse order)."""
+        raise NotImplementedError
+
+    # ---- one optimiser step ------------------------------------------------------------------------------------------
+    def _optimizer(self):
+        self.state.advance()
+        ops.grad_sumsq(self.flat.g, self.normsq)
+        ops.adamw_step(self.flat.p, self.flat.g, self.flat.m, self.flat.v, self.state, self.normsq, self.grad_norm,
+                       1.0 / self.world, self.clip, 1e-8, self.wd)
+
+    def _run_eager(self):
+        segs, ranges = self._segments()
+        self.flat.g.zero_()
+        for i, seg in enumerate(segs):
+            seg()
+            self._reduce_bucket(ranges[i] if self.world > 1 else None)
+        self._finish_comm()
+        self._optimizer()
+
+    def _reduce_bucket(self, rng):
+        if rng is None or self.world == 1:
+            return
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.flat.g[rng[0]:rng[1]], group=self.pg)
+
+    def _finish_comm(self):
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+
+    def _capture(self):
+        from ._lib import lib
+        segs, ranges = self._segments()
+        c0 = lib.trt_launch_count()
+        graphs = []
+        pool = None
+        first = True
+        for seg in segs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                if first:
+                    self.flat.g.zero_()
+                seg()
+            pool = g.pool()
+            graphs.append(g)
+            first = False
+        gopt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gopt, pool=pool):
+            self._optimizer()
+        self._graphs = (graphs, gopt, ranges)
+        self.launches_per_step = int(lib.trt_launch_count() - c0)     # kernels recorded into the replayed graphs
+
+    def _replay(self):
+        graphs, gopt, ranges = self._graphs
+        for i, g in enumerate(graphs):
+            g.replay()
+            self._reduce_bucket(ranges[i] if self.world > 1 else None)
+        self._finish_comm()
+        gopt.replay()
+
+    def _step(self, *inputs):
+        if self._static is None:
+            self._make_static(*inputs)
+        for dst, src in zip(self._static, inputs):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        if self.use_graph and self._nsteps >= self.graph_warmup:
+            if self._graphs is None:
+                torch.cuda.synchronize()
+                self._capture()
+            self._replay()
+        else:
+            self._run_eager()
+        self._nsteps += 1
+        return self.loss
+
+    def lr(self):
+        return self.state.read()["lr"]
+
+
+class DualTaskTrainer(_FusedTrainer):
+    """MMJointDualHead + dual BCE + clip + AdamW + cosine (train_mm_joint_dualtask.py:217-256)."""
+
+    def __init__(self, model, lr=3e-4, weight_decay=1e-4, t_max=0, alpha=1.0, beta=0.3, grad_clip=1.0,
+                 use_sample_weights=False, graph=True, process_group=None, num_buckets=3, seed=0):
+        super().__init__(model, lr, weight_decay, t_max, grad_clip, graph, process_group, num_buckets)
+        self.alpha, self.beta, self.use_w, self.seed = float(alpha), float(beta), bool(use_sample_weights), int(seed)
+
+    def _make_static(self, x_img, x_tab, y_h, y_s, w):
+        dev = self.dev
+        B = x_img.shape[0]
+        self._static = [torch.empty(tuple(x_img.shape), device=dev, dtype=x_img.dtype if x_img.dtype == torch.bfloat16 else torch.float32),
+                        torch.empty((B, x_tab.shape[1]), device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev),
+                        torch.ones(B, device=dev)]
+        self.scratch = ops.tab_heads_scratch(B, self.model.tab_hidden, dev)
+        self.head_out = {k: torch.empty(B, device=dev) for k in ("logit", "reg", "dlogit", "dreg")}
+        self.head_out["loss"] = self.loss
+        self.dfeat = torch.empty((B, self.model.backbone.num_features), device=dev)
+
+    def _segments(self):
+        m, fl = self.model, self.flat
+        x_img, x_tab, y_h, y_s, w = self._static
+        enc = m.backbone
+        step_ptr = self.state.buf            # first 8 bytes = u64 step counter: mixes into the dropout seed
+        bn = m.tab[1]
+        params = [fl.p[fl.offsets[k][0]:fl.offsets[k][0] + fl.offsets[k][1]].view(fl.offsets[k][2]) for k in TAB_PARAM_KEYS]
+        grads = [fl.grads[k] for k in TAB_PARAM_KEYS]
+        enc_grads = {n[len("backbone."):]: g for n, g in fl.grads.items() if n.startswith("backbone.")}
+        holder = {}
+
+        def fwd_and_heads():
+            feat, ctx = forward_train(enc, x_img)
+            holder["feat"], holder["ctx"] = feat, ctx
+            ops.tab_heads_fwd(feat, x_tab, params, bn.running_mean, bn.running_var, bn.num_batches_tracked, self.scratch, True,
+                              m.drop_p, targets=(y_h, y_s, w if self.use_w else None), alpha=self.alpha, beta=self.beta,
+                              seed=self.seed, step=step_ptr, out=self.head_out)
+            ops.tab_heads_bwd(feat, x_tab, params, bn.running_mean, bn.running_var, self.head_out["dlogit"],
+                              self.head_out["dreg"], self.dfeat, grads, self.scratch, True, m.drop_p, seed=self.seed,
+                              step=step_ptr)
+
+        def enc_backward():
+            backward_train(enc, holder["ctx"], self.dfeat, enc_grads)
+            holder.clear()
+
+        # bucket 0 = tab + heads (everything after the backbone in the flat buffer), bucket 1 = the backbone
+        first_head = min(fl.offsets[k][0] for k in TAB_PARAM_KEYS)
+        return [fwd_and_heads, enc_backward], self._bucket_ranges([first_head])
+
+    def step(self, x_img, x_tab, y_h, y_s, w=None):
+        """One train step; returns the (device-resident) loss tensor — read it whenever convenient, no per-step sync."""
+        if x_img.shape[0] < 2:
+            raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d needs batch > 1)")
+        return self._step(x_img, x_tab, y_h, y_s, w)
+
+
+class MILTrainer(_FusedTrainer):
+    """MILNet + BCE + clip + AdamW + cosine (train_mil_attention_v1.py:168-189)."""
+
+    def __init__(self, model, lr=2e-4, weight_decay=1e-4, t_max=0, grad_clip=1.0, graph=True, process_group=None, seed=0):
+        super().__init__(model, lr, weight_decay, t_max, grad_clip, graph, process_group, 2)
+        self.seed = int(seed)
+
+    def _make_static(self, bags, y):
+        dev = self.dev
+        self._static = [torch.empty(tuple(bags.shape), device=dev, dtype=bags.dtype if bags.dtype == torch.bfloat16 else torch.float32),
+                        torch.empty(bags.shape[0], device=dev)]
+
+    def _segments(self):
+        m, fl = self.model, self.flat
+        bags, y = self._static
+        B, K = bags.shape[:2]
+        enc = m.encoder
+        step_ptr = self.state.buf
+        P = lambda k: fl.p[fl.offsets[k][0]:fl.offsets[k][0] + fl.offsets[k][1]].view(fl.offsets[k][2])
+        G = fl.grads
+        enc_grads = {n[len("encoder."):]: g for n, g in G.items() if n.startswith("encoder.")}
+        holder = {}
+
+        def fwd_and_pool():
+            feat, ctx = forward_train(enc, bags.view(B * K, *bags.shape[2:]))
+            H = feat.view(B, K, -1)
+            M, A, gV, gU = ops.mil_attn_fwd(H, P("mil.attention_V.weight"), P("mil.attention_V.bias"),
+                                            P("mil.attention_U.weight"), P("mil.attention_U.bias"),
+                                            P("mil.attention_w.weight").view(-1), P("mil.attention_w.bias"), save=True)
+            logit = ops.linear1_fwd(M, P("head.weight").view(-1), P("head.bias"), m.drop_p, self.seed, step_ptr)
+            loss, dlogit = ops.bce_logits(logit, y)
+            self.loss.copy_(loss)
+            dM = ops.linear1_bwd(dlogit, M, P("head.weight").view(-1), G["head.weight"], G["head.bias"], m.drop_p, self.seed,
+                                 step_ptr)
+            dH = ops.mil_attn_bwd(dM, H, A, gV, gU, P("mil.attention_V.weight"), P("mil.attention_U.weight"),
+                                  P("mil.attention_w.weight").view(-1), G["mil.attention_V.weight"], G["mil.attention_V.bias"],
+                                  G["mil.attention_U.weight"], G["mil.attention_U.bias"], G["mil.attention_w.weight"],
+                                  G["mil.attention_w.bias"])
+            holder["ctx"], holder["dfeat"] = ctx, dH.view(B * K, -1)
+
+        def enc_backward():
+            backward_train(enc, holder["ctx"], holder["dfeat"], enc_grads)
+            holder.clear()
+
+        first_head = min(o for n, (o, _, _) in fl.offsets.items() if not n.startswith("encoder."))
+        return [fwd_and_pool, enc_backward], self._bucket_ranges([first_head])
+
+    def step(self, bags, y):
+        return self._step(bags, y)

@@ -1,0 +1,251 @@
+"""GPU parity, model level: the teethrt modules (C-ABI kernels underneath) against the oracle (oracle/ref_models.py, the
+restatement pinned to the reference's own classes) and the golden fixtures minted from the reference.
+
+Tolerances (SURVEY.md §8c, bf16 activations / fp32 accumulate vs the fp32 oracle):
+  eval logits |d| <= 5e-2, probabilities |d| <= 1e-2; train step: loss |d| <= 3e-2, per-tensor gradient cosine >= 0.99
+  for tensors carrying real signal, grad-norm within 5 %.
+"""
+import os
+
+import pytest
+import torch
+
+import ref_models as R   # oracle (checker only)
+
+pytestmark = pytest.mark.gpu
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "models_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def T():
+    import teethrt
+    teethrt.init()
+    from teethrt import modules, train, backbone  # noqa: F401
+    return teethrt
+
+
+def mm_inputs(B, img, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, img, img, generator=g)
+    xt = torch.randn(B, 9, generator=g)
+    yh = (torch.rand(B, generator=g) < 0.6).float()
+    ys = (yh * 0.8 + 0.2 * torch.rand(B, generator=g)).clamp(0, 1)
+    return x, xt, yh, ys
+
+
+def test_state_dict_contract(T):
+    from teethrt.modules import MMJointDualHead, MMNet, MILNet, MILNetTwin
+    ora = R.MMJointDualHead()
+    mine = MMJointDualHead()
+    a, b = ora.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    assert mine.load_state_dict(a, strict=True)
+    assert set(MMNet().state_dict().keys()) == set(a.keys())
+    assert list(R.MILNet().state_dict().keys()) == list(MILNet().state_dict().keys())
+    assert set(R.MILNetTwin().state_dict().keys()) == set(MILNetTwin().state_dict().keys())
+    assert sum(p.numel() for p in mine.parameters()) == 17_557_258
+
+
+def test_mm_eval_forward_config0_vs_golden_and_oracle(T):
+    """BASELINE.json configs[0]: MM dual-task fwd, B4, batch 8 @224."""
+    from teethrt.modules import MMJointDualHead
+    ora = R.seeded_model("mm", seed=0, warm=2, img=64)
+    m = MMJointDualHead().cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    m.eval()
+    x, xt, _, _ = mm_inputs(8, 224, 100)
+    with torch.no_grad():
+        logit, reg = m(x.cuda(), xt.cuda())
+        lo, ro = ora(x, xt)
+    g = GOLD["mm_b4_fwd224"]
+    assert torch.allclose(lo, g["logit"], atol=1e-5)                       # oracle still equals the reference's output
+    assert (logit.cpu() - g["logit"]).abs().max() < 5e-2 and (reg.cpu() - g["reg"]).abs().max() < 5e-2
+    assert (torch.sigmoid(logit.cpu()) - torch.sigmoid(g["logit"])).abs().max() < 1e-2
+    # state dict round trip is lossless (fp32 masters untouched by the bf16 compute path)
+    sd = m.state_dict()
+    assert all(torch.equal(sd[k].cpu(), v) for k, v in ora.state_dict().items())
+
+
+def test_mm_batch1_and_tta(T):
+    from teethrt.modules import MMNet
+    from teethrt.infer import tta_logit
+    ora = R.seeded_model("mm", seed=0, warm=2, img=64)
+    m = MMNet().cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    m.eval()
+    x, xt, _, _ = mm_inputs(8, 224, 100)
+    with torch.no_grad():
+        l1, _ = m(x[:1].cuda(), xt[:1].cuda())
+        tta = tta_logit(m, x[:2].cuda(), xt[:2].cuda())
+    assert abs(float(l1[0]) - float(GOLD["mm_b4_fwd224"]["logit"][0])) < 5e-2
+    g = GOLD["mm_b4_tta224"]
+    assert (tta.cpu() - g["logit"]).abs().max() < 5e-2
+    assert (torch.sigmoid(tta.cpu() / 2.5) - g["prob_T2p5"]).abs().max() < 1e-2
+
+
+def grad_report(mine_named, ora_named):
+    """cosine / relative-norm per tensor between two gradient dicts"""
+    rep = {}
+    for n, go in ora_named.items():
+        gm = mine_named[n].detach().float().cpu().flatten()
+        go = go.flatten()
+        no, nm = float(go.norm()), float(gm.norm())
+        cos = float(torch.dot(gm, go) / (nm * no + 1e-30))
+        rep[n] = (cos, nm, no)
+    return rep
+
+
+@pytest.mark.parametrize("backbone,B,img", [("tf_efficientnet_b0_ns", 8, 64), ("tf_efficientnet_b4_ns", 4, 96)])
+def test_mm_train_forward_backward_autograd_path(T, backbone, B, img):
+    """The reference's own loop shape: logits via module.forward in train mode, loss by torch, loss.backward()."""
+    from teethrt.modules import MMJointDualHead
+    ora = R.seeded_model("mm", seed=1, warm=1, img=img, backbone=backbone, drop=0.0).train()
+    m = MMJointDualHead(backbone=backbone, drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    m.train()
+    x, xt, yh, ys = mm_inputs(B, img, 200)
+    lo, ro = ora(x, xt)
+    R.dual_bce_loss(lo, ro, yh, ys).backward()
+    lm, rm = m(x.cuda(), xt.cuda())
+    loss = R.dual_bce_loss(lm, rm, yh.cuda(), ys.cuda())
+    loss.backward()
+    assert (lm.detach().cpu() - lo.detach()).abs().max() < 5e-2 and (rm.detach().cpu() - ro.detach()).abs().max() < 5e-2
+    # BN running statistics updated like torch's
+    assert torch.allclose(m.backbone.bn1.running_mean.cpu(), ora.backbone.bn1.running_mean, atol=2e-3)
+    assert torch.allclose(m.tab[1].running_var.cpu(), ora.tab[1].running_var, atol=1e-4)
+    assert int(m.backbone.bn1.num_batches_tracked) == int(ora.backbone.bn1.num_batches_tracked)
+    rep = grad_report({n: p.grad for n, p in m.named_parameters()}, {n: p.grad for n, p in ora.named_parameters()})
+    total_o = sum(v[2] ** 2 for v in rep.values()) ** 0.5
+    total_m = sum(v[1] ** 2 for v in rep.values()) ** 0.5
+    assert abs(total_m - total_o) / total_o < 0.05
+    big = {n: v for n, v in rep.items() if v[2] > 1e-3 * total_o}        # tensors that carry real signal
+    bad = {n: v for n, v in big.items() if v[0] < 0.99}
+    assert len(big) > 50 and not bad, f"low-cosine gradients: {sorted(bad.items(), key=lambda kv: kv[1][0])[:8]}"
+
+
+def test_fused_trainer_matches_golden_train_steps(T):
+    """3 steps of the reference loop (train_mm_joint_dualtask.py:241-256) minted into tests/golden from the reference's
+    classes, replayed by DualTaskTrainer (eager steps, then a captured CUDA-graph step)."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    g = GOLD["mm_b0_train64"]
+    ora = R.seeded_model("mm", seed=1, warm=1, img=64, backbone="tf_efficientnet_b0_ns", drop=0.0)
+    m = MMJointDualHead(backbone="tf_efficientnet_b0_ns", drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    tr = DualTaskTrainer(m, lr=3e-4, weight_decay=1e-4, t_max=10, alpha=1.0, beta=0.3, grad_clip=1.0, graph=True)
+    tr.graph_warmup = 2
+    for s in range(3):
+        x, xt, yh, ys = mm_inputs(8, 64, 200 + s)
+        loss = tr.step(x.cuda(), xt.cuda(), yh.cuda(), ys.cuda())
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(g["losses"][s])) < 3e-2, (s, float(loss), float(g["losses"][s]))
+        assert abs(float(tr.grad_norm) - float(g["grad_norms"][s])) < 0.05 * float(g["grad_norms"][s]) + 1e-3
+    assert tr._graphs is not None                                          # third step ran as a graph replay
+    assert abs(tr.lr() - 3e-4 * (1 + __import__("math").cos(__import__("math").pi * 2 / 10)) / 2) < 1e-9
+    m.eval()
+    x, xt, _, _ = mm_inputs(8, 64, 299)
+    with torch.no_grad():
+        lg, rg = m(x.cuda(), xt.cuda())
+    assert (lg.cpu() - g["logit_after"]).abs().max() < 5e-2 and (rg.cpu() - g["reg_after"]).abs().max() < 5e-2
+    assert torch.allclose(m.backbone.bn1.running_mean.cpu(), g["bn1_running_mean"], atol=5e-3)
+    # checkpoint layout of the reference (train_mm_joint_dualtask.py:302-313) round-trips through torch.save/load
+    import io
+    buf = io.BytesIO()
+    torch.save({"model": m.state_dict(), "scaler_mean": None, "scaler_scale": None, "thr": 0.5, "T": 1.0,
+                "args": {"backbone": "tf_efficientnet_b0_ns", "img_size": 64, "tab_hidden": 64, "dropout": 0.0}, "epoch": 1}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location="cpu", weights_only=False)
+    assert R.MMJointDualHead(backbone="tf_efficientnet_b0_ns").load_state_dict(ck["model"], strict=True)
+
+
+def test_mil_forward_and_twin_vs_golden(T):
+    from teethrt.modules import MILNet, MILNetTwin
+    ora = R.seeded_model("mil", seed=2, warm=1, img=64)
+    m = MILNet(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    m.eval()
+    gen = torch.Generator().manual_seed(300)
+    bags = torch.randn(2, 16, 3, 96, 96, generator=gen)
+    H = torch.randn(6, 16, 1280, generator=gen)
+    with torch.no_grad():
+        lg, A = m(bags.cuda())
+        M, A2 = m.mil(H.cuda())
+    assert (lg.cpu() - GOLD["mil_b0_fwd96"]["logit"]).abs().max() < 5e-2
+    assert (A.cpu() - GOLD["mil_b0_fwd96"]["A"]).abs().max() < 1e-2
+    assert torch.allclose(M.cpu(), GOLD["mil_pool"]["M"], atol=1e-4) and torch.allclose(A2.cpu(), GOLD["mil_pool"]["A"], atol=1e-5)
+    tw_o = R.seeded_model("mil_twin", seed=3, warm=1, img=64)
+    tw = MILNetTwin().cuda()
+    tw.load_state_dict(tw_o.state_dict(), strict=True)
+    tw.eval()
+    with torch.no_grad():
+        out = tw(bags[0].cuda())
+    assert abs(float(out) - float(GOLD["mil_twin_fwd96"]["logit"])) < 5e-2
+
+
+def test_mil_trainer_step_vs_oracle(T):
+    from teethrt.modules import MILNet
+    from teethrt.train import MILTrainer
+    ora = R.seeded_model("mil", seed=2, warm=1, img=64, drop=0.0).train()
+    m = MILNet(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    opt, sched = torch.optim.AdamW(ora.parameters(), lr=2e-4, weight_decay=1e-4), None
+    tr = MILTrainer(m, lr=2e-4, weight_decay=1e-4, t_max=0, graph=True)
+    gen = torch.Generator().manual_seed(5)
+    for s in range(3):
+        bags = torch.randn(2, 4, 3, 64, 64, generator=gen)
+        y = (torch.rand(2, generator=gen) < 0.5).float()
+        lo, gn = R.mil_train_step(ora, opt, sched, bags, y)
+        loss = tr.step(bags.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        assert abs(float(loss) - lo) < 3e-2
+        assert abs(float(tr.grad_norm) - gn) < 0.08 * gn + 1e-3
+
+
+def test_ensembles_mirror_reference_behaviour(T, tmp_path):
+    import numpy as np
+    from PIL import Image
+    from teethrt.infer import MMEnsemble, MILEnsemble
+    # --- MM: two folds with different temperatures
+    ora = [R.seeded_model("mm", seed=s, warm=1, img=64, backbone="tf_efficientnet_b0_ns") for s in (0, 1)]
+    Ts, mean, scale = [2.5, 3.1], np.arange(9, dtype=np.float64), np.array([1, 2, 0, 1, 1, 2, 1, 1, 3], dtype=np.float64)
+    for f, (o, Tf) in enumerate(zip(ora, Ts)):
+        torch.save({"model": o.state_dict(), "scaler_mean": mean, "scaler_scale": scale, "thr": 0.5, "T": Tf,
+                    "args": {"backbone": "tf_efficientnet_b0_ns", "img_size": 64, "tab_hidden": 64, "dropout": 0.2}, "epoch": 3},
+                   tmp_path / f"mm_dualtask_fold{f}.pt")
+    rng = np.random.default_rng(0)
+    img_path = tmp_path / "tooth.png"
+    Image.fromarray(rng.integers(0, 256, size=(90, 120, 3), dtype=np.uint8)).save(img_path)
+    ens = MMEnsemble(tmp_path, device="cuda")
+    assert ens.num_folds == 2
+    tab = {k: float(i) for i, k in enumerate(R.TAB_FEATURES)}
+    import timm  # the oracle's shim provides the reference's eval transform
+    tf = timm.data.create_transform(input_size=64, is_training=False, interpolation="bicubic")
+    xi = tf(Image.open(img_path).convert("RGB")).unsqueeze(0)
+    for td in (tab, None):
+        want, _ = R.mm_ensemble_prob(list(zip(ora, Ts)), [(mean, scale)] * 2, xi, td)
+        got, dbg = ens.predict(img_path, td)
+        assert abs(got - want) < 1e-2 and "fold_probs" in dbg
+    assert MMEnsemble(tmp_path / "nothing", device="cuda").predict(img_path, None) == (0.5, "MM not loaded")
+    # --- MIL: trainer-format checkpoints ('model' key, hid 128) load and run (the reference twin silently cannot, q9)
+    mo = R.seeded_model("mil", seed=2, warm=1, img=64)
+    mil_dir = tmp_path / "mil"
+    mil_dir.mkdir()
+    torch.save({"model": mo.state_dict(), "args": {}, "thr": 0.5, "epoch": 1}, mil_dir / "mil_v1_fold0.pt")
+    inst = tmp_path / "inst"
+    inst.mkdir()
+    for i in range(3):
+        Image.fromarray(rng.integers(0, 256, size=(530, 540, 3), dtype=np.uint8)).save(inst / f"{i}.png")
+    me = MILEnsemble(mil_dir, device="cuda")
+    assert me.num_folds == 1
+    prob, dbg = me.predict(inst)
+    tw = R.MILNetTwin(hid_dim=128)
+    tw.load_state_dict(R.remap_mil_keys(mo.state_dict()), strict=True)
+    tw.eval()
+    from torchvision import transforms
+    tfm = transforms.Compose([transforms.Resize(512), transforms.CenterCrop(480), transforms.ToTensor()])
+    xs = torch.stack([tfm(Image.open(p).convert("RGB")) for p in sorted(inst.iterdir())])
+    with torch.no_grad():
+        want = float(torch.sigmoid(tw(xs)))
+    assert abs(prob - want) < 1e-2 and "Instances=3" in dbg
+    assert me.predict(tmp_path / "empty_dir_that_does_not_exist")[0] is None
