@@ -179,8 +179,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = MMJointDualHead('tf_efficientnet_b4_ns', tab_in=TAB, tab_hidden=64, drop=0.2).to(dev)
     total_steps = 2 * (args.steps + args.warmup) + 8
-    tr = DualTaskTrainer(model, lr=3e-4, weight_decay=1e-4, t_max=total_steps, alpha=1.0, beta=0.3, grad_clip=1.0, graph=True,
-                         seed=1234)
+    tr = DualTaskTrainer(model, lr=3e-4, weight_decay=1e-4, t_max=total_steps, alpha=1.0, beta=0.3, grad_clip=1.0,
+                         graph=os.environ.get('TEETHRT_NO_GRAPH') != '1', seed=1234)
     dev_batches = [synth_batch(BATCH, 1000 + rank * 17 + i, device=dev) for i in range(2)]
     host_batches = [synth_batch(BATCH, 2000 + rank * 17 + i, pin=True) for i in range(2)]
 
