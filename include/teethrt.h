@@ -103,7 +103,7 @@ int trt_bn_apply(const void* x, const float* rec, const void* residual, void* ou
                  trt_stream_t stream);
 /* pooled_sum[n,c] = sum_hw act(bn(x)) (zeroed here; rec may be NULL = plain sum) — SE squeeze and global average pool */
 int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int N, int HW, int C, int act, trt_stream_t stream);
-/* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 (pre-activation of the reduce conv, [N,rd]) may be NULL */
+/* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 [N,rd] receives the pre-activation of the reduce conv */
 int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
                float* s1, float* gate, int N, int C, int rd, trt_stream_t stream);
 /* out = (rec ? silu(bn(x)) : x) * gate[n,c] */

@@ -220,7 +220,7 @@ def _check_input(enc, x):
 
 def _se_gate(blk, pooled, inv_hw, N, C, dev, save):
     rd = blk.cfg["rd"]
-    s1 = torch.empty((N, rd), device=dev, dtype=torch.float32) if save else None
+    s1 = torch.empty((N, rd), device=dev, dtype=torch.float32)
     gate = torch.empty((N, C), device=dev, dtype=torch.float32)
     se = blk.se
     ops.se_fwd(pooled, inv_hw, se.conv_reduce.weight.detach(), se.conv_reduce.bias.detach(), se.conv_expand.weight.detach(),

@@ -52,7 +52,7 @@ __device__ __forceinline__ f8 ldf8(const float* p) {  // 8 consecutive fp32 (32 
   return r;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // d/dx silu(x) = s * (1 + x * (1 - s))
 __device__ __forceinline__ float silu_gradf_(float x) { float s = sigmoidf_(x); return s * (1.0f + x * (1.0f - s)); }

@@ -159,34 +159,52 @@ __global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ SE MLP forward (one block per image)
-__global__ void __launch_bounds__(TPB) se_fwd_kernel(const float* __restrict__ pooled, float inv_hw,
-                                                     const float* __restrict__ Wr, const float* __restrict__ br,
-                                                     const float* __restrict__ We, const float* __restrict__ be,
-                                                     float* __restrict__ s1_out, float* __restrict__ gate, int C, int rd) {
-  extern __shared__ float s_mem[];
-  float* s_mean = s_mem;        // [C]
-  float* s_a1 = s_mem + C;      // [rd]
-  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += TPB) s_mean[c] = pooled[(size_t)n * C + c] * inv_hw;
+// ------------------------------------------------------------------------------------------------ SE MLP forward
+// Two batched micro-GEMMs over the whole batch so every weight is read once:
+//   (1) s1[n,r] = br[r] + <mean[n,:], Wr[r,:]>   grid = rd blocks, one warp per image, lanes over channels
+//   (2) gate[n,c] = sigmoid(be[c] + <silu(s1[n,:]), We[c,:]>)   grid = (C/64, image splits), We chunk + silu(s1) in smem
+__global__ void __launch_bounds__(TPB) se_reduce_kernel(const float* __restrict__ pooled, float inv_hw,
+                                                        const float* __restrict__ Wr, const float* __restrict__ br,
+                                                        float* __restrict__ s1, int N, int C, int rd) {
+  extern __shared__ float s_mem[];   // [C] one row of Wr, pre-scaled by 1/HW
+  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += TPB) s_mem[c] = __ldg(Wr + (size_t)r * C + c) * inv_hw;
   __syncthreads();
-  for (int r = warp; r < rd; r += TPB / 32) {
+  const float bias = br[r];
+  for (int n = warp; n < N; n += TPB / 32) {
     float acc = 0.f;
-    const float* w = Wr + (size_t)r * C;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w + c), s_mean[c], acc);
+    const float* p = pooled + (size_t)n * C;
+    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(p + c), s_mem[c], acc);
     acc = warp_sum(acc);
-    if (lane == 0) {
-      const float s1 = acc + br[r];
-      if (s1_out) s1_out[(size_t)n * rd + r] = s1;
-      s_a1[r] = siluf_(s1);
-    }
+    if (lane == 0) s1[(size_t)n * rd + r] = acc + bias;
   }
+}
+
+constexpr int SE_CC = 64;   // channels per block in the expand kernels
+__global__ void __launch_bounds__(TPB) se_expand_kernel(const float* __restrict__ s1, const float* __restrict__ We,
+                                                        const float* __restrict__ be, float* __restrict__ gate, int N, int C,
+                                                        int rd, int n_per_block) {
+  extern __shared__ float s_mem[];
+  float* s_we = s_mem;                         // [SE_CC][rd+1]
+  float* s_a1 = s_mem + SE_CC * (rd + 1);      // [n_per_block][rd]
+  const int c0 = blockIdx.x * SE_CC, n0 = blockIdx.y * n_per_block;
+  const int nn = min(n_per_block, N - n0);
+  for (int i = threadIdx.x; i < SE_CC * rd; i += TPB) {
+    const int cl = i / rd, r = i - cl * rd;
+    s_we[cl * (rd + 1) + r] = (c0 + cl < C) ? __ldg(We + (size_t)(c0 + cl) * rd + r) : 0.f;
+  }
+  for (int i = threadIdx.x; i < nn * rd; i += TPB) s_a1[i] = siluf_(s1[(size_t)n0 * rd + i]);
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    float acc = be[c];
-    const float* w = We + (size_t)c * rd;
-    for (int r = 0; r < rd; ++r) acc = fmaf(__ldg(w + r), s_a1[r], acc);
-    gate[(size_t)n * C + c] = sigmoidf_(acc);
+  const int cl = threadIdx.x % SE_CC, nsub = threadIdx.x / SE_CC;
+  const int c = c0 + cl;
+  if (c >= C) return;
+  const float bias = be[c];
+  const float* wrow = s_we + cl * (rd + 1);
+  for (int n = nsub; n < nn; n += TPB / SE_CC) {
+    float acc = bias;
+    const float* a = s_a1 + n * rd;
+    for (int r = 0; r < rd; ++r) acc = fmaf(a[r], wrow[r], acc);
+    gate[(size_t)(n0 + n) * C + c] = sigmoidf_(acc);
   }
 }
 
@@ -283,37 +301,50 @@ __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restr
   }
 }
 
-// SE MLP backward per image: ds2[n,C], ds1[n,rd], dmean[n,C]
-__global__ void __launch_bounds__(TPB) se_bwd_kernel(const float* __restrict__ dgate_pre, const float* __restrict__ gate,
-                                                     const float* __restrict__ s1, const float* __restrict__ Wr,
-                                                     const float* __restrict__ We, float* __restrict__ ds2_out,
-                                                     float* __restrict__ ds1_out, float* __restrict__ dmean, int C, int rd) {
-  extern __shared__ float s_mem[];
-  float* s_ds2 = s_mem;        // [C]
-  float* s_ds1 = s_mem + C;    // [rd]
-  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    const float g = gate[(size_t)n * C + c];
-    const float d = dgate_pre[(size_t)n * C + c] * g * (1.f - g);
-    s_ds2[c] = d;
-    ds2_out[(size_t)n * C + c] = d;
-  }
+// SE MLP backward, batched like the forward:
+//   (a) ds2[n,c] = dgate_pre*g*(1-g);  ds1[n,r] = silu'(s1[n,r]) * sum_c ds2[n,c] We[c,r]     grid = rd blocks
+//   (b) dmean[n,c] = sum_r ds1[n,r] Wr[r,c]                                                   grid = (C/256, image splits)
+__global__ void __launch_bounds__(TPB) se_bwd_a_kernel(const float* __restrict__ dgate_pre, const float* __restrict__ gate,
+                                                       const float* __restrict__ s1, const float* __restrict__ We,
+                                                       float* __restrict__ ds2_out, float* __restrict__ ds1_out, int N, int C,
+                                                       int rd) {
+  extern __shared__ float s_mem[];   // [C] column r of We
+  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += TPB) s_mem[c] = __ldg(We + (size_t)c * rd + r);
   __syncthreads();
-  for (int r = warp; r < rd; r += TPB / 32) {
+  for (int n = warp; n < N; n += TPB / 32) {
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(s_ds2[c], __ldg(We + (size_t)c * rd + r), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float d = acc * silu_gradf_(s1[(size_t)n * rd + r]);
-      s_ds1[r] = d;
-      ds1_out[(size_t)n * rd + r] = d;
+    for (int c = lane; c < C; c += 32) {
+      const float g = __ldg(gate + (size_t)n * C + c);
+      const float d = __ldg(dgate_pre + (size_t)n * C + c) * g * (1.f - g);
+      if (r == 0) ds2_out[(size_t)n * C + c] = d;
+      acc = fmaf(d, s_mem[c], acc);
     }
+    acc = warp_sum(acc);
+    if (lane == 0) ds1_out[(size_t)n * rd + r] = acc * silu_gradf_(s1[(size_t)n * rd + r]);
   }
+}
+
+__global__ void __launch_bounds__(TPB) se_bwd_b_kernel(const float* __restrict__ ds1, const float* __restrict__ Wr,
+                                                       float* __restrict__ dmean, int N, int C, int rd, int n_per_block) {
+  extern __shared__ float s_mem[];   // [n_per_block][rd]
+  const int n0 = blockIdx.y * n_per_block;
+  const int nn = min(n_per_block, N - n0);
+  for (int i = threadIdx.x; i < nn * rd; i += TPB) s_mem[i] = ds1[(size_t)n0 * rd + i];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    float acc = 0.f;
-    for (int r = 0; r < rd; ++r) acc = fmaf(s_ds1[r], __ldg(Wr + (size_t)r * C + c), acc);
-    dmean[(size_t)n * C + c] = acc;
+  const int c = blockIdx.x * TPB + threadIdx.x;
+  if (c >= C) return;
+  for (int nb = 0; nb < nn; nb += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < rd; ++r) {
+      const float w = __ldg(Wr + (size_t)r * C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (nb + j < nn) acc[j] = fmaf(s_mem[(nb + j) * rd + r], w, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (nb + j < nn) dmean[(size_t)(n0 + nb + j) * C + c] = acc[j];
   }
 }
 
@@ -487,8 +518,17 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
 
 extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We,
                           const float* be, float* s1, float* gate, int N, int C, int rd, cudaStream_t stream) {
-  TRT_REQUIRE(pooled_sum && Wr && br && We && be && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
-  se_fwd_kernel<<<N, TPB, (size_t)(C + rd) * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, We, be, s1, gate, C, rd);
+  TRT_REQUIRE(pooled_sum && Wr && br && We && be && s1 && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
+  se_reduce_kernel<<<rd, TPB, (size_t)C * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, s1, N, C, rd);
+  int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
+  const int npb = (N + splits - 1) / splits;
+  splits = (N + npb - 1) / npb;
+  const size_t smem = ((size_t)SE_CC * (rd + 1) + (size_t)npb * rd) * sizeof(float);
+  TRT_REQUIRE(smem <= 96 * 1024, "trt_se_fwd: batch %d x rd %d too large for one block", N, rd);
+  static bool attr = false;
+  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(se_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  se_expand_kernel<<<dim3((C + SE_CC - 1) / SE_CC, splits), TPB, smem, stream>>>(s1, We, be, gate, N, C, rd, npb);
+  trt_count_launch(1);
   return trt_check_launch("trt_se_fwd");
 }
 
@@ -542,7 +582,14 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
                           float* dWe, float* dbe, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
               "trt_se_bwd: null pointer");
-  se_bwd_kernel<<<N, TPB, (size_t)(C + rd) * sizeof(float), stream>>>(dgate_pre, gate, s1, Wr, We, ds2, ds1, dmean, C, rd);
+  se_bwd_a_kernel<<<rd, TPB, (size_t)C * sizeof(float), stream>>>(dgate_pre, gate, s1, We, ds2, ds1, N, C, rd);
+  {
+    int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
+    const int npb = (N + splits - 1) / splits;
+    splits = (N + npb - 1) / npb;
+    se_bwd_b_kernel<<<dim3((C + TPB - 1) / TPB, splits), TPB, (size_t)npb * rd * sizeof(float), stream>>>(ds1, Wr, dmean, N, C, rd, npb);
+  }
+  trt_count_launch(1);
   se_bwd_w_kernel<<<(C * rd + TPB - 1) / TPB, TPB, 0, stream>>>(ds2, ds1, s1, pooled_sum, inv_hw, dWr, dbr, dWe, dbe, N, C, rd);
   trt_count_launch(1);
   return trt_check_launch("trt_se_bwd");
