@@ -21,21 +21,25 @@ struct DwGeom {
 
 __device__ __forceinline__ uint4 zero4() { return make_uint4(0, 0, 0, 0); }
 
+// Block reduction of per-thread channel partials over the 32 pixel-threads of each channel lane: every thread parks its
+// NV x 8 values in shared memory, then thread t < NV*64 sums the 32 entries of (k = t/64, channel c = t%64) — consecutive
+// threads read consecutive floats (conflict-free) — and returns the total; other threads return 0.
 template <int NV>
-__device__ __forceinline__ void reduce_over_pt(float (&acc)[NV][8], float* s_red, int lane, int pt) {
+__device__ __forceinline__ float reduce_over_pt(float (&acc)[NV][8], float* s_red, int lane, int pt) {
+  static_assert(NV * 64 <= TPB, "one thread per reduced value");
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) s_red[(k * NPT + pt) * 64 + lane * 8 + i] = acc[k][i];
   __syncthreads();
-  if (pt == 0) {
-    for (int q = 1; q < NPT; ++q)
-#pragma unroll
-      for (int k = 0; k < NV; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k][i] += s_red[(k * NPT + q) * 64 + lane * 8 + i];
+  float total = 0.f;
+  if (threadIdx.x < NV * 64) {
+    const int k = threadIdx.x / 64, c = threadIdx.x % 64;
+#pragma unroll 8
+    for (int q = 0; q < NPT; ++q) total += s_red[(k * NPT + q) * 64 + c];
   }
+  return total;
 }
 
 // ---- tile loaders: all global loads first, then transform + store to shared memory
@@ -211,15 +215,12 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const uint4* __restr
     }
   }
   if (stats || pooled) {
-    reduce_over_pt<2>(red, s_red, lane, pt);
-    if (pt == 0 && cvalid) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (stats) {
-          atomicAdd(stats + 8 * cv + i, (double)red[0][i]);
-          atomicAdd(stats + g.C + 8 * cv + i, (double)red[1][i]);
-        }
-        if (pooled) atomicAdd(pooled + (size_t)n * g.C + 8 * cv + i, red[0][i]);
+    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+    if (threadIdx.x < 128) {
+      const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
+      if (c < g.C) {
+        if (stats) atomicAdd(stats + k * g.C + c, (double)total);
+        if (pooled && k == 0) atomicAdd(pooled + (size_t)n * g.C + c, total);
       }
     }
   }
@@ -230,7 +231,7 @@ template <int P>
 __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4* __restrict__ x_raw,
                                                   const float* __restrict__ x_rec, uint4* __restrict__ g_out,
                                                   double* __restrict__ bstats, const DwGeom& g, int n, int iy, int ixb, int cv,
-                                                  bool cvalid, int lane, int pt, float* s_red, int V) {
+                                                  bool cvalid, int lane, int pt, float* s_red, int V, int cb) {
   float red[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
@@ -271,13 +272,10 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
     }
   }
   if (x_rec && bstats) {
-    reduce_over_pt<2>(red, s_red, lane, pt);
-    if (pt == 0 && cvalid) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(bstats + 8 * cv + i, (double)red[0][i]);
-        atomicAdd(bstats + g.C + 8 * cv + i, (double)red[1][i]);
-      }
+    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+    if (threadIdx.x < 128) {
+      const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
+      if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
     }
   }
 }
@@ -312,7 +310,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const uint4*
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
   conv_rows<K, 1, T::P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
-  bwd_data_epilogue<T::P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, lane, pt, s_red, V);
+  bwd_data_epilogue<T::P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, lane, pt, s_red, V, cb);
 }
 
 // ------------------------------------------------------------------------------------------------ backward data, generic stride
@@ -366,7 +364,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
       }
     }
   }
-  bwd_data_epilogue<P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy, ixb, cv, cvalid, lane, pt, s_red, V);
+  bwd_data_epilogue<P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy, ixb, cv, cvalid, lane, pt, s_red, V, cb);
 }
 
 // ------------------------------------------------------------------------------------------------ backward weight

@@ -9,6 +9,7 @@
 namespace {
 
 constexpr int TPB = 256;
+constexpr int UNR = 4;    // rows in flight per thread (memory-level parallelism of the streaming kernels)
 
 // ---- thread mapping: rows x (C/8) vectors; a thread keeps a fixed channel vector so it can own channel accumulators
 struct RowMap {
@@ -121,17 +122,32 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const uint4* __restrict__
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
   if (!m.active) return;
   const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
-  for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
-    const size_t idx = (size_t)r * V + m.v;
-    f8 a = unpack8(__ldg(x + idx));
+  const int step = gridDim.x * RY;
+  for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
+    uint4 xa[UNR], xr[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act);
-    if (res) {
-      const f8 b = unpack8(__ldg(res + idx));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
+    for (int u = 0; u < UNR; ++u) {
+      const int rr = r + u * step;
+      if (rr < rows) {
+        xa[u] = __ldg(x + (size_t)rr * V + m.v);
+        if (res) xr[u] = __ldg(res + (size_t)rr * V + m.v);
+      }
     }
-    out[idx] = pack8(a);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int rr = r + u * step;
+      if (rr < rows) {
+        f8 a = unpack8(xa[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.v[i] = act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act);
+        if (res) {
+          const f8 b = unpack8(xr[u]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
+        }
+        out[(size_t)rr * V + m.v] = pack8(a);
+      }
+    }
   }
 }
 
@@ -146,10 +162,20 @@ __global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__
   if (m.active) {
     f8 sc, sh;
     if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
-    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
-      f8 a = unpack8(__ldg(x + ((size_t)n * HW + r) * V + m.v));
+    const int step = gridDim.x * RY;
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+      uint4 xa[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += rec ? act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act) : a.v[i];
+      for (int u = 0; u < UNR; ++u)
+        if (r + u * step < HW) xa[u] = __ldg(x + ((size_t)n * HW + r + u * step) * V + m.v);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          const f8 a = unpack8(xa[u]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += rec ? act_apply(fmaf(a.v[i], sc.v[i], sh.v[i]), act) : a.v[i];
+        }
+      }
     }
   }
   block_reduce_rows<8>(acc, s_red, m);
@@ -218,12 +244,21 @@ __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict
   f8 sc, sh;
   if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
   const f8 g = ldf8(gate + (size_t)n * C + 8 * m.v);
-  for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
-    const size_t idx = ((size_t)n * HW + r) * V + m.v;
-    f8 a = unpack8(__ldg(x + idx));
+  const int step = gridDim.x * RY;
+  for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+    uint4 xa[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = (rec ? siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : a.v[i]) * g.v[i];
-    out[idx] = pack8(a);
+    for (int u = 0; u < UNR; ++u)
+      if (r + u * step < HW) xa[u] = __ldg(x + ((size_t)n * HW + r + u * step) * V + m.v);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (r + u * step < HW) {
+        f8 a = unpack8(xa[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.v[i] = (rec ? siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : a.v[i]) * g.v[i];
+        out[((size_t)n * HW + r + u * step) * V + m.v] = pack8(a);
+      }
+    }
   }
 }
 
@@ -239,13 +274,26 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (m.active) {
     const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
-    for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
-      const size_t idx = (size_t)r * V + m.v;
-      const f8 d = unpack8(__ldg(dy + idx)), a = unpack8(__ldg(x + idx));
+    const int step = gridDim.x * RY;
+    for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
+      uint4 da[UNR], xa[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] += d.v[i];
-        acc[8 + i] = fmaf(d.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < rows) {
+          da[u] = __ldg(dy + (size_t)(r + u * step) * V + m.v);
+          xa[u] = __ldg(x + (size_t)(r + u * step) * V + m.v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < rows) {
+          const f8 d = unpack8(da[u]), a = unpack8(xa[u]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i] += d.v[i];
+            acc[8 + i] = fmaf(d.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+          }
+        }
       }
     }
   }
@@ -266,13 +314,26 @@ __global__ void __launch_bounds__(TPB) affine2_kernel(const uint4* __restrict__ 
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
   if (!m.active) return;
   const f8 ca = ldf8(coef + 8 * m.v), cb = ldf8(coef + C + 8 * m.v), cc = ldf8(coef + 2 * C + 8 * m.v);
-  for (int r = blockIdx.x * RY + m.ry; r < rows; r += gridDim.x * RY) {
-    const size_t idx = (size_t)r * V + m.v;
-    const f8 d = unpack8(__ldg(dy + idx)), a = unpack8(__ldg(x + idx));
-    f8 o;
+  const int step = gridDim.x * RY;
+  for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
+    uint4 da[UNR], xa[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = fmaf(ca.v[i], d.v[i], fmaf(cb.v[i], a.v[i], cc.v[i]));
-    out[idx] = pack8(o);
+    for (int u = 0; u < UNR; ++u) {
+      if (r + u * step < rows) {
+        da[u] = __ldg(dy + (size_t)(r + u * step) * V + m.v);
+        xa[u] = __ldg(x + (size_t)(r + u * step) * V + m.v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (r + u * step < rows) {
+        const f8 d = unpack8(da[u]), a = unpack8(xa[u]);
+        f8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = fmaf(ca.v[i], d.v[i], fmaf(cb.v[i], a.v[i], cc.v[i]));
+        out[(size_t)(r + u * step) * V + m.v] = pack8(o);
+      }
+    }
   }
 }
 
@@ -287,11 +348,24 @@ __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restr
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
     const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
-    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
-      const size_t idx = ((size_t)n * HW + r) * V + m.v;
-      const f8 d = unpack8(__ldg(dA + idx)), a = unpack8(__ldg(x + idx));
+    const int step = gridDim.x * RY;
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+      uint4 da[UNR], xa[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(d.v[i], siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])), acc[i]);
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          da[u] = __ldg(dA + ((size_t)n * HW + r + u * step) * V + m.v);
+          xa[u] = __ldg(x + ((size_t)n * HW + r + u * step) * V + m.v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          const f8 d = unpack8(da[u]), a = unpack8(xa[u]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(d.v[i], siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])), acc[i]);
+        }
+      }
     }
   }
   block_reduce_rows<8>(acc, s_red, m);
@@ -406,25 +480,39 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) dm.v[i] *= inv_hw;
     }
-    for (int r = blockIdx.x * RY + m.ry; r < HW; r += gridDim.x * RY) {
-      const size_t idx = ((size_t)n * HW + r) * V + m.v;
-      const f8 a = unpack8(__ldg(x + idx));
-      f8 d;
-      if (dA) d = unpack8(__ldg(dA + idx));
-      f8 o;
+    const int step = gridDim.x * RY;
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+      uint4 da[UNR], xa[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float up = (dA ? d.v[i] * gt.v[i] : 0.f) + dm.v[i];
-        const float gg = act ? up * silu_gradf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : up;
-        o.v[i] = gg;
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          const size_t idx = ((size_t)n * HW + r + u * step) * V + m.v;
+          xa[u] = __ldg(x + idx);
+          if (dA) da[u] = __ldg(dA + idx);
+        }
       }
-      const uint4 packed = pack8(o);
-      g_out[idx] = packed;
-      const f8 oq = unpack8(packed);   // statistics over the bf16-rounded values that are stored
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] += oq.v[i];
-        acc[8 + i] = fmaf(oq.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          const size_t idx = ((size_t)n * HW + r + u * step) * V + m.v;
+          const f8 a = unpack8(xa[u]);
+          f8 d;
+          if (dA) d = unpack8(da[u]);
+          f8 o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float up = (dA ? d.v[i] * gt.v[i] : 0.f) + dm.v[i];
+            o.v[i] = act ? up * silu_gradf_(fmaf(a.v[i], sc.v[i], sh.v[i])) : up;
+          }
+          const uint4 packed = pack8(o);
+          g_out[idx] = packed;
+          const f8 oq = unpack8(packed);   // statistics over the bf16-rounded values that are stored
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i] += oq.v[i];
+            acc[8 + i] = fmaf(oq.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+          }
+        }
       }
     }
   }
@@ -497,7 +585,7 @@ extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residua
   CHECK_C(C);
   TRT_REQUIRE(x && rec && out && rows > 0, "trt_bn_apply: bad argument");
   const Launch L = plan(C);
-  dim3 grid(row_blocks(rows, L.RY, L.slabs, 16 * trt_num_sms()), L.slabs);
+  dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
   bn_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, (const uint4*)residual, (uint4*)out, rows, C, L.V, L.VX,
                                             L.RY, act);
   return trt_check_launch("trt_bn_apply");
@@ -509,9 +597,9 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   TRT_REQUIRE(x && pooled_sum && N > 0 && HW > 0, "trt_pool_act: bad argument");
   const Launch L = plan(C);
   TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
-  int target = 8 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
-  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act);
   return trt_check_launch("trt_pool_act");
 }
@@ -537,9 +625,9 @@ extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate
   CHECK_C(C);
   TRT_REQUIRE(x && gate && out && N > 0 && HW > 0, "trt_gate_apply: bad argument");
   const Launch L = plan(C);
-  int target = 16 * trt_num_sms() / (N * L.slabs);
+  int target = 6 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
-  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   gate_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, gate, (uint4*)out, HW, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_gate_apply");
 }
@@ -549,7 +637,7 @@ extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec
   CHECK_C(C);
   TRT_REQUIRE(dy && x && rec && bstats && rows > 0, "trt_bn_bwd_reduce: bad argument");
   const Launch L = plan(C);
-  dim3 grid(row_blocks(rows, L.RY, L.slabs, 8 * trt_num_sms()), L.slabs);
+  dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 3 * trt_num_sms()), L.slabs);
   bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_bn_bwd_reduce");
 }
@@ -559,7 +647,7 @@ extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, voi
   CHECK_C(C);
   TRT_REQUIRE(dy && x && coef && out && rows > 0, "trt_affine2: bad argument");
   const Launch L = plan(C);
-  dim3 grid(row_blocks(rows, L.RY, L.slabs, 16 * trt_num_sms()), L.slabs);
+  dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
   affine2_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, coef, (uint4*)out, rows, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_affine2");
 }
@@ -570,9 +658,9 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
   TRT_REQUIRE(dA && x && rec && dgate_pre && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
   const Launch L = plan(C);
   TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
-  int target = 8 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
-  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   se_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, dgate_pre, HW, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_se_bwd_reduce");
 }
@@ -601,9 +689,9 @@ extern "C" int trt_act_bwd(const void* dA, const float* gate, const float* dmean
   CHECK_C(C);
   TRT_REQUIRE(x && rec && g_out && bstats && N > 0 && HW > 0 && (dA || dmean), "trt_act_bwd: bad argument");
   const Launch L = plan(C);
-  int target = 8 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
-  dim3 grid(row_blocks(HW, L.RY, 1, target), N, L.slabs);
+  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   act_bwd_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, (uint4*)g_out,
                                            bstats, HW, C, L.V, L.VX, L.RY, act);
   return trt_check_launch("trt_act_bwd");

@@ -265,7 +265,7 @@ struct WgradParams {
   int M, Cp, Cq;
   int block_q;              // UMMA N (multiple of 16, <= 256)
   int num_p_blocks, num_q_blocks, splits, mblocks_per_split, num_mblocks;
-  int stages, tmem_cols;
+  int stages, tmem_cols, vec4;
   long long so_p, so_q;     // output strides (elements)
   float* out;
   // descriptor knobs (defaults follow the canonical MN-major SW128 layout; overridable by the bring-up test)
@@ -355,10 +355,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
       ptx::tmem_ld_wait();
       if (pr < p.Cp) {
         float* o = p.out + (long long)pr * p.so_p;
+        if (p.vec4) {      // contiguous q, 16-byte aligned rows: one red.global.add.v4.f32 per 4 columns
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int qc = q0 + c0 + i;
-          if (qc < p.Cq) atomicAdd(o + (long long)qc * p.so_q, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; i += 4) {
+            const int qc = q0 + c0 + i;
+            if (qc < p.Cq)
+              atomicAdd(reinterpret_cast<float4*>(o + qc), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                         __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int qc = q0 + c0 + i;
+            if (qc < p.Cq) atomicAdd(o + (long long)qc * p.so_q, __uint_as_float(r[i]));
+          }
         }
       }
     }
@@ -447,13 +457,15 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
   p.num_q_blocks = (Cq + p.block_q - 1) / p.block_q;
   p.num_mblocks = (M + BK - 1) / BK;
   const int tiles = p.num_p_blocks * p.num_q_blocks;
+  // split the row reduction across CTAs, but keep >= 4 k-blocks per CTA: every extra split costs a full tile of atomics
   int splits = (2 * trt_num_sms() + tiles - 1) / tiles;
-  if (splits > p.num_mblocks) splits = p.num_mblocks;
+  if (splits > p.num_mblocks / 4) splits = p.num_mblocks / 4;
   if (splits < 1) splits = 1;
   p.mblocks_per_split = (p.num_mblocks + splits - 1) / splits;
   p.splits = (p.num_mblocks + p.mblocks_per_split - 1) / p.mblocks_per_split;   // no empty split
   p.tmem_cols = pow2_cols(p.block_q);
   p.so_p = so_p; p.so_q = so_q; p.out = out;
+  p.vec4 = (so_q == 1 && (so_p % 4) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
   p.lbo = lbo > 0 ? (uint32_t)lbo : 8192u;
   p.sbo = sbo > 0 ? (uint32_t)sbo : 1024u;
   p.kstep_bytes = kstep_bytes > 0 ? (uint32_t)kstep_bytes : 2048u;

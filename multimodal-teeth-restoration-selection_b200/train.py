@@ -14,6 +14,7 @@ import torch.distributed as dist
 
 from . import ops
 from .backbone import forward_train, backward_train
+from .ddp import GradSync
 from .modules import TAB_PARAM_KEYS
 
 ALIGN = 8  # floats: every parameter starts on a 32-byte boundary inside the flat buffer
@@ -63,10 +64,8 @@ class _FusedTrainer:
         self.normsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=dev)
         self.loss = torch.zeros(1, device=dev)
-        self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or (dist.is_available() and dist.is_initialized())) else 1
-        if self.world > 1 and self.pg is None:
-            self.pg = dist.group.WORLD
+        self.sync = GradSync(self.flat, process_group)
+        self.world = self.sync.world
         self.num_buckets = max(1, num_buckets)
         self.use_graph = graph
         self.graph_warmup = graph_warmup
@@ -74,20 +73,10 @@ class _FusedTrainer:
         self._nsteps = 0
         self._static = None
         self.launches_per_step = None
-        if self.world > 1:
-            self._comm_stream = torch.cuda.Stream(device=dev)
-            self._sync_initial_state()
-
-    # ---- data parallel -----------------------------------------------------------------------------------------------
-    def _sync_initial_state(self):
-        dist.broadcast(self.flat.p, src=0, group=self.pg)
-        for b in self.model.buffers():
-            dist.broadcast(b, src=0, group=self.pg)
+        self.sync.sync_initial_state(self.model)
 
     def _bucket_ranges(self, boundaries):
-        """Contiguous ranges of the flat gradient, last-executed parameters first (reverse forward order)."""
-        edges = sorted(set([0, self.flat.numel] + boundaries))
-        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)][::-1]
+        return self.sync.bucket_ranges(boundaries)
 
     # ---- to be provided by subclasses --------------------------------------------------------------------------------
     def _make_static(self, *inputs):
@@ -102,7 +91,7 @@ class _FusedTrainer:
         self.state.advance()
         ops.grad_sumsq(self.flat.g, self.normsq)
         ops.adamw_step(self.flat.p, self.flat.g, self.flat.m, self.flat.v, self.state, self.normsq, self.grad_norm,
-                       1.0 / self.world, self.clip, 1e-8, self.wd)
+                       self.sync.grad_scale, self.clip, 1e-8, self.wd)
 
     def _run_eager(self):
         segs, ranges = self._segments()
@@ -114,16 +103,10 @@ class _FusedTrainer:
         self._optimizer()
 
     def _reduce_bucket(self, rng):
-        if rng is None or self.world == 1:
-            return
-        cur = torch.cuda.current_stream()
-        self._comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self._comm_stream):
-            dist.all_reduce(self.flat.g[rng[0]:rng[1]], group=self.pg)
+        self.sync.reduce(rng)
 
     def _finish_comm(self):
-        if self.world > 1:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self.sync.finish()
 
     def _capture(self):
         from ._lib import lib
