@@ -168,7 +168,7 @@ template <int K, int S> struct FwdTile {
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int K, int S>
-__global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ in_rec,
+__global__ void __launch_bounds__(TPB, 3) dwconv_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ in_rec,
                                                             const float* __restrict__ w, uint4* __restrict__ out,
                                                             const float* __restrict__ out_rec, float* __restrict__ pooled,
                                                             double* __restrict__ stats, const DwGeom g) {
@@ -228,7 +228,17 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const uint4* __restr
 
 // epilogue shared by both data-gradient kernels: g = dIn * silu'(bn(x_raw)) + BN-backward sums, or plain dIn
 template <int P>
-__device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4* __restrict__ x_raw,
+__device__ __forceinline__ void prefetch_x(uint4 (&xr4)[P], const uint4* __restrict__ x_raw, const float* x_rec,
+                                           const DwGeom& g, int n, int iy, int ixb, int cv, bool cvalid, int V) {
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    xr4[p] = zero4();
+    if (x_rec && cvalid && iy < g.H && ixb + p < g.W) xr4[p] = __ldg(x_raw + ((size_t)(n * g.H + iy) * g.W + ixb + p) * V + cv);
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4 (&xr4)[P], const uint4* __restrict__ x_raw,
                                                   const float* __restrict__ x_rec, uint4* __restrict__ g_out,
                                                   double* __restrict__ bstats, const DwGeom& g, int n, int iy, int ixb, int cv,
                                                   bool cvalid, int lane, int pt, float* s_red, int V, int cb) {
@@ -239,12 +249,6 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
   if (x_rec && cvalid) {
     sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
     mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
-  }
-  uint4 xr4[P];
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    xr4[p] = zero4();
-    if (x_rec && cvalid && iy < g.H && ixb + p < g.W) xr4[p] = __ldg(x_raw + ((size_t)(n * g.H + iy) * g.W + ixb + p) * V + cv);
   }
 #pragma unroll
   for (int p = 0; p < P; ++p) {
@@ -301,16 +305,18 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const uint4*
   const bool cvalid = cv < V;
   constexpr int PAD = (K - 1) / 2;
   load_weights<K>(s_w, w, cb, g.C, true);
+  const int oy = pt / 4, oxb = (pt % 4) * T::P;
+  uint4 xr4[T::P];
+  prefetch_x<T::P>(xr4, x_raw, x_rec, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, V);      // needed only by the epilogue
   load_grad_tile<T::IH, T::IW>(s_in, gy_, y_raw, coef, n, g.OH, g.OW, V, g.C, iy0 - PAD, ix0 - PAD, cv, cvalid, lane, pt);
   __syncthreads();
-  const int oy = pt / 4, oxb = (pt % 4) * T::P;
   float acc[T::P][8];
 #pragma unroll
   for (int p = 0; p < T::P; ++p)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
   conv_rows<K, 1, T::P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
-  bwd_data_epilogue<T::P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, lane, pt, s_red, V, cb);
+  bwd_data_epilogue<T::P>(acc, xr4, x_raw, x_rec, g_out, bstats, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, lane, pt, s_red, V, cb);
 }
 
 // ------------------------------------------------------------------------------------------------ backward data, generic stride
@@ -335,9 +341,11 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
   const int ny = iy0 + g.pad_t - (K - 1), nx = ix0 + g.pad_l - (K - 1);
   const int oyb = ny <= 0 ? 0 : (ny + S - 1) / S, oxb0 = nx <= 0 ? 0 : (nx + S - 1) / S;
   load_weights<K>(s_w, w, cb, g.C, false);
+  const int iy = iy0 + pt / 4, ixb = ix0 + (pt % 4) * P;
+  uint4 xr4[P];
+  prefetch_x<P>(xr4, x_raw, x_rec, g, n, iy, ixb, cv, cvalid, V);
   load_grad_tile<DH, DW>(s_d, gy_, y_raw, coef, n, g.OH, g.OW, V, g.C, oyb, oxb0, cv, cvalid, lane, pt);
   __syncthreads();
-  const int iy = iy0 + pt / 4, ixb = ix0 + (pt % 4) * P;
   float acc[P][8];
 #pragma unroll
   for (int p = 0; p < P; ++p)
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
       }
     }
   }
-  bwd_data_epilogue<P>(acc, x_raw, x_rec, g_out, bstats, g, n, iy, ixb, cv, cvalid, lane, pt, s_red, V, cb);
+  bwd_data_epilogue<P>(acc, xr4, x_raw, x_rec, g_out, bstats, g, n, iy, ixb, cv, cvalid, lane, pt, s_red, V, cb);
 }
 
 // ------------------------------------------------------------------------------------------------ backward weight
@@ -406,17 +414,19 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const uint4* 
         const uint4* xrow = s_in + ((oy * S + kh) * IW) * CL + lane;
         const uint4* drow = s_d + (oy * TOW) * CL + lane;
         if (S == 1) {
-          f8 win[K];
+          f8 win[K];     // sliding window over the input row; the shifts below are register renames after unrolling
 #pragma unroll
           for (int j = 0; j < K - 1; ++j) win[j] = unpack8(xrow[j * CL]);
 #pragma unroll
           for (int ox = 0; ox < TOW; ++ox) {
-            win[(ox + K - 1) % K] = unpack8(xrow[(ox + K - 1) * CL]);
+            win[K - 1] = unpack8(xrow[(ox + K - 1) * CL]);
             const f8 d = unpack8(drow[ox * CL]);
 #pragma unroll
             for (int kw = 0; kw < K; ++kw)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[kw][i] = fmaf(d.v[i], win[(ox + kw) % K].v[i], acc[kw][i]);
+              for (int i = 0; i < 8; ++i) acc[kw][i] = fmaf(d.v[i], win[kw].v[i], acc[kw][i]);
+#pragma unroll
+            for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
           }
         } else {
 #pragma unroll

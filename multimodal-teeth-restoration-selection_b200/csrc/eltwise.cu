@@ -197,10 +197,17 @@ __global__ void __launch_bounds__(TPB) se_reduce_kernel(const float* __restrict_
   for (int c = threadIdx.x; c < C; c += TPB) s_mem[c] = __ldg(Wr + (size_t)r * C + c) * inv_hw;
   __syncthreads();
   const float bias = br[r];
-  for (int n = warp; n < N; n += TPB / 32) {
+  for (int n = blockIdx.y * (TPB / 32) + warp; n < N; n += gridDim.y * (TPB / 32)) {
     float acc = 0.f;
     const float* p = pooled + (size_t)n * C;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(p + c), s_mem[c], acc);
+    for (int c = lane; c < C; c += 128) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (c + 32 * u < C) ? __ldg(p + c + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + 32 * u < C) acc = fmaf(v[u], s_mem[c + 32 * u], acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) s1[(size_t)n * rd + r] = acc + bias;
   }
@@ -386,13 +393,25 @@ __global__ void __launch_bounds__(TPB) se_bwd_a_kernel(const float* __restrict__
   const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += TPB) s_mem[c] = __ldg(We + (size_t)c * rd + r);
   __syncthreads();
-  for (int n = warp; n < N; n += TPB / 32) {
+  for (int n = blockIdx.y * (TPB / 32) + warp; n < N; n += gridDim.y * (TPB / 32)) {
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float g = __ldg(gate + (size_t)n * C + c);
-      const float d = __ldg(dgate_pre + (size_t)n * C + c) * g * (1.f - g);
-      if (r == 0) ds2_out[(size_t)n * C + c] = d;
-      acc = fmaf(d, s_mem[c], acc);
+    for (int c = lane; c < C; c += 128) {
+      float gv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + 32 * u;
+        gv[u] = cc < C ? __ldg(gate + (size_t)n * C + cc) : 0.f;
+        dv[u] = cc < C ? __ldg(dgate_pre + (size_t)n * C + cc) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + 32 * u;
+        if (cc < C) {
+          const float d = dv[u] * gv[u] * (1.f - gv[u]);
+          if (r == 0) ds2_out[(size_t)n * C + cc] = d;
+          acc = fmaf(d, s_mem[cc], acc);
+        }
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) ds1_out[(size_t)n * rd + r] = acc * silu_gradf_(s1[(size_t)n * rd + r]);
@@ -422,35 +441,42 @@ __global__ void __launch_bounds__(TPB) se_bwd_b_kernel(const float* __restrict__
   }
 }
 
-// SE parameter gradients: reduction over the batch (no atomics): one thread per weight element
+// SE parameter gradients: reduction over the batch without atomics.  A warp owns 4 weight elements x 8 batch slices
+// (lane = 8*e + slice); each lane walks every 8th image, then the 8 slices are combined with shuffles.
 __global__ void __launch_bounds__(TPB) se_bwd_w_kernel(const float* __restrict__ ds2, const float* __restrict__ ds1,
                                                        const float* __restrict__ s1, const float* __restrict__ pooled,
                                                        float inv_hw, float* __restrict__ dWr, float* __restrict__ dbr,
                                                        float* __restrict__ dWe, float* __restrict__ dbe, int N, int C,
                                                        int rd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * rd) return;
-  {  // dWe[c][r] = sum_n ds2[n][c] * silu(s1[n][r])
-    const int c = i / rd, r = i - c * rd;
-    float acc = 0.f, accb = 0.f;
-    for (int n = 0; n < N; ++n) {
-      const float d = ds2[(size_t)n * C + c];
-      acc = fmaf(d, siluf_(s1[(size_t)n * rd + r]), acc);
-      accb += d;
+  const int lane = threadIdx.x & 31, slice = lane & 7;
+  const int i = (blockIdx.x * TPB + threadIdx.x) / 8;
+  const bool valid = i < C * rd;
+  float a_we = 0.f, a_be = 0.f, a_wr = 0.f, a_br = 0.f;
+  if (valid) {
+    const int c1 = i / rd, r1 = i - c1 * rd;     // dWe[c1][r1]
+    const int r2 = i / C, c2 = i - r2 * C;       // dWr[r2][c2]
+    for (int n = slice; n < N; n += 8) {
+      const float d2 = __ldg(ds2 + (size_t)n * C + c1), sv = __ldg(s1 + (size_t)n * rd + r1);
+      const float d1 = __ldg(ds1 + (size_t)n * rd + r2), pv = __ldg(pooled + (size_t)n * C + c2);
+      a_we = fmaf(d2, siluf_(sv), a_we);
+      a_be += d2;
+      a_wr = fmaf(d1, pv * inv_hw, a_wr);
+      a_br += d1;
     }
-    dWe[i] = acc;
-    if (r == 0) dbe[c] = accb;
   }
-  {  // dWr[r][c] = sum_n ds1[n][r] * mean[n][c]
-    const int r = i / C, c = i - r * C;
-    float acc = 0.f, accb = 0.f;
-    for (int n = 0; n < N; ++n) {
-      const float d = ds1[(size_t)n * rd + r];
-      acc = fmaf(d, pooled[(size_t)n * C + c] * inv_hw, acc);
-      accb += d;
-    }
-    dWr[i] = acc;
-    if (c == 0) dbr[r] = accb;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    a_we += __shfl_xor_sync(0xffffffffu, a_we, o);
+    a_be += __shfl_xor_sync(0xffffffffu, a_be, o);
+    a_wr += __shfl_xor_sync(0xffffffffu, a_wr, o);
+    a_br += __shfl_xor_sync(0xffffffffu, a_br, o);
+  }
+  if (valid && slice == 0) {
+    const int c1 = i / rd, r1 = i - c1 * rd, r2 = i / C, c2 = i - r2 * C;
+    dWe[i] = a_we;
+    if (r1 == 0) dbe[c1] = a_be;
+    dWr[i] = a_wr;
+    if (c2 == 0) dbr[r2] = a_br;
   }
 }
 
@@ -607,7 +633,7 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
 extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We,
                           const float* be, float* s1, float* gate, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(pooled_sum && Wr && br && We && be && s1 && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
-  se_reduce_kernel<<<rd, TPB, (size_t)C * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, s1, N, C, rd);
+  se_reduce_kernel<<<dim3(rd, (N + 7) / 8), TPB, (size_t)C * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, s1, N, C, rd);
   int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
   const int npb = (N + splits - 1) / splits;
   splits = (N + npb - 1) / npb;
@@ -670,7 +696,7 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
                           float* dWe, float* dbe, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
               "trt_se_bwd: null pointer");
-  se_bwd_a_kernel<<<rd, TPB, (size_t)C * sizeof(float), stream>>>(dgate_pre, gate, s1, We, ds2, ds1, N, C, rd);
+  se_bwd_a_kernel<<<dim3(rd, (N + 7) / 8), TPB, (size_t)C * sizeof(float), stream>>>(dgate_pre, gate, s1, We, ds2, ds1, N, C, rd);
   {
     int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
     const int npb = (N + splits - 1) / splits;
@@ -678,7 +704,7 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
     se_bwd_b_kernel<<<dim3((C + TPB - 1) / TPB, splits), TPB, (size_t)npb * rd * sizeof(float), stream>>>(ds1, Wr, dmean, N, C, rd, npb);
   }
   trt_count_launch(1);
-  se_bwd_w_kernel<<<(C * rd + TPB - 1) / TPB, TPB, 0, stream>>>(ds2, ds1, s1, pooled_sum, inv_hw, dWr, dbr, dWe, dbe, N, C, rd);
+  se_bwd_w_kernel<<<(C * rd * 8 + TPB - 1) / TPB, TPB, 0, stream>>>(ds2, ds1, s1, pooled_sum, inv_hw, dWr, dbr, dWe, dbe, N, C, rd);
   trt_count_launch(1);
   return trt_check_launch("trt_se_bwd");
 }
