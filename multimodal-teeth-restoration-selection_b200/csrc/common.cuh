@@ -52,7 +52,13 @@ __device__ __forceinline__ f8 ldf8(const float* p) {  // 8 consecutive fp32 (32 
   return r;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid = rcp(1 + 2^(-x log2 e)): two MUFU ops, no range fix-ups needed (2^+big = inf -> rcp = 0; 2^-big = 0 -> rcp(1) = 1)
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // d/dx silu(x) = s * (1 + x * (1 - s))
 __device__ __forceinline__ float silu_gradf_(float x) { float s = sigmoidf_(x); return s * (1.0f + x * (1.0f - s)); }

@@ -21,6 +21,22 @@ struct DwGeom {
 
 __device__ __forceinline__ uint4 zero4() { return make_uint4(0, 0, 0, 0); }
 
+// Blackwell mixed-precision FMA (FHFMA.BF16): fp32 acc += bf16 * bf16, operands picked straight out of register halves, so
+// the packed tiles in shared memory are never unpacked.  The product of two bf16 is exact in fp32 (one rounding, at the add).
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& a, const uint4& b) {
+  const uint32_t as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fhfma((uint16_t)(as[i] & 0xffffu), (uint16_t)(bs[i] & 0xffffu), acc[2 * i]);
+    acc[2 * i + 1] = fhfma((uint16_t)(as[i] >> 16), (uint16_t)(bs[i] >> 16), acc[2 * i + 1]);
+  }
+}
+
 // Block reduction of per-thread channel partials over the 32 pixel-threads of each channel lane: every thread parks its
 // NV x 8 values in shared memory, then thread t < NV*64 sums the 32 entries of (k = t/64, channel c = t%64) — consecutive
 // threads read consecutive floats (conflict-free) — and returns the total; other threads return 0.
@@ -127,34 +143,32 @@ __device__ __forceinline__ void load_grad_tile(uint4* s_tile, const uint4* __res
   }
 }
 
-// weights of the block's 64 channels -> shared [K*K][64]; flip = rotate the filter by 180 degrees (data gradient)
+// weights of the block's 64 channels -> shared bf16 [K*K][64] (one uint4 per tap and channel lane); flip = rotate the
+// filter by 180 degrees (data gradient).  bf16 weights: the same rounding the 1x1 convs apply to theirs.
 template <int K>
-__device__ __forceinline__ void load_weights(float* s_w, const float* __restrict__ w, int cb, int C, bool flip) {
+__device__ __forceinline__ void load_weights(uint4* s_w4, const float* __restrict__ w, int cb, int C, bool flip) {
+  __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_w4);
   for (int i = threadIdx.x; i < K * K * 64; i += TPB) {
     const int tap = i / 64, c = cb * 64 + (i % 64);
     const int src_tap = flip ? (K * K - 1 - tap) : tap;
-    s_w[i] = c < C ? __ldg(w + (size_t)c * K * K + src_tap) : 0.f;
+    s_w[i] = __float2bfloat16_rn(c < C ? __ldg(w + (size_t)c * K * K + src_tap) : 0.f);
   }
 }
 
 // sliding-window tile convolution: thread (lane, pt) computes P outputs of row oy starting at column oxb
 template <int K, int S, int P, int IW>
-__device__ __forceinline__ void conv_rows(const uint4* s_in, const float* s_w, int oy, int oxb, int lane, float (&acc)[P][8]) {
+__device__ __forceinline__ void conv_rows(const uint4* s_in, const uint4* s_w, int oy, int oxb, int lane, float (&acc)[P][8]) {
   constexpr int ROWV = (P - 1) * S + K;
 #pragma unroll
   for (int kh = 0; kh < K; ++kh) {
-    f8 row[ROWV];
+    uint4 row[ROWV];
 #pragma unroll
-    for (int j = 0; j < ROWV; ++j) row[j] = unpack8(s_in[((oy * S + kh) * IW + oxb * S + j) * CL + lane]);
+    for (int j = 0; j < ROWV; ++j) row[j] = s_in[((oy * S + kh) * IW + oxb * S + j) * CL + lane];
 #pragma unroll
     for (int kw = 0; kw < K; ++kw) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * K + kw) * 64 + lane * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * K + kw) * 64 + lane * 8 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const uint4 wv = s_w[(kh * K + kw) * CL + lane];
 #pragma unroll
-      for (int p = 0; p < P; ++p)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(row[p * S + kw].v[i], wv[i], acc[p][i]);
+      for (int p = 0; p < P; ++p) fma8(acc[p], row[p * S + kw], wv);
     }
   }
 }
@@ -163,7 +177,7 @@ template <int K, int S> struct FwdTile {
   static constexpr int TOW = S == 1 ? 16 : 8;
   static constexpr int P = TOW / 4;
   static constexpr int IH = (TOH - 1) * S + K, IW = (TOW - 1) * S + K;
-  static constexpr size_t smem = (size_t)IH * IW * CL * 16 + (size_t)K * K * 64 * 4;
+  static constexpr size_t smem = (size_t)IH * IW * CL * 16 + (size_t)K * K * CL * 16;
 };
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(TPB, 3) dwconv_fwd_kernel(const uint4* __restr
   using T = FwdTile<K, S>;
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* s_in = reinterpret_cast<uint4*>(smem);
-  float* s_w = reinterpret_cast<float*>(smem + (size_t)T::IH * T::IW * CL * 16);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)T::IH * T::IW * CL * 16);
   float* s_red = reinterpret_cast<float*>(smem);
   const int V = g.C / 8;
   const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const uint4*
   using T = FwdTile<K, 1>;
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* s_in = reinterpret_cast<uint4*>(smem);
-  float* s_w = reinterpret_cast<float*>(smem + (size_t)T::IH * T::IW * CL * 16);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)T::IH * T::IW * CL * 16);
   float* s_red = reinterpret_cast<float*>(smem);
   const int V = g.C / 8;
   const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
   constexpr int DH = (TOH + K - 2) / 2 + 2, DW = (TIW + K - 2) / 2 + 2;      // stride 2
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* s_d = reinterpret_cast<uint4*>(smem);
-  float* s_w = reinterpret_cast<float*>(smem + (size_t)DH * DW * CL * 16);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)DH * DW * CL * 16);
   float* s_red = reinterpret_cast<float*>(smem);
   const int V = g.C / 8, S = g.S;
   const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
@@ -357,18 +371,14 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
     const int oy = ty / S;
     if (oy >= g.OH) continue;
     for (int kw = 0; kw < K; ++kw) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * K + kw) * 64 + lane * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * K + kw) * 64 + lane * 8 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const uint4 wv = s_w[(kh * K + kw) * CL + lane];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const int tx = ixb + p + g.pad_l - kw;
         if (tx < 0 || (tx % S) != 0) continue;
         const int ox = tx / S;
         if (ox >= g.OW) continue;
-        const f8 d = unpack8(s_d[((oy - oyb) * DW + (ox - oxb0)) * CL + lane]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(d.v[i], wv[i], acc[p][i]);
+        fma8(acc[p], s_d[((oy - oyb) * DW + (ox - oxb0)) * CL + lane], wv);
       }
     }
   }
@@ -414,30 +424,24 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const uint4* 
         const uint4* xrow = s_in + ((oy * S + kh) * IW) * CL + lane;
         const uint4* drow = s_d + (oy * TOW) * CL + lane;
         if (S == 1) {
-          f8 win[K];     // sliding window over the input row; the shifts below are register renames after unrolling
+          uint4 win[K];     // sliding window over the input row; the shifts below are register renames after unrolling
 #pragma unroll
-          for (int j = 0; j < K - 1; ++j) win[j] = unpack8(xrow[j * CL]);
+          for (int j = 0; j < K - 1; ++j) win[j] = xrow[j * CL];
 #pragma unroll
           for (int ox = 0; ox < TOW; ++ox) {
-            win[K - 1] = unpack8(xrow[(ox + K - 1) * CL]);
-            const f8 d = unpack8(drow[ox * CL]);
+            win[K - 1] = xrow[(ox + K - 1) * CL];
+            const uint4 d = drow[ox * CL];
 #pragma unroll
-            for (int kw = 0; kw < K; ++kw)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[kw][i] = fmaf(d.v[i], win[kw].v[i], acc[kw][i]);
+            for (int kw = 0; kw < K; ++kw) fma8(acc[kw], d, win[kw]);
 #pragma unroll
             for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
           }
         } else {
 #pragma unroll
           for (int ox = 0; ox < TOW; ++ox) {
-            const f8 d = unpack8(drow[ox * CL]);
+            const uint4 d = drow[ox * CL];
 #pragma unroll
-            for (int kw = 0; kw < K; ++kw) {
-              const f8 a = unpack8(xrow[(ox * S + kw) * CL]);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[kw][i] = fmaf(d.v[i], a.v[i], acc[kw][i]);
-            }
+            for (int kw = 0; kw < K; ++kw) fma8(acc[kw], d, xrow[(ox * S + kw) * CL]);
           }
         }
       }
@@ -530,7 +534,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const void* y_raw, const float* co
     static bool attr = false;                                                                                      \
     if (!attr) { int rc = set_smem_attr(dwconv_bwd_data_kernel<KK>); if (rc) return rc; attr = true; }              \
     const int DH = (TOH + KK - 2) / 2 + 2, DW = (16 + KK - 2) / 2 + 2;                                             \
-    size_t smem = (size_t)DH * DW * CL * 16 + (size_t)KK * KK * 64 * 4;                                            \
+    size_t smem = (size_t)DH * DW * CL * 16 + (size_t)KK * KK * CL * 16;                                            \
     if (smem < red_bytes) smem = red_bytes;                                                                        \
     dwconv_bwd_data_kernel<KK><<<grid, TPB, smem, stream>>>((const uint4*)gy, (const uint4*)y_raw, coef, w, (const uint4*)x_raw, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)

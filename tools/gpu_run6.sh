@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "exit=$?"; tail -n ${TAILN:-6} gpurun_out/$name.log | cut -c1-300; }
+run gpu_tests python -m pytest tests -m gpu -q --timeout 600 -x
+run stepprof_plain python tools/step_profile.py --log gpurun_out/step_ops_plain.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py --log gpurun_out/step_ops.json > gpurun_out/stepprof_ncu.log 2>&1
+echo "ncu exit=$?"; tail -2 gpurun_out/stepprof_ncu.log
