@@ -135,11 +135,11 @@ int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N, int K, trt
  * pooled_sum[n,c] (optional, zeroed here) += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output. */
 int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec, float* pooled_sum,
                    double* stats, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
-/* upstream dD = coef ? a*gy + b*y_raw + c : gy.  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1),
- * bstats += {sum g, sum g*xhat}; dw[C,1,k,k] += correlation of dD with act(x) (act = silu(bn) when x_rec). */
-int trt_dwconv_bwd(const void* gy, const void* y_raw, const float* coef, const float* w, const void* x_raw,
-                   const float* x_rec, void* g_out, double* bstats, float* dw, int N, int H, int W, int C, int k, int s,
-                   trt_stream_t stream);
+/* gy = dD, the gradient w.r.t. the RAW depthwise output (the BN-backward affine of the following BatchNorm has already been
+ * applied by trt_affine2).  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1), bstats += {sum g, sum g*xhat};
+ * dw[C,1,k,k] += correlation of dD with act(x) (act = silu(bn) when x_rec). */
+int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out, double* bstats,
+                   float* dw, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
 /* x: NCHW [N,3,H,W] fp32 or bf16 -> out NHWC bf16 [N,ceil(H/2),ceil(W/2),CS]; CS in {32, 48} */
 int trt_stem_fwd(const void* x, int x_is_bf16, const float* w, void* out, const float* out_rec, double* stats, int N, int H,
                  int W, int CS, trt_stream_t stream);

@@ -411,12 +411,13 @@ def backward_train(enc, ctx, dfeat, grads):
         bst = bstats.take(2 * cm)
         g2 = ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, dA, bst, N, ohw, act=1)
         coef_d = bn_back(sv["bn_dw"], bst, N * ohw)
+        dD = ops.affine2(g2, sv["d_raw"], coef_d, g2)           # gradient w.r.t. the raw depthwise output
         dw_grad = grads[name + ".conv_dw.weight"]
         if c["type"] == "ir":
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
             bst = bstats.take(2 * cm)
             g1 = torch.empty_like(e_raw)
-            ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, dw_grad, N, h, w, k, s)
+            ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, dw_grad, N, h, w, k, s)
             coef1 = bn_back(name + ".bn1", bst, N * h * w)
             de = ops.affine2(g1, e_raw, coef1, g1)
             flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
@@ -429,16 +430,14 @@ def backward_train(enc, ctx, dfeat, grads):
             if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
                 bst = bstats.take(2 * c["cin"])
                 g_in = torch.empty_like(x_in)
-                ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h,
-                               w, k, s)
+                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h, w, k, s)
                 coef_s = bn_back("bn1", bst, N * h * w)
                 ds = ops.affine2(g_in, x_in, coef_s, g_in)
                 ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
                 dy = None
             else:
                 g_in = torch.empty_like(x_in)
-                ops.dwconv_bwd(g2, sv["d_raw"], coef_d, blk.conv_dw.weight.detach(), x_in, None, g_in, None, dw_grad, N, h,
-                               w, k, s)
+                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, None, g_in, None, dw_grad, N, h, w, k, s)
                 if sv["has_skip"]:
                     g_in = ops.affine2(g_in, dy, _add_coef(c["cin"], dev), g_in)
                 dy = g_in

@@ -77,6 +77,26 @@ int trt_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return TRT_OK;
 }
 
+int trt_make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int C, int box_c, int box_w, int box_h) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) return trt_set_error(TRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  if (((uintptr_t)base & 15) || (C % 8) != 0)
+    return trt_set_error(TRT_ERR_INVALID, "TMA NHWC operand must be 16-byte aligned with C %% 8 == 0");
+  if (box_c > 256 || box_w > 256 || box_h > 256 || (box_c * 2) % 16 != 0)
+    return trt_set_error(TRT_ERR_INVALID, "TMA NHWC box %d x %d x %d not encodable", box_h, box_w, box_c);
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return trt_set_error(TRT_ERR_CUDA, "cuTensorMapEncodeTiled(NHWC) failed (%d) N=%d H=%d W=%d C=%d box=%dx%dx%d", (int)r, N, H, W,
+                         C, box_h, box_w, box_c);
+  return TRT_OK;
+}
+
 extern "C" int trt_init(int device) {
   TRT_CUDA(cudaSetDevice(device));
   int major = 0, minor = 0;

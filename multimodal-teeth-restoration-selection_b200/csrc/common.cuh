@@ -112,6 +112,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4D tiled TMA load (NHWC activations: c0 = channel, c1 = x, c2 = y, c3 = image); coordinates may be negative or run past
+// the tensor: out-of-bounds elements arrive as zeros, which is exactly the convolution's zero padding.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
@@ -192,3 +200,5 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n, int a_mn, i
 // 2D row-major bf16 tensor [rows, cols] (cols contiguous, row pitch = ld elements), box [box_rows, box_cols], 128B swizzle.
 int trt_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                      uint32_t box_rows, uint32_t box_cols);
+// 4D NHWC bf16 tensor [N,H,W,C] (C % 8 == 0), box [1, box_h, box_w, box_c], no swizzle (smem tile = [box_h][box_w][box_c]).
+int trt_make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int C, int box_c, int box_w, int box_h);

@@ -1,8 +1,13 @@
 // Depthwise k3/k5 stride-1/2 convolutions, forward and backward, TF-'same' padding, NHWC bf16.
-// Memory-bound: every block stages one input tile (with halo) in shared memory — all global loads of the tile are issued
-// before any is consumed (memory-level parallelism), the producer's BatchNorm+SiLU (forward) or the BatchNorm-backward
-// affine (backward) is applied once per element on the way in — then each thread keeps an input row segment in registers
-// and slides the filter over it.  Outputs carry BN batch statistics (train) or folded BN + SiLU + SE pooling (eval).
+//
+// B200 design: PERSISTENT blocks fed by 4D TMA.  A block owns one 64-channel group and walks a strided list of
+// (image, tile) items.  For every item one thread issues `cp.async.bulk.tensor.4d` for the input tile WITH its halo —
+// coordinates run negative / past the edge and the TMA unit zero-fills, which is the convolution's padding — into a
+// double-buffered shared-memory tile, so the next tile streams in while the current one is computed.  The producer's
+// BatchNorm+SiLU is applied in place in shared memory (once per element), then every thread slides the filter over packed
+// bf16 rows with FHFMA.BF16 (`fma.rn.f32.bf16`: fp32 accumulate, operands taken from register halves, no unpack).
+// Filter taps are staged once per block; BN batch statistics and weight gradients accumulate in registers across all the
+// block's items and are reduced / published once per block.
 //
 // Replaces cuDNN/ATen depthwise conv launches inside `self.backbone(x_img)`
 // (experiments/multimodal_v1/train_mm_joint_dualtask.py:154) and their autograd backward (:248).
@@ -14,9 +19,11 @@ constexpr int TPB = 256;
 constexpr int CL = 8;     // channel lanes per block (8 lanes x 8 channels = 64 channels)
 constexpr int NPT = TPB / CL;   // 32 pixel-threads per channel lane
 constexpr int TOH = 8;    // output tile height
+constexpr int PX_BYTES = CL * 16;   // one pixel of a 64-channel tile
 
 struct DwGeom {
   int N, H, W, C, OH, OW, S, pad_t, pad_l, tiles_x, tiles_y;
+  uint32_t magic_tiles, magic_tx;      // ceil(2^32 / d): exact quotients by __umulhi for the item counts that occur
 };
 
 __device__ __forceinline__ uint4 zero4() { return make_uint4(0, 0, 0, 0); }
@@ -58,87 +65,20 @@ __device__ __forceinline__ float reduce_over_pt(float (&acc)[NV][8], float* s_re
   return total;
 }
 
-// ---- tile loaders: all global loads first, then transform + store to shared memory
-// act tile: v = in_rec ? silu(x*scale+shift) : x ; zero outside the image (conv padding applies to the ACTIVATED tensor)
+// gradient tile for the generic-stride data-gradient kernel (plain loads, zero outside [0,OH)x[0,OW))
 template <int TH, int TW>
-__device__ __forceinline__ void load_act_tile(uint4* s_tile, const uint4* __restrict__ x, const float* __restrict__ in_rec,
-                                              int n, int H, int W, int V, int C, int gy0, int gx0, int cv, bool cvalid,
-                                              int lane, int pt) {
-  constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT, CH = 6;
-  f8 sc, sh;
-  if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + C + 8 * cv); }
+__device__ __forceinline__ void load_grad_tile(uint4* s_tile, const uint4* __restrict__ gy_, int n, int OH, int OW, int V,
+                                               int oy0, int ox0, int cv, bool cvalid, int lane, int pt) {
+  constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT;
 #pragma unroll
-  for (int j0 = 0; j0 < NL; j0 += CH) {
-    uint4 v[CH];
-    uint32_t ok = 0;
-#pragma unroll
-    for (int jj = 0; jj < CH; ++jj) {
-      const int i = pt + NPT * (j0 + jj);
-      const int iy = i / TW, ix = i - iy * TW;
-      const int gy = gy0 + iy, gx = gx0 + ix;
-      v[jj] = zero4();
-      if (j0 + jj < NL && i < NPIX && cvalid && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v[jj] = __ldg(x + ((size_t)(n * H + gy) * W + gx) * V + cv);
-        ok |= 1u << jj;
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < CH; ++jj) {
-      const int i = pt + NPT * (j0 + jj);
-      if (j0 + jj < NL && i < NPIX) {
-        uint4 o = v[jj];
-        if (in_rec && ((ok >> jj) & 1u)) {
-          f8 a = unpack8(o);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) a.v[k] = siluf_(fmaf(a.v[k], sc.v[k], sh.v[k]));
-          o = pack8(a);
-        }
-        s_tile[i * CL + lane] = o;
-      }
-    }
-  }
-}
-
-// gradient tile: v = coef ? a*gy + b*y_raw + c : gy ; zero outside [0,OH)x[0,OW)
-template <int TH, int TW>
-__device__ __forceinline__ void load_grad_tile(uint4* s_tile, const uint4* __restrict__ gy_, const uint4* __restrict__ y_raw,
-                                               const float* __restrict__ coef, int n, int OH, int OW, int V, int C, int oy0,
-                                               int ox0, int cv, bool cvalid, int lane, int pt) {
-  constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT, CH = 4;
-  f8 ca, cb, cc;
-  if (coef && cvalid) { ca = ldf8(coef + 8 * cv); cb = ldf8(coef + C + 8 * cv); cc = ldf8(coef + 2 * C + 8 * cv); }
-#pragma unroll
-  for (int j0 = 0; j0 < NL; j0 += CH) {
-    uint4 v[CH], y[CH];
-    uint32_t ok = 0;
-#pragma unroll
-    for (int jj = 0; jj < CH; ++jj) {
-      const int i = pt + NPT * (j0 + jj);
-      const int dy = i / TW, dx = i - dy * TW;
-      const int oy = oy0 + dy, ox = ox0 + dx;
-      v[jj] = zero4();
-      y[jj] = zero4();
-      if (j0 + jj < NL && i < NPIX && cvalid && oy >= 0 && oy < OH && ox >= 0 && ox < OW) {
-        const size_t idx = ((size_t)(n * OH + oy) * OW + ox) * V + cv;
-        v[jj] = __ldg(gy_ + idx);
-        if (coef) y[jj] = __ldg(y_raw + idx);
-        ok |= 1u << jj;
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < CH; ++jj) {
-      const int i = pt + NPT * (j0 + jj);
-      if (j0 + jj < NL && i < NPIX) {
-        uint4 o = v[jj];
-        if (coef && ((ok >> jj) & 1u)) {
-          f8 a = unpack8(o);
-          const f8 yr = unpack8(y[jj]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) a.v[k] = fmaf(ca.v[k], a.v[k], fmaf(cb.v[k], yr.v[k], cc.v[k]));
-          o = pack8(a);
-        }
-        s_tile[i * CL + lane] = o;
-      }
+  for (int j = 0; j < NL; ++j) {
+    const int i = pt + NPT * j;
+    const int dy = i / TW, dx = i - dy * TW;
+    const int oy = oy0 + dy, ox = ox0 + dx;
+    if (i < NPIX) {
+      uint4 v = zero4();
+      if (cvalid && oy >= 0 && oy < OH && ox >= 0 && ox < OW) v = __ldg(gy_ + ((size_t)(n * OH + oy) * OW + ox) * V + cv);
+      s_tile[i * CL + lane] = v;
     }
   }
 }
@@ -149,9 +89,30 @@ template <int K>
 __device__ __forceinline__ void load_weights(uint4* s_w4, const float* __restrict__ w, int cb, int C, bool flip) {
   __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_w4);
   for (int i = threadIdx.x; i < K * K * 64; i += TPB) {
-    const int tap = i / 64, c = cb * 64 + (i % 64);
-    const int src_tap = flip ? (K * K - 1 - tap) : tap;
-    s_w[i] = __float2bfloat16_rn(c < C ? __ldg(w + (size_t)c * K * K + src_tap) : 0.f);
+    const int cl = i / (K * K), tap = i % (K * K);        // consecutive threads read consecutive floats
+    const int c = cb * 64 + cl;
+    const int dst_tap = flip ? (K * K - 1 - tap) : tap;
+    s_w[dst_tap * 64 + cl] = __float2bfloat16_rn(c < C ? __ldg(w + (size_t)c * K * K + tap) : 0.f);
+  }
+}
+
+// in-place producer activation of a staged tile: v = silu(x*scale+shift) for the pixels inside the image (the zero-filled
+// halo must stay zero: padding applies to the ACTIVATED tensor)
+template <int TH, int TW>
+__device__ __forceinline__ void activate_tile(uint4* s_tile, const f8& sc, const f8& sh, int gy0, int gx0, int H, int W,
+                                              int lane, int pt) {
+  constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int i = pt + NPT * j;
+    const int iy = i / TW, ix = i - iy * TW;
+    const int gy = gy0 + iy, gx = gx0 + ix;
+    if (i < NPIX && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      f8 a = unpack8(s_tile[i * CL + lane]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] = siluf_(fmaf(a.v[k], sc.v[k], sh.v[k]));
+      s_tile[i * CL + lane] = pack8(a);
+    }
   }
 }
 
@@ -173,97 +134,131 @@ __device__ __forceinline__ void conv_rows(const uint4* s_in, const uint4* s_w, i
   }
 }
 
-template <int K, int S> struct FwdTile {
-  static constexpr int TOW = S == 1 ? 16 : 8;
-  static constexpr int P = TOW / 4;
+// output tile = TOH x (4*P); P = outputs per thread along x
+template <int K, int S, int P> struct FwdTile {
+  static constexpr int TOW = 4 * P;
   static constexpr int IH = (TOH - 1) * S + K, IW = (TOW - 1) * S + K;
-  static constexpr size_t smem = (size_t)IH * IW * CL * 16 + (size_t)K * K * CL * 16;
+  static constexpr int IN_BYTES = IH * IW * PX_BYTES;           // multiple of 128
+  static constexpr int OUT_BYTES = TOH * TOW * PX_BYTES;
 };
 
+__device__ __forceinline__ uint8_t* align128(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
+}
+
+struct Item { int n, ty, tx; };
+__device__ __forceinline__ Item decode_item(int it, int tiles, const DwGeom& g) {
+  Item r;
+  r.n = tiles == 1 ? it : (int)__umulhi((uint32_t)it, g.magic_tiles);
+  const int t = it - r.n * tiles;
+  r.ty = g.tiles_x == 1 ? t : (int)__umulhi((uint32_t)t, g.magic_tx);
+  r.tx = t - r.ty * g.tiles_x;
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-template <int K, int S>
-__global__ void __launch_bounds__(TPB, 3) dwconv_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ in_rec,
+template <int K, int S, int P>
+__global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ in_rec,
                                                             const float* __restrict__ w, uint4* __restrict__ out,
                                                             const float* __restrict__ out_rec, float* __restrict__ pooled,
                                                             double* __restrict__ stats, const DwGeom g) {
-  using T = FwdTile<K, S>;
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint4* s_in = reinterpret_cast<uint4*>(smem);
-  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)T::IH * T::IW * CL * 16);
-  float* s_red = reinterpret_cast<float*>(smem);
-  const int V = g.C / 8;
-  const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
-  const int oy0 = (tile / g.tiles_x) * TOH, ox0 = (tile % g.tiles_x) * T::TOW;
+  using T = FwdTile<K, S, P>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align128(smem_raw);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + 2 * T::IN_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * T::IN_BYTES + K * K * PX_BYTES);
+  const int V = g.C / 8, cb = blockIdx.y;
   const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
   const int cv = cb * CL + lane;
   const bool cvalid = cv < V;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
   load_weights<K>(s_w, w, cb, g.C, false);
-  load_act_tile<T::IH, T::IW>(s_in, x, in_rec, n, g.H, g.W, V, g.C, oy0 * S - g.pad_t, ox0 * S - g.pad_l, cv, cvalid, lane, pt);
   __syncthreads();
-  const int oy = pt / 4, oxb = (pt % 4) * T::P;
-  float acc[T::P][8];
-#pragma unroll
-  for (int p = 0; p < T::P; ++p)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
-  conv_rows<K, S, T::P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
-
+  const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
+  auto issue = [&](int it, int st) {
+    const Item q = decode_item(it, tiles, g);
+    ptx::mbar_expect_tx(&bar[st], T::IN_BYTES);
+    ptx::tma_load_4d(smem + st * T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW * S - g.pad_l, q.ty * TOH * S - g.pad_t, q.n);
+  };
+  f8 sc, sh, osc, osh;
+  if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + g.C + 8 * cv); }
+  if (out_rec && cvalid) { osc = ldf8(out_rec + 8 * cv); osh = ldf8(out_rec + g.C + 8 * cv); }
   float red[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
-  f8 osc, osh;
-  if (out_rec && cvalid) { osc = ldf8(out_rec + 8 * cv); osh = ldf8(out_rec + g.C + 8 * cv); }
-  const int gy = oy0 + oy;
-#pragma unroll
-  for (int p = 0; p < T::P; ++p) {
-    const int gx = ox0 + oxb + p;
-    if (cvalid && gy < g.OH && gx < g.OW) {
-      f8 o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = out_rec ? siluf_(fmaf(acc[p][i], osc.v[i], osh.v[i])) : acc[p][i];
-      const uint4 q = pack8(o);
-      out[((size_t)(n * g.OH + gy) * g.OW + gx) * V + cv] = q;
-      const f8 r = unpack8(q);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { red[0][i] += r.v[i]; red[1][i] = fmaf(r.v[i], r.v[i], red[1][i]); }
+  const int oy = pt / 4, oxb = (pt % 4) * P;
+  int it = blockIdx.x, st = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0 && it < items) issue(it, 0);
+  for (; it < items; it += G, st ^= 1) {
+    const Item q = decode_item(it, tiles, g);
+    const int oy0 = q.ty * TOH, ox0 = q.tx * T::TOW;
+    if (threadIdx.x == 0 && it + G < items) {
+      ptx::fence_proxy_async();          // the other buffer was last touched by generic-proxy stores (in-place activation)
+      issue(it + G, st ^ 1);
     }
+    uint4* s_in = reinterpret_cast<uint4*>(smem + st * T::IN_BYTES);
+    ptx::mbar_wait(&bar[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    if (in_rec) {
+      if (cvalid) activate_tile<T::IH, T::IW>(s_in, sc, sh, oy0 * S - g.pad_t, ox0 * S - g.pad_l, g.H, g.W, lane, pt);
+      __syncthreads();
+    }
+    float acc[P][8];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
+    conv_rows<K, S, P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
+    const int gy = oy0 + oy;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int gx = ox0 + oxb + p;
+      if (cvalid && gy < g.OH && gx < g.OW) {
+        f8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = out_rec ? siluf_(fmaf(acc[p][i], osc.v[i], osh.v[i])) : acc[p][i];
+        const uint4 qv = pack8(o);
+        out[((size_t)(q.n * g.OH + gy) * g.OW + gx) * V + cv] = qv;
+        const f8 r = unpack8(qv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[0][i] += r.v[i]; red[1][i] = fmaf(r.v[i], r.v[i], red[1][i]); }
+      }
+    }
+    if (pooled) {      // eval: SE pooling is per image -> publish per tile (few tiles at inference batch sizes)
+      float red1[1][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red1[0][i] = red[0][i];
+      const float total = reduce_over_pt<1>(red1, reinterpret_cast<float*>(s_in), lane, pt);    // 8 KB <= any tile
+      if (threadIdx.x < 64) {
+        const int c = cb * 64 + threadIdx.x;
+        if (c < g.C) atomicAdd(pooled + (size_t)q.n * g.C + c, total);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
+    }
+    __syncthreads();                     // everyone is done reading this buffer: the next-but-one tile may land in it
   }
-  if (stats || pooled) {
-    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+  if (stats) {
+    const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
-      if (c < g.C) {
-        if (stats) atomicAdd(stats + k * g.C + c, (double)total);
-        if (pooled && k == 0) atomicAdd(pooled + (size_t)n * g.C + c, total);
-      }
+      if (c < g.C) atomicAdd(stats + k * g.C + c, (double)total);
     }
   }
 }
 
 // epilogue shared by both data-gradient kernels: g = dIn * silu'(bn(x_raw)) + BN-backward sums, or plain dIn
 template <int P>
-__device__ __forceinline__ void prefetch_x(uint4 (&xr4)[P], const uint4* __restrict__ x_raw, const float* x_rec,
-                                           const DwGeom& g, int n, int iy, int ixb, int cv, bool cvalid, int V) {
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    xr4[p] = zero4();
-    if (x_rec && cvalid && iy < g.H && ixb + p < g.W) xr4[p] = __ldg(x_raw + ((size_t)(n * g.H + iy) * g.W + ixb + p) * V + cv);
-  }
-}
-
-template <int P>
-__device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4 (&xr4)[P], const uint4* __restrict__ x_raw,
-                                                  const float* __restrict__ x_rec, uint4* __restrict__ g_out,
-                                                  double* __restrict__ bstats, const DwGeom& g, int n, int iy, int ixb, int cv,
-                                                  bool cvalid, int lane, int pt, float* s_red, int V, int cb) {
-  float red[2][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
-  f8 sc, sh, mu, rs;
-  if (x_rec && cvalid) {
-    sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
-    mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
-  }
+__device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4 (&xr4)[P], const float* __restrict__ x_rec,
+                                                  uint4* __restrict__ g_out, float (&red)[2][8], const f8& sc, const f8& sh,
+                                                  const f8& mu, const f8& rs, const DwGeom& g, int n, int iy, int ixb, int cv,
+                                                  bool cvalid, int V) {
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const int ix = ixb + p;
@@ -289,8 +284,77 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ backward data, stride 1
+// stride 1 + symmetric 'same' padding: dIn = conv(dD, rot180(w)) with the same padding -> the forward machinery.
+// Per item two TMA tiles: dD with halo, and (when the input carried a BatchNorm+SiLU) the raw input tile for silu'.
+template <int K, int P>
+__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const __grid_constant__ CUtensorMap tm_d,
+                                                                    const __grid_constant__ CUtensorMap tm_x,
+                                                                    const float* __restrict__ w, const float* __restrict__ x_rec,
+                                                                    uint4* __restrict__ g_out, double* __restrict__ bstats,
+                                                                    const DwGeom g) {
+  using T = FwdTile<K, 1, P>;
+  constexpr int STAGE = T::IN_BYTES + T::OUT_BYTES;
+  constexpr int PAD = (K - 1) / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align128(smem_raw);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + 2 * STAGE);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE + K * K * PX_BYTES);
+  const int V = g.C / 8, cb = blockIdx.y;
+  const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
+  const int cv = cb * CL + lane;
+  const bool cvalid = cv < V;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tm_d);
+    ptx::prefetch_tmap(&tm_x);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  load_weights<K>(s_w, w, cb, g.C, true);
+  __syncthreads();
+  const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
+  auto issue = [&](int it, int st) {
+    const Item q = decode_item(it, tiles, g);
+    ptx::mbar_expect_tx(&bar[st], x_rec ? STAGE : T::IN_BYTES);
+    ptx::tma_load_4d(smem + st * STAGE, &tm_d, &bar[st], cb * 64, q.tx * T::TOW - PAD, q.ty * TOH - PAD, q.n);
+    if (x_rec) ptx::tma_load_4d(smem + st * STAGE + T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW, q.ty * TOH, q.n);
+  };
+  f8 sc, sh, mu, rs;
+  if (x_rec && cvalid) {
+    sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
+    mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
+  }
+  float red[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
+  const int oy = pt / 4, oxb = (pt % 4) * P;
+  int it = blockIdx.x, st = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0 && it < items) issue(it, 0);
+  for (; it < items; it += G, st ^= 1) {
+    const Item q = decode_item(it, tiles, g);
+    if (threadIdx.x == 0 && it + G < items) issue(it + G, st ^ 1);
+    const uint4* s_in = reinterpret_cast<const uint4*>(smem + st * STAGE);
+    const uint4* s_x = reinterpret_cast<const uint4*>(smem + st * STAGE + T::IN_BYTES);
+    ptx::mbar_wait(&bar[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    float acc[P][8];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
+    conv_rows<K, 1, P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
+    uint4 xr4[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) xr4[p] = x_rec ? s_x[(oy * T::TOW + oxb + p) * CL + lane] : zero4();
+    bwd_data_epilogue<P>(acc, xr4, x_rec, g_out, red, sc, sh, mu, rs, g, q.n, q.ty * TOH + oy, q.tx * T::TOW + oxb, cv, cvalid, V);
+    __syncthreads();
+  }
   if (x_rec && bstats) {
-    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+    const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
@@ -298,45 +362,9 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
   }
 }
 
-// ------------------------------------------------------------------------------------------------ backward data, stride 1
-// stride 1 + symmetric 'same' padding: dIn = conv(dD, rot180(w)) with the same padding -> the forward machinery
-template <int K>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const uint4* __restrict__ gy_, const uint4* __restrict__ y_raw,
-                                                                    const float* __restrict__ coef, const float* __restrict__ w,
-                                                                    const uint4* __restrict__ x_raw, const float* __restrict__ x_rec,
-                                                                    uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                    const DwGeom g) {
-  using T = FwdTile<K, 1>;
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint4* s_in = reinterpret_cast<uint4*>(smem);
-  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)T::IH * T::IW * CL * 16);
-  float* s_red = reinterpret_cast<float*>(smem);
-  const int V = g.C / 8;
-  const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
-  const int iy0 = (tile / g.tiles_x) * TOH, ix0 = (tile % g.tiles_x) * T::TOW;
-  const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
-  const int cv = cb * CL + lane;
-  const bool cvalid = cv < V;
-  constexpr int PAD = (K - 1) / 2;
-  load_weights<K>(s_w, w, cb, g.C, true);
-  const int oy = pt / 4, oxb = (pt % 4) * T::P;
-  uint4 xr4[T::P];
-  prefetch_x<T::P>(xr4, x_raw, x_rec, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, V);      // needed only by the epilogue
-  load_grad_tile<T::IH, T::IW>(s_in, gy_, y_raw, coef, n, g.OH, g.OW, V, g.C, iy0 - PAD, ix0 - PAD, cv, cvalid, lane, pt);
-  __syncthreads();
-  float acc[T::P][8];
-#pragma unroll
-  for (int p = 0; p < T::P; ++p)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
-  conv_rows<K, 1, T::P, T::IW>(s_in, s_w, oy, oxb, lane, acc);
-  bwd_data_epilogue<T::P>(acc, xr4, x_raw, x_rec, g_out, bstats, g, n, iy0 + oy, ix0 + oxb, cv, cvalid, lane, pt, s_red, V, cb);
-}
-
 // ------------------------------------------------------------------------------------------------ backward data, generic stride
 template <int K>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __restrict__ gy_, const uint4* __restrict__ y_raw,
-                                                                 const float* __restrict__ coef, const float* __restrict__ w,
+__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __restrict__ gy_, const float* __restrict__ w,
                                                                  const uint4* __restrict__ x_raw, const float* __restrict__ x_rec,
                                                                  uint4* __restrict__ g_out, double* __restrict__ bstats,
                                                                  const DwGeom g) {
@@ -357,8 +385,12 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
   load_weights<K>(s_w, w, cb, g.C, false);
   const int iy = iy0 + pt / 4, ixb = ix0 + (pt % 4) * P;
   uint4 xr4[P];
-  prefetch_x<P>(xr4, x_raw, x_rec, g, n, iy, ixb, cv, cvalid, V);
-  load_grad_tile<DH, DW>(s_d, gy_, y_raw, coef, n, g.OH, g.OW, V, g.C, oyb, oxb0, cv, cvalid, lane, pt);
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    xr4[p] = zero4();
+    if (x_rec && cvalid && iy < g.H && ixb + p < g.W) xr4[p] = __ldg(x_raw + ((size_t)(n * g.H + iy) * g.W + ixb + p) * V + cv);
+  }
+  load_grad_tile<DH, DW>(s_d, gy_, n, g.OH, g.OW, V, oyb, oxb0, cv, cvalid, lane, pt);
   __syncthreads();
   float acc[P][8];
 #pragma unroll
@@ -382,43 +414,86 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
       }
     }
   }
-  bwd_data_epilogue<P>(acc, xr4, x_raw, x_rec, g_out, bstats, g, n, iy, ixb, cv, cvalid, lane, pt, s_red, V, cb);
+  f8 sc, sh, mu, rs;
+  if (x_rec && cvalid) {
+    sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
+    mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
+  }
+  float red[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
+  bwd_data_epilogue<P>(acc, xr4, x_rec, g_out, red, sc, sh, mu, rs, g, n, iy, ixb, cv, cvalid, V);
+  if (x_rec && bstats) {
+    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+    if (threadIdx.x < 128) {
+      const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
+      if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ backward weight
 // dW[c][kh][kw] += sum_{n,oy,ox} dD[n,oy,ox,c] * act(x)[n, oy*S-pad_t+kh, ox*S-pad_l+kw, c]
 // thread = (channel lane, filter row kh, output-row subset); the filter row slides over an input row kept in registers.
+// The gradient does not depend on the tile position, so the accumulators live in registers across ALL the block's items.
 template <int K, int S>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const uint4* __restrict__ gy_, const uint4* __restrict__ y_raw,
-                                                                   const float* __restrict__ coef, const uint4* __restrict__ x,
+__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                   const __grid_constant__ CUtensorMap tm_d,
                                                                    const float* __restrict__ in_rec, float* __restrict__ dw,
                                                                    const DwGeom g) {
   constexpr int TOW = 8;
   constexpr int IH = (TOH - 1) * S + K, IW = (TOW - 1) * S + K;
+  constexpr int X_BYTES = IH * IW * PX_BYTES, D_BYTES = TOH * TOW * PX_BYTES, STAGE = X_BYTES + D_BYTES;
   constexpr int SUBS = NPT / K;                 // row subsets per filter row (K=3: 10, K=5: 6)
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint4* s_in = reinterpret_cast<uint4*>(smem);                       // [IH][IW][CL]
-  uint4* s_d = s_in + (size_t)IH * IW * CL;                           // [TOH][TOW][CL]
-  float* s_acc = reinterpret_cast<float*>(s_d + (size_t)TOH * TOW * CL);   // [K*K][64]
-  const int V = g.C / 8;
-  const int tile = blockIdx.x, cb = blockIdx.y;
-  const int oy0 = (tile / g.tiles_x) * TOH, ox0 = (tile % g.tiles_x) * TOW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align128(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
+  float* s_acc = reinterpret_cast<float*>(smem);                       // [K*K][64], overlays the tiles after the loop
+  const int V = g.C / 8, cb = blockIdx.y;
   const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
   const int cv = cb * CL + lane;
   const bool cvalid = cv < V;
   const int kh = pt % K, sub = pt / K;
   const bool worker = sub < SUBS;
-  for (int i = threadIdx.x; i < K * K * 64; i += TPB) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_d);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
+  auto issue = [&](int it, int st) {
+    const Item q = decode_item(it, tiles, g);
+    ptx::mbar_expect_tx(&bar[st], STAGE);
+    ptx::tma_load_4d(smem + st * STAGE, &tm_x, &bar[st], cb * 64, q.tx * TOW * S - g.pad_l, q.ty * TOH * S - g.pad_t, q.n);
+    ptx::tma_load_4d(smem + st * STAGE + X_BYTES, &tm_d, &bar[st], cb * 64, q.tx * TOW, q.ty * TOH, q.n);
+  };
+  f8 sc, sh;
+  if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + g.C + 8 * cv); }
   float acc[K][8];
 #pragma unroll
   for (int a = 0; a < K; ++a)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
-  for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
-    __syncthreads();
-    load_act_tile<IH, IW>(s_in, x, in_rec, n, g.H, g.W, V, g.C, oy0 * S - g.pad_t, ox0 * S - g.pad_l, cv, cvalid, lane, pt);
-    load_grad_tile<TOH, TOW>(s_d, gy_, y_raw, coef, n, g.OH, g.OW, V, g.C, oy0, ox0, cv, cvalid, lane, pt);
-    __syncthreads();
+  int it = blockIdx.x, st = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0 && it < items) issue(it, 0);
+  for (; it < items; it += G, st ^= 1) {
+    const Item q = decode_item(it, tiles, g);
+    if (threadIdx.x == 0 && it + G < items) {
+      ptx::fence_proxy_async();
+      issue(it + G, st ^ 1);
+    }
+    uint4* s_in = reinterpret_cast<uint4*>(smem + st * STAGE);
+    const uint4* s_d = reinterpret_cast<const uint4*>(smem + st * STAGE + X_BYTES);
+    ptx::mbar_wait(&bar[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    if (in_rec) {
+      if (cvalid) activate_tile<IH, IW>(s_in, sc, sh, q.ty * TOH * S - g.pad_t, q.tx * TOW * S - g.pad_l, g.H, g.W, lane, pt);
+      __syncthreads();
+    }
     if (worker) {
       for (int oy = sub; oy < TOH; oy += SUBS) {
         const uint4* xrow = s_in + ((oy * S + kh) * IW) * CL + lane;
@@ -446,7 +521,9 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const uint4* 
         }
       }
     }
+    __syncthreads();
   }
+  for (int i = threadIdx.x; i < K * K * 64; i += TPB) s_acc[i] = 0.f;
   __syncthreads();
   if (worker) {
 #pragma unroll
@@ -461,6 +538,12 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const uint4* 
   }
 }
 
+inline uint32_t magic_div(int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); }
+inline void set_magic(DwGeom& g) {     // exact while item_index * divisor < 2^32 (asserted by the entry points)
+  g.magic_tiles = magic_div(g.tiles_x * g.tiles_y);
+  g.magic_tx = magic_div(g.tiles_x);
+}
+
 inline void same_pad(int i, int k, int s, int& out, int& pad_before) {
   out = (i + s - 1) / s;
   int total = (out - 1) * s + k - i;
@@ -468,9 +551,27 @@ inline void same_pad(int i, int k, int s, int& out, int& pad_before) {
   pad_before = total / 2;
 }
 
+// persistent grid: every block resident at once (one wave), a fixed channel group per blockIdx.y
+struct OccEntry { const void* fn; int occ; };
+OccEntry g_occ[32];
+int g_occ_n = 0;
+
 template <typename Kern>
-int set_smem_attr(Kern kern) {
-  TRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+int persistent_blocks(Kern kern, size_t smem, int cblocks, int items, int* out) {
+  const void* key = reinterpret_cast<const void*>(kern);     // smem is a compile-time function of the instantiation
+  int occ = -1;
+  for (int i = 0; i < g_occ_n; ++i)
+    if (g_occ[i].fn == key) occ = g_occ[i].occ;
+  if (occ < 0) {
+    TRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem));
+    if (occ < 1) return trt_set_error(TRT_ERR_CUDA, "depthwise kernel does not fit on an SM (smem %zu)", smem);
+    if (g_occ_n < 32) { g_occ[g_occ_n].fn = key; g_occ[g_occ_n].occ = occ; ++g_occ_n; }
+  }
+  int G = (trt_num_sms() * occ) / cblocks;
+  if (G < 1) G = 1;
+  if (G > items) G = items;
+  *out = G;
   return TRT_OK;
 }
 
@@ -485,80 +586,99 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
   g.N = N; g.H = H; g.W = W; g.C = C; g.S = s;
   same_pad(H, k, s, g.OH, g.pad_t);
   same_pad(W, k, s, g.OW, g.pad_l);
-  const int tow = s == 1 ? 16 : 8;
-  g.tiles_x = (g.OW + tow - 1) / tow;
+  const int p = (s == 1 && g.OW > 8) ? 4 : 2;        // outputs per thread along x: tile width 4*p
+  g.tiles_x = (g.OW + 4 * p - 1) / (4 * p);
   g.tiles_y = (g.OH + TOH - 1) / TOH;
+  set_magic(g);
   if (pooled_sum) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
-  const size_t red_bytes = 2 * NPT * 64 * 4;
-  dim3 grid(g.tiles_x * g.tiles_y, (C / 8 + CL - 1) / CL, N);
-#define LAUNCH_DW(KK, SS)                                                                                          \
+  const int cblocks = (C / 8 + CL - 1) / CL;
+  const int items = N * g.tiles_x * g.tiles_y;
+  TRT_REQUIRE((long long)items * g.tiles_x * g.tiles_y < (1ll << 32), "trt_dwconv_fwd: too many tiles");
+  int rc;
+#define LAUNCH_DW(KK, SS, PP)                                                                                      \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) { int rc = set_smem_attr(dwconv_fwd_kernel<KK, SS>); if (rc) return rc; attr = true; }               \
-    size_t smem = FwdTile<KK, SS>::smem < red_bytes ? red_bytes : FwdTile<KK, SS>::smem;                            \
-    dwconv_fwd_kernel<KK, SS><<<grid, TPB, smem, stream>>>((const uint4*)x, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g); \
+    using T = FwdTile<KK, SS, PP>;                                                                                 \
+    const size_t smem = 2 * T::IN_BYTES + KK * KK * PX_BYTES + 16 + 128;                                           \
+    CUtensorMap tm;                                                                                                \
+    if ((rc = trt_make_tmap_nhwc(&tm, x, N, H, W, C, 64, T::IW, T::IH))) return rc;                                \
+    int G;                                                                                                         \
+    if ((rc = persistent_blocks(dwconv_fwd_kernel<KK, SS, PP>, smem, cblocks, items, &G))) return rc;              \
+    dwconv_fwd_kernel<KK, SS, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(tm, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g); \
   } while (0)
-  if (k == 3 && s == 1) LAUNCH_DW(3, 1);
-  else if (k == 3 && s == 2) LAUNCH_DW(3, 2);
-  else if (k == 5 && s == 1) LAUNCH_DW(5, 1);
-  else LAUNCH_DW(5, 2);
+  if (k == 3 && s == 1) { if (p == 4) LAUNCH_DW(3, 1, 4); else LAUNCH_DW(3, 1, 2); }
+  else if (k == 5 && s == 1) { if (p == 4) LAUNCH_DW(5, 1, 4); else LAUNCH_DW(5, 1, 2); }
+  else if (k == 3) LAUNCH_DW(3, 2, 2);
+  else LAUNCH_DW(5, 2, 2);
 #undef LAUNCH_DW
   return trt_check_launch("trt_dwconv_fwd");
 }
 
-extern "C" int trt_dwconv_bwd(const void* gy, const void* y_raw, const float* coef, const float* w, const void* x_raw,
-                              const float* x_rec, void* g_out, double* bstats, float* dw, int N, int H, int W, int C, int k,
-                              int s, cudaStream_t stream) {
+extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out,
+                              double* bstats, float* dw, int N, int H, int W, int C, int k, int s, cudaStream_t stream) {
   TRT_REQUIRE(gy && w && x_raw && dw && N > 0 && C > 0 && C % 8 == 0, "trt_dwconv_bwd: bad argument");
-  TRT_REQUIRE(!coef || y_raw, "trt_dwconv_bwd: coef needs y_raw");
   TRT_REQUIRE((k == 3 || k == 5) && (s == 1 || s == 2), "trt_dwconv_bwd: only k in {3,5}, s in {1,2}");
   DwGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.S = s;
   same_pad(H, k, s, g.OH, g.pad_t);
   same_pad(W, k, s, g.OW, g.pad_l);
   const int cblocks = (C / 8 + CL - 1) / CL;
-  const size_t red_bytes = 2 * NPT * 64 * 4;
+  int rc;
   if (g_out) {   // data gradient (skipped for a first layer whose input needs no gradient)
-    g.tiles_x = (W + 15) / 16;
-    g.tiles_y = (H + TOH - 1) / TOH;
-    dim3 grid(g.tiles_x * g.tiles_y, cblocks, N);
-#define LAUNCH_BD_S1(KK)                                                                                           \
+    if (s == 1) {
+      const int p = W <= 8 ? 2 : 4;
+      g.tiles_x = (W + 4 * p - 1) / (4 * p);
+      g.tiles_y = (H + TOH - 1) / TOH;
+      set_magic(g);
+      const int items = N * g.tiles_x * g.tiles_y;
+#define LAUNCH_BD_S1(KK, PP)                                                                                       \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) { int rc = set_smem_attr(dwconv_bwd_data_s1_kernel<KK>); if (rc) return rc; attr = true; }           \
-    size_t smem = FwdTile<KK, 1>::smem < red_bytes ? red_bytes : FwdTile<KK, 1>::smem;                              \
-    dwconv_bwd_data_s1_kernel<KK><<<grid, TPB, smem, stream>>>((const uint4*)gy, (const uint4*)y_raw, coef, w, (const uint4*)x_raw, x_rec, (uint4*)g_out, bstats, g); \
+    using T = FwdTile<KK, 1, PP>;                                                                                  \
+    const size_t smem = 2 * (T::IN_BYTES + T::OUT_BYTES) + KK * KK * PX_BYTES + 16 + 128;                          \
+    CUtensorMap td, tx;                                                                                            \
+    if ((rc = trt_make_tmap_nhwc(&td, gy, N, g.OH, g.OW, C, 64, T::IW, T::IH))) return rc;                         \
+    if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TOW, TOH))) return rc;                             \
+    int G;                                                                                                         \
+    if ((rc = persistent_blocks(dwconv_bwd_data_s1_kernel<KK, PP>, smem, cblocks, items, &G))) return rc;          \
+    dwconv_bwd_data_s1_kernel<KK, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)
+      if (k == 3) { if (p == 4) LAUNCH_BD_S1(3, 4); else LAUNCH_BD_S1(3, 2); }
+      else { if (p == 4) LAUNCH_BD_S1(5, 4); else LAUNCH_BD_S1(5, 2); }
+#undef LAUNCH_BD_S1
+    } else {
+      g.tiles_x = (W + 15) / 16;
+      g.tiles_y = (H + TOH - 1) / TOH;
+      g.magic_tiles = g.magic_tx = 0;
+      dim3 grid(g.tiles_x * g.tiles_y, cblocks, N);
+      const size_t red_bytes = 2 * NPT * 64 * 4;
 #define LAUNCH_BD(KK)                                                                                              \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) { int rc = set_smem_attr(dwconv_bwd_data_kernel<KK>); if (rc) return rc; attr = true; }              \
     const int DH = (TOH + KK - 2) / 2 + 2, DW = (16 + KK - 2) / 2 + 2;                                             \
-    size_t smem = (size_t)DH * DW * CL * 16 + (size_t)KK * KK * CL * 16;                                            \
+    size_t smem = (size_t)DH * DW * CL * 16 + (size_t)KK * KK * CL * 16;                                           \
     if (smem < red_bytes) smem = red_bytes;                                                                        \
-    dwconv_bwd_data_kernel<KK><<<grid, TPB, smem, stream>>>((const uint4*)gy, (const uint4*)y_raw, coef, w, (const uint4*)x_raw, x_rec, (uint4*)g_out, bstats, g); \
+    dwconv_bwd_data_kernel<KK><<<grid, TPB, smem, stream>>>((const uint4*)gy, w, (const uint4*)x_raw, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)
-    if (s == 1) { if (k == 3) LAUNCH_BD_S1(3); else LAUNCH_BD_S1(5); }
-    else { if (k == 3) LAUNCH_BD(3); else LAUNCH_BD(5); }
-#undef LAUNCH_BD_S1
+      if (k == 3) LAUNCH_BD(3); else LAUNCH_BD(5);
 #undef LAUNCH_BD
-    int rc = trt_check_launch("trt_dwconv_bwd(data)");
+    }
+    rc = trt_check_launch("trt_dwconv_bwd(data)");
     if (rc) return rc;
   }
   {
     g.tiles_x = (g.OW + 7) / 8;
     g.tiles_y = (g.OH + TOH - 1) / TOH;
-    int zsplit = (4 * trt_num_sms()) / (g.tiles_x * g.tiles_y * cblocks);
-    if (zsplit < 1) zsplit = 1;
-    if (zsplit > N) zsplit = N;
-    dim3 grid(g.tiles_x * g.tiles_y, cblocks, zsplit);
+    set_magic(g);
+    const int items = N * g.tiles_x * g.tiles_y;
+    TRT_REQUIRE((long long)items * g.tiles_x * g.tiles_y < (1ll << 32), "trt_dwconv_bwd: too many tiles");
 #define LAUNCH_BW(KK, SS)                                                                                          \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) { int rc = set_smem_attr(dwconv_bwd_weight_kernel<KK, SS>); if (rc) return rc; attr = true; }        \
     const int IH = (TOH - 1) * SS + KK, IW = 7 * SS + KK;                                                          \
-    const size_t smem = ((size_t)IH * IW + TOH * 8) * CL * 16 + (size_t)KK * KK * 64 * 4;                           \
-    dwconv_bwd_weight_kernel<KK, SS><<<grid, TPB, smem, stream>>>((const uint4*)gy, (const uint4*)y_raw, coef, (const uint4*)x_raw, x_rec, dw, g); \
+    const size_t smem = 2 * ((size_t)IH * IW + TOH * 8) * PX_BYTES + 16 + 128;                                     \
+    CUtensorMap tx, td;                                                                                            \
+    if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, IW, IH))) return rc;                                  \
+    if ((rc = trt_make_tmap_nhwc(&td, gy, N, g.OH, g.OW, C, 64, 8, TOH))) return rc;                               \
+    int G;                                                                                                         \
+    if ((rc = persistent_blocks(dwconv_bwd_weight_kernel<KK, SS>, smem, cblocks, items, &G))) return rc;           \
+    dwconv_bwd_weight_kernel<KK, SS><<<dim3(G, cblocks), TPB, smem, stream>>>(tx, td, x_rec, dw, g);               \
   } while (0)
     if (k == 3 && s == 1) LAUNCH_BW(3, 1);
     else if (k == 3 && s == 2) LAUNCH_BW(3, 2);

@@ -101,7 +101,8 @@ def bn_bwd_reduce(dy, x, rec, bstats):
 
 
 def affine2(dy, x, coef, out):
-    rows, Cc = x.shape
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
     check(lib.trt_affine2(ptr(dy), ptr(x), ptr(coef), ptr(out), rows, Cc, stream()))
     return out
 
@@ -129,9 +130,10 @@ def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stat
     return out
 
 
-def dwconv_bwd(gy, y_raw, coef, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s):
-    check(lib.trt_dwconv_bwd(ptr(gy), ptr(y_raw), ptr(coef), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats),
-                             ptr(dw), N, H, W, x_raw.shape[-1], k, s, stream()))
+def dwconv_bwd(dD, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s):
+    """dD: gradient w.r.t. the raw depthwise output (BN-backward affine already applied, see affine2)."""
+    check(lib.trt_dwconv_bwd(ptr(dD), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats), ptr(dw), N, H, W,
+                             x_raw.shape[-1], k, s, stream()))
 
 
 def stem_fwd(x, w, out, out_rec=None, stats=None):

@@ -54,9 +54,14 @@ for i, (H, C, k, s, cnt) in enumerate(SHAPES):
     bst = torch.zeros(2, C, device="cuda", dtype=torch.float64)
     dw = torch.zeros_like(w)
     tf = timed(lambda: ops.dwconv_fwd(x, rec, w, y, N, H, H, k, s, stats=stats))
-    tb = timed(lambda: ops.dwconv_bwd(gy, y, coef, w, x, rec, g_out, bst, dw, N, H, H, k, s))
+    dD = torch.empty_like(gy)
+
+    def bwd():
+        ops.affine2(gy, y, coef, dD)
+        ops.dwconv_bwd(dD, w, x, rec, g_out, bst, dw, N, H, H, k, s)
+    tb = timed(bwd)
     bf = (x.numel() + y.numel()) * 2
-    bb = (2 * y.numel() + 2 * x.numel()) * 2          # gy, y_raw, x_raw read once, g_out written
+    bb = (2 * y.numel() + 2 * x.numel()) * 2          # gy, y_raw, x_raw read once, g_out written (layer-fused lower bound)
     print(f"[{i:2d}] H={H:3d} C={C:4d} k{k} s{s} x{cnt}: fwd {tf:7.1f} us {bf / tf / 1e3:6.0f} GB/s ({100 * bf / tf / 1e3 / PK:4.1f}%)   "
           f"bwd {tb:7.1f} us {bb / tb / 1e3:6.0f} GB/s ({100 * bb / tb / 1e3 / PK:4.1f}%)", flush=True)
     tot["fwd"] += cnt * tf; tot["bwd"] += cnt * tb
