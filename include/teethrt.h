@@ -52,9 +52,10 @@ int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, in
                   const float* shift, const void* residual, double* stats, int block_n_override, trt_stream_t stream);
 
 /* out[p*so_p + q*so_q] (fp32) += sum_m P[m,p] * Q[m,q]   (P:[M,Cp], Q:[M,Cq] bf16 row-major; weight gradient).
+ * q_store: 0 = Cq; otherwise only columns q < q_store are stored (Q zero-padded beyond, e.g. the stem's 27 of 32 taps).
  * lbo/sbo/kstep_bytes: 0 = canonical MN-major 128B-swizzle descriptor values (bring-up knobs). */
 int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int M, int Cp, int Cq, long long so_p, long long so_q,
-                        int lbo, int sbo, int kstep_bytes, trt_stream_t stream);
+                        int q_store, int lbo, int sbo, int kstep_bytes, trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * On-device input stage (byte-exact vs OpenCV 4.x).
@@ -125,6 +126,9 @@ int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv
 int trt_scale_f32(float* x, size_t n, float alpha, trt_stream_t stream);
 /* fp32 [N,K] -> bf16 [N,K] and (optional) bf16 [K,N] */
 int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N, int K, trt_stream_t stream);
+/* the same for `count` weights in one launch.  table_dev: device array of count x 6 int64 {w, w_bf16, wt_bf16 (or 0), N, K,
+ * first_tile}, first_tile = running sum of ceil(N/32)*ceil(K/32) over the preceding entries; total_tiles = the full sum. */
+int trt_pack_w1x1_batch(const long long* table_dev, int count, int total_tiles, trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Depthwise and stem convolutions (TF 'same' padding), forward + backward.  Replace timm's Conv2dSame / depthwise
@@ -144,6 +148,11 @@ int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const floa
 int trt_stem_fwd(const void* x, int x_is_bf16, const float* w, void* out, const float* out_rec, double* stats, int N, int H,
                  int W, int CS, trt_stream_t stream);
 int trt_stem_wgrad(const void* x, int x_is_bf16, const void* ds, float* dw, int N, int H, int W, int CS, trt_stream_t stream);
+/* Train-mode stem as tcgen05 GEMMs: patches [N*OH*OW, 32] bf16 = im2col(x) (column ci*9+kh*3+kw, 5 zero columns);
+ * forward = trt_gemm_bf16(patches, w_bf16[CS,32]) with BN statistics, weight gradient = trt_gemm_wgrad_bf16(dS, patches,
+ * q_store = 27).  trt_stem_pack_w: fp32 [CS,3,3,3] -> bf16 [CS,32]. */
+int trt_stem_im2col(const void* x, int x_is_bf16, void* patches, int N, int H, int W, trt_stream_t stream);
+int trt_stem_pack_w(const float* w, void* w_bf16, int CS, trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * MIL gated-attention pooling.  Replaces AttentionMIL.forward (experiments/vision_v2/train_mil_attention_v1.py:124-130)

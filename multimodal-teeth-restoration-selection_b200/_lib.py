@@ -35,7 +35,7 @@ _SIGS = {
     "trt_init": (i32, [i32]),
     "trt_launch_count": (u64, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
-    "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, vp]),
+    "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp]),
     "trt_clahe_workspace_bytes": (sz, [i32]),
     "trt_clahe_bgr_u8": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
     "trt_resize_linear_u8": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
@@ -54,10 +54,13 @@ _SIGS = {
     "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_scale_f32": (i32, [vp, sz, f32, vp]),
     "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),
+    "trt_pack_w1x1_batch": (i32, [vp, i32, i32, vp]),
     "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_stem_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_stem_wgrad": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_stem_im2col": (i32, [vp, i32, vp, i32, i32, i32, vp]),
+    "trt_stem_pack_w": (i32, [vp, vp, i32, vp]),
     "trt_mil_attn_smem_bytes": (sz, [i32, i32, i32, i32]),
     "trt_mil_attn_fwd": (i32, [vp] * 11 + [i32, i32, i32, i32, vp]),
     "trt_mil_attn_bwd": (i32, [vp] * 15 + [i32, i32, i32, i32, vp]),

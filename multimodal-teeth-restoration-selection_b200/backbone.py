@@ -185,15 +185,27 @@ def create_model(model_name, pretrained=False, num_classes=0, global_pool="avg",
 
 # ================================================================================================= runtime
 def _packed_weights(enc, dev, transposed):
-    """bf16 copies of every 1x1 conv weight ([Cout,Cin] and, for training, [Cin,Cout])."""
-    out = {}
-    for name, cv in enc.conv1x1_list():
-        n, k = cv.weight.shape[0], cv.weight.shape[1]
-        wb = torch.empty((n, k), device=dev, dtype=bf16)
-        wt = torch.empty((k, n), device=dev, dtype=bf16) if transposed else None
-        ops.pack_w1x1(cv.weight.detach(), wb, wt)
-        out[name] = (wb, wt)
-    return out
+    """bf16 copies of every 1x1 conv weight ([Cout,Cin] and, for training, [Cin,Cout]), refreshed by ONE batched launch.
+    The bf16 buffers and the device-side pointer table persist on the encoder (keyed by the parameters' storage, so
+    re-homing them into a flat buffer or moving the module rebuilds the table)."""
+    convs = enc.conv1x1_list()
+    key = (transposed, str(dev)) + tuple(cv.weight.data_ptr() for _, cv in convs)
+    cache = enc.__dict__.get("_pack_cache")
+    if cache is None or cache["key"] != key:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("teethrt: run one eager step before capturing a CUDA graph (weight-pack table not built yet)")
+        out, rows, tiles = {}, [], 0
+        for name, cv in convs:
+            n, k = cv.weight.shape[0], cv.weight.shape[1]
+            wb = torch.empty((n, k), device=dev, dtype=bf16)
+            wt = torch.empty((k, n), device=dev, dtype=bf16) if transposed else None
+            out[name] = (wb, wt)
+            rows.append([cv.weight.data_ptr(), wb.data_ptr(), wt.data_ptr() if transposed else 0, n, k, tiles])
+            tiles += ((n + 31) // 32) * ((k + 31) // 32)
+        cache = dict(key=key, w=out, table=torch.tensor(rows, dtype=torch.int64).to(dev), tiles=tiles)
+        enc.__dict__["_pack_cache"] = cache
+    ops.pack_w1x1_batch(cache["table"], cache["tiles"])
+    return cache["w"]
 
 
 def _eval_cache(enc, dev):
@@ -288,11 +300,13 @@ def forward_train(enc, x, save=True):
 
     h, w = ops.same_out(H, 2), ops.same_out(W, 2)
     cs = enc.conv_stem.weight.shape[0]
-    s_raw = torch.empty((N * h * w, cs), device=dev, dtype=bf16)
     st = stats.take(2 * cs)
-    ops.stem_fwd(x, enc.conv_stem.weight.detach(), s_raw, stats=st)
+    # the stem as tcgen05 GEMMs over an explicit im2col (K = 27 padded to 32); the patches are kept for the weight gradient
+    patches = ops.stem_im2col(x, torch.empty((N * h * w, 32), device=dev, dtype=bf16))
+    w_stem = ops.stem_pack_w(enc.conv_stem.weight.detach(), torch.empty((cs, 32), device=dev, dtype=bf16))
+    s_raw = ops.gemm(patches, w_stem, ops.EPI_STATS, stats=st)
     cur, cur_rec = s_raw, finalize("bn1", st, N * h * w)          # lazy: (raw, pending BN+SiLU)
-    ctx["stem"] = dict(raw=s_raw, h=h, w=w)
+    ctx["stem"] = dict(raw=s_raw, h=h, w=w, patches=patches)
     for name, blk in enc.block_list():
         c = blk.cfg
         k, s = c["k"], c["s"]
@@ -352,6 +366,11 @@ def _add_coef(C, dev):
         t[:2] = 1.0
         _ones_coef[key] = t
     return _ones_coef[key]
+
+
+def _stem_wgrad(ctx, ds, grads):
+    g = grads["conv_stem.weight"]
+    ops.gemm_wgrad(ds, ctx["stem"]["patches"], g.view(g.shape[0], 27), so_p=27, so_q=1, q_store=27)
 
 
 def backward_train(enc, ctx, dfeat, grads):
@@ -433,7 +452,7 @@ def backward_train(enc, ctx, dfeat, grads):
                 ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h, w, k, s)
                 coef_s = bn_back("bn1", bst, N * h * w)
                 ds = ops.affine2(g_in, x_in, coef_s, g_in)
-                ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+                _stem_wgrad(ctx, ds, grads)
                 dy = None
             else:
                 g_in = torch.empty_like(x_in)
@@ -449,7 +468,7 @@ def backward_train(enc, ctx, dfeat, grads):
                     g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
                     coef_s = bn_back("bn1", bst, N * hw0)
                     ds = ops.affine2(g_s, st_raw, coef_s, g_s)
-                    ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+                    _stem_wgrad(ctx, ds, grads)
                     dy = None
         if c["type"] == "ir" and sv.get("materialised_from"):
             st_raw = ctx["stem"]["raw"]
@@ -458,7 +477,7 @@ def backward_train(enc, ctx, dfeat, grads):
             g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
             coef_s = bn_back("bn1", bst, N * hw0)
             ds = ops.affine2(g_s, st_raw, coef_s, g_s)
-            ops.stem_wgrad(ctx["x"], ds, grads["conv_stem.weight"])
+            _stem_wgrad(ctx, ds, grads)
             dy = None
     return grads
 

@@ -135,6 +135,48 @@ __global__ void __launch_bounds__(128) stem_wgrad_kernel(const InT* __restrict__
   }
 }
 
+// im2col of the stem: NCHW image -> patches [N*OH*OW, 32] bf16, column = ci*9 + kh*3 + kw (27 taps, 5 zero columns), so the
+// train-mode stem runs as tcgen05 GEMMs: forward = patches . W^T (BN statistics in the epilogue), weight gradient =
+// dS^T . patches.  One thread per output pixel; the 64-byte row is written as four 16-byte stores.
+template <typename InT>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const InT* __restrict__ x, uint4* __restrict__ patches, int N, int H,
+                                                          int W, int OH, int OW, int pad_t, int pad_l) {
+  const long long total = (long long)N * OH * OW;
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total) return;
+  const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  float v[32];
+#pragma unroll
+  for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = oy * 2 - pad_t + kh;
+      const InT* row = x + ((size_t)(n * 3 + ci) * H + (iy >= 0 && iy < H ? iy : 0)) * W;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = ox * 2 - pad_l + kw;
+        v[ci * 9 + kh * 3 + kw] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? (float)row[ix] : 0.f;
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q;
+    q.x = pack_bf16(v[8 * j], v[8 * j + 1]); q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+    q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+    patches[(size_t)pix * 4 + j] = q;
+  }
+}
+
+// stem weight [CS,3,3,3] fp32 -> bf16 [CS,32] (27 taps + 5 zero columns)
+__global__ void stem_pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int CS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CS * 32) return;
+  const int co = i / 32, t = i % 32;
+  o[i] = __float2bfloat16_rn(t < 27 ? w[co * 27 + t] : 0.f);
+}
+
 inline void same_pad(int i, int k, int s, int& out, int& pad_before) {
   out = (i + s - 1) / s;
   int total = (out - 1) * s + k - i;
@@ -162,6 +204,24 @@ extern "C" int trt_stem_fwd(const void* x, int x_is_bf16, const float* w, void* 
     else stem_fwd_kernel<48, float><<<grid, 128, 0, stream>>>((const float*)x, w, o, out_rec, stats, N, H, W, OH, OW, pt, pl);
   }
   return trt_check_launch("trt_stem_fwd");
+}
+
+extern "C" int trt_stem_im2col(const void* x, int x_is_bf16, void* patches, int N, int H, int W, cudaStream_t stream) {
+  TRT_REQUIRE(x && patches && N > 0 && H > 0 && W > 0, "trt_stem_im2col: bad argument");
+  int OH, OW, pt, pl;
+  same_pad(H, 3, 2, OH, pt);
+  same_pad(W, 3, 2, OW, pl);
+  const long long total = (long long)N * OH * OW;
+  const int grid = (int)((total + 255) / 256);
+  if (x_is_bf16) stem_im2col_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (uint4*)patches, N, H, W, OH, OW, pt, pl);
+  else stem_im2col_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (uint4*)patches, N, H, W, OH, OW, pt, pl);
+  return trt_check_launch("trt_stem_im2col");
+}
+
+extern "C" int trt_stem_pack_w(const float* w, void* w_bf16, int CS, cudaStream_t stream) {
+  TRT_REQUIRE(w && w_bf16 && CS > 0, "trt_stem_pack_w: bad argument");
+  stem_pack_w_kernel<<<(CS * 32 + 127) / 128, 128, 0, stream>>>(w, (__nv_bfloat16*)w_bf16, CS);
+  return trt_check_launch("trt_stem_pack_w");
 }
 
 extern "C" int trt_stem_wgrad(const void* x, int x_is_bf16, const void* ds, float* dw, int N, int H, int W, int CS,

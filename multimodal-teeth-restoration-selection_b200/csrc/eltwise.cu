@@ -575,6 +575,44 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
+// all 1x1-conv weights of a model in ONE launch: table[i] = {w, o, ot, N, K, first_tile} (int64 each, device memory)
+__global__ void pack_w_batch_kernel(const long long* __restrict__ table, int count) {
+  __shared__ float tile[32][33];
+  __shared__ int s_entry;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {                               // last entry whose first tile is <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid * 6 + 5] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_entry = lo;
+  }
+  __syncthreads();
+  const long long* e = table + s_entry * 6;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(e[2]);
+  const int N = (int)e[3], K = (int)e[4];
+  const int local = blockIdx.x - (int)e[5], tiles_k = (K + 31) / 32;
+  const int k0 = (local % tiles_k) * 32, n0 = (local / tiles_k) * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int n = n0 + j, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[(size_t)n * K + k];
+      o[(size_t)n * K + k] = __float2bfloat16_rn(v);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (ot) {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int k = k0 + j, n = n0 + threadIdx.x;
+      if (n < N && k < K) ot[(size_t)k * N + n] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+  }
+}
+
 __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float alpha) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= alpha;
 }
@@ -728,6 +766,12 @@ extern "C" int trt_pack_w1x1(const float* w, void* w_bf16, void* wt_bf16, int N,
   dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
   pack_w_kernel<<<grid, block, 0, stream>>>(w, (__nv_bfloat16*)w_bf16, (__nv_bfloat16*)wt_bf16, N, K);
   return trt_check_launch("trt_pack_w1x1");
+}
+
+extern "C" int trt_pack_w1x1_batch(const long long* table_dev, int count, int total_tiles, cudaStream_t stream) {
+  TRT_REQUIRE(table_dev && count > 0 && total_tiles > 0, "trt_pack_w1x1_batch: bad argument");
+  pack_w_batch_kernel<<<total_tiles, dim3(32, 8), 0, stream>>>(table_dev, count);
+  return trt_check_launch("trt_pack_w1x1_batch");
 }
 
 extern "C" int trt_scale_f32(float* x, size_t n, float alpha, cudaStream_t stream) {

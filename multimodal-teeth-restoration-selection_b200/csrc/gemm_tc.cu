@@ -266,6 +266,7 @@ struct WgradParams {
   int block_q;              // UMMA N (multiple of 16, <= 256)
   int num_p_blocks, num_q_blocks, splits, mblocks_per_split, num_mblocks;
   int stages, tmem_cols, vec4;
+  int q_store;              // columns q >= q_store are computed but not stored (zero-padded operands, e.g. the stem's 27 taps)
   long long so_p, so_q;     // output strides (elements)
   float* out;
   // descriptor knobs (defaults follow the canonical MN-major SW128 layout; overridable by the bring-up test)
@@ -359,7 +360,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const int qc = q0 + c0 + i;
-            if (qc < p.Cq)
+            if (qc < p.q_store)
               atomicAdd(reinterpret_cast<float4*>(o + qc), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                                                          __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
           }
@@ -367,7 +368,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int qc = q0 + c0 + i;
-            if (qc < p.Cq) atomicAdd(o + (long long)qc * p.so_q, __uint_as_float(r[i]));
+            if (qc < p.q_store) atomicAdd(o + (long long)qc * p.so_q, __uint_as_float(r[i]));
           }
         }
       }
@@ -447,7 +448,7 @@ extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N
 }
 
 extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int M, int Cp, int Cq, long long so_p,
-                                   long long so_q, int lbo, int sbo, int kstep_bytes, cudaStream_t stream) {
+                                   long long so_q, int q_store, int lbo, int sbo, int kstep_bytes, cudaStream_t stream) {
   TRT_REQUIRE(P && Q && out, "trt_gemm_wgrad_bf16: null operand");
   TRT_REQUIRE(M > 0 && Cp > 0 && Cq > 0 && (Cp % 8) == 0 && (Cq % 8) == 0, "trt_gemm_wgrad_bf16: bad shape %d %d %d", M, Cp, Cq);
   WgradParams p;
@@ -465,7 +466,8 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
   p.splits = (p.num_mblocks + p.mblocks_per_split - 1) / p.mblocks_per_split;   // no empty split
   p.tmem_cols = pow2_cols(p.block_q);
   p.so_p = so_p; p.so_q = so_q; p.out = out;
-  p.vec4 = (so_q == 1 && (so_p % 4) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
+  p.q_store = (q_store > 0 && q_store < Cq) ? q_store : Cq;
+  p.vec4 = (so_q == 1 && (so_p % 4) == 0 && (p.q_store % 4) == 0 && (((uintptr_t)out) & 15) == 0) ? 1 : 0;
   p.lbo = lbo > 0 ? (uint32_t)lbo : 8192u;
   p.sbo = sbo > 0 ? (uint32_t)sbo : 1024u;
   p.kstep_bytes = kstep_bytes > 0 ? (uint32_t)kstep_bytes : 2048u;

@@ -221,9 +221,7 @@ __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
   float* a1 = z0 + (size_t)B * Hd;
   float* ft = a1 + (size_t)B * Hd;
   float* bnstat = ft + (size_t)B * Hd;   // mean[Hd], rstd[Hd]
-  __shared__ float s_loss[TPB / 32];
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < B * Hd; i += TPB) {
     const int b = i / Hd, j = i % Hd;
     float acc = p.b0[j];
@@ -266,39 +264,40 @@ __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
     for (int t = 0; t < Hd; ++t) acc = fmaf(a1[b * Hd + t], p.W1[j * Hd + t], acc);
     ft[i] = fmaxf(acc, 0.f);
   }
-  __syncthreads();
-  float loss_part = 0.f;
-  for (int b = warp; b < B; b += TPB / 32) {
-    float lc = 0.f, lr = 0.f;
-    for (int i = lane; i < F + Hd; i += 32) {
-      float f = i < F ? p.feat[(size_t)b * F + i] : ft[b * Hd + (i - F)];
-      if (p.train) f *= keep_scale(p.drop_p, seed, 2, (unsigned long long)b * (F + Hd) + i);
-      lc = fmaf(f, p.cls_w[i], lc);
-      lr = fmaf(f, p.reg_w[i], lr);
-    }
-    lc = warp_sum(lc) + p.cls_b[0];
-    lr = warp_sum(lr) + p.reg_b[0];
-    if (lane == 0) {
-      p.logit[b] = lc;
-      p.reg[b] = lr;
-      if (p.y_hard) {
-        const float w = p.sample_w ? p.sample_w[b] : 1.f;
-        const float yh = p.y_hard[b], ys = p.y_soft[b];
-        const float bh = fmaxf(lc, 0.f) - lc * yh + log1pf(expf(-fabsf(lc)));
-        const float bs = fmaxf(lr, 0.f) - lr * ys + log1pf(expf(-fabsf(lr)));
-        loss_part += w * (p.alpha * bh + p.beta * bs) / B;
-        p.dlogit[b] = p.alpha * w * (1.f / (1.f + expf(-lc)) - yh) / B;
-        p.dreg[b] = p.beta * w * (1.f / (1.f + expf(-lr)) - ys) / B;
-      }
-    }
+  if (threadIdx.x == 0 && p.loss) p.loss[0] = 0.f;     // the heads kernel (next launch) accumulates into it
+}
+
+// fused vector -> two heads (+ dual BCE): one block per sample, lanes over the F + Hd inputs
+__global__ void __launch_bounds__(TPB) heads_fwd_kernel(const TabParams p) {
+  const int B = p.B, Hd = p.Hd, F = p.F, b = blockIdx.x;
+  const float* ft = p.scratch + (size_t)2 * B * Hd;
+  __shared__ float s_c[TPB / 32], s_r[TPB / 32];
+  const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float lc = 0.f, lr = 0.f;
+  for (int i = threadIdx.x; i < F + Hd; i += TPB) {
+    float f = i < F ? __ldg(p.feat + (size_t)b * F + i) : ft[b * Hd + (i - F)];
+    if (p.train) f *= keep_scale(p.drop_p, seed, 2, (unsigned long long)b * (F + Hd) + i);
+    lc = fmaf(f, __ldg(p.cls_w + i), lc);
+    lr = fmaf(f, __ldg(p.reg_w + i), lr);
   }
-  if (p.y_hard) {
-    if (lane == 0) s_loss[warp] = loss_part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int i = 0; i < TPB / 32; ++i) s += s_loss[i];
-      p.loss[0] = s;
+  lc = warp_sum(lc);
+  lr = warp_sum(lr);
+  if (lane == 0) { s_c[warp] = lc; s_r[warp] = lr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lc = p.cls_b[0]; lr = p.reg_b[0];
+    for (int i = 0; i < TPB / 32; ++i) { lc += s_c[i]; lr += s_r[i]; }
+    p.logit[b] = lc;
+    p.reg[b] = lr;
+    if (p.y_hard) {
+      const float w = p.sample_w ? p.sample_w[b] : 1.f;
+      const float yh = p.y_hard[b], ys = p.y_soft[b];
+      const float bh = fmaxf(lc, 0.f) - lc * yh + log1pf(expf(-fabsf(lc)));
+      const float bs = fmaxf(lr, 0.f) - lr * ys + log1pf(expf(-fabsf(lr)));
+      atomicAdd(p.loss, w * (p.alpha * bh + p.beta * bs) / B);
+      p.dlogit[b] = p.alpha * w * (1.f / (1.f + expf(-lc)) - yh) / B;
+      p.dreg[b] = p.beta * w * (1.f / (1.f + expf(-lr)) - ys) / B;
     }
   }
 }
@@ -311,22 +310,19 @@ struct TabBwdParams {
   float* scratch2;             // dz1 [B,Hd], da1 [B,Hd]
 };
 
-__global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q) {
+// head weight gradients + gradient into the fused vector: one thread per input of the fused vector, blocks over inputs
+__global__ void __launch_bounds__(TPB) heads_bwd_kernel(const TabBwdParams q) {
   const TabParams& p = q.f;
-  const int B = p.B, T = p.T, Hd = p.Hd, F = p.F;
-  const float* z0 = p.scratch;
-  const float* a1 = z0 + (size_t)B * Hd;
-  const float* ft = a1 + (size_t)B * Hd;
-  const float* bnstat = ft + (size_t)B * Hd;
+  const int B = p.B, Hd = p.Hd, F = p.F;
+  const float* ft = p.scratch + (size_t)2 * B * Hd;
   float* dz1 = q.scratch2;
-  float* da1 = dz1 + (size_t)B * Hd;
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
-  // head weight gradients + gradient into the fused vector
-  for (int i = threadIdx.x; i < F + Hd; i += TPB) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i < F + Hd) {
     float gc = 0.f, gr = 0.f;
     const float wc = p.cls_w[i], wr = p.reg_w[i];
     for (int b = 0; b < B; ++b) {
-      float f = i < F ? p.feat[(size_t)b * F + i] : ft[b * Hd + (i - F)];
+      float f = i < F ? __ldg(p.feat + (size_t)b * F + i) : ft[b * Hd + (i - F)];
       const float ks = p.train ? keep_scale(p.drop_p, seed, 2, (unsigned long long)b * (F + Hd) + i) : 1.f;
       f *= ks;
       const float dl = q.dlogit[b], dr = q.dreg[b];
@@ -339,13 +335,24 @@ __global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q
     q.dcls_w[i] = gc;
     q.dreg_w[i] = gr;
   }
-  if (threadIdx.x == 0) {
+  if (i == 0) {
     float sc = 0.f, sr = 0.f;
     for (int b = 0; b < B; ++b) { sc += q.dlogit[b]; sr += q.dreg[b]; }
     q.dcls_b[0] = sc;
     q.dreg_b[0] = sr;
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q) {
+  const TabParams& p = q.f;
+  const int B = p.B, T = p.T, Hd = p.Hd;
+  const float* z0 = p.scratch;
+  const float* a1 = z0 + (size_t)B * Hd;
+  const float* ft = a1 + (size_t)B * Hd;
+  const float* bnstat = ft + (size_t)B * Hd;
+  float* dz1 = q.scratch2;
+  float* da1 = dz1 + (size_t)B * Hd;
+  const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
   // second linear: dW1[j][t] = sum_b dz1[b][j] a1[b][t]; db1; da1 = dz1 . W1
   for (int i = threadIdx.x; i < Hd * Hd; i += TPB) {
     const int j = i / Hd, t = i % Hd;
@@ -524,6 +531,8 @@ extern "C" int trt_tab_heads_fwd(const float* feat, const float* xtab, const flo
   p.logit = logit; p.reg = reg; p.loss = loss; p.dlogit = dlogit; p.dreg = dreg;
   p.scratch = scratch;
   tab_heads_fwd_kernel<<<1, TPB, 0, stream>>>(p);
+  trt_count_launch(1);
+  heads_fwd_kernel<<<B, TPB, 0, stream>>>(p);
   return trt_check_launch("trt_tab_heads_fwd");
 }
 
@@ -548,6 +557,8 @@ extern "C" int trt_tab_heads_bwd(const float* feat, const float* xtab, const flo
   q.dW0 = grads_host[0]; q.db0 = grads_host[1]; q.dbn_g = grads_host[2]; q.dbn_b = grads_host[3]; q.dW1 = grads_host[4]; q.db1 = grads_host[5];
   q.dcls_w = grads_host[6]; q.dcls_b = grads_host[7]; q.dreg_w = grads_host[8]; q.dreg_b = grads_host[9];
   q.scratch2 = scratch + (size_t)3 * B * Hd + 2 * Hd;
+  heads_bwd_kernel<<<(F + Hd + TPB - 1) / TPB, TPB, 0, stream>>>(q);
+  trt_count_launch(1);
   tab_heads_bwd_kernel<<<1, TPB, 0, stream>>>(q);
   return trt_check_launch("trt_tab_heads_bwd");
 }

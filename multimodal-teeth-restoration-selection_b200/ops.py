@@ -36,21 +36,25 @@ def gemm(A, B, flags=0, scale=None, shift=None, residual=None, stats=None, out=N
     return out
 
 
-def gemm_wgrad(P, Q, out, so_p=None, so_q=None, lbo=0, sbo=0, kstep=0):
-    """out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]  (fp32 accumulate/atomics)."""
+def gemm_wgrad(P, Q, out, so_p=None, so_q=None, lbo=0, sbo=0, kstep=0, q_store=0):
+    """out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]  (fp32 accumulate/atomics); only columns q < q_store are stored."""
     _c(P, bf16), _c(Q, bf16), _c(out, torch.float32)
     M, Cp = P.shape
     Cq = Q.shape[1]
     assert Q.shape[0] == M
     if so_p is None:
         so_p, so_q = Cq, 1
-    check(lib.trt_gemm_wgrad_bf16(ptr(P), ptr(Q), ptr(out), M, Cp, Cq, so_p, so_q, lbo, sbo, kstep, stream()))
+    check(lib.trt_gemm_wgrad_bf16(ptr(P), ptr(Q), ptr(out), M, Cp, Cq, so_p, so_q, q_store, lbo, sbo, kstep, stream()))
     return out
 
 
 def pack_w1x1(w, w_bf16, wt_bf16=None):
     N, K = w.shape[0], w.shape[1]
     check(lib.trt_pack_w1x1(ptr(w), ptr(w_bf16), ptr(wt_bf16), N, K, stream()))
+
+
+def pack_w1x1_batch(table, total_tiles):
+    check(lib.trt_pack_w1x1_batch(ptr(table), table.shape[0], total_tiles, stream()))
 
 
 # ------------------------------------------------------------------------------------------------ BN / SE / pool
@@ -142,6 +146,18 @@ def stem_fwd(x, w, out, out_rec=None, stats=None):
     check(lib.trt_stem_fwd(ptr(x), int(x.dtype == bf16), ptr(w), ptr(out), ptr(out_rec), ptr(stats), N, H, W, w.shape[0],
                            stream()))
     return out
+
+
+def stem_im2col(x, patches):
+    """patches [N*OH*OW, 32] bf16 = im2col of the 3x3 stride-2 'same' stem (27 taps + 5 zero columns)."""
+    N, _, H, W = x.shape
+    check(lib.trt_stem_im2col(ptr(x), int(x.dtype == bf16), ptr(patches), N, H, W, stream()))
+    return patches
+
+
+def stem_pack_w(w, w_bf16):
+    check(lib.trt_stem_pack_w(ptr(w), ptr(w_bf16), w.shape[0], stream()))
+    return w_bf16
 
 
 def stem_wgrad(x, ds, dw):

@@ -271,6 +271,17 @@ def test_stem_forward_wgrad(ops, CS, N, H, W, dt):
     dw = torch.zeros_like(w)
     ops.stem_wgrad(x, ds, dw)
     assert rel_err(dw, wt.grad) < 1e-2
+    # train path: explicit im2col (27 taps padded to 32) + tcgen05 GEMMs for the forward and the weight gradient
+    patches = ops.stem_im2col(x, torch.empty(N * OH * OW, 32, device="cuda", dtype=bf16))
+    cols = F.unfold(same_pad_t(xt, 3, 2), 3, stride=2).transpose(1, 2).reshape(-1, 27)      # column = ci*9 + kh*3 + kw
+    assert torch.equal(patches[:, :27].float(), cols) and float(patches[:, 27:].abs().max()) == 0.0
+    wp = ops.stem_pack_w(w, torch.empty(CS, 32, device="cuda", dtype=bf16))
+    stats2 = torch.zeros(2, CS, device="cuda", dtype=torch.float64)
+    out3 = ops.gemm(patches, wp, ops.EPI_STATS, stats=stats2).view(N, OH, OW, CS)
+    assert rel_err(out3, ref) < 1e-2
+    dw2 = torch.zeros_like(w)
+    ops.gemm_wgrad(ds.view(-1, CS), patches, dw2.view(CS, 27), so_p=27, so_q=1, q_store=27)
+    assert rel_err(dw2, wt.grad) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------------ MIL pooling
