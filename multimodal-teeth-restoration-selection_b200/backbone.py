@@ -9,6 +9,7 @@ CUDA library: activations are NHWC bf16, 1x1 convs are tcgen05 GEMMs with BN sta
 the epilogue, depthwise convs apply the producer's BN+SiLU on load.  No PyTorch compute fallback exists.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -368,9 +369,39 @@ def _add_coef(C, dev):
     return _ones_coef[key]
 
 
-def _stem_wgrad(ctx, ds, grads):
+class _SideQueue:
+    """Weight-gradient GEMMs only feed the optimiser, so they run on a second stream beside the data-gradient chain (in a
+    captured graph: a parallel branch).  Every tensor they read is kept alive until join() so the caching allocator cannot
+    hand its memory to later work on the main stream."""
+    _streams = {}
+
+    def __init__(self, dev):
+        self.enabled = os.environ.get("TEETHRT_WGRAD_STREAM", "1") != "0"
+        self.keep = []
+        if self.enabled:
+            key = (dev.type, dev.index)
+            if key not in _SideQueue._streams:
+                _SideQueue._streams[key] = torch.cuda.Stream(device=dev)
+            self.side = _SideQueue._streams[key]
+            self.main = torch.cuda.current_stream(dev)
+
+    def wgrad(self, P, Q, out, **kw):
+        if not self.enabled:
+            return ops.gemm_wgrad(P, Q, out, **kw)
+        self.keep += [P, Q]
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            ops.gemm_wgrad(P, Q, out, **kw)
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
+def _stem_wgrad(ctx, ds, grads, sq):
     g = grads["conv_stem.weight"]
-    ops.gemm_wgrad(ds, ctx["stem"]["patches"], g.view(g.shape[0], 27), so_p=27, so_q=1, q_store=27)
+    sq.wgrad(ds, ctx["stem"]["patches"], g.view(g.shape[0], 27), so_p=27, so_q=1, q_store=27)
 
 
 def backward_train(enc, ctx, dfeat, grads):
@@ -382,6 +413,7 @@ def backward_train(enc, ctx, dfeat, grads):
     total_c = sum(b.weight.numel() for b in bns.values())
     bstats = _Arena(2 * total_c, torch.float64, dev)
     dfeat = dfeat.contiguous().float()
+    sq = _SideQueue(dev)
 
     def bn_back(bn_name, bst, count):
         bn = bns[bn_name]
@@ -400,7 +432,7 @@ def backward_train(enc, ctx, dfeat, grads):
     coef = bn_back("bn2", bst, N * hw)
     d_raw = ops.affine2(g, hd["raw"], coef, g)
     dy = ops.gemm(d_raw, Wp["conv_head"][1])
-    ops.gemm_wgrad(d_raw, hd["x"], grads["conv_head.weight"])
+    sq.wgrad(d_raw, hd["x"], grads["conv_head.weight"])
     del g, d_raw
 
     for blk, sv in reversed(ctx["blocks"]):
@@ -415,7 +447,7 @@ def backward_train(enc, ctx, dfeat, grads):
         coef = bn_back(sv["bn_out"], bst, N * ohw)
         dp = ops.affine2(dy, sv["p_raw"], coef, torch.empty_like(dy))
         dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
-        ops.gemm_wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
+        sq.wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
         # squeeze-excite + activation + BN of the depthwise output
         rec_d = REC[sv["bn_dw"]]
         dgate_pre = torch.empty((N, cm), device=dev, dtype=torch.float32)
@@ -441,7 +473,7 @@ def backward_train(enc, ctx, dfeat, grads):
             de = ops.affine2(g1, e_raw, coef1, g1)
             flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
             dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
-            ops.gemm_wgrad(de, sv["x"], grads[name + ".conv_pw.weight"])
+            sq.wgrad(de, sv["x"], grads[name + ".conv_pw.weight"])
             dy = dx
         else:
             x_in, in_rec = sv["x"], sv["in_rec"]
@@ -452,7 +484,7 @@ def backward_train(enc, ctx, dfeat, grads):
                 ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h, w, k, s)
                 coef_s = bn_back("bn1", bst, N * h * w)
                 ds = ops.affine2(g_in, x_in, coef_s, g_in)
-                _stem_wgrad(ctx, ds, grads)
+                _stem_wgrad(ctx, ds, grads, sq)
                 dy = None
             else:
                 g_in = torch.empty_like(x_in)
@@ -468,7 +500,7 @@ def backward_train(enc, ctx, dfeat, grads):
                     g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
                     coef_s = bn_back("bn1", bst, N * hw0)
                     ds = ops.affine2(g_s, st_raw, coef_s, g_s)
-                    _stem_wgrad(ctx, ds, grads)
+                    _stem_wgrad(ctx, ds, grads, sq)
                     dy = None
         if c["type"] == "ir" and sv.get("materialised_from"):
             st_raw = ctx["stem"]["raw"]
@@ -477,8 +509,9 @@ def backward_train(enc, ctx, dfeat, grads):
             g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
             coef_s = bn_back("bn1", bst, N * hw0)
             ds = ops.affine2(g_s, st_raw, coef_s, g_s)
-            _stem_wgrad(ctx, ds, grads)
+            _stem_wgrad(ctx, ds, grads, sq)
             dy = None
+    sq.join()
     return grads
 
 

@@ -142,10 +142,6 @@ template <int K, int S, int P> struct FwdTile {
   static constexpr int OUT_BYTES = TOH * TOW * PX_BYTES;
 };
 
-__device__ __forceinline__ uint8_t* align128(uint8_t* p) {
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
-}
-
 struct Item { int n, ty, tx; };
 __device__ __forceinline__ Item decode_item(int it, int tiles, const DwGeom& g) {
   Item r;
@@ -164,7 +160,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const __grid_constan
                                                             double* __restrict__ stats, const DwGeom g) {
   using T = FwdTile<K, S, P>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
   uint4* s_w = reinterpret_cast<uint4*>(smem + 2 * T::IN_BYTES);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * T::IN_BYTES + K * K * PX_BYTES);
   const int V = g.C / 8, cb = blockIdx.y;
@@ -299,7 +295,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const __grid
   constexpr int STAGE = T::IN_BYTES + T::OUT_BYTES;
   constexpr int PAD = (K - 1) / 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
   uint4* s_w = reinterpret_cast<uint4*>(smem + 2 * STAGE);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE + K * K * PX_BYTES);
   const int V = g.C / 8, cb = blockIdx.y;
@@ -446,7 +442,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const __grid_
   constexpr int X_BYTES = IH * IW * PX_BYTES, D_BYTES = TOH * TOW * PX_BYTES, STAGE = X_BYTES + D_BYTES;
   constexpr int SUBS = NPT / K;                 // row subsets per filter row (K=3: 10, K=5: 6)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
   float* s_acc = reinterpret_cast<float*>(smem);                       // [K*K][64], overlays the tiles after the loop
   const int V = g.C / 8, cb = blockIdx.y;

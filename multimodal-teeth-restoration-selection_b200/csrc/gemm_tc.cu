@@ -19,16 +19,20 @@ namespace {
 constexpr int BM = 128;          // UMMA M (rows of the output tile = TMEM lanes)
 constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 448;        // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..13 = three epilogue groups
+constexpr int EPI_THREADS = 128;         // threads of one epilogue group (one warp per TMEM lane quarter)
+constexpr int MAX_GROUPS = 3;
+constexpr int WGRAD_THREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int CHUNK_BYTES = BM * 128;        // one 64-column chunk of the staged C tile
 
 struct GemmParams {
   int M, N, K;
   int block_n, num_m_blocks, num_n_blocks, num_k_blocks;
-  int stages, acc_stride, tmem_cols, flags;
+  int stages, acc_stride, nacc, tmem_cols, flags;
+  int ngroups;    // epilogue groups in use (each owns one staging buffer); tile i of a CTA goes to group i % ngroups
+  int b_resident; // 1: the whole B operand (all k-blocks, one n-block) is loaded once per CTA and stays in shared memory
+  __nv_bfloat16* C;
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
@@ -36,32 +40,36 @@ struct GemmParams {
 };
 
 struct SmemLayout {
-  uint32_t a_off, b_off, c_off, bar_off, total;
+  uint32_t a_off, b_off, c_off, cpitch, cbuf_bytes, bar_off, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int block_n, int stages) {
+__host__ __device__ inline SmemLayout make_layout(int block_n, int stages, int ngroups, int b_slots) {
   SmemLayout L;
   uint32_t b_stage = (uint32_t)block_n * 128u;
   L.a_off = 0;
   L.b_off = L.a_off + (uint32_t)stages * A_STAGE_BYTES;
-  L.c_off = L.b_off + (uint32_t)stages * b_stage;
-  uint32_t chunks = (uint32_t)(block_n + 63) / 64;
-  L.bar_off = L.c_off + chunks * CHUNK_BYTES;
+  L.c_off = L.b_off + (uint32_t)b_slots * b_stage;      // b_slots = stages (streamed) or k-blocks (resident)
+  // staged C tile: row-major [128][block_n] bf16 with the row pitch padded to an ODD number of 16-byte granules, so the
+  // drain (32 lanes = 32 consecutive rows, same column granule) hits 8 distinct bank groups per quarter-warp
+  L.cpitch = (((uint32_t)block_n >> 3) | 1u) * 16u;
+  L.cbuf_bytes = (BM * L.cpitch + 1023u) & ~1023u;
+  if (L.cbuf_bytes < 16384u) L.cbuf_bytes = 16384u;       // also the scratch of the statistics flush
+  L.bar_off = L.c_off + (uint32_t)ngroups * L.cbuf_bytes;
   L.total = L.bar_off + 256;
   return L;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                   const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16B-aligned by the ABI: align up to 1024 for the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const SmemLayout L = make_layout(p.block_n, p.stages);
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 1024);
+  const SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;     // [nacc] accumulator complete (MMA -> epilogue group)
+  uint64_t* tempty_bar = tfull_bar + 4;             // [nacc] accumulator drained (epilogue group -> MMA)
+  uint64_t* bres_bar = tempty_bar + 4;              // resident B landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,15 +79,15 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
-    ptx::prefetch_tmap(&tmap_c);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.nacc; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], EPI_THREADS);
+      ptx::mbar_init(&tempty_bar[a], 1);      // one elected arrival per group (after the group's own barrier)
     }
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -96,14 +104,21 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_resident) {
+        // thin GEMMs are bound by the TMA unit's box-row rate (~8 cycles per <=128-byte row, measured): the weights are the
+        // same for every tile of the CTA, so their rows are fetched once instead of once per tile
+        ptx::mbar_expect_tx(bres_bar, (uint32_t)p.num_k_blocks * b_stage_bytes);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          ptx::tma_load_2d(smem + L.b_off + kb * b_stage_bytes, &tmap_b, bres_bar, kb * BK, 0);
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / p.num_n_blocks) * BM;
         const int n0 = (t % p.num_n_blocks) * p.block_n;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + b_stage_bytes);
+          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes));
           ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d(smem + L.b_off + stage * b_stage_bytes, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (!p.b_resident) ptx::tma_load_2d(smem + L.b_off + stage * b_stage_bytes, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -116,6 +131,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -124,7 +140,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + L.a_off + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem + L.b_off + stage * b_stage_bytes);
+          const uint32_t b_addr = ptx::smem_u32(smem + L.b_off + (p.b_resident ? kb : stage) * b_stage_bytes);
           const int k_rem = p.K - kb * BK;
           const int nk = k_rem >= BK ? BK / UK : (k_rem + UK - 1) / UK;
           for (int k = 0; k < nk; ++k) {
@@ -136,123 +152,144 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
-        if ((acc ^= 1) == 0) acc_phase ^= 1;
+        if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row_l = q * 32 + lane;              // row inside the 128-row tile
-    const int et = threadIdx.x - 64;              // 0..127
-    const bool leader = (et == 0);
-    uint8_t* cstage = smem + L.c_off;
-    const bool f_ss = p.flags & TRT_EPI_SCALE_SHIFT, f_silu = p.flags & TRT_EPI_SILU;
-    const bool f_res = p.flags & TRT_EPI_RESIDUAL, f_stats = p.flags & TRT_EPI_STATS;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    double st_acc[4] = {0, 0, 0, 0};
-    int st_n0 = -1;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / p.num_n_blocks) * BM;
-      const int n0 = (t % p.num_n_blocks) * p.block_n;
-      const int row = m0 + row_l;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld16(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        float v[16];
+    // ===================== epilogue: up to three independent groups of four warps =====================
+    // Group g owns the CTA's tiles g, g + G, g + 2G, ... and one staging buffer.  For its tile it (1) drains the TMEM
+    // accumulator (one warp per lane quarter, 32 columns per tcgen05.ld): epilogue math -> bf16 -> shared memory; (2) walks
+    // the staged tile 16 bytes per access: the same shared-memory read feeds a fully coalesced st.global (the tile's rows
+    // are contiguous in HBM) and the BatchNorm column sums (FHFMA on the packed bf16, kept in registers across tiles).
+    // Three tiles are in flight per SM, so one group's TMEM round trips and store issue overlap the others' (a single group,
+    // a drain/store role split and a TMA tensor store of the 288-byte-pitch rows were all measured slower: profiles/).
+    const int g = (warp - 2) >> 2;
+    if (g < p.ngroups) {
+      const int q = warp & 3;                       // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
+      const int row_l = q * 32 + lane;              // row inside the 128-row tile
+      const int gt = threadIdx.x - 64 - g * EPI_THREADS;   // 0..127 inside the group
+      const bool f_ss = p.flags & TRT_EPI_SCALE_SHIFT, f_silu = p.flags & TRT_EPI_SILU;
+      const bool f_res = p.flags & TRT_EPI_RESIDUAL, f_stats = p.flags & TRT_EPI_STATS;
+      const uint32_t cpitch = L.cpitch;
+      uint8_t* cstage = smem + L.c_off + g * L.cbuf_bytes;
+      const int n_oct = p.block_n >> 3;             // 8-column octets per tile row
+      const int rg_count = EPI_THREADS / n_oct;     // row groups of the store pass
+      const int so = gt % n_oct, srg = gt / n_oct;  // this thread's octet / row group
+      const bool s_active = srg < rg_count;
+      const int bar_id = 1 + g;
+      float st_s[8], st_q[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        const int col = n0 + c0;
-        if (f_ss) {
+      for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+      int st_n0 = -1;
+      auto flush_stats = [&]() {
+        // the group's staging buffer (free between tiles) holds partial[rg][block_n] for sum and sum^2
+        float* ps = reinterpret_cast<float*>(cstage);
+        float* pq = ps + rg_count * p.block_n;
+        if (s_active) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (col + h * 8 < p.N) {
-              f8 sc = ldf8(p.scale + col + h * 8), sh = ldf8(p.shift + col + h * 8);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[h * 8 + i] = fmaf(v[h * 8 + i], sc.v[i], sh.v[i]);
-            }
+          for (int i = 0; i < 8; ++i) {
+            ps[srg * p.block_n + so * 8 + i] = st_s[i];
+            pq[srg * p.block_n + so * 8 + i] = st_q[i];
           }
         }
-        if (f_silu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = siluf_(v[i]);
+        ptx::named_bar_sync(bar_id, EPI_THREADS);
+        for (int c = gt; c < 2 * p.block_n; c += EPI_THREADS) {
+          const int k = c >= p.block_n, cc = c - k * p.block_n;
+          const float* src = k ? pq : ps;
+          float tot = 0.f;
+          for (int r = 0; r < rg_count; ++r) tot += src[r * p.block_n + cc];
+          if (st_n0 + cc < p.N) atomicAdd(p.stats + (size_t)k * p.N + st_n0 + cc, (double)tot);
         }
-        if (f_res && row < p.M) {
+        ptx::named_bar_sync(bar_id, EPI_THREADS);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (col + h * 8 < p.N) {
-              f8 rr = unpack8(ldg16(p.residual + (size_t)row * p.N + col + h * 8));
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[h * 8 + i] += rr.v[i];
-            }
-          }
-        }
-        uint8_t* crow = cstage + (c0 >> 6) * CHUNK_BYTES + row_l * 128;
-        const int piece = (c0 & 63) >> 3;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 o;
-          o.x = pack_bf16(v[h * 8 + 0], v[h * 8 + 1]);
-          o.y = pack_bf16(v[h * 8 + 2], v[h * 8 + 3]);
-          o.z = pack_bf16(v[h * 8 + 4], v[h * 8 + 5]);
-          o.w = pack_bf16(v[h * 8 + 6], v[h * 8 + 7]);
-          *reinterpret_cast<uint4*>(crow + (((piece + h) ^ (row_l & 7)) << 4)) = o;
-        }
-      }
-      // TMEM accumulator drained: hand it back to the MMA warp before the stores
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
-
-      ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, EPI_THREADS);
-      if (leader) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 64)
-          ptx::tma_store_2d(&tmap_c, cstage + (c0 >> 6) * CHUNK_BYTES, n0 + c0, m0);
-        ptx::tma_store_commit();
-      }
-      if (f_stats) {
-        // thread et owns columns (2et, 2et+1) of the tile; sums run over the bf16-rounded values that were stored
-        if (st_n0 != n0) {
-          if (st_n0 >= 0) {
-            const int c = st_n0 + 2 * et;
-            if (2 * et < p.block_n && c < p.N) {
-              atomicAdd(p.stats + c, st_acc[0]); atomicAdd(p.stats + c + 1, st_acc[1]);
-              atomicAdd(p.stats + p.N + c, st_acc[2]); atomicAdd(p.stats + p.N + c + 1, st_acc[3]);
-            }
-          }
-          st_acc[0] = st_acc[1] = st_acc[2] = st_acc[3] = 0;
+        for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+      };
+      int seq = g;                                  // index of the tile in this CTA's sequence
+      for (int t = blockIdx.x + g * gridDim.x; t < num_tiles; t += p.ngroups * gridDim.x, seq += p.ngroups) {
+        const int m0 = (t / p.num_n_blocks) * BM;
+        const int n0 = (t % p.num_n_blocks) * p.block_n;
+        const int row = m0 + row_l;
+        const int acc = seq % p.nacc;
+        const uint32_t acc_par = (uint32_t)(seq / p.nacc) & 1u;
+        if (f_stats && st_n0 != n0) {
+          if (st_n0 >= 0) flush_stats();
           st_n0 = n0;
         }
-        if (2 * et < p.block_n) {
-          const int cc = 2 * et;
-          const uint8_t* cb = cstage + (cc >> 6) * CHUNK_BYTES;
-          const int piece = (cc & 63) >> 3, within = (cc & 7) * 2;
-          float s0 = 0, s1 = 0, q0 = 0, q1 = 0;
-#pragma unroll 8
-          for (int rr = 0; rr < BM; ++rr) {
-            uint32_t w = *reinterpret_cast<const uint32_t*>(cb + rr * 128 + ((piece ^ (rr & 7)) << 4) + within);
-            float a = bf16_lo(w), b = bf16_hi(w);
-            s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+        ptx::mbar_wait_sleep(&tfull_bar[acc], acc_par, 32);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t r[32];
+          const bool full = c0 + 32 <= p.block_n;    // the tile may end on a 16-column boundary
+          if (full) ptx::tmem_ld32(taddr + c0, r);
+          else ptx::tmem_ld16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int o8 = 0; o8 < 4; ++o8) {
+            if (o8 >= 2 && !full) break;
+            const int col = n0 + c0 + o8 * 8;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[o8 * 8 + i]);
+            if (f_ss && col < p.N) {
+              const f8 sc = ldf8(p.scale + col), sh = ldf8(p.shift + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc.v[i], sh.v[i]);
+            }
+            if (f_silu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = siluf_(v[i]);
+            }
+            if (f_res && row < p.M && col < p.N) {
+              const f8 rr = unpack8(ldg16(p.residual + (size_t)row * p.N + col));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += rr.v[i];
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(cstage + row_l * cpitch + ((c0 >> 3) + o8) * 16) = o;
           }
-          st_acc[0] += s0; st_acc[1] += s1; st_acc[2] += q0; st_acc[3] += q1;
         }
+        ptx::tc_fence_before();
+        ptx::named_bar_sync(bar_id, EPI_THREADS);            // accumulator drained + tile staged, by all four warps
+        if (gt == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        if (s_active && n0 + so * 8 < p.N) {
+          // store + statistics over the bf16-rounded values (rows past M are exact zeros: zero-filled A rows)
+          const uint8_t* cbase = cstage + so * 16;
+          __nv_bfloat16* gbase = p.C + (size_t)m0 * p.N + n0 + so * 8;
+          const int rows_here = min(BM, p.M - m0);
+          const uint32_t one2 = 0x3f803f80u;                  // bf16x2 {1, 1}
+          for (int r0 = srg; r0 < rows_here; r0 += 4 * rg_count) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (r0 + u * rg_count < rows_here) w[u] = *reinterpret_cast<const uint4*>(cbase + (r0 + u * rg_count) * cpitch);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (r0 + u * rg_count < rows_here) *reinterpret_cast<uint4*>(gbase + (size_t)(r0 + u * rg_count) * p.N) = w[u];
+            if (f_stats) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (r0 + u * rg_count < rows_here) {
+                  const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint16_t lo = (uint16_t)(ws[i] & 0xffffu), hi = (uint16_t)(ws[i] >> 16);
+                    st_s[2 * i] = ptx::fhfma(lo, (uint16_t)(one2 & 0xffffu), st_s[2 * i]);
+                    st_s[2 * i + 1] = ptx::fhfma(hi, (uint16_t)(one2 >> 16), st_s[2 * i + 1]);
+                    st_q[2 * i] = ptx::fhfma(lo, lo, st_q[2 * i]);
+                    st_q[2 * i + 1] = ptx::fhfma(hi, hi, st_q[2 * i + 1]);
+                  }
+                }
+              }
+            }
+          }
+        }
+        ptx::named_bar_sync(bar_id, EPI_THREADS);            // staging buffer free for the group's next tile
       }
-      if (leader) ptx::tma_store_wait_read0();
-      ptx::named_bar_sync(1, EPI_THREADS);   // staging buffer free again
+      if (f_stats && st_n0 >= 0) flush_stats();
     }
-    if (f_stats && st_n0 >= 0) {
-      const int c = st_n0 + 2 * et;
-      if (2 * et < p.block_n && c < p.N) {
-        atomicAdd(p.stats + c, st_acc[0]); atomicAdd(p.stats + c + 1, st_acc[1]);
-        atomicAdd(p.stats + p.N + c, st_acc[2]); atomicAdd(p.stats + p.N + c + 1, st_acc[3]);
-      }
-    }
-    if (leader) ptx::tma_store_wait0();
   }
 
   ptx::tc_fence_before();
@@ -273,11 +310,11 @@ struct WgradParams {
   uint32_t lbo, sbo, kstep_bytes;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q,
                   const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 1024);
   const int q_chunks = (p.block_q + 63) / 64;
   const uint32_t p_stage = 2 * 8192, q_stage = (uint32_t)q_chunks * 8192;
   uint8_t* sp = smem;
@@ -396,6 +433,31 @@ int pick_block_n(int N) {
   return best;
 }
 
+// Forward/dgrad tile width.  These GEMMs are bound by the TMA unit's box-row rate (one <=128-byte row per ~6-8 cycles,
+// measured), so the model counts box rows on the busiest CTA: waves x k-blocks x (128 A rows + block_n B rows); a single
+// n-block whose weights fit in shared memory loads them once per CTA instead (b_resident).
+int pick_block_n_fwd(int M, int N, int K) {
+  const int mb = (M + BM - 1) / BM, kb = (K + BK - 1) / BK, sms = trt_num_sms();
+  int cand[5], nc = 0;
+  if (N <= 256) cand[nc++] = (N + 15) / 16 * 16;
+  const int tiled[3] = {192, 128, 64};
+  for (int i = 0; i < 3; ++i)
+    if (tiled[i] < N) cand[nc++] = tiled[i];
+  int best = cand[0];
+  double best_cost = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cand[i], nb = (N + bn - 1) / bn;
+    const long long tiles = (long long)mb * nb;
+    const long long waves = (tiles + sms - 1) / sms;
+    const bool resident = nb == 1 && kb * bn * 128 <= 64 * 1024;
+    double rows = (double)waves * kb * (128 + (resident ? 0 : bn)) + (resident ? (double)kb * bn : 0.0);
+    rows += 600.0 * waves * (bn <= 160 ? 1.0 : 1.5);         // per-tile epilogue (three groups fit up to ~160 columns)
+    rows *= 1.0 + 0.15 * ((double)(nb * bn - N) / N);        // padded columns are wasted MMA + epilogue work
+    if (rows < best_cost) { best_cost = rows; best = bn; }
+  }
+  return best;
+}
+
 bool g_attr_set = false;
 }  // namespace
 
@@ -409,33 +471,48 @@ extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N
   TRT_REQUIRE(!(flags & TRT_EPI_STATS) || stats, "trt_gemm_bf16: stats missing");
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.block_n = block_n_override > 0 ? block_n_override : pick_block_n(N);
+  p.block_n = block_n_override > 0 ? block_n_override : pick_block_n_fwd(M, N, K);
   TRT_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "trt_gemm_bf16: bad block_n %d", p.block_n);
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
   TRT_REQUIRE(p.num_n_blocks == 1 || p.block_n % 64 == 0, "trt_gemm_bf16: tiled N needs block_n %% 64 == 0");
   p.num_k_blocks = (K + BK - 1) / BK;
-  p.tmem_cols = pow2_cols(2 * p.block_n);
-  p.acc_stride = p.tmem_cols / 2;
+  p.acc_stride = (p.block_n + 31) & ~31;
+  p.nacc = 512 / p.acc_stride < 3 ? 512 / p.acc_stride : 3;
+  p.tmem_cols = pow2_cols(p.nacc * p.acc_stride);
   p.flags = flags;
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.stats = stats;
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
-  const int chunks = (p.block_n + 63) / 64;
-  const int budget = 220 * 1024 - chunks * CHUNK_BYTES - 2048;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  const int b_stage = p.block_n * 128;
+  p.b_resident = (p.num_n_blocks == 1 && p.num_k_blocks * b_stage <= 64 * 1024) ? 1 : 0;
+  const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage);
+  const int fixed_bytes = (p.b_resident ? p.num_k_blocks * b_stage : 0) + 2048;
+  const int cbuf_bytes = (int)make_layout(p.block_n, 2, 1, 2).cbuf_bytes;
+  // as many epilogue groups (one staging buffer each) as fit beside min(k-blocks + 1, 4) pipeline stages
+  const int want_stages = p.num_k_blocks + 1 < 3 ? p.num_k_blocks + 1 : 3;
+  // Several groups must each be the ONLY consumer of "their" accumulator barrier (mbarrier parity waits alias if a waiter can
+  // fall two phases behind), so with G > 1 groups the accumulators are G as well: tile i -> group i % G -> accumulator i % G.
+  const int max_acc = 512 / p.acc_stride;
+  p.ngroups = 1;
+  for (int gq = MAX_GROUPS < max_acc ? MAX_GROUPS : max_acc; gq >= 1; --gq)
+    if ((220 * 1024 - gq * cbuf_bytes - fixed_bytes) / stage_bytes >= (gq == 1 ? 2 : want_stages)) { p.ngroups = gq; break; }
+  p.nacc = p.ngroups > 1 ? p.ngroups : (max_acc >= 2 ? 2 : 1);
+  p.tmem_cols = pow2_cols(p.nacc * p.acc_stride);
+  const int budget = 220 * 1024 - p.ngroups * cbuf_bytes - fixed_bytes;
   int stages = budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  SmemLayout L = make_layout(p.block_n, p.stages);
+  SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages);
   size_t smem_bytes = (size_t)L.total + 1024;      // slack for the manual 1024B alignment
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // > half an SM's smem: exactly one persistent CTA per SM
-  CUtensorMap ta, tb, tc;
+  CUtensorMap ta, tb;
   int rc;
   if ((rc = trt_make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
   if ((rc = trt_make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)p.block_n, BK))) return rc;
-  if ((rc = trt_make_tmap_2d(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64))) return rc;
+  TRT_REQUIRE((((uintptr_t)C) & 15) == 0, "trt_gemm_bf16: C must be 16-byte aligned");
   if (!g_attr_set) {
     TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -443,9 +520,17 @@ extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
-  gemm_kmajor_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, tc, p);
+  gemm_kmajor_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
   return trt_check_launch("trt_gemm_bf16");
 }
+
+#ifdef TRT_GEMM_TIMING
+extern "C" int trt_debug_gemm_timing(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_gemm_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int M, int Cp, int Cq, long long so_p,
                                    long long so_q, int q_store, int lbo, int sbo, int kstep_bytes, cudaStream_t stream) {
@@ -488,6 +573,6 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
     TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
-  gemm_wgrad_kernel<<<tiles * p.splits, GEMM_THREADS, smem_bytes, stream>>>(tp, tq, p);
+  gemm_wgrad_kernel<<<tiles * p.splits, WGRAD_THREADS, smem_bytes, stream>>>(tp, tq, p);
   return trt_check_launch("trt_gemm_wgrad_bf16");
 }
