@@ -19,6 +19,9 @@ constexpr int TPB = 256;
 constexpr int CL = 8;     // channel lanes per block (8 lanes x 8 channels = 64 channels)
 constexpr int NPT = TPB / CL;   // 32 pixel-threads per channel lane
 constexpr int TOH = 8;    // output tile height
+#ifndef DW_MINB
+#define DW_MINB 2         // resident blocks per SM the persistent kernels are compiled for (register cap 65536 / (256 * DW_MINB))
+#endif
 constexpr int PX_BYTES = CL * 16;   // one pixel of a 64-channel tile
 
 struct DwGeom {
@@ -63,24 +66,6 @@ __device__ __forceinline__ float reduce_over_pt(float (&acc)[NV][8], float* s_re
     for (int q = 0; q < NPT; ++q) total += s_red[(k * NPT + q) * 64 + c];
   }
   return total;
-}
-
-// gradient tile for the generic-stride data-gradient kernel (plain loads, zero outside [0,OH)x[0,OW))
-template <int TH, int TW>
-__device__ __forceinline__ void load_grad_tile(uint4* s_tile, const uint4* __restrict__ gy_, int n, int OH, int OW, int V,
-                                               int oy0, int ox0, int cv, bool cvalid, int lane, int pt) {
-  constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT;
-#pragma unroll
-  for (int j = 0; j < NL; ++j) {
-    const int i = pt + NPT * j;
-    const int dy = i / TW, dx = i - dy * TW;
-    const int oy = oy0 + dy, ox = ox0 + dx;
-    if (i < NPIX) {
-      uint4 v = zero4();
-      if (cvalid && oy >= 0 && oy < OH && ox >= 0 && ox < OW) v = __ldg(gy_ + ((size_t)(n * OH + oy) * OW + ox) * V + cv);
-      s_tile[i * CL + lane] = v;
-    }
-  }
 }
 
 // weights of the block's 64 channels -> shared bf16 [K*K][64] (one uint4 per tap and channel lane); flip = rotate the
@@ -154,7 +139,7 @@ __device__ __forceinline__ Item decode_item(int it, int tiles, const DwGeom& g) 
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int K, int S, int P>
-__global__ void __launch_bounds__(TPB, 2) dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ in_rec,
+__global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ in_rec,
                                                             const float* __restrict__ w, uint4* __restrict__ out,
                                                             const float* __restrict__ out_rec, float* __restrict__ pooled,
                                                             double* __restrict__ stats, const DwGeom g) {
@@ -286,7 +271,7 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
 // stride 1 + symmetric 'same' padding: dIn = conv(dD, rot180(w)) with the same padding -> the forward machinery.
 // Per item two TMA tiles: dD with halo, and (when the input carried a BatchNorm+SiLU) the raw input tile for silu'.
 template <int K, int P>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const __grid_constant__ CUtensorMap tm_d,
+__global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const __grid_constant__ CUtensorMap tm_d,
                                                                     const __grid_constant__ CUtensorMap tm_x,
                                                                     const float* __restrict__ w, const float* __restrict__ x_rec,
                                                                     uint4* __restrict__ g_out, double* __restrict__ bstats,
@@ -358,58 +343,69 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s1_kernel(const __grid
   }
 }
 
-// ------------------------------------------------------------------------------------------------ backward data, generic stride
+// ------------------------------------------------------------------------------------------------ backward data, stride 2
+// Parity decomposition: an input pixel (iy, ix) only sees the taps kh = (iy+pad_t) mod 2 + 2a, kw = (ix+pad_l) mod 2 + 2b, and
+// dIn[iy,ix] = sum_{a,b} dD[(iy+pad_t-kh)/2, (ix+pad_l-kw)/2] * w[kh,kw]: each of the four parity classes is a small
+// stride-1 correlation over dD, so a thread that owns 8 same-parity pixels of one row slides its sub-filter over one packed
+// row of dD.  A warp is one parity class (no divergence); tile = 16x16 input pixels, dD tile + raw input tile via TMA.
+template <int K> struct S2Tile {
+  static constexpr int TI = 16;                                   // input tile (rows and columns)
+  static constexpr int DH = TI / 2 + (K - 1) / 2 + 1, DW = DH;    // dD rows/cols that can touch the tile
+  static constexpr int D_BYTES = DH * DW * PX_BYTES, X_BYTES = TI * TI * PX_BYTES, STAGE = D_BYTES + X_BYTES;
+};
+
+template <int K, int PY, int PX>
+__device__ __forceinline__ void s2_class_rows(const uint4* s_d, const uint4* s_w, int dy, int dx, int lane, float (&acc)[8][8]) {
+  // taps of this class: kh = PY + 2a (a < NA), kw = PX + 2b (b < NB); dD row = dy - a, dD col = dx - b + p
+  constexpr int NA = (K - PY + 1) / 2, NB = (K - PX + 1) / 2, DW = S2Tile<K>::DW;
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    uint4 row[8 + NB - 1];
+#pragma unroll
+    for (int j = 0; j < 8 + NB - 1; ++j) row[j] = s_d[((dy - a) * DW + dx - (NB - 1) + j) * CL + lane];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint4 wv = s_w[((PY + 2 * a) * K + PX + 2 * b) * CL + lane];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) fma8(acc[p], row[p + (NB - 1) - b], wv);
+    }
+  }
+}
+
 template <int K>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __restrict__ gy_, const float* __restrict__ w,
-                                                                 const uint4* __restrict__ x_raw, const float* __restrict__ x_rec,
-                                                                 uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                 const DwGeom g) {
-  constexpr int TIW = 16, P = 4;
-  constexpr int DH = (TOH + K - 2) / 2 + 2, DW = (TIW + K - 2) / 2 + 2;      // stride 2
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint4* s_d = reinterpret_cast<uint4*>(smem);
-  uint4* s_w = reinterpret_cast<uint4*>(smem + (size_t)DH * DW * CL * 16);
-  float* s_red = reinterpret_cast<float*>(smem);
-  const int V = g.C / 8, S = g.S;
-  const int tile = blockIdx.x, cb = blockIdx.y, n = blockIdx.z;
-  const int iy0 = (tile / g.tiles_x) * TOH, ix0 = (tile % g.tiles_x) * TIW;
+__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid_constant__ CUtensorMap tm_d,
+                                                                    const __grid_constant__ CUtensorMap tm_x,
+                                                                    const float* __restrict__ w, const float* __restrict__ x_rec,
+                                                                    uint4* __restrict__ g_out, double* __restrict__ bstats,
+                                                                    const DwGeom g) {
+  using T = S2Tile<K>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
+  uint4* s_w = reinterpret_cast<uint4*>(smem + 2 * T::STAGE);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * T::STAGE + K * K * PX_BYTES);
+  const int V = g.C / 8, cb = blockIdx.y;
   const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
   const int cv = cb * CL + lane;
   const bool cvalid = cv < V;
-  const int ny = iy0 + g.pad_t - (K - 1), nx = ix0 + g.pad_l - (K - 1);
-  const int oyb = ny <= 0 ? 0 : (ny + S - 1) / S, oxb0 = nx <= 0 ? 0 : (nx + S - 1) / S;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tm_d);
+    ptx::prefetch_tmap(&tm_x);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
   load_weights<K>(s_w, w, cb, g.C, false);
-  const int iy = iy0 + pt / 4, ixb = ix0 + (pt % 4) * P;
-  uint4 xr4[P];
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    xr4[p] = zero4();
-    if (x_rec && cvalid && iy < g.H && ixb + p < g.W) xr4[p] = __ldg(x_raw + ((size_t)(n * g.H + iy) * g.W + ixb + p) * V + cv);
-  }
-  load_grad_tile<DH, DW>(s_d, gy_, n, g.OH, g.OW, V, oyb, oxb0, cv, cvalid, lane, pt);
   __syncthreads();
-  float acc[P][8];
-#pragma unroll
-  for (int p = 0; p < P; ++p)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
-  for (int kh = 0; kh < K; ++kh) {
-    const int ty = iy + g.pad_t - kh;
-    if (ty < 0 || (ty % S) != 0) continue;
-    const int oy = ty / S;
-    if (oy >= g.OH) continue;
-    for (int kw = 0; kw < K; ++kw) {
-      const uint4 wv = s_w[(kh * K + kw) * CL + lane];
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const int tx = ixb + p + g.pad_l - kw;
-        if (tx < 0 || (tx % S) != 0) continue;
-        const int ox = tx / S;
-        if (ox >= g.OW) continue;
-        fma8(acc[p], s_d[((oy - oyb) * DW + (ox - oxb0)) * CL + lane], wv);
-      }
-    }
-  }
+  const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
+  // first dD row/col a tile can touch: floor((i0 + pad - (K-1)) / 2); i0 is a multiple of 16 and pad <= K-1, so the
+  // numerator is >= -(K-1) and the floor is taken on a shifted non-negative value
+  auto d_origin = [&](int i0, int pad) { return (i0 + pad - (K - 1) + 16) / 2 - 8; };
+  auto issue = [&](int it, int st) {
+    const Item q = decode_item(it, tiles, g);
+    ptx::mbar_expect_tx(&bar[st], x_rec ? T::STAGE : T::D_BYTES);
+    ptx::tma_load_4d(smem + st * T::STAGE, &tm_d, &bar[st], cb * 64, d_origin(q.tx * T::TI, g.pad_l), d_origin(q.ty * T::TI, g.pad_t), q.n);
+    if (x_rec) ptx::tma_load_4d(smem + st * T::STAGE + T::D_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TI, q.ty * T::TI, q.n);
+  };
   f8 sc, sh, mu, rs;
   if (x_rec && cvalid) {
     sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
@@ -418,9 +414,68 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
   float red[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
-  bwd_data_epilogue<P>(acc, xr4, x_rec, g_out, red, sc, sh, mu, rs, g, n, iy, ixb, cv, cvalid, V);
+  // warp -> parity class (py, px) of (iy + pad_t, ix + pad_l); the warp's 4 pixel-threads and its twin warp cover 8 rows
+  const int warp = threadIdx.x >> 5;
+  const int py = (warp >> 1) & 1, px = warp & 1;
+  const int u = (warp >> 2) * 4 + (pt & 3);                       // 0..7: which row of parity py
+  const int ry = (py + g.pad_t) & 1, rx = (px + g.pad_l) & 1;     // tile-local offset of the class's first row / column
+  const int r = 2 * u + ry;                                       // tile-local input row; the thread's columns are rx + 2p
+  int it = blockIdx.x, st = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0 && it < items) issue(it, 0);
+  for (; it < items; it += G, st ^= 1) {
+    const Item q = decode_item(it, tiles, g);
+    if (threadIdx.x == 0 && it + G < items) issue(it + G, st ^ 1);
+    const uint4* s_d = reinterpret_cast<const uint4*>(smem + st * T::STAGE);
+    const uint4* s_x = reinterpret_cast<const uint4*>(smem + st * T::STAGE + T::D_BYTES);
+    ptx::mbar_wait(&bar[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    const int iy0 = q.ty * T::TI, ix0 = q.tx * T::TI;
+    // dD coordinates (tile-local) of tap (a = 0, b = 0) for this thread's first pixel
+    const int dy = (iy0 + r + g.pad_t - py) / 2 - d_origin(iy0, g.pad_t);
+    const int dx = (ix0 + rx + g.pad_l - px) / 2 - d_origin(ix0, g.pad_l);
+    float acc[8][8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
+    if (py == 0) {
+      if (px == 0) s2_class_rows<K, 0, 0>(s_d, s_w, dy, dx, lane, acc);
+      else s2_class_rows<K, 0, 1>(s_d, s_w, dy, dx, lane, acc);
+    } else {
+      if (px == 0) s2_class_rows<K, 1, 0>(s_d, s_w, dy, dx, lane, acc);
+      else s2_class_rows<K, 1, 1>(s_d, s_w, dy, dx, lane, acc);
+    }
+    const int iy = iy0 + r;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int ix = ix0 + rx + 2 * p;
+      if (cvalid && iy < g.H && ix < g.W) {
+        const size_t idx = ((size_t)(q.n * g.H + iy) * g.W + ix) * V + cv;
+        f8 o;
+        if (x_rec) {
+          const f8 xr = unpack8(s_x[(r * T::TI + rx + 2 * p) * CL + lane]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i] * silu_gradf_(fmaf(xr.v[i], sc.v[i], sh.v[i]));
+          const uint4 qv = pack8(o);
+          g_out[idx] = qv;
+          const f8 rr = unpack8(qv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            red[0][i] += rr.v[i];
+            red[1][i] = fmaf(rr.v[i], (xr.v[i] - mu.v[i]) * rs.v[i], red[1][i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i];
+          g_out[idx] = pack8(o);
+        }
+      }
+    }
+    __syncthreads();
+  }
   if (x_rec && bstats) {
-    const float total = reduce_over_pt<2>(red, s_red, lane, pt);
+    const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
@@ -433,7 +488,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_kernel(const uint4* __
 // thread = (channel lane, filter row kh, output-row subset); the filter row slides over an input row kept in registers.
 // The gradient does not depend on the tile position, so the accumulators live in registers across ALL the block's items.
 template <int K, int S>
-__global__ void __launch_bounds__(TPB, 2) dwconv_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x,
+__global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                    const __grid_constant__ CUtensorMap tm_d,
                                                                    const float* __restrict__ in_rec, float* __restrict__ dw,
                                                                    const DwGeom g) {
@@ -642,19 +697,22 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
 #undef LAUNCH_BD_S1
     } else {
       g.tiles_x = (W + 15) / 16;
-      g.tiles_y = (H + TOH - 1) / TOH;
-      g.magic_tiles = g.magic_tx = 0;
-      dim3 grid(g.tiles_x * g.tiles_y, cblocks, N);
-      const size_t red_bytes = 2 * NPT * 64 * 4;
-#define LAUNCH_BD(KK)                                                                                              \
+      g.tiles_y = (H + 15) / 16;
+      set_magic(g);
+      const int items = N * g.tiles_x * g.tiles_y;
+#define LAUNCH_BD_S2(KK)                                                                                           \
   do {                                                                                                             \
-    const int DH = (TOH + KK - 2) / 2 + 2, DW = (16 + KK - 2) / 2 + 2;                                             \
-    size_t smem = (size_t)DH * DW * CL * 16 + (size_t)KK * KK * CL * 16;                                           \
-    if (smem < red_bytes) smem = red_bytes;                                                                        \
-    dwconv_bwd_data_kernel<KK><<<grid, TPB, smem, stream>>>((const uint4*)gy, w, (const uint4*)x_raw, x_rec, (uint4*)g_out, bstats, g); \
+    using T = S2Tile<KK>;                                                                                          \
+    const size_t smem = 2 * T::STAGE + KK * KK * PX_BYTES + 16 + 128;                                              \
+    CUtensorMap td, tx;                                                                                            \
+    if ((rc = trt_make_tmap_nhwc(&td, gy, N, g.OH, g.OW, C, 64, T::DW, T::DH))) return rc;                         \
+    if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TI, T::TI))) return rc;                            \
+    int G;                                                                                                         \
+    if ((rc = persistent_blocks(dwconv_bwd_data_s2_kernel<KK>, smem, cblocks, items, &G))) return rc;              \
+    dwconv_bwd_data_s2_kernel<KK><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)
-      if (k == 3) LAUNCH_BD(3); else LAUNCH_BD(5);
-#undef LAUNCH_BD
+      if (k == 3) LAUNCH_BD_S2(3); else LAUNCH_BD_S2(5);
+#undef LAUNCH_BD_S2
     }
     rc = trt_check_launch("trt_dwconv_bwd(data)");
     if (rc) return rc;

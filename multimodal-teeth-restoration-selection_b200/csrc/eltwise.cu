@@ -480,6 +480,181 @@ __global__ void __launch_bounds__(TPB) se_bwd_w_kernel(const float* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ SE MLP backward, fused
+// Two launches, each a grid over 16-channel chunks with 4x4 register tiles (the old three kernels were latency-bound chains
+// of dependent L2 loads, ~37 us per block for ~20 MFLOP):
+//   K1  ds2 = dgate_pre*g*(1-g);  dWe[c,r] = sum_n ds2[n,c]*silu(s1[n,r]);  dbe[c];  ds1_acc[n,r] += sum_{c in chunk} ds2[n,c]*We[c,r]
+//   K2  ds1 = silu'(s1)*ds1_acc;  dmean[n,c] = sum_r ds1[n,r]*Wr[r,c];  dWr[r,c] = inv_hw*sum_n ds1[n,r]*pooled[n,c];  dbr[r]
+constexpr int SEB_CC = 16;     // channels per block (small chunks: the launch is latency-bound, so spread it over all SMs)
+constexpr int SEB_NT = 64;     // images per pass
+constexpr int SEB_RD = 128;    // max rd handled by the fused kernels
+
+__global__ void __launch_bounds__(TPB) se_bwd_k1_kernel(const float* __restrict__ dgate_pre, const float* __restrict__ gate,
+                                                        const float* __restrict__ s1, const float* __restrict__ We,
+                                                        float* __restrict__ ds2_out, float* __restrict__ ds1_acc,
+                                                        float* __restrict__ dWe, float* __restrict__ dbe, int N, int C, int rd) {
+  extern __shared__ __align__(16) float s_mem[];
+  const int rdp = (rd + 3) & ~3;
+  float* s_a1 = s_mem;                         // [SEB_NT][rdp]  silu(s1)
+  float* s_d2 = s_a1 + SEB_NT * rdp;           // [SEB_NT][SEB_CC]
+  float* s_we = s_d2 + SEB_NT * SEB_CC;        // [SEB_CC][rdp]
+  const int c0 = blockIdx.x * SEB_CC, t = threadIdx.x;
+  for (int i = t; i < SEB_CC * rdp; i += TPB) {
+    const int cl = i / rdp, r = i - cl * rdp;
+    s_we[i] = (c0 + cl < C && r < rd) ? __ldg(We + (size_t)(c0 + cl) * rd + r) : 0.f;
+  }
+  const int rgroups = rdp >> 2;
+  // dWe tile: thread = (4 channels, 4 r)
+  const int wc = (t % (SEB_CC / 4)) * 4, wr = (t / (SEB_CC / 4)) * 4;
+  const bool w_active = t / (SEB_CC / 4) < rgroups;
+  float acc_w[4][4] = {};
+  float acc_b = 0.f;                            // dbe: threads 0..31
+  for (int n0 = 0; n0 < N; n0 += SEB_NT) {
+    const int nn = min(SEB_NT, N - n0);
+    __syncthreads();
+    for (int i = t; i < SEB_NT * rdp; i += TPB) {
+      const int n = i / rdp, r = i - n * rdp;
+      s_a1[i] = (n < nn && r < rd) ? siluf_(__ldg(s1 + (size_t)(n0 + n) * rd + r)) : 0.f;
+    }
+    for (int i = t; i < SEB_NT * SEB_CC; i += TPB) {
+      const int n = i / SEB_CC, cl = i % SEB_CC;
+      float d = 0.f;
+      if (n < nn && c0 + cl < C) {
+        const size_t idx = (size_t)(n0 + n) * C + c0 + cl;
+        const float g = __ldg(gate + idx);
+        d = __ldg(dgate_pre + idx) * g * (1.f - g);
+        ds2_out[idx] = d;
+      }
+      s_d2[i] = d;
+    }
+    __syncthreads();
+    if (w_active) {
+#pragma unroll 4
+      for (int n = 0; n < SEB_NT; ++n) {
+        const float4 d = *reinterpret_cast<const float4*>(s_d2 + n * SEB_CC + wc);
+        const float4 a = *reinterpret_cast<const float4*>(s_a1 + n * rdp + wr);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc_w[i][j] = fmaf(dv[i], av[j], acc_w[i][j]);
+      }
+    }
+    if (t < SEB_CC)
+      for (int n = 0; n < SEB_NT; ++n) acc_b += s_d2[n * SEB_CC + t];
+    // ds1 partial: item = (4 images, 4 r); sum over the chunk's channels
+    for (int item = t; item < (SEB_NT / 4) * rgroups; item += TPB) {
+      const int nb = (item % (SEB_NT / 4)) * 4, rb = (item / (SEB_NT / 4)) * 4;
+      float acc[4][4] = {};
+#pragma unroll 4
+      for (int cl = 0; cl < SEB_CC; ++cl) {
+        const float4 w = *reinterpret_cast<const float4*>(s_we + cl * rdp + rb);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = s_d2[(nb + i) * SEB_CC + cl];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(d, wv[j], acc[i][j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + i < nn && rb + j < rd) atomicAdd(ds1_acc + (size_t)(n0 + nb + i) * rd + rb + j, acc[i][j]);
+    }
+  }
+  if (w_active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + wc + i < C && wr + j < rd) dWe[(size_t)(c0 + wc + i) * rd + wr + j] = acc_w[i][j];
+  }
+  if (t < SEB_CC && c0 + t < C) dbe[c0 + t] = acc_b;
+}
+
+__global__ void __launch_bounds__(TPB) se_bwd_k2_kernel(const float* __restrict__ ds1_acc, const float* __restrict__ s1,
+                                                        const float* __restrict__ pooled, float inv_hw,
+                                                        const float* __restrict__ Wr, float* __restrict__ dmean, float* __restrict__ dWr,
+                                                        float* __restrict__ dbr, int N, int C, int rd) {
+  extern __shared__ __align__(16) float s_mem[];
+  const int rdp = (rd + 3) & ~3;
+  float* s_d1 = s_mem;                         // [SEB_NT][rdp]
+  float* s_wr = s_d1 + SEB_NT * rdp;           // [rdp][SEB_CC]
+  float* s_po = s_wr + rdp * SEB_CC;           // [SEB_NT][SEB_CC]
+  const int c0 = blockIdx.x * SEB_CC, t = threadIdx.x;
+  for (int i = t; i < rdp * SEB_CC; i += TPB) {
+    const int r = i / SEB_CC, cl = i % SEB_CC;
+    s_wr[i] = (r < rd && c0 + cl < C) ? __ldg(Wr + (size_t)r * C + c0 + cl) : 0.f;
+  }
+  const int rgroups = rdp >> 2;
+  const int wc = (t % (SEB_CC / 4)) * 4, wr = (t / (SEB_CC / 4)) * 4;      // dWr tile: (4 r, 4 channels)
+  const bool w_active = t / (SEB_CC / 4) < rgroups;
+  float acc_w[4][4] = {};
+  float acc_b = 0.f;                            // dbr: block 0, threads 0..rd-1
+  for (int n0 = 0; n0 < N; n0 += SEB_NT) {
+    const int nn = min(SEB_NT, N - n0);
+    __syncthreads();
+    for (int i = t; i < SEB_NT * rdp; i += TPB) {
+      const int n = i / rdp, r = i - n * rdp;
+      float d = 0.f;
+      if (n < nn && r < rd) {
+        const size_t idx = (size_t)(n0 + n) * rd + r;
+        d = __ldg(ds1_acc + idx) * silu_gradf_(__ldg(s1 + idx));
+      }
+      s_d1[i] = d;
+    }
+    for (int i = t; i < SEB_NT * SEB_CC; i += TPB) {
+      const int n = i / SEB_CC, cl = i % SEB_CC;
+      s_po[i] = (n < nn && c0 + cl < C) ? __ldg(pooled + (size_t)(n0 + n) * C + c0 + cl) * inv_hw : 0.f;
+    }
+    __syncthreads();
+    // dmean: thread = (2 images, 4 channels)
+    if ((t / (SEB_CC / 4)) * 2 < SEB_NT) {
+      const int dc = (t % (SEB_CC / 4)) * 4, dn = (t / (SEB_CC / 4)) * 2;
+      float acc[2][4] = {};
+#pragma unroll 4
+      for (int r = 0; r < rd; ++r) {
+        const float4 w = *reinterpret_cast<const float4*>(s_wr + r * SEB_CC + dc);
+        const float a0 = s_d1[dn * rdp + r], a1 = s_d1[(dn + 1) * rdp + r];
+        acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (dn + i < nn && c0 + dc + j < C) dmean[(size_t)(n0 + dn + i) * C + c0 + dc + j] = acc[i][j];
+    }
+    if (w_active) {
+#pragma unroll 4
+      for (int n = 0; n < SEB_NT; ++n) {
+        const float4 d = *reinterpret_cast<const float4*>(s_d1 + n * rdp + wr);
+        const float4 q = *reinterpret_cast<const float4*>(s_po + n * SEB_CC + wc);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, pv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc_w[i][j] = fmaf(dv[i], pv[j], acc_w[i][j]);
+      }
+    }
+    if (blockIdx.x == 0 && t < rd)
+      for (int n = 0; n < SEB_NT; ++n) acc_b += s_d1[n * rdp + t];
+  }
+  if (w_active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (wr + i < rd && c0 + wc + j < C) dWr[(size_t)(wr + i) * C + c0 + wc + j] = acc_w[i][j];
+  }
+  if (blockIdx.x == 0 && t < rd) dbr[t] = acc_b;
+}
+
 // ------------------------------------------------------------------------------------------------ activation backward
 // g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * silu'(bn(x)) ; bstats += (sum g, sum g*xhat).  dA / gate / dmean may be null.
 // act == 0: no SiLU (g = upstream), used for BN layers without activation.
@@ -734,6 +909,24 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
                           float* dWe, float* dbe, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
               "trt_se_bwd: null pointer");
+  if (rd <= SEB_RD && (SEB_NT / 4) * ((rd + 3) / 4) >= 1) {
+    // fused path: ds1 (scratch) accumulates K1's per-chunk partial sums of ds2.We (zeroed here); K2 applies silu' on load
+    const int rdp = (rd + 3) & ~3;
+    TRT_CUDA(cudaMemsetAsync(ds1, 0, (size_t)N * rd * sizeof(float), stream));
+    const int blocks = (C + SEB_CC - 1) / SEB_CC;
+    const size_t smem1 = ((size_t)SEB_NT * rdp + (size_t)SEB_NT * SEB_CC + (size_t)SEB_CC * rdp) * sizeof(float);
+    const size_t smem2 = ((size_t)SEB_NT * rdp + (size_t)rdp * SEB_CC + (size_t)SEB_NT * SEB_CC) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      TRT_CUDA(cudaFuncSetAttribute(se_bwd_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      TRT_CUDA(cudaFuncSetAttribute(se_bwd_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    se_bwd_k1_kernel<<<blocks, TPB, smem1, stream>>>(dgate_pre, gate, s1, We, ds2, ds1, dWe, dbe, N, C, rd);
+    trt_count_launch(1);
+    se_bwd_k2_kernel<<<blocks, TPB, smem2, stream>>>(ds1, s1, pooled_sum, inv_hw, Wr, dmean, dWr, dbr, N, C, rd);
+    return trt_check_launch("trt_se_bwd");
+  }
   se_bwd_a_kernel<<<dim3(rd, (N + 7) / 8), TPB, (size_t)C * sizeof(float), stream>>>(dgate_pre, gate, s1, We, ds2, ds1, N, C, rd);
   {
     int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
