@@ -4,6 +4,7 @@
 //
 // Replaces the ATen/cuDNN launches behind timm's BatchNormAct2d / SqueezeExcite / global_pool inside
 // `self.backbone(x_img)` (experiments/multimodal_v1/train_mm_joint_dualtask.py:154) and their autograd backward (:248).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -794,6 +795,21 @@ __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float alpha) {
 
 }  // namespace
 
+// Block count of the kernels that end in per-channel fp64 atomics.  Same-address atomics serialise at the L2 (~25-50 ns
+// each, measured: 4x the blocks = 3x the time on the 7x7 layers), so the grid follows the bytes streamed - about 384 KB per
+// block - between half a wave and three blocks per SM.  (env TEETHRT_RED_KB overrides the per-block quantum: bring-up knob)
+static int red_blocks(size_t bytes) {
+  static int kb = 0;
+  if (kb == 0) {
+    const char* e = getenv("TEETHRT_RED_KB");
+    kb = e ? atoi(e) : 384;
+    if (kb < 1) kb = 384;
+  }
+  long long b = (long long)(bytes / ((size_t)kb << 10));
+  const int lo = trt_num_sms() / 2, hi = 3 * trt_num_sms();
+  return b < lo ? lo : (b > hi ? hi : (int)b);
+}
+
 #define CHECK_C(C) TRT_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channels must be a positive multiple of 8 (got %d)", __func__, (C))
 
 extern "C" int trt_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
@@ -836,7 +852,7 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   TRT_REQUIRE(x && pooled_sum && N > 0 && HW > 0, "trt_pool_act: bad argument");
   const Launch L = plan(C);
   TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
-  int target = 3 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act);
@@ -876,7 +892,7 @@ extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec
   CHECK_C(C);
   TRT_REQUIRE(dy && x && rec && bstats && rows > 0, "trt_bn_bwd_reduce: bad argument");
   const Launch L = plan(C);
-  dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 3 * trt_num_sms()), L.slabs);
+  dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, red_blocks((size_t)rows * C * 4)), L.slabs);
   bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_bn_bwd_reduce");
 }
@@ -897,7 +913,7 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
   TRT_REQUIRE(dA && x && rec && dgate_pre && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
   const Launch L = plan(C);
   TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
-  int target = 3 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   se_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, dgate_pre, HW, C, L.V, L.VX, L.RY);
@@ -946,7 +962,7 @@ extern "C" int trt_act_bwd(const void* dA, const float* gate, const float* dmean
   CHECK_C(C);
   TRT_REQUIRE(x && rec && g_out && bstats && N > 0 && HW > 0 && (dA || dmean), "trt_act_bwd: bad argument");
   const Launch L = plan(C);
-  int target = 3 * trt_num_sms() / (N * L.slabs);
+  int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   act_bwd_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, (uint4*)g_out,
