@@ -278,6 +278,13 @@ def forward_eval(enc, x):
     return feat
 
 
+def _gemm_stats(A, B, st, fin, out):
+    """1x1 conv with BN statistics; with `fin` the last epilogue group also finalises the BatchNorm record."""
+    if fin is not None:
+        return ops.gemm_bn(A, B, st, fin, out=out)
+    return ops.gemm(A, B, ops.EPI_STATS, stats=st, out=out)
+
+
 def forward_train(enc, x, save=True):
     """Train-mode forward (batch statistics, running-stat update).  Returns (feat [N,F] fp32, ctx for backward)."""
     x = _check_input(enc, x)
@@ -290,14 +297,33 @@ def forward_train(enc, x, save=True):
     recs = _Arena(4 * total_c, torch.float32, dev)
     ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
 
-    def finalize(bn_name, st, count):
+    counters = _Arena(len(bns), torch.int32, dev)       # one "blocks done" word per BatchNorm, zeroed once per pass
+    pool_arena = _Arena(N * sum(blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()) + N * enc.num_features,
+                        torch.float32, dev)                # every SE / global pooling target of the pass: one memset
+
+    def fin_for(bn_name, count):
+        """(rec, fin): the BatchNorm record and the host struct that makes the PRODUCER of its statistics finalise it."""
         bn = bns[bn_name]
         c = bn.weight.numel()
         rec = recs.take(4 * c, (4, c))
-        ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                        rec, count, BN_EPS, BN_MOM)
         ctx["rec"][bn_name] = rec
+        return rec, ops.bn_fin(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                               rec, counters.take(1), count, BN_EPS, BN_MOM)
+
+    fuse = os.environ.get("TEETHRT_FUSE_BN_FWD", "0") != "0"     # measured: the last-block tail costs more than a 4 us launch (DESIGN.md)
+
+    def bn_stage(bn_name, count, st, launch):
+        """Run the kernel that produces the statistics `st` of BatchNorm `bn_name` (launch(fin)); returns its record."""
+        rec, fin = fin_for(bn_name, count)
+        if fuse:
+            launch(fin)
+        else:
+            launch(None)
+            bn = bns[bn_name]
+            ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                            rec, count, BN_EPS, BN_MOM)
         return rec
+
 
     h, w = ops.same_out(H, 2), ops.same_out(W, 2)
     cs = enc.conv_stem.weight.shape[0]
@@ -305,8 +331,9 @@ def forward_train(enc, x, save=True):
     # the stem as tcgen05 GEMMs over an explicit im2col (K = 27 padded to 32); the patches are kept for the weight gradient
     patches = ops.stem_im2col(x, torch.empty((N * h * w, 32), device=dev, dtype=bf16))
     w_stem = ops.stem_pack_w(enc.conv_stem.weight.detach(), torch.empty((cs, 32), device=dev, dtype=bf16))
-    s_raw = ops.gemm(patches, w_stem, ops.EPI_STATS, stats=st)
-    cur, cur_rec = s_raw, finalize("bn1", st, N * h * w)          # lazy: (raw, pending BN+SiLU)
+    s_raw = torch.empty((N * h * w, cs), device=dev, dtype=bf16)
+    rec_s = bn_stage("bn1", N * h * w, st, lambda fin: _gemm_stats(patches, w_stem, st, fin, s_raw))
+    cur, cur_rec = s_raw, rec_s                                   # lazy: (raw, pending BN+SiLU)
     ctx["stem"] = dict(raw=s_raw, h=h, w=w, patches=patches)
     for name, blk in enc.block_list():
         c = blk.cfg
@@ -322,8 +349,8 @@ def forward_train(enc, x, save=True):
         if c["type"] == "ir":
             cm = c["mid"]
             st = stats.take(2 * cm)
-            e_raw = ops.gemm(cur, Wp[name + ".conv_pw"][0], ops.EPI_STATS, stats=st)
-            rec1 = finalize(name + ".bn1", st, N * h * w)
+            e_raw = torch.empty((N * h * w, cm), device=dev, dtype=bf16)
+            rec1 = bn_stage(name + ".bn1", N * h * w, st, lambda fin: _gemm_stats(cur, Wp[name + ".conv_pw"][0], st, fin, e_raw))
             dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, rec1, name + ".bn2", name + ".conv_pwl", name + ".bn3"
             sv["e_raw"] = e_raw
         else:
@@ -333,25 +360,25 @@ def forward_train(enc, x, save=True):
         oh, ow = ops.same_out(h, s), ops.same_out(w, s)
         d_raw = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         st = stats.take(2 * cm)
-        ops.dwconv_fwd(dw_in, dw_rec, blk.conv_dw.weight.detach(), d_raw, N, h, w, k, s, stats=st)
-        rec_d = finalize(bn_dw, st, N * oh * ow)
-        pooled = torch.empty((N, cm), device=dev, dtype=torch.float32)
-        ops.pool_act(d_raw, rec_d, pooled, N, oh * ow, act=1)
+        rec_d = bn_stage(bn_dw, N * oh * ow, st, lambda fin: ops.dwconv_fwd(dw_in, dw_rec, blk.conv_dw.weight.detach(), d_raw, N, h,
+                                                                          w, k, s, stats=st, fin=fin))
+        pooled = pool_arena.take(N * cm, (N, cm))
+        ops.pool_act(d_raw, rec_d, pooled, N, oh * ow, act=1, zeroed=True)
         s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
         a = ops.gate_apply(d_raw, rec_d, gate, torch.empty_like(d_raw), N, oh * ow)
         st = stats.take(2 * c["cout"])
-        p_raw = ops.gemm(a, Wp[pw_name][0], ops.EPI_STATS, stats=st)
-        rec_o = finalize(bn_out, st, N * oh * ow)
+        p_raw = torch.empty((N * oh * ow, c["cout"]), device=dev, dtype=bf16)
+        rec_o = bn_stage(bn_out, N * oh * ow, st, lambda fin: _gemm_stats(a, Wp[pw_name][0], st, fin, p_raw))
         y = ops.bn_apply(p_raw, rec_o, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0)
         sv.update(d_raw=d_raw, pooled=pooled, s1=s1, gate=gate, a=a, p_raw=p_raw, oh=oh, ow=ow, has_skip=has_skip,
                   bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out)
         ctx["blocks"].append((blk, sv))
         cur, cur_rec, h, w = y, None, oh, ow
     st = stats.take(2 * enc.num_features)
-    hd_raw = ops.gemm(cur, Wp["conv_head"][0], ops.EPI_STATS, stats=st)
-    rec_h = finalize("bn2", st, N * h * w)
-    feat = torch.empty((N, enc.num_features), device=dev, dtype=torch.float32)
-    ops.pool_act(hd_raw, rec_h, feat, N, h * w, act=1)
+    hd_raw = torch.empty((N * h * w, enc.num_features), device=dev, dtype=bf16)
+    rec_h = bn_stage("bn2", N * h * w, st, lambda fin: _gemm_stats(cur, Wp["conv_head"][0], st, fin, hd_raw))
+    feat = pool_arena.take(N * enc.num_features, (N, enc.num_features))
+    ops.pool_act(hd_raw, rec_h, feat, N, h * w, act=1, zeroed=True)
     ops.scale_f32(feat, 1.0 / (h * w))
     ctx.update(head=dict(x=cur, raw=hd_raw, h=h, w=w))
     return feat, ctx
@@ -415,21 +442,38 @@ def backward_train(enc, ctx, dfeat, grads):
     dfeat = dfeat.contiguous().float()
     sq = _SideQueue(dev)
 
-    def bn_back(bn_name, bst, count):
+    counters = _Arena(len(bns), torch.int32, dev)       # one "blocks done" word per BatchNorm, zeroed once per pass
+    zeros = _Arena(sum(N * (sv["d_raw"].shape[1] + blk.cfg["rd"]) for blk, sv in ctx["blocks"]), torch.float32, dev)
+
+    fuse_b = os.environ.get("TEETHRT_FUSE_BN_BWD", "0") != "0"   # measured slower than separate launches
+
+    def bn_back(bn_name, count, bst, launch):
+        """Run the kernel that produces the backward sums `bst` of BatchNorm `bn_name` (launch(fin)); returns its dx
+        coefficients (dgamma / dbeta land in `grads`)."""
+        coef, fin = bwd_fin(bn_name, count)
+        if fuse_b:
+            return coef, launch(fin)
+        out = launch(None)
+        bn = bns[bn_name]
+        ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"], count)
+        return coef, out
+
+    def bwd_fin(bn_name, count):
+        """(coef, fin): dx = a*dy + b*x + c coefficients of this BatchNorm and the host struct that makes the kernel producing
+        its backward sums finalise them (coef, dgamma, dbeta) in the same launch."""
         bn = bns[bn_name]
         c = bn.weight.numel()
         coef = torch.empty((3, c), device=dev, dtype=torch.float32)
-        ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"],
-                            count)
-        return coef
+        return coef, ops.bn_bwd_fin(REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"],
+                                    counters.take(1), count)
 
     # ---- head: feat = mean_hw silu(bn2(conv_head(y)))
     hd = ctx["head"]
     hw = hd["h"] * hd["w"]
     F_ = enc.num_features
     bst = bstats.take(2 * F_)
-    g = ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"], torch.empty_like(hd["raw"]), bst, N, hw, act=1)
-    coef = bn_back("bn2", bst, N * hw)
+    coef, g = bn_back("bn2", N * hw, bst, lambda fin: ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"],
+                                                                  torch.empty_like(hd["raw"]), bst, N, hw, act=1, fin=fin))
     d_raw = ops.affine2(g, hd["raw"], coef, g)
     dy = ops.gemm(d_raw, Wp["conv_head"][1])
     sq.wgrad(d_raw, hd["x"], grads["conv_head.weight"])
@@ -443,33 +487,32 @@ def backward_train(enc, ctx, dfeat, grads):
         cm = sv["d_raw"].shape[1]
         # project conv + its BN (no activation)
         bst = bstats.take(2 * c["cout"])
-        ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst)
-        coef = bn_back(sv["bn_out"], bst, N * ohw)
+        coef, _ = bn_back(sv["bn_out"], N * ohw, bst, lambda fin: ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst, fin=fin))
         dp = ops.affine2(dy, sv["p_raw"], coef, torch.empty_like(dy))
         dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
         sq.wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
         # squeeze-excite + activation + BN of the depthwise output
         rec_d = REC[sv["bn_dw"]]
-        dgate_pre = torch.empty((N, cm), device=dev, dtype=torch.float32)
-        ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw)
+        dgate_pre = zeros.take(N * cm, (N, cm))
+        ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw, zeroed=True)
         ds2, dmean = torch.empty_like(dgate_pre), torch.empty_like(dgate_pre)
-        ds1 = torch.empty((N, c["rd"]), device=dev, dtype=torch.float32)
+        ds1 = zeros.take(N * c["rd"], (N, c["rd"]))
         se = blk.se
         ops.se_bwd(dgate_pre, sv["gate"], sv["s1"], sv["pooled"], 1.0 / ohw, se.conv_reduce.weight.detach(),
                    se.conv_expand.weight.detach(), ds2, ds1, dmean, grads[name + ".se.conv_reduce.weight"],
                    grads[name + ".se.conv_reduce.bias"], grads[name + ".se.conv_expand.weight"],
-                   grads[name + ".se.conv_expand.bias"])
+                   grads[name + ".se.conv_expand.bias"], ds1_zeroed=True)
         bst = bstats.take(2 * cm)
-        g2 = ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, dA, bst, N, ohw, act=1)
-        coef_d = bn_back(sv["bn_dw"], bst, N * ohw)
+        coef_d, g2 = bn_back(sv["bn_dw"], N * ohw, bst, lambda fin: ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d,
+                                                                                dA, bst, N, ohw, act=1, fin=fin))
         dD = ops.affine2(g2, sv["d_raw"], coef_d, g2)           # gradient w.r.t. the raw depthwise output
         dw_grad = grads[name + ".conv_dw.weight"]
         if c["type"] == "ir":
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
             bst = bstats.take(2 * cm)
             g1 = torch.empty_like(e_raw)
-            ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, dw_grad, N, h, w, k, s)
-            coef1 = bn_back(name + ".bn1", bst, N * h * w)
+            coef1, _ = bn_back(name + ".bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1,
+                                                                                         g1, bst, dw_grad, N, h, w, k, s, fin=fin))
             de = ops.affine2(g1, e_raw, coef1, g1)
             flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
             dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
@@ -481,8 +524,8 @@ def backward_train(enc, ctx, dfeat, grads):
             if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
                 bst = bstats.take(2 * c["cin"])
                 g_in = torch.empty_like(x_in)
-                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, dw_grad, N, h, w, k, s)
-                coef_s = bn_back("bn1", bst, N * h * w)
+                coef_s, _ = bn_back("bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec,
+                                                                                      g_in, bst, dw_grad, N, h, w, k, s, fin=fin))
                 ds = ops.affine2(g_in, x_in, coef_s, g_in)
                 _stem_wgrad(ctx, ds, grads, sq)
                 dy = None
@@ -497,8 +540,8 @@ def backward_train(enc, ctx, dfeat, grads):
                     st_raw = ctx["stem"]["raw"]
                     hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
                     bst = bstats.take(2 * c["cin"])
-                    g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
-                    coef_s = bn_back("bn1", bst, N * hw0)
+                    coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
+                                                                                       torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
                     ds = ops.affine2(g_s, st_raw, coef_s, g_s)
                     _stem_wgrad(ctx, ds, grads, sq)
                     dy = None
@@ -506,8 +549,8 @@ def backward_train(enc, ctx, dfeat, grads):
             st_raw = ctx["stem"]["raw"]
             hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
             bst = bstats.take(2 * st_raw.shape[1])
-            g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
-            coef_s = bn_back("bn1", bst, N * hw0)
+            coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
+                                                                               torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
             ds = ops.affine2(g_s, st_raw, coef_s, g_s)
             _stem_wgrad(ctx, ds, grads, sq)
             dy = None

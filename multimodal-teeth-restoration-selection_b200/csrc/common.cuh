@@ -81,6 +81,87 @@ __device__ __forceinline__ float warp_max(float v) {
   ((raw) + ((((uint32_t)__cvta_generic_to_shared(raw) + (uint32_t)((align) - 1)) & ~(uint32_t)((align) - 1)) - \
             (uint32_t)__cvta_generic_to_shared(raw)))
 
+// ---------------------------------------------------------------- fused BatchNorm finalisation (last block done)
+// forward: stats {sum, sum^2} (fp64) -> rec {scale, shift, mean, rstd}, running statistics (what bn_finalize_kernel does).
+// One block finalises ALL channels, so the loads are batched: FIN_CH channels per thread per round, every load of a round
+// issued before the first use (a plain strided loop is a chain of dependent L2 round trips, ~0.6 us each).
+constexpr int FIN_CH = 4;
+__device__ __forceinline__ void bn_finalize_channels(const trt_bn_fin_t& f, const double* stats, int C, int tid, int nthreads) {
+  for (int c0 = tid; c0 < C; c0 += nthreads * FIN_CH) {
+    double s[FIN_CH], q[FIN_CH];
+    float gm[FIN_CH], bt[FIN_CH], rm[FIN_CH], rv[FIN_CH];
+#pragma unroll
+    for (int j = 0; j < FIN_CH; ++j) {
+      const int c = c0 + j * nthreads;
+      if (c < C) {
+        s[j] = __ldcg(stats + c); q[j] = __ldcg(stats + C + c);
+        gm[j] = f.gamma[c]; bt[j] = f.beta[c];
+        if (f.running_mean) { rm[j] = f.running_mean[c]; rv[j] = f.running_var[c]; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FIN_CH; ++j) {
+      const int c = c0 + j * nthreads;
+      if (c < C) {
+        const double mean = s[j] / f.count;
+        double var = q[j] / f.count - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)f.eps));
+        const float sc = gm[j] * rstd;
+        f.rec[c] = sc;
+        f.rec[C + c] = bt[j] - (float)mean * sc;
+        f.rec[2 * C + c] = (float)mean;
+        f.rec[3 * C + c] = rstd;
+        if (f.running_mean) {
+          const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
+          f.running_mean[c] = (1.f - f.momentum) * rm[j] + f.momentum * (float)mean;
+          f.running_var[c] = (1.f - f.momentum) * rv[j] + f.momentum * (float)unb;
+        }
+      }
+    }
+  }
+  if (tid == 0 && f.num_batches_tracked) *f.num_batches_tracked += 1;
+}
+// backward: bstats {sum dy, sum dy*xhat} -> coef {a, b, c} with dx = a*dy + b*x + c, dgamma, dbeta (bn_bwd_finalize_kernel)
+__device__ __forceinline__ void bn_bwd_finalize_channels(const trt_bn_bwd_fin_t& f, const double* bstats, int C, int tid, int nthreads) {
+  for (int c0 = tid; c0 < C; c0 += nthreads * FIN_CH) {
+    double sdy[FIN_CH], sdyx[FIN_CH];
+    float mean[FIN_CH], rstd[FIN_CH], gm[FIN_CH];
+#pragma unroll
+    for (int j = 0; j < FIN_CH; ++j) {
+      const int c = c0 + j * nthreads;
+      if (c < C) {
+        sdy[j] = __ldcg(bstats + c); sdyx[j] = __ldcg(bstats + C + c);
+        mean[j] = f.rec[2 * C + c]; rstd[j] = f.rec[3 * C + c]; gm[j] = f.gamma[c];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FIN_CH; ++j) {
+      const int c = c0 + j * nthreads;
+      if (c < C) {
+        const float a = gm[j] * rstd[j];
+        const float m1 = (float)(sdy[j] / f.count), m2 = (float)(sdyx[j] / f.count);
+        f.coef[c] = a;
+        f.coef[C + c] = -a * rstd[j] * m2;
+        f.coef[2 * C + c] = a * (mean[j] * rstd[j] * m2 - m1);
+        f.dgamma[c] = (float)sdyx[j];
+        f.dbeta[c] = (float)sdy[j];
+      }
+    }
+  }
+}
+// Called by ALL threads of a block after their global atomics: true in every thread of the last block to get here.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int expected) {
+  __shared__ int s_last_block;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last_block = (atomicAdd(counter, 1u) == expected - 1u);
+  __syncthreads();
+  const bool last = s_last_block != 0;
+  if (last) __threadfence();
+  return last;
+}
+
 // ---------------------------------------------------------------- PTX: mbarrier / TMA / tcgen05
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -142,7 +142,8 @@ template <int K, int S, int P>
 __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ in_rec,
                                                             const float* __restrict__ w, uint4* __restrict__ out,
                                                             const float* __restrict__ out_rec, float* __restrict__ pooled,
-                                                            double* __restrict__ stats, const DwGeom g) {
+                                                            double* __restrict__ stats, const DwGeom g, const int has_fin,
+                                                            const trt_bn_fin_t fin) {
   using T = FwdTile<K, S, P>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(stats + k * g.C + c, (double)total);
     }
+    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_finalize_channels(fin, stats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -275,7 +277,8 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
                                                                     const __grid_constant__ CUtensorMap tm_x,
                                                                     const float* __restrict__ w, const float* __restrict__ x_rec,
                                                                     uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                    const DwGeom g) {
+                                                                    const DwGeom g, const int has_fin,
+                                                                    const trt_bn_bwd_fin_t fin) {
   using T = FwdTile<K, 1, P>;
   constexpr int STAGE = T::IN_BYTES + T::OUT_BYTES;
   constexpr int PAD = (K - 1) / 2;
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
     }
+    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -377,7 +381,8 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tm_x,
                                                                     const float* __restrict__ w, const float* __restrict__ x_rec,
                                                                     uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                    const DwGeom g) {
+                                                                    const DwGeom g, const int has_fin,
+                                                                    const trt_bn_bwd_fin_t fin) {
   using T = S2Tile<K>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
@@ -480,6 +485,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
     }
+    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -629,8 +635,13 @@ int persistent_blocks(Kern kern, size_t smem, int cblocks, int items, int* out) 
 }  // namespace
 
 extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec,
-                              float* pooled_sum, double* stats, int N, int H, int W, int C, int k, int s,
-                              cudaStream_t stream) {
+                              float* pooled_sum, double* stats, const trt_bn_fin_t* fin_host, int N, int H, int W, int C,
+                              int k, int s, cudaStream_t stream) {
+  TRT_REQUIRE(!fin_host || (stats && fin_host->gamma && fin_host->beta && fin_host->rec && fin_host->counter),
+              "trt_dwconv_fwd: incomplete finalisation record");
+  trt_bn_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
+  const int has_fin = fin_host ? 1 : 0;
   TRT_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "trt_dwconv_fwd: bad argument");
   TRT_REQUIRE((k == 3 || k == 5) && (s == 1 || s == 2), "trt_dwconv_fwd: only k in {3,5}, s in {1,2}");
   DwGeom g;
@@ -654,7 +665,7 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
     if ((rc = trt_make_tmap_nhwc(&tm, x, N, H, W, C, 64, T::IW, T::IH))) return rc;                                \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_fwd_kernel<KK, SS, PP>, smem, cblocks, items, &G))) return rc;              \
-    dwconv_fwd_kernel<KK, SS, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(tm, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g); \
+    dwconv_fwd_kernel<KK, SS, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(tm, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g, has_fin, fin); \
   } while (0)
   if (k == 3 && s == 1) { if (p == 4) LAUNCH_DW(3, 1, 4); else LAUNCH_DW(3, 1, 2); }
   else if (k == 5 && s == 1) { if (p == 4) LAUNCH_DW(5, 1, 4); else LAUNCH_DW(5, 1, 2); }
@@ -665,7 +676,13 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
 }
 
 extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out,
-                              double* bstats, float* dw, int N, int H, int W, int C, int k, int s, cudaStream_t stream) {
+                              double* bstats, const trt_bn_bwd_fin_t* fin_host, float* dw, int N, int H, int W, int C, int k,
+                              int s, cudaStream_t stream) {
+  TRT_REQUIRE(!fin_host || (g_out && x_rec && bstats && fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->counter),
+              "trt_dwconv_bwd: incomplete finalisation record");
+  trt_bn_bwd_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
+  const int has_fin = fin_host ? 1 : 0;
   TRT_REQUIRE(gy && w && x_raw && dw && N > 0 && C > 0 && C % 8 == 0, "trt_dwconv_bwd: bad argument");
   TRT_REQUIRE((k == 3 || k == 5) && (s == 1 || s == 2), "trt_dwconv_bwd: only k in {3,5}, s in {1,2}");
   DwGeom g;
@@ -690,7 +707,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
     if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TOW, TOH))) return rc;                             \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_bwd_data_s1_kernel<KK, PP>, smem, cblocks, items, &G))) return rc;          \
-    dwconv_bwd_data_s1_kernel<KK, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
+    dwconv_bwd_data_s1_kernel<KK, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g, has_fin, fin); \
   } while (0)
       if (k == 3) { if (p == 4) LAUNCH_BD_S1(3, 4); else LAUNCH_BD_S1(3, 2); }
       else { if (p == 4) LAUNCH_BD_S1(5, 4); else LAUNCH_BD_S1(5, 2); }
@@ -709,7 +726,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
     if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TI, T::TI))) return rc;                            \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_bwd_data_s2_kernel<KK>, smem, cblocks, items, &G))) return rc;              \
-    dwconv_bwd_data_s2_kernel<KK><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
+    dwconv_bwd_data_s2_kernel<KK><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g, has_fin, fin); \
   } while (0)
       if (k == 3) LAUNCH_BD_S2(3); else LAUNCH_BD_S2(5);
 #undef LAUNCH_BD_S2

@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict
 // bstats[0][c] += sum dy ; bstats[1][c] += sum dy * xhat
 __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                                             const float* __restrict__ rec, double* __restrict__ bstats,
-                                                            int rows, int C, int V, int VX, int RY) {
+                                                            int rows, int C, int V, int VX, int RY, const int has_fin,
+                                                            const trt_bn_bwd_fin_t fin) {
   __shared__ float s_red[16 * TPB];
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
   float acc[16];
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
       atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
+  if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);
 }
 
 // out = a*dy + b*x + c (per channel)   [BN backward apply]
@@ -663,7 +665,8 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
                                                       const float* __restrict__ dmean, float inv_hw,
                                                       const uint4* __restrict__ x, const float* __restrict__ rec,
                                                       uint4* __restrict__ g_out, double* __restrict__ bstats, int HW, int C,
-                                                      int V, int VX, int RY, int act) {
+                                                      int V, int VX, int RY, int act, const int has_fin,
+                                                      const trt_bn_bwd_fin_t fin) {
   __shared__ float s_red[16 * TPB];
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   const int n = blockIdx.y;
@@ -726,6 +729,7 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
       atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
+  if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);
 }
 
 // fp32 [N, K] weight -> bf16 [N, K] and bf16 [K, N] (transposed copy for dgrad)
@@ -846,12 +850,12 @@ extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residua
   return trt_check_launch("trt_bn_apply");
 }
 
-extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int N, int HW, int C, int act,
+extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, int N, int HW, int C, int act,
                             cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(x && pooled_sum && N > 0 && HW > 0, "trt_pool_act: bad argument");
   const Launch L = plan(C);
-  TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
+  if (!zeroed) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
@@ -887,13 +891,18 @@ extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate
   return trt_check_launch("trt_gate_apply");
 }
 
-extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C,
-                                 cudaStream_t stream) {
+extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats,
+                                 const trt_bn_bwd_fin_t* fin_host, int rows, int C, cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(dy && x && rec && bstats && rows > 0, "trt_bn_bwd_reduce: bad argument");
+  TRT_REQUIRE(!fin_host || (fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->dgamma && fin_host->dbeta && fin_host->counter),
+              "trt_bn_bwd_reduce: incomplete finalisation record");
+  trt_bn_bwd_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, red_blocks((size_t)rows * C * 4)), L.slabs);
-  bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY);
+  bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY,
+                                                 fin_host ? 1 : 0, fin);
   return trt_check_launch("trt_bn_bwd_reduce");
 }
 
@@ -907,12 +916,12 @@ extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, voi
   return trt_check_launch("trt_affine2");
 }
 
-extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int N, int HW, int C,
-                                 cudaStream_t stream) {
+extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int zeroed, int N, int HW,
+                                 int C, cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(dA && x && rec && dgate_pre && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
   const Launch L = plan(C);
-  TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
+  if (!zeroed) TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
@@ -922,13 +931,13 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
 
 extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
                           const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr,
-                          float* dWe, float* dbe, int N, int C, int rd, cudaStream_t stream) {
+                          float* dWe, float* dbe, int ds1_zeroed, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
               "trt_se_bwd: null pointer");
   if (rd <= SEB_RD && (SEB_NT / 4) * ((rd + 3) / 4) >= 1) {
     // fused path: ds1 (scratch) accumulates K1's per-chunk partial sums of ds2.We (zeroed here); K2 applies silu' on load
     const int rdp = (rd + 3) & ~3;
-    TRT_CUDA(cudaMemsetAsync(ds1, 0, (size_t)N * rd * sizeof(float), stream));
+    if (!ds1_zeroed) TRT_CUDA(cudaMemsetAsync(ds1, 0, (size_t)N * rd * sizeof(float), stream));
     const int blocks = (C + SEB_CC - 1) / SEB_CC;
     const size_t smem1 = ((size_t)SEB_NT * rdp + (size_t)SEB_NT * SEB_CC + (size_t)SEB_CC * rdp) * sizeof(float);
     const size_t smem2 = ((size_t)SEB_NT * rdp + (size_t)rdp * SEB_CC + (size_t)SEB_NT * SEB_CC) * sizeof(float);
@@ -957,16 +966,20 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
 }
 
 extern "C" int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x,
-                           const float* rec, void* g_out, double* bstats, int N, int HW, int C, int act,
-                           cudaStream_t stream) {
+                           const float* rec, void* g_out, double* bstats, const trt_bn_bwd_fin_t* fin_host, int N, int HW,
+                           int C, int act, cudaStream_t stream) {
   CHECK_C(C);
+  TRT_REQUIRE(!fin_host || (fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->dgamma && fin_host->dbeta && fin_host->counter),
+              "trt_act_bwd: incomplete finalisation record");
+  trt_bn_bwd_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
   TRT_REQUIRE(x && rec && g_out && bstats && N > 0 && HW > 0 && (dA || dmean), "trt_act_bwd: bad argument");
   const Launch L = plan(C);
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   act_bwd_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, (uint4*)g_out,
-                                           bstats, HW, C, L.V, L.VX, L.RY, act);
+                                           bstats, HW, C, L.V, L.VX, L.RY, act, fin_host ? 1 : 0, fin);
   return trt_check_launch("trt_act_bwd");
 }
 

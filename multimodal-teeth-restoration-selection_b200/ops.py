@@ -6,7 +6,7 @@ import math
 
 import torch
 
-from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS  # noqa: F401
+from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS, BnFin, BnBwdFin  # noqa: F401
 
 bf16 = torch.bfloat16
 
@@ -33,6 +33,30 @@ def gemm(A, B, flags=0, scale=None, shift=None, residual=None, stats=None, out=N
         out = torch.empty((M, N), device=A.device, dtype=bf16)
     check(lib.trt_gemm_bf16(ptr(A), ptr(B), ptr(out), M, N, K, flags, ptr(scale), ptr(shift), ptr(residual), ptr(stats),
                             block_n, stream()))
+    return out
+
+
+def bn_fin(gamma, beta, rm, rv, nbt, rec, counter, count, eps, momentum=0.1):
+    """Host record for a BatchNorm finalisation fused into the producing kernel (`counter`: one zeroed int32 element)."""
+    return BnFin(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), ptr(counter), float(count), eps, momentum)
+
+
+def bn_bwd_fin(rec, gamma, coef, dgamma, dbeta, counter, count):
+    return BnBwdFin(ptr(rec), ptr(gamma), ptr(coef), ptr(dgamma), ptr(dbeta), ptr(counter), float(count))
+
+
+def _ref(st):
+    return None if st is None else C.byref(st)
+
+
+def gemm_bn(A, B, stats, fin, out=None):
+    """C = A @ B^T with BN statistics in the epilogue AND the BatchNorm record finalised by the last epilogue group."""
+    _c(A, bf16), _c(B, bf16)
+    M, K = A.shape
+    N = B.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=bf16)
+    check(lib.trt_gemm_bf16_bn(ptr(A), ptr(B), ptr(out), M, N, K, ptr(stats), C.byref(fin), stream()))
     return out
 
 
@@ -78,8 +102,8 @@ def bn_apply(x, rec, out, residual=None, act=0):
     return out
 
 
-def pool_act(x, rec, pooled, N, HW, act=1):
-    check(lib.trt_pool_act(ptr(x), ptr(rec), ptr(pooled), N, HW, x.shape[-1], act, stream()))
+def pool_act(x, rec, pooled, N, HW, act=1, zeroed=False):
+    check(lib.trt_pool_act(ptr(x), ptr(rec), ptr(pooled), int(zeroed), N, HW, x.shape[-1], act, stream()))
     return pooled
 
 
@@ -99,9 +123,9 @@ def scale_f32(x, alpha):
     return x
 
 
-def bn_bwd_reduce(dy, x, rec, bstats):
+def bn_bwd_reduce(dy, x, rec, bstats, fin=None):
     rows, Cc = x.shape
-    check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), rows, Cc, stream()))
+    check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), _ref(fin), rows, Cc, stream()))
 
 
 def affine2(dy, x, coef, out):
@@ -111,32 +135,32 @@ def affine2(dy, x, coef, out):
     return out
 
 
-def se_bwd_reduce(dA, x, rec, dgate_pre, N, HW):
-    check(lib.trt_se_bwd_reduce(ptr(dA), ptr(x), ptr(rec), ptr(dgate_pre), N, HW, x.shape[-1], stream()))
+def se_bwd_reduce(dA, x, rec, dgate_pre, N, HW, zeroed=False):
+    check(lib.trt_se_bwd_reduce(ptr(dA), ptr(x), ptr(rec), ptr(dgate_pre), int(zeroed), N, HW, x.shape[-1], stream()))
 
 
-def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe):
+def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe, ds1_zeroed=False):
     N, Cc = gate.shape
     check(lib.trt_se_bwd(ptr(dgate_pre), ptr(gate), ptr(s1), ptr(pooled), inv_hw, ptr(Wr), ptr(We), ptr(ds2), ptr(ds1),
-                         ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), N, Cc, Wr.shape[0], stream()))
+                         ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), int(ds1_zeroed), N, Cc, Wr.shape[0], stream()))
 
 
-def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1):
-    check(lib.trt_act_bwd(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(g_out), ptr(bstats), N, HW,
+def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1, fin=None):
+    check(lib.trt_act_bwd(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(g_out), ptr(bstats), _ref(fin), N, HW,
                           x.shape[-1], act, stream()))
     return g_out
 
 
 # ------------------------------------------------------------------------------------------------ spatial convs
-def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None):
-    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), N, H, W,
+def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, fin=None):
+    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), _ref(fin), N, H, W,
                              x.shape[-1], k, s, stream()))
     return out
 
 
-def dwconv_bwd(dD, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s):
+def dwconv_bwd(dD, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s, fin=None):
     """dD: gradient w.r.t. the raw depthwise output (BN-backward affine already applied, see affine2)."""
-    check(lib.trt_dwconv_bwd(ptr(dD), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats), ptr(dw), N, H, W,
+    check(lib.trt_dwconv_bwd(ptr(dD), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats), _ref(fin), ptr(dw), N, H, W,
                              x_raw.shape[-1], k, s, stream()))
 
 

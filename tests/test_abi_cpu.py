@@ -37,7 +37,8 @@ def test_sass_is_blackwell_native(built):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):      # tcgen05.mma / TMA load / TMA store / tcgen05.ld
+    # tcgen05.mma / TMA tile loads (2D GEMM operands, 4D depthwise tiles) / tcgen05.ld / mixed-precision bf16 FMA
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "FHFMA.BF16"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass                                  # no legacy mma.sync path
 
