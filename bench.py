@@ -138,7 +138,7 @@ def time_dominant_kernel(torch, ops, pk):
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     Wt = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    stats = ops.new_stats(N, "cuda")
     flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)      # > 126 MB L2
     for _ in range(3):
         ops.gemm(A, Wt, ops.EPI_STATS, stats=stats, out=C)

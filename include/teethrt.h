@@ -28,6 +28,12 @@ typedef struct CUstream_st* trt_stream_t; /* == cudaStream_t */
 
 enum { TRT_OK = 0, TRT_ERR_INVALID = -1, TRT_ERR_CUDA = -2, TRT_ERR_UNSUPPORTED = -3 };
 
+/* BatchNorm statistics buffers (`stats`, `bstats` below) are REPLICATED: [TRT_STAT_REPLICAS][2][C] fp64, zeroed by the caller.
+ * Same-address fp64 atomics serialise at the L2 (~23 ns each, measured: a 444-block grid spends 10 us draining one chain), so
+ * each block adds into replica (block index mod TRT_STAT_REPLICAS) and the finalise step sums the replicas. */
+#define TRT_STAT_REPLICAS 8
+int trt_stat_replicas(void);
+
 /* Fused BatchNorm finalisation.  A kernel that accumulates BN statistics can also turn them into the per-layer record: the
  * last of its blocks to finish (a device counter, ZEROED by the caller before the launch) does what trt_bn_finalize /
  * trt_bn_bwd_finalize would do in a launch of their own.  Host structs; every pointer inside is a device pointer. */

@@ -34,6 +34,7 @@ _SIGS = {
     "trt_last_error_string": (C.c_char_p, []),
     "trt_init": (i32, [i32]),
     "trt_launch_count": (u64, []),
+    "trt_stat_replicas": (i32, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "trt_gemm_bf16_bn": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp]),

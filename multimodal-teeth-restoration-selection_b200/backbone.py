@@ -293,7 +293,7 @@ def forward_train(enc, x, save=True):
     Wp = _packed_weights(enc, dev, True)
     bns = dict(enc.bn_list())
     total_c = sum(b.weight.numel() for b in bns.values())
-    stats = _Arena(2 * total_c, torch.float64, dev)
+    stats = _Arena(ops.STAT_REPLICAS * 2 * total_c, torch.float64, dev)
     recs = _Arena(4 * total_c, torch.float32, dev)
     ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
 
@@ -327,7 +327,7 @@ def forward_train(enc, x, save=True):
 
     h, w = ops.same_out(H, 2), ops.same_out(W, 2)
     cs = enc.conv_stem.weight.shape[0]
-    st = stats.take(2 * cs)
+    st = stats.take(ops.STAT_REPLICAS * 2 * cs)
     # the stem as tcgen05 GEMMs over an explicit im2col (K = 27 padded to 32); the patches are kept for the weight gradient
     patches = ops.stem_im2col(x, torch.empty((N * h * w, 32), device=dev, dtype=bf16))
     w_stem = ops.stem_pack_w(enc.conv_stem.weight.detach(), torch.empty((cs, 32), device=dev, dtype=bf16))
@@ -348,7 +348,7 @@ def forward_train(enc, x, save=True):
         sv["x"] = cur
         if c["type"] == "ir":
             cm = c["mid"]
-            st = stats.take(2 * cm)
+            st = stats.take(ops.STAT_REPLICAS * 2 * cm)
             e_raw = torch.empty((N * h * w, cm), device=dev, dtype=bf16)
             rec1 = bn_stage(name + ".bn1", N * h * w, st, lambda fin: _gemm_stats(cur, Wp[name + ".conv_pw"][0], st, fin, e_raw))
             dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, rec1, name + ".bn2", name + ".conv_pwl", name + ".bn3"
@@ -359,14 +359,14 @@ def forward_train(enc, x, save=True):
             sv["in_rec"] = cur_rec
         oh, ow = ops.same_out(h, s), ops.same_out(w, s)
         d_raw = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
-        st = stats.take(2 * cm)
+        st = stats.take(ops.STAT_REPLICAS * 2 * cm)
         rec_d = bn_stage(bn_dw, N * oh * ow, st, lambda fin: ops.dwconv_fwd(dw_in, dw_rec, blk.conv_dw.weight.detach(), d_raw, N, h,
                                                                           w, k, s, stats=st, fin=fin))
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.pool_act(d_raw, rec_d, pooled, N, oh * ow, act=1, zeroed=True)
         s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
         a = ops.gate_apply(d_raw, rec_d, gate, torch.empty_like(d_raw), N, oh * ow)
-        st = stats.take(2 * c["cout"])
+        st = stats.take(ops.STAT_REPLICAS * 2 * c["cout"])
         p_raw = torch.empty((N * oh * ow, c["cout"]), device=dev, dtype=bf16)
         rec_o = bn_stage(bn_out, N * oh * ow, st, lambda fin: _gemm_stats(a, Wp[pw_name][0], st, fin, p_raw))
         y = ops.bn_apply(p_raw, rec_o, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0)
@@ -374,7 +374,7 @@ def forward_train(enc, x, save=True):
                   bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out)
         ctx["blocks"].append((blk, sv))
         cur, cur_rec, h, w = y, None, oh, ow
-    st = stats.take(2 * enc.num_features)
+    st = stats.take(ops.STAT_REPLICAS * 2 * enc.num_features)
     hd_raw = torch.empty((N * h * w, enc.num_features), device=dev, dtype=bf16)
     rec_h = bn_stage("bn2", N * h * w, st, lambda fin: _gemm_stats(cur, Wp["conv_head"][0], st, fin, hd_raw))
     feat = pool_arena.take(N * enc.num_features, (N, enc.num_features))
@@ -438,7 +438,7 @@ def backward_train(enc, ctx, dfeat, grads):
     N, Wp, REC = ctx["N"], ctx["Wp"], ctx["rec"]
     bns = dict(enc.bn_list())
     total_c = sum(b.weight.numel() for b in bns.values())
-    bstats = _Arena(2 * total_c, torch.float64, dev)
+    bstats = _Arena(ops.STAT_REPLICAS * 2 * total_c, torch.float64, dev)
     dfeat = dfeat.contiguous().float()
     sq = _SideQueue(dev)
 
@@ -471,7 +471,7 @@ def backward_train(enc, ctx, dfeat, grads):
     hd = ctx["head"]
     hw = hd["h"] * hd["w"]
     F_ = enc.num_features
-    bst = bstats.take(2 * F_)
+    bst = bstats.take(ops.STAT_REPLICAS * 2 * F_)
     coef, g = bn_back("bn2", N * hw, bst, lambda fin: ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"],
                                                                   torch.empty_like(hd["raw"]), bst, N, hw, act=1, fin=fin))
     d_raw = ops.affine2(g, hd["raw"], coef, g)
@@ -486,7 +486,7 @@ def backward_train(enc, ctx, dfeat, grads):
         ohw = oh * ow
         cm = sv["d_raw"].shape[1]
         # project conv + its BN (no activation)
-        bst = bstats.take(2 * c["cout"])
+        bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cout"])
         coef, _ = bn_back(sv["bn_out"], N * ohw, bst, lambda fin: ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst, fin=fin))
         dp = ops.affine2(dy, sv["p_raw"], coef, torch.empty_like(dy))
         dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
@@ -502,14 +502,14 @@ def backward_train(enc, ctx, dfeat, grads):
                    se.conv_expand.weight.detach(), ds2, ds1, dmean, grads[name + ".se.conv_reduce.weight"],
                    grads[name + ".se.conv_reduce.bias"], grads[name + ".se.conv_expand.weight"],
                    grads[name + ".se.conv_expand.bias"], ds1_zeroed=True)
-        bst = bstats.take(2 * cm)
+        bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
         coef_d, g2 = bn_back(sv["bn_dw"], N * ohw, bst, lambda fin: ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d,
                                                                                 dA, bst, N, ohw, act=1, fin=fin))
         dD = ops.affine2(g2, sv["d_raw"], coef_d, g2)           # gradient w.r.t. the raw depthwise output
         dw_grad = grads[name + ".conv_dw.weight"]
         if c["type"] == "ir":
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
-            bst = bstats.take(2 * cm)
+            bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
             g1 = torch.empty_like(e_raw)
             coef1, _ = bn_back(name + ".bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1,
                                                                                          g1, bst, dw_grad, N, h, w, k, s, fin=fin))
@@ -522,7 +522,7 @@ def backward_train(enc, ctx, dfeat, grads):
             x_in, in_rec = sv["x"], sv["in_rec"]
             is_first = blk is ctx["blocks"][0][0]
             if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
-                bst = bstats.take(2 * c["cin"])
+                bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
                 g_in = torch.empty_like(x_in)
                 coef_s, _ = bn_back("bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec,
                                                                                       g_in, bst, dw_grad, N, h, w, k, s, fin=fin))
@@ -539,7 +539,7 @@ def backward_train(enc, ctx, dfeat, grads):
                     # the block input was silu(bn1(stem)) materialised by bn_apply: continue into the stem
                     st_raw = ctx["stem"]["raw"]
                     hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
-                    bst = bstats.take(2 * c["cin"])
+                    bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
                     coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
                                                                                        torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
                     ds = ops.affine2(g_s, st_raw, coef_s, g_s)
@@ -548,7 +548,7 @@ def backward_train(enc, ctx, dfeat, grads):
         if c["type"] == "ir" and sv.get("materialised_from"):
             st_raw = ctx["stem"]["raw"]
             hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
-            bst = bstats.take(2 * st_raw.shape[1])
+            bst = bstats.take(ops.STAT_REPLICAS * 2 * st_raw.shape[1])
             coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
                                                                                torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
             ds = ops.affine2(g_s, st_raw, coef_s, g_s)

@@ -28,6 +28,7 @@ int trt_check_launch(const char* what) {
 
 extern "C" const char* trt_last_error_string(void) { return g_err; }
 extern "C" int trt_version(void) { return TEETHRT_VERSION; }
+extern "C" int trt_stat_replicas(void) { return TRT_STAT_REPLICAS; }
 
 static int g_num_sms = 0;
 int trt_num_sms() {

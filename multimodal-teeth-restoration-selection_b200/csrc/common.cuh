@@ -86,6 +86,13 @@ __device__ __forceinline__ float warp_max(float v) {
 // One block finalises ALL channels, so the loads are batched: FIN_CH channels per thread per round, every load of a round
 // issued before the first use (a plain strided loop is a chain of dependent L2 round trips, ~0.6 us each).
 constexpr int FIN_CH = 4;
+// total of a replicated statistics entry: stats is [TRT_STAT_REPLICAS][2][C]; idx in [0, 2C)
+__device__ __forceinline__ double stat_total(const double* stats, int C, int idx) {
+  double t = 0;
+#pragma unroll
+  for (int r = 0; r < TRT_STAT_REPLICAS; ++r) t += __ldcg(stats + (size_t)r * 2 * C + idx);
+  return t;
+}
 __device__ __forceinline__ void bn_finalize_channels(const trt_bn_fin_t& f, const double* stats, int C, int tid, int nthreads) {
   for (int c0 = tid; c0 < C; c0 += nthreads * FIN_CH) {
     double s[FIN_CH], q[FIN_CH];
@@ -94,7 +101,7 @@ __device__ __forceinline__ void bn_finalize_channels(const trt_bn_fin_t& f, cons
     for (int j = 0; j < FIN_CH; ++j) {
       const int c = c0 + j * nthreads;
       if (c < C) {
-        s[j] = __ldcg(stats + c); q[j] = __ldcg(stats + C + c);
+        s[j] = stat_total(stats, C, c); q[j] = stat_total(stats, C, C + c);
         gm[j] = f.gamma[c]; bt[j] = f.beta[c];
         if (f.running_mean) { rm[j] = f.running_mean[c]; rv[j] = f.running_var[c]; }
       }
@@ -131,7 +138,7 @@ __device__ __forceinline__ void bn_bwd_finalize_channels(const trt_bn_bwd_fin_t&
     for (int j = 0; j < FIN_CH; ++j) {
       const int c = c0 + j * nthreads;
       if (c < C) {
-        sdy[j] = __ldcg(bstats + c); sdyx[j] = __ldcg(bstats + C + c);
+        sdy[j] = stat_total(bstats, C, c); sdyx[j] = stat_total(bstats, C, C + c);
         mean[j] = f.rec[2 * C + c]; rstd[j] = f.rec[3 * C + c]; gm[j] = f.gamma[c];
       }
     }

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const InT* __restrict__ x
         const float v = __bfloat162float(s_o[r * CS + threadIdx.x]);
         s += v; q = fmaf(v, v, q);
       }
-      atomicAdd(stats + threadIdx.x, (double)s);
-      atomicAdd(stats + CS + threadIdx.x, (double)q);
+      double* rep = stats + (size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 * CS;
+      atomicAdd(rep + threadIdx.x, (double)s);
+      atomicAdd(rep + CS + threadIdx.x, (double)q);
     }
   }
 }

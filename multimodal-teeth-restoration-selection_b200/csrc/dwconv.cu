@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
     const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
-      if (c < g.C) atomicAdd(stats + k * g.C + c, (double)total);
+      if (c < g.C) atomicAdd(stats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
     if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_finalize_channels(fin, stats, g.C, threadIdx.x, TPB);
   }
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
     const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
-      if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
+      if (c < g.C) atomicAdd(bstats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
     if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
-      if (c < g.C) atomicAdd(bstats + k * g.C + c, (double)total);
+      if (c < g.C) atomicAdd(bstats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
     if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }

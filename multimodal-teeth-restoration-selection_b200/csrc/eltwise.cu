@@ -70,8 +70,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  const double mean = stats[c] / count;
-  double var = stats[C + c] / count - mean * mean;
+  const double mean = stat_total(stats, C, c) / count;
+  double var = stat_total(stats, C, C + c) / count - mean * mean;
   if (var < 0) var = 0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float sc = gamma[c] * rstd;
@@ -105,7 +105,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bstats, const 
                                        float* __restrict__ dbeta, int C, double count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double sdy = bstats[c], sdyx = bstats[C + c];
+  const double sdy = stat_total(bstats, C, c), sdyx = stat_total(bstats, C, C + c);
   const float mean = rec[2 * C + c], rstd = rec[3 * C + c];
   const float a = gamma[c] * rstd;
   const float m1 = (float)(sdy / count), m2 = (float)(sdyx / count);
@@ -308,10 +308,11 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
   }
   block_reduce_rows<16>(acc, s_red, m);
   if (m.ry == 0 && m.active) {
+    double* rep = bstats + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % TRT_STAT_REPLICAS) * 2 * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(bstats + 8 * m.v + i, (double)acc[i]);
-      atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
+      atomicAdd(rep + 8 * m.v + i, (double)acc[i]);
+      atomicAdd(rep + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
   if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);
@@ -723,10 +724,11 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
   }
   block_reduce_rows<16>(acc, s_red, m);
   if (m.ry == 0 && m.active) {
+    double* rep = bstats + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % TRT_STAT_REPLICAS) * 2 * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(bstats + 8 * m.v + i, (double)acc[i]);
-      atomicAdd(bstats + C + 8 * m.v + i, (double)acc[8 + i]);
+      atomicAdd(rep + 8 * m.v + i, (double)acc[i]);
+      atomicAdd(rep + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
   if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);

@@ -200,7 +200,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const float* src = k ? pq : ps;
           float tot = 0.f;
           for (int r = 0; r < rg_count; ++r) tot += src[r * p.block_n + cc];
-          if (st_n0 + cc < p.N) atomicAdd(p.stats + (size_t)k * p.N + st_n0 + cc, (double)tot);
+          if (st_n0 + cc < p.N)
+            atomicAdd(p.stats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * p.N + st_n0 + cc, (double)tot);
         }
         ptx::named_bar_sync(bar_id, EPI_THREADS);
 #pragma unroll

@@ -11,6 +11,19 @@ from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDU
 bf16 = torch.bfloat16
 
 
+STAT_REPLICAS = int(lib.trt_stat_replicas())
+
+
+def new_stats(C_, device):
+    """Zeroed BatchNorm statistics buffer [STAT_REPLICAS, 2, C] (fp64): blocks spread their atomics over the replicas."""
+    return torch.zeros((STAT_REPLICAS, 2, C_), device=device, dtype=torch.float64)
+
+
+def stats_total(st, C_=None):
+    """[2, C] totals of a replicated statistics buffer."""
+    return st.view(STAT_REPLICAS, 2, -1).sum(0)
+
+
 def _c(t, dtype=None):
     assert t.is_cuda and t.is_contiguous(), "teethrt ops need contiguous CUDA tensors"
     if dtype is not None:

@@ -63,13 +63,14 @@ def test_gemm_epilogues(ops, M, N, K):
     assert rel_err(C, acc * sc + sh + res.float()) < 1e-2
     C = ops.gemm(A, B, ops.EPI_RESIDUAL, residual=res)
     assert rel_err(C, acc + res.float()) < 1e-2
-    stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    stats = ops.new_stats(N, "cuda")
     C = ops.gemm(A, B, ops.EPI_STATS, stats=stats)
     torch.cuda.synchronize()
     assert rel_err(C, acc) < 1e-2
     cf = C.double()
-    assert torch.allclose(stats[0], cf.sum(0), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[1], (cf * cf).sum(0), rtol=1e-4, atol=1e-2)
+    tot = ops.stats_total(stats)
+    assert torch.allclose(tot[0], cf.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[1], (cf * cf).sum(0), rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("M,Cp,Cq", [(4096, 144, 24), (1000, 24, 144), (50000, 32, 192), (3136, 448, 2688), (777, 1632, 272),
@@ -98,7 +99,8 @@ def make_rec(ops, xr, gamma, beta, eps=1e-3):
     """rec via trt_bn_finalize from fp64 sums of the stored (bf16) tensor; also returns the running stats it updated."""
     C = xr.shape[-1]
     x2 = xr.reshape(-1, C).double()
-    stats = torch.stack([x2.sum(0), (x2 * x2).sum(0)])
+    stats = ops.new_stats(x2.shape[1], "cuda")
+    stats[0] = torch.stack([x2.sum(0), (x2 * x2).sum(0)])
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     nbt = torch.zeros((), device="cuda", dtype=torch.int64)
     rec = torch.empty(4, C, device="cuda")
@@ -150,7 +152,7 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd):
     ops.se_bwd(dgate_pre, gate, s1, pooled, 1.0 / HW, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe)
     for got, want in ((dWr, Wr_.grad), (dbr, br_.grad), (dWe, We_.grad), (dbe, be_.grad)):
         assert rel_err(got, want) < 2e-2
-    bstats = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    bstats = ops.new_stats(C, "cuda")
     g = ops.act_bwd(dA.view(N * HW, C), gate, dmean, 1.0 / HW, x2, rec, torch.empty_like(x2), bstats, N, HW, act=1)
     coef, dgamma, dbeta = torch.empty(3, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_bwd_finalize(bstats, rec, gamma, coef, dgamma, dbeta, N * HW)
@@ -160,7 +162,7 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd):
     # standalone reduce == the fused sums
     bs2 = torch.zeros_like(bstats)
     ops.bn_bwd_reduce(g, x2, rec, bs2)
-    assert torch.allclose(bs2, bstats, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(ops.stats_total(bs2), ops.stats_total(bstats), rtol=1e-3, atol=1e-2)
 
 
 def test_bn_fold_eval_and_act0(ops):
@@ -174,7 +176,7 @@ def test_bn_fold_eval_and_act0(ops):
     N, HW = 3, 10
     x = rnd(N * HW, C, seed=5, dtype=bf16)
     dmean = rnd(N, C, seed=6)
-    bst = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    bst = ops.new_stats(C, "cuda")
     g = ops.act_bwd(None, None, dmean, 1.0 / HW, x, rec, torch.empty_like(x), bst, N, HW, act=0)
     ref = (dmean / HW)[:, None, :].expand(N, HW, C).reshape(N * HW, C)
     assert rel_err(g, ref) < 1e-2
@@ -202,13 +204,14 @@ def test_dwconv_forward_backward(ops, k, s, N, H, W, C):
     xa = F.silu(xt * rec1[0] + rec1[1])                       # same folded scale/shift as the kernel
     y_ref = F.conv2d(same_pad_t(xa.permute(0, 3, 1, 2), k, s), wt, stride=s, groups=C).permute(0, 2, 3, 1)
     # forward (train flavour: raw output + statistics)
-    stats = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    stats = ops.new_stats(C, "cuda")
     y = torch.empty(N, OH, OW, C, device="cuda", dtype=bf16)
     ops.dwconv_fwd(x_raw, rec1, w, y, N, H, W, k, s, stats=stats)
     assert y_ref.shape == y.shape
     assert rel_err(y, y_ref) < 1e-2
     yd = y.double().view(-1, C)
-    assert torch.allclose(stats[0], yd.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(stats[1], (yd * yd).sum(0), rtol=1e-4, atol=1e-2)
+    tot = ops.stats_total(stats)
+    assert torch.allclose(tot[0], yd.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(tot[1], (yd * yd).sum(0), rtol=1e-4, atol=1e-2)
     # forward (eval flavour: folded BN + SiLU + SE pooling in the epilogue), no input transform
     g2, b2 = rnd(C, seed=25) * 0.1 + 1, rnd(C, seed=26) * 0.1
     rec2, _, _, _ = make_rec(ops, y, g2, b2)
@@ -226,7 +229,7 @@ def test_dwconv_forward_backward(ops, k, s, N, H, W, C):
     dD = dD.to(bf16).float()                                  # the kernel rounds the staged tile to bf16
     y_ref.backward(dD)
     g_out = torch.empty_like(x_raw)
-    bst = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    bst = ops.new_stats(C, "cuda")
     dw = torch.zeros_like(w)
     dD_dev = ops.affine2(gy, y, coef, torch.empty_like(gy))   # the BN-backward affine runs as its own streaming pass
     ops.dwconv_bwd(dD_dev, w, x_raw, rec1, g_out, bst, dw, N, H, W, k, s)
@@ -236,7 +239,8 @@ def test_dwconv_forward_backward(ops, k, s, N, H, W, C):
     assert rel_err(dw, wt.grad) < 2e-2
     gd = g_out.double().view(-1, C)
     xh = (x_raw.double().view(-1, C) - rec1[2].double()) * rec1[3].double()
-    assert torch.allclose(bst[0], gd.sum(0), rtol=1e-3, atol=1e-2) and torch.allclose(bst[1], (gd * xh).sum(0), rtol=1e-3, atol=1e-2)
+    bt = ops.stats_total(bst)
+    assert torch.allclose(bt[0], gd.sum(0), rtol=1e-3, atol=1e-2) and torch.allclose(bt[1], (gd * xh).sum(0), rtol=1e-3, atol=1e-2)
     # no-transform / no-coef flavour (DS block whose input is already an activation)
     xt2 = x_raw.float().requires_grad_(True)
     y2 = F.conv2d(same_pad_t(xt2.permute(0, 3, 1, 2), k, s), w, stride=s, groups=C).permute(0, 2, 3, 1)
@@ -257,11 +261,12 @@ def test_stem_forward_wgrad(ops, CS, N, H, W, dt):
     ref = F.conv2d(same_pad_t(xt, 3, 2), wt, stride=2).permute(0, 2, 3, 1)
     OH, OW = ref.shape[1:3]
     out = torch.empty(N, OH, OW, CS, device="cuda", dtype=bf16)
-    stats = torch.zeros(2, CS, device="cuda", dtype=torch.float64)
+    stats = ops.new_stats(CS, "cuda")
     ops.stem_fwd(x, w, out, stats=stats)
     assert rel_err(out, ref) < 1e-2
     od = out.double().view(-1, CS)
-    assert torch.allclose(stats[0], od.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(stats[1], (od * od).sum(0), rtol=1e-4, atol=1e-2)
+    tot = ops.stats_total(stats)
+    assert torch.allclose(tot[0], od.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(tot[1], (od * od).sum(0), rtol=1e-4, atol=1e-2)
     rec = torch.stack([rnd(CS, seed=33) * 0.1 + 1, rnd(CS, seed=34) * 0.1, torch.zeros(CS, device="cuda"), torch.ones(CS, device="cuda")])
     out2 = torch.empty_like(out)
     ops.stem_fwd(x, w, out2, out_rec=rec)
@@ -276,7 +281,7 @@ def test_stem_forward_wgrad(ops, CS, N, H, W, dt):
     cols = F.unfold(same_pad_t(xt, 3, 2), 3, stride=2).transpose(1, 2).reshape(-1, 27)      # column = ci*9 + kh*3 + kw
     assert torch.equal(patches[:, :27].float(), cols) and float(patches[:, 27:].abs().max()) == 0.0
     wp = ops.stem_pack_w(w, torch.empty(CS, 32, device="cuda", dtype=bf16))
-    stats2 = torch.zeros(2, CS, device="cuda", dtype=torch.float64)
+    stats2 = ops.new_stats(CS, "cuda")
     out3 = ops.gemm(patches, wp, ops.EPI_STATS, stats=stats2).view(N, OH, OW, CS)
     assert rel_err(out3, ref) < 1e-2
     dw2 = torch.zeros_like(w)

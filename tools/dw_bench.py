@@ -47,11 +47,11 @@ for i, (H, C, k, s, cnt) in enumerate(SHAPES):
                        torch.rand(C, device="cuda") + 0.5]).contiguous()
     w = torch.randn(C, 1, k, k, device="cuda") / k
     y = torch.empty(N, OH, OH, C, device="cuda", dtype=bf16)
-    stats = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    stats = ops.new_stats(C, "cuda")
     gy = torch.randn(N, OH, OH, C, device="cuda").to(bf16)
     coef = torch.stack([torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.05, torch.randn(C, device="cuda") * 0.05]).contiguous()
     g_out = torch.empty_like(x)
-    bst = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    bst = ops.new_stats(C, "cuda")
     dw = torch.zeros_like(w)
     tf = timed(lambda: ops.dwconv_fwd(x, rec, w, y, N, H, H, k, s, stats=stats))
     dD = torch.empty_like(gy)

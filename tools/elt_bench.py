@@ -27,7 +27,7 @@ for hw, C, cnt in SHAPES:
     x = torch.randn(N * HW, C, device="cuda").to(bf16); dA = torch.randn(N * HW, C, device="cuda").to(bf16)
     rec = torch.stack([torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1, torch.randn(C, device="cuda") * 0.1, torch.rand(C, device="cuda") + 0.5]).contiguous()
     gate = torch.rand(N, C, device="cuda"); dmean = torch.randn(N, C, device="cuda"); coef = torch.randn(3, C, device="cuda")
-    out = torch.empty_like(x); bst = torch.zeros(2, C, device="cuda", dtype=torch.float64); pooled = torch.empty(N, C, device="cuda")
+    out = torch.empty_like(x); bst = ops.new_stats(C, "cuda"); pooled = torch.empty(N, C, device="cuda")
     B = x.numel() * 2
     res = {
         "act_bwd": (timed(lambda: ops.act_bwd(dA, gate, dmean, 1.0 / HW, x, rec, out, bst, N, HW, act=1)), 3 * B),

@@ -35,7 +35,7 @@ for hw, ci, co, cnt in LAYERS:
     Wt = W.t().contiguous()
     C = torch.empty(M, co, device="cuda", dtype=torch.bfloat16)
     dA = torch.empty(M, ci, device="cuda", dtype=torch.bfloat16)
-    st = torch.zeros(2, co, device="cuda", dtype=torch.float64)
+    st = ops.new_stats(co, "cuda")
     dW = torch.zeros(co, ci, device="cuda")
     tf = timed(lambda: ops.gemm(A, W, ops.EPI_STATS, stats=st, out=C))
     td = timed(lambda: ops.gemm(C, Wt, 0, out=dA))

@@ -7,7 +7,7 @@ hw, ci, co = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 M = 64 * hw * hw
 A = torch.randn(M, ci, device="cuda").to(torch.bfloat16); W = torch.randn(co, ci, device="cuda").to(torch.bfloat16); Wt = W.t().contiguous()
 C = torch.empty(M, co, device="cuda", dtype=torch.bfloat16); dA = torch.empty(M, ci, device="cuda", dtype=torch.bfloat16)
-st = torch.zeros(2, co, device="cuda", dtype=torch.float64)
+st = ops.new_stats(co, "cuda")
 print("fwd...", flush=True); ops.gemm(A, W, ops.EPI_STATS, stats=st, out=C); torch.cuda.synchronize(); print("fwd ok", flush=True)
 ref = (A.float() @ W.float().t())
 print("fwd err", float((C.float() - ref).abs().max() / ref.abs().max()), flush=True)

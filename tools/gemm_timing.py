@@ -15,7 +15,7 @@ SHAPES_OLD = [(64 * 112 * 112, 64, 144, ops.EPI_STATS), (64 * 112 * 112, 32, 144
 for (M, K, N, flags) in SHAPES[:1] + SHAPES[-1:] + [(64 * 112 * 112, 24, 144, ops.EPI_STATS), (64 * 112 * 112, 24, 24, ops.EPI_STATS), (64 * 112 * 112, 144, 24, 0),
                          (64 * 56 * 56, 32, 192, ops.EPI_STATS), (64 * 14 * 14, 160, 960, ops.EPI_STATS), (64 * 7 * 7, 1632, 272, ops.EPI_STATS)]:
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16); W = torch.randn(N, K, device="cuda").to(torch.bfloat16)
-    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); st = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); st = ops.new_stats(N, "cuda")
     for _ in range(2): ops.gemm(A, W, flags, stats=st if flags else None, out=C)
     torch.cuda.synchronize(); lib.trt_debug_gemm_timing(None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -10,7 +10,7 @@ M, K, N = 64 * 112 * 112, 24, 144
 A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 W = torch.randn(N, K, device="cuda").to(torch.bfloat16)
 C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-stats = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+stats = ops.new_stats(N, "cuda")
 dW = torch.zeros(N, K, device="cuda")
 for _ in range(6):
     ops.gemm(A, W, ops.EPI_STATS, stats=stats, out=C)
