@@ -177,7 +177,8 @@ int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out
                    double* stats, const trt_bn_fin_t* fin_host, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
 /* gy = dD, the gradient w.r.t. the RAW depthwise output (the BN-backward affine of the following BatchNorm has already been
  * applied by trt_affine2).  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1), bstats += {sum g, sum g*xhat};
- * dw[C,1,k,k] += correlation of dD with act(x) (act = silu(bn) when x_rec). */
+ * dw[C,1,k,k] (NULL = skip) += correlation of dD with act(x) (act = silu(bn) when x_rec).  The two halves are independent:
+ * a caller may issue them as two calls on two streams. */
 int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out, double* bstats,
                    const trt_bn_bwd_fin_t* fin_host, float* dw, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
 /* x: NCHW [N,3,H,W] fp32 or bf16 -> out NHWC bf16 [N,ceil(H/2),ceil(W/2),CS]; CS in {32, 48} */

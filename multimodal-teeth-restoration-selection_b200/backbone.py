@@ -420,6 +420,15 @@ class _SideQueue:
         with torch.cuda.stream(self.side):
             ops.gemm_wgrad(P, Q, out, **kw)
 
+    def dw_wgrad(self, dD, w, x_raw, x_rec, dw, N, h, w_, k, s):
+        """Depthwise weight gradient: independent of the data gradient (both read dD), so it joins the side stream."""
+        if not self.enabled:
+            return ops.dwconv_bwd(dD, w, x_raw, x_rec, None, None, dw, N, h, w_, k, s)
+        self.keep += [dD, x_raw]
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            ops.dwconv_bwd(dD, w, x_raw, x_rec, None, None, dw, N, h, w_, k, s)
+
     def join(self):
         if self.enabled:
             self.main.wait_stream(self.side)
@@ -511,8 +520,9 @@ def backward_train(enc, ctx, dfeat, grads):
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
             bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
             g1 = torch.empty_like(e_raw)
+            sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), e_raw, rec1, dw_grad, N, h, w, k, s)
             coef1, _ = bn_back(name + ".bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1,
-                                                                                         g1, bst, dw_grad, N, h, w, k, s, fin=fin))
+                                                                                         g1, bst, None, N, h, w, k, s, fin=fin))
             de = ops.affine2(g1, e_raw, coef1, g1)
             flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
             dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
@@ -524,14 +534,16 @@ def backward_train(enc, ctx, dfeat, grads):
             if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
                 bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
                 g_in = torch.empty_like(x_in)
+                sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), x_in, in_rec, dw_grad, N, h, w, k, s)
                 coef_s, _ = bn_back("bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec,
-                                                                                      g_in, bst, dw_grad, N, h, w, k, s, fin=fin))
+                                                                                      g_in, bst, None, N, h, w, k, s, fin=fin))
                 ds = ops.affine2(g_in, x_in, coef_s, g_in)
                 _stem_wgrad(ctx, ds, grads, sq)
                 dy = None
             else:
                 g_in = torch.empty_like(x_in)
-                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, None, g_in, None, dw_grad, N, h, w, k, s)
+                sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), x_in, None, dw_grad, N, h, w, k, s)
+                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, None, g_in, None, None, N, h, w, k, s)
                 if sv["has_skip"]:
                     g_in = ops.affine2(g_in, dy, _add_coef(c["cin"], dev), g_in)
                 dy = g_in

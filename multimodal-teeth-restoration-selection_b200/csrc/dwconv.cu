@@ -683,7 +683,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
   trt_bn_bwd_fin_t fin = {};
   if (fin_host) fin = *fin_host;
   const int has_fin = fin_host ? 1 : 0;
-  TRT_REQUIRE(gy && w && x_raw && dw && N > 0 && C > 0 && C % 8 == 0, "trt_dwconv_bwd: bad argument");
+  TRT_REQUIRE(gy && w && x_raw && (dw || g_out) && N > 0 && C > 0 && C % 8 == 0, "trt_dwconv_bwd: bad argument");
   TRT_REQUIRE((k == 3 || k == 5) && (s == 1 || s == 2), "trt_dwconv_bwd: only k in {3,5}, s in {1,2}");
   DwGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.S = s;
@@ -734,6 +734,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
     rc = trt_check_launch("trt_dwconv_bwd(data)");
     if (rc) return rc;
   }
+  if (!dw) return TRT_OK;            // data gradient only (the weight gradient may run as its own call on another stream)
   {
     g.tiles_x = (g.OW + 7) / 8;
     g.tiles_y = (g.OH + TOH - 1) / TOH;
