@@ -567,6 +567,20 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
                                    long long so_q, int q_store, int lbo, int sbo, int kstep_bytes, cudaStream_t stream) {
   TRT_REQUIRE(P && Q && out, "trt_gemm_wgrad_bf16: null operand");
   TRT_REQUIRE(M > 0 && Cp > 0 && Cq > 0 && (Cp % 8) == 0 && (Cq % 8) == 0, "trt_gemm_wgrad_bf16: bad shape %d %d %d", M, Cp, Cq);
+  {
+    // out[p,q] = sum_m P[m,p] Q[m,q] is symmetric in the roles of P and Q: put the operand on the 128-row UMMA M side that
+    // gives fewer output tiles, so each operand column block is streamed from HBM fewer times (e.g. 144 x 24: one tile
+    // instead of two; measured 422 MB of DRAM reads for 270 MB of operands before)
+    auto tiles_of = [](int cp, int cq) {
+      const int bq = cq <= 256 ? cq : pick_block_n(cq);
+      return ((cp + BM - 1) / BM) * ((cq + bq - 1) / bq);
+    };
+    if (q_store <= 0 && tiles_of(Cq, Cp) < tiles_of(Cp, Cq)) {
+      const void* t = P; P = Q; Q = t;
+      int c = Cp; Cp = Cq; Cq = c;
+      long long so = so_p; so_p = so_q; so_q = so;
+    }
+  }
   WgradParams p;
   p.M = M; p.Cp = Cp; p.Cq = Cq;
   p.block_q = Cq <= 256 ? (Cq + 15) / 16 * 16 : pick_block_n(Cq);

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Evidence run for profiles/: (1) bench without ncu, (2) ncu launch list of the same command, (3) per-op step profile,
+# (4) ncu --set full of the top kernels.  Every ncu pass only after its command exited 0 without ncu.
+mkdir -p gpurun_out
+T=${TAG:-r01}
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err || { echo "bench failed"; tail -3 gpurun_out/${T}_bench.err; exit 1; }
+tail -c 600 gpurun_out/${T}_bench.json
+TEETHRT_NO_GRAPH=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
+TEETHRT_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4500 -c 1900 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1
+echo "launch list exit=$?"
+timeout 300 python tools/step_profile.py --log gpurun_out/${T}_step_ops_plain.json > /dev/null 2>&1 && \
+TEETHRT_WGRAD_STREAM=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv --log-file gpurun_out/${T}_step_launches.csv python tools/step_profile.py --log gpurun_out/${T}_step_ops.json > gpurun_out/${T}_stepprof.log 2>&1
+echo "step profile exit=$?"
+timeout 200 python tools/prof_top.py > /dev/null 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${T}_top_kernels python tools/prof_top.py > gpurun_out/${T}_ncu_top.log 2>&1
+echo "ncu full exit=$?"; tail -1 gpurun_out/${T}_ncu_top.log
+timeout 200 python bench.py --infer --steps 20 > gpurun_out/${T}_infer.json 2>&1; tail -c 400 gpurun_out/${T}_infer.json
+timeout 300 python tools/microbench.py > gpurun_out/${T}_micro.log 2>&1; echo "micro exit=$?"
