@@ -199,8 +199,9 @@ size_t trt_mil_attn_smem_bytes(int K, int D, int hid, int backward);
 int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub, const float* ww,
                      const float* wb, float* M, float* A, float* gV, float* gU, int B, int K, int D, int hid,
                      trt_stream_t stream);
-/* parameter gradients are ACCUMULATED (+=) with atomics: zero them first */
-int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, const float* gV, const float* gU, const float* Vw,
+/* parameter gradients are ACCUMULATED (+=): zero them first.  gV / gU (the gate activations saved by the forward) are
+ * CONSUMED: they are overwritten with the gate gradients dv / du, which the weight-gradient and dH kernels then read. */
+int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, float* gV, float* gU, const float* Vw,
                      const float* Uw, const float* ww, float* dH, float* dVw, float* dVb, float* dUw, float* dUb, float* dww,
                      float* dwb, int B, int K, int D, int hid, trt_stream_t stream);
 

@@ -14,57 +14,86 @@ constexpr int TPB = 256;
 constexpr int KC = 16;   // instances processed per register chunk
 
 // ================================================================================================= MIL attention
-__global__ void __launch_bounds__(TPB) mil_attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Vw,
-                                                           const float* __restrict__ Vb, const float* __restrict__ Uw,
-                                                           const float* __restrict__ Ub, const float* __restrict__ ww,
-                                                           const float* __restrict__ wb, float* __restrict__ M,
-                                                           float* __restrict__ A, float* __restrict__ gV,
-                                                           float* __restrict__ gU, int K, int D, int hid) {
+// Forward = two launches.  (1) scores: grid (bag, hidden-slice); the bag's instance matrix H[K][D] is staged once in shared
+// memory with coalesced float4 reads; a warp owns one hidden unit j and computes BOTH gate rows <V_j, H_k> and <U_j, H_k>
+// for 16 instances per pass (each H value read from shared memory feeds two FMAs), finishes them with warp shuffles, applies
+// tanh * sigmoid and adds w_j * gate into the bag's K scores (shared-memory atomics, then one global atomic per instance).
+// (2) pool: one CTA per bag: softmax over the K scores (warp shuffles) and M = sum_k alpha_k H_k with coalesced reads.
+// The hidden slice count adapts to the batch so that small batches (6 training bags) still fill the GPU.
+// HU = hidden units per warp: 1 when the batch is small (more blocks), 4 when it is large (each instance value read from
+// shared memory then feeds 8 gate rows = 32 FMAs, so the loop is FMA- rather than shared-memory-bound).
+template <int HU>
+__global__ void __launch_bounds__(TPB) mil_score_kernel(const float* __restrict__ H, const float* __restrict__ Vw,
+                                                        const float* __restrict__ Vb, const float* __restrict__ Uw,
+                                                        const float* __restrict__ Ub, const float* __restrict__ ww,
+                                                        float* __restrict__ score, float* __restrict__ gV,
+                                                        float* __restrict__ gU, int K, int D, int hid, int JH) {
+  constexpr int KCH = HU == 1 ? 16 : 8;      // instances per register pass
   extern __shared__ __align__(16) float sm[];
   float* s_H = sm;                       // [K][D]
-  float* s_pre = s_H + (size_t)K * D;    // [2*hid][K]  pre-activations (V rows then U rows)
-  float* s_att = s_pre + (size_t)2 * hid * K;   // [K]
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_sc = s_H + (size_t)K * D;     // [K] partial scores of this hidden slice
+  const int b = blockIdx.x, j0 = blockIdx.y * JH, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* Hg = reinterpret_cast<const float4*>(H + (size_t)b * K * D);
   const int D4 = D / 4;
   for (int i = threadIdx.x; i < K * D4; i += TPB) reinterpret_cast<float4*>(s_H)[i] = __ldg(Hg + i);
+  for (int k = threadIdx.x; k < K; k += TPB) s_sc[k] = 0.f;
   __syncthreads();
-  for (int j = warp; j < 2 * hid; j += TPB / 32) {
-    const float4* wrow = reinterpret_cast<const float4*>((j < hid ? Vw + (size_t)j * D : Uw + (size_t)(j - hid) * D));
-    const float bias = j < hid ? Vb[j] : Ub[j - hid];
-    for (int k0 = 0; k0 < K; k0 += KC) {
-      float acc[KC];
+  const int jend = min(j0 + JH, hid);
+  for (int jb = j0 + warp * HU; jb < jend; jb += (TPB / 32) * HU) {
+    for (int k0 = 0; k0 < K; k0 += KCH) {
+      float av[HU][KCH], au[HU][KCH];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+      for (int u = 0; u < HU; ++u)
+#pragma unroll
+        for (int k = 0; k < KCH; ++k) av[u][k] = au[u][k] = 0.f;
       for (int d = lane; d < D4; d += 32) {
-        const float4 w4 = __ldg(wrow + d);
+        float4 v4[HU], u4[HU];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
+        for (int u = 0; u < HU; ++u) {
+          const int j = min(jb + u, hid - 1);            // clamped rows are computed and dropped
+          v4[u] = __ldg(reinterpret_cast<const float4*>(Vw + (size_t)j * D) + d);
+          u4[u] = __ldg(reinterpret_cast<const float4*>(Uw + (size_t)j * D) + d);
+        }
+#pragma unroll
+        for (int k = 0; k < KCH; ++k) {
           if (k0 + k < K) {
             const float4 h = reinterpret_cast<const float4*>(s_H + (size_t)(k0 + k) * D)[d];
-            acc[k] = fmaf(w4.x, h.x, fmaf(w4.y, h.y, fmaf(w4.z, h.z, fmaf(w4.w, h.w, acc[k]))));
+#pragma unroll
+            for (int u = 0; u < HU; ++u) {
+              av[u][k] = fmaf(v4[u].x, h.x, fmaf(v4[u].y, h.y, fmaf(v4[u].z, h.z, fmaf(v4[u].w, h.w, av[u][k]))));
+              au[u][k] = fmaf(u4[u].x, h.x, fmaf(u4[u].y, h.y, fmaf(u4[u].z, h.z, fmaf(u4[u].w, h.w, au[u][k]))));
+            }
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (lane == 0 && k0 + k < K) s_pre[(size_t)j * K + k0 + k] = s + bias;
+      for (int u = 0; u < HU; ++u) {
+        const int j = jb + u;
+#pragma unroll
+        for (int k = 0; k < KCH; ++k) {
+          if (k0 + k < K && j < jend) {                    // uniform across the warp
+            const float sv = warp_sum(av[u][k]) + Vb[j], su = warp_sum(au[u][k]) + Ub[j];
+            if (lane == 0) {
+              const float tv = tanhf(sv), sg = 1.0f / (1.0f + expf(-su));
+              if (gV) { gV[((size_t)b * K + k0 + k) * hid + j] = tv; gU[((size_t)b * K + k0 + k) * hid + j] = sg; }
+              atomicAdd(s_sc + k0 + k, ww[j] * tv * sg);
+            }
+          }
+        }
       }
     }
   }
   __syncthreads();
-  for (int k = warp; k < K; k += TPB / 32) {
-    float acc = 0.f;
-    for (int j = lane; j < hid; j += 32) {
-      const float tv = tanhf(s_pre[(size_t)j * K + k]);
-      const float su = 1.0f / (1.0f + expf(-s_pre[(size_t)(hid + j) * K + k]));
-      if (gV) { gV[((size_t)b * K + k) * hid + j] = tv; gU[((size_t)b * K + k) * hid + j] = su; }
-      acc = fmaf(ww[j], tv * su, acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) s_att[k] = acc + wb[0];
-  }
+  for (int k = threadIdx.x; k < K; k += TPB) atomicAdd(score + (size_t)b * K + k, s_sc[k]);
+}
+
+// A holds the raw scores on entry and the softmax weights on exit
+__global__ void __launch_bounds__(TPB) mil_pool_kernel(const float* __restrict__ H, const float* __restrict__ wb,
+                                                       float* __restrict__ A, float* __restrict__ M, int K, int D) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_att = sm;   // [K]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < K; k += TPB) s_att[k] = A[(size_t)b * K + k] + wb[0];
   __syncthreads();
   if (warp == 0) {   // softmax over the K instances (dim=1 of [B,K]; dim=0 of the twin's single bag)
     float mx = -INFINITY;
@@ -80,36 +109,42 @@ __global__ void __launch_bounds__(TPB) mil_attn_fwd_kernel(const float* __restri
     }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < D; d += TPB) {
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc = fmaf(s_att[k], s_H[(size_t)k * D + d], acc);
-    M[(size_t)b * D + d] = acc;
+  const float4* Hg = reinterpret_cast<const float4*>(H + (size_t)b * K * D);
+  const int D4 = D / 4;
+  for (int d = threadIdx.x; d < D4; d += TPB) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int k = 0; k < K; ++k) {
+      const float a = s_att[k];
+      const float4 h = __ldg(Hg + (size_t)k * D4 + d);
+      acc.x = fmaf(a, h.x, acc.x); acc.y = fmaf(a, h.y, acc.y); acc.z = fmaf(a, h.z, acc.z); acc.w = fmaf(a, h.w, acc.w);
+    }
+    reinterpret_cast<float4*>(M + (size_t)b * D)[d] = acc;
   }
 }
 
-__global__ void __launch_bounds__(TPB) mil_attn_bwd_kernel(const float* __restrict__ dM, const float* __restrict__ H,
-                                                           const float* __restrict__ A, const float* __restrict__ gV,
-                                                           const float* __restrict__ gU, const float* __restrict__ Vw,
-                                                           const float* __restrict__ Uw, const float* __restrict__ ww,
-                                                           float* __restrict__ dH, float* __restrict__ dVw,
-                                                           float* __restrict__ dVb, float* __restrict__ dUw,
-                                                           float* __restrict__ dUb, float* __restrict__ dww,
-                                                           float* __restrict__ dwb, int K, int D, int hid) {
+// Backward = three launches:
+//   (1) per bag: dalpha_k = <dM, H_k>, softmax backward, gate gradients; gV / gU are OVERWRITTEN with dv / du [B,K,hid]
+//   (2) weight gradients as a blocked product over ALL bags: dW[j][d] += sum_{b,k} dvu[b,k,j] H[b,k,d]; each output element
+//       is owned by one block (no atomics; the old kernel issued 2*hid*D global atomics per bag)
+//   (3) dH[b,k,d] = alpha_k dM[d] + sum_j dv[b,k,j] Vw[j][d] + du[b,k,j] Uw[j][d]; grid (bag, D-slice)
+__global__ void __launch_bounds__(TPB) mil_bwd_gate_kernel(const float* __restrict__ dM, const float* __restrict__ H,
+                                                           const float* __restrict__ A, float* __restrict__ gV,
+                                                           float* __restrict__ gU, const float* __restrict__ ww,
+                                                           float* __restrict__ dVb, float* __restrict__ dUb,
+                                                           float* __restrict__ dww, float* __restrict__ dwb, int K, int D,
+                                                           int hid) {
   extern __shared__ __align__(16) float sm[];
-  float* s_H = sm;                          // [K][D]
-  float* s_dM = s_H + (size_t)K * D;        // [D]
-  float* s_dv = s_dM + D;                   // [K][hid]
-  float* s_du = s_dv + (size_t)K * hid;     // [K][hid]
-  float* s_da = s_du + (size_t)K * hid;     // [K]
+  float* s_da = sm;   // [K]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D4 = D / 4;
   const float4* Hg = reinterpret_cast<const float4*>(H + (size_t)b * K * D);
-  for (int i = threadIdx.x; i < K * D4; i += TPB) reinterpret_cast<float4*>(s_H)[i] = __ldg(Hg + i);
-  for (int i = threadIdx.x; i < D; i += TPB) s_dM[i] = dM[(size_t)b * D + i];
-  __syncthreads();
+  const float4* dMg = reinterpret_cast<const float4*>(dM + (size_t)b * D);
   for (int k = warp; k < K; k += TPB / 32) {   // dalpha_k = <dM, H_k>
     float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc = fmaf(s_dM[d], s_H[(size_t)k * D + d], acc);
+    for (int d = lane; d < D4; d += 32) {
+      const float4 m = __ldg(dMg + d), h = __ldg(Hg + (size_t)k * D4 + d);
+      acc = fmaf(m.x, h.x, fmaf(m.y, h.y, fmaf(m.z, h.z, fmaf(m.w, h.w, acc))));
+    }
     acc = warp_sum(acc);
     if (lane == 0) s_da[k] = acc;
   }
@@ -132,50 +167,99 @@ __global__ void __launch_bounds__(TPB) mil_attn_bwd_kernel(const float* __restri
     float aw = 0.f, av = 0.f, au = 0.f;
     const float wj = ww[j];
     for (int k = 0; k < K; ++k) {
-      const float tv = gV[((size_t)b * K + k) * hid + j], su = gU[((size_t)b * K + k) * hid + j];
+      const size_t idx = ((size_t)b * K + k) * hid + j;
+      const float tv = gV[idx], su = gU[idx];
       const float da = s_da[k];
       aw = fmaf(da, tv * su, aw);
       const float dg = da * wj;
       const float dv = dg * su * (1.f - tv * tv), du = dg * tv * su * (1.f - su);
-      s_dv[(size_t)k * hid + j] = dv;
-      s_du[(size_t)k * hid + j] = du;
+      gV[idx] = dv;
+      gU[idx] = du;
       av += dv; au += du;
     }
     atomicAdd(dww + j, aw);
     atomicAdd(dVb + j, av);
     atomicAdd(dUb + j, au);
   }
-  __syncthreads();
-  for (int j = warp; j < 2 * hid; j += TPB / 32) {   // weight gradients: dW[j][:] += sum_k dv[k][j] * H_k
-    const float* sd = j < hid ? s_dv + j : s_du + (j - hid);
-    float* dst = j < hid ? dVw + (size_t)j * D : dUw + (size_t)(j - hid) * D;
-    for (int d = lane; d < D4; d += 32) {
-      float4 acc = make_float4(0, 0, 0, 0);
-      for (int k = 0; k < K; ++k) {
-        const float c = sd[(size_t)k * hid];
-        const float4 h = reinterpret_cast<const float4*>(s_H + (size_t)k * D)[d];
-        acc.x = fmaf(c, h.x, acc.x); acc.y = fmaf(c, h.y, acc.y); acc.z = fmaf(c, h.z, acc.z); acc.w = fmaf(c, h.w, acc.w);
+}
+
+constexpr int MW_R = 16;     // gate rows per block
+constexpr int MW_C = 256;    // feature columns per block (one per thread)
+constexpr int MW_CH = 32;    // (bag, instance) rows per shared-memory chunk
+__global__ void __launch_bounds__(TPB) mil_bwd_weight_kernel(const float* __restrict__ H, const float* __restrict__ dv,
+                                                             const float* __restrict__ du, float* __restrict__ dVw,
+                                                             float* __restrict__ dUw, int BK, int D, int hid) {
+  __shared__ __align__(16) float s_h[MW_CH][MW_C];
+  __shared__ __align__(16) float s_g[MW_CH][MW_R];
+  const int nb = gridDim.x / 2, d0 = blockIdx.y * MW_C, t = threadIdx.x;   // first half of the row blocks = V, second = U
+  const bool is_u = (int)blockIdx.x >= nb;
+  const float* g = is_u ? du : dv;
+  const int j0 = ((int)blockIdx.x - (is_u ? nb : 0)) * MW_R;
+  float acc[MW_R];
+#pragma unroll
+  for (int i = 0; i < MW_R; ++i) acc[i] = 0.f;
+  for (int r0 = 0; r0 < BK; r0 += MW_CH) {
+    __syncthreads();
+    for (int i = t; i < MW_CH * MW_C; i += TPB) {
+      const int r = i / MW_C, c = i % MW_C;
+      s_h[r][c] = (r0 + r < BK && d0 + c < D) ? __ldg(H + (size_t)(r0 + r) * D + d0 + c) : 0.f;
+    }
+    for (int i = t; i < MW_CH * MW_R; i += TPB) {
+      const int r = i / MW_R, c = i % MW_R;
+      s_g[r][c] = (r0 + r < BK && j0 + c < hid) ? __ldg(g + (size_t)(r0 + r) * hid + j0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < MW_CH; ++r) {
+      const float h = s_h[r][t];
+#pragma unroll
+      for (int i4 = 0; i4 < MW_R / 4; ++i4) {
+        const float4 gg = *reinterpret_cast<const float4*>(&s_g[r][4 * i4]);
+        acc[4 * i4] = fmaf(gg.x, h, acc[4 * i4]); acc[4 * i4 + 1] = fmaf(gg.y, h, acc[4 * i4 + 1]);
+        acc[4 * i4 + 2] = fmaf(gg.z, h, acc[4 * i4 + 2]); acc[4 * i4 + 3] = fmaf(gg.w, h, acc[4 * i4 + 3]);
       }
-      atomicAdd(dst + 4 * d, acc.x); atomicAdd(dst + 4 * d + 1, acc.y);
-      atomicAdd(dst + 4 * d + 2, acc.z); atomicAdd(dst + 4 * d + 3, acc.w);
     }
   }
-  // dH[k][d] = alpha_k * dM[d] + sum_j dv[k][j] Vw[j][d] + du[k][j] Uw[j][d]
-  for (int d = threadIdx.x; d < D; d += TPB) {
-    for (int k0 = 0; k0 < K; k0 += KC) {
-      float acc[KC];
+  float* dst = is_u ? dUw : dVw;
+  if (d0 + t < D) {
 #pragma unroll
-      for (int k = 0; k < KC; ++k) acc[k] = 0.f;
-      for (int j = 0; j < hid; ++j) {
-        const float wv = __ldg(Vw + (size_t)j * D + d), wu = __ldg(Uw + (size_t)j * D + d);
+    for (int i = 0; i < MW_R; ++i)
+      if (j0 + i < hid) dst[(size_t)(j0 + i) * D + d0 + t] += acc[i];      // this block owns these elements
+  }
+}
+
+constexpr int MH_C = 128;    // feature columns per block of the dH kernel
+__global__ void __launch_bounds__(TPB) mil_bwd_dh_kernel(const float* __restrict__ dM, const float* __restrict__ A,
+                                                         const float* __restrict__ dv, const float* __restrict__ du,
+                                                         const float* __restrict__ Vw, const float* __restrict__ Uw,
+                                                         float* __restrict__ dH, int K, int D, int hid) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_dv = sm;                         // [K][hid]
+  float* s_du = s_dv + (size_t)K * hid;     // [K][hid]
+  const int b = blockIdx.x, d0 = blockIdx.y * MH_C;
+  for (int i = threadIdx.x; i < K * hid; i += TPB) {
+    s_dv[i] = dv[(size_t)b * K * hid + i];
+    s_du[i] = du[(size_t)b * K * hid + i];
+  }
+  __syncthreads();
+  const int dl = threadIdx.x % MH_C, kh = threadIdx.x / MH_C;      // two instance halves per column
+  const int d = d0 + dl;
+  if (d >= D) return;
+  const float dm = dM[(size_t)b * D + d];
+  for (int k0 = kh * 8; k0 < K; k0 += 16) {
+    float acc[8];
 #pragma unroll
-        for (int k = 0; k < KC; ++k)
-          if (k0 + k < K) acc[k] = fmaf(s_dv[(size_t)(k0 + k) * hid + j], wv, fmaf(s_du[(size_t)(k0 + k) * hid + j], wu, acc[k]));
-      }
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < hid; ++j) {
+      const float wv = __ldg(Vw + (size_t)j * D + d), wu = __ldg(Uw + (size_t)j * D + d);
 #pragma unroll
-      for (int k = 0; k < KC; ++k)
-        if (k0 + k < K) dH[((size_t)b * K + k0 + k) * D + d] = fmaf(A[(size_t)b * K + k0 + k], s_dM[d], acc[k]);
+      for (int k = 0; k < 8; ++k)
+        if (k0 + k < K) acc[k] = fmaf(s_dv[(size_t)(k0 + k) * hid + j], wv, fmaf(s_du[(size_t)(k0 + k) * hid + j], wu, acc[k]));
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k0 + k < K) dH[((size_t)b * K + k0 + k) * D + d] = fmaf(A[(size_t)b * K + k0 + k], dm, acc[k]);
   }
 }
 
@@ -475,8 +559,8 @@ __global__ void __launch_bounds__(TPB) bce_logits_kernel(const float* __restrict
 }  // namespace
 
 extern "C" size_t trt_mil_attn_smem_bytes(int K, int D, int hid, int backward) {
-  if (backward) return ((size_t)K * D + D + 2 * (size_t)K * hid + K) * sizeof(float);
-  return ((size_t)K * D + 2 * (size_t)hid * K + K) * sizeof(float);
+  if (backward) return (size_t)2 * K * hid * sizeof(float);
+  return ((size_t)K * D + K) * sizeof(float);
 }
 
 extern "C" int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub,
@@ -488,12 +572,30 @@ extern "C" int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb
   const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 0);
   TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_fwd: bag of %d x %d does not fit in shared memory", K, D);
   static bool attr = false;
-  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-  mil_attn_fwd_kernel<<<B, TPB, smem, stream>>>(H, Vw, Vb, Uw, Ub, ww, wb, M, A, gV, gU, K, D, hid);
+  if (!attr) {
+    TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  // hidden slices: enough blocks for ~2 per SM on small batches, one slice (H staged once per bag) on large ones
+  // hidden units per warp: the 4-unit variant (8 gate rows per shared-memory read) was measured SLOWER at B = 1024 (203
+  // registers, one block per SM, exposed L2 latency on the weight rows), so the 1-unit variant serves every batch size
+  const int hu = 1;
+  int JS = (2 * trt_num_sms() + B - 1) / B;
+  const int max_js = (hid + 8 * hu - 1) / (8 * hu);           // at least one pass of the block's 8 warps
+  if (JS > max_js) JS = max_js;
+  if (JS < 1) JS = 1;
+  const int JH = ((hid + JS - 1) / JS + hu - 1) / hu * hu;
+  JS = (hid + JH - 1) / JH;
+  TRT_CUDA(cudaMemsetAsync(A, 0, (size_t)B * K * sizeof(float), stream));      // A accumulates the raw scores first
+  if (hu == 4) mil_score_kernel<4><<<dim3(B, JS), TPB, smem, stream>>>(H, Vw, Vb, Uw, Ub, ww, A, gV, gU, K, D, hid, JH);
+  else mil_score_kernel<1><<<dim3(B, JS), TPB, smem, stream>>>(H, Vw, Vb, Uw, Ub, ww, A, gV, gU, K, D, hid, JH);
+  trt_count_launch(1);
+  mil_pool_kernel<<<B, TPB, (size_t)K * sizeof(float), stream>>>(H, wb, A, M, K, D);
   return trt_check_launch("trt_mil_attn_fwd");
 }
 
-extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, const float* gV, const float* gU,
+extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, float* gV, float* gU,
                                 const float* Vw, const float* Uw, const float* ww, float* dH, float* dVw, float* dVb,
                                 float* dUw, float* dUb, float* dww, float* dwb, int B, int K, int D, int hid,
                                 cudaStream_t stream) {
@@ -501,10 +603,14 @@ extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A,
               "trt_mil_attn_bwd: null pointer");
   TRT_REQUIRE(B > 0 && K > 0 && D > 0 && D % 4 == 0 && hid > 0, "trt_mil_attn_bwd: bad shape");
   const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 1);
-  TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_bwd: bag of %d x %d does not fit in shared memory", K, D);
+  TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_bwd: bag of %d x %d does not fit in shared memory", K, hid);
   static bool attr = false;
-  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-  mil_attn_bwd_kernel<<<B, TPB, smem, stream>>>(dM, H, A, gV, gU, Vw, Uw, ww, dH, dVw, dVb, dUw, dUb, dww, dwb, K, D, hid);
+  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  mil_bwd_gate_kernel<<<B, TPB, (size_t)K * sizeof(float), stream>>>(dM, H, A, gV, gU, ww, dVb, dUb, dww, dwb, K, D, hid);
+  trt_count_launch(1);
+  mil_bwd_weight_kernel<<<dim3(2 * ((hid + MW_R - 1) / MW_R), (D + MW_C - 1) / MW_C), TPB, 0, stream>>>(H, gV, gU, dVw, dUw, B * K, D, hid);
+  trt_count_launch(1);
+  mil_bwd_dh_kernel<<<dim3(B, (D + MH_C - 1) / MH_C), TPB, smem, stream>>>(dM, A, gV, gU, Vw, Uw, dH, K, D, hid);
   return trt_check_launch("trt_mil_attn_bwd");
 }
 

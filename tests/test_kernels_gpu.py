@@ -290,7 +290,7 @@ def test_stem_forward_wgrad(ops, CS, N, H, W, dt):
 
 
 # ------------------------------------------------------------------------------------------------ MIL pooling
-@pytest.mark.parametrize("B,K,D,hid", [(6, 16, 1280, 128), (1, 5, 1280, 256), (3, 12, 64, 32), (2, 31, 1280, 128)])
+@pytest.mark.parametrize("B,K,D,hid", [(6, 16, 1280, 128), (1, 5, 1280, 256), (3, 12, 64, 32), (2, 31, 1280, 128), (160, 7, 64, 40)])
 def test_mil_attention_forward_backward(ops, B, K, D, hid):
     H = rnd(B, K, D, seed=41)
     Vw, Vb = rnd(hid, D, seed=42, scale=D ** -0.5), rnd(hid, seed=43, scale=0.1)
