@@ -299,53 +299,83 @@ struct TabParams {
   float* scratch;
 };
 
+// Tab MLP in ONE block with the whole problem in shared memory (z0 / a1 [B][Hd] in place, W1 padded): the earlier version
+// walked global scratch with dependent loads (170 us for ~0.6 MFLOP).  Global scratch still receives z0, a1, ft and the BN
+// statistics for the backward pass.
 __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
-  const int B = p.B, T = p.T, Hd = p.Hd, F = p.F;
+  extern __shared__ __align__(16) float tsm[];
+  const int B = p.B, T = p.T, Hd = p.Hd;
+  float* s_z = tsm;                        // [B][Hd]   z0, then a1 in place
+  float* s_w1 = s_z + (size_t)B * Hd;      // [Hd][Hd+1]
+  float* s_part = s_w1 + (size_t)Hd * (Hd + 1);   // [2][TPB] partial sums of the BatchNorm1d statistics
+  float* s_stat = s_part + 2 * TPB;        // mean[Hd], rstd[Hd]
   float* z0 = p.scratch;
   float* a1 = z0 + (size_t)B * Hd;
   float* ft = a1 + (size_t)B * Hd;
   float* bnstat = ft + (size_t)B * Hd;   // mean[Hd], rstd[Hd]
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
-  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
+  const int t = threadIdx.x;
+  for (int i = t; i < Hd * Hd; i += TPB) s_w1[(i / Hd) * (Hd + 1) + (i % Hd)] = __ldg(p.W1 + i);
+  for (int i = t; i < B * Hd; i += TPB) {
     const int b = i / Hd, j = i % Hd;
     float acc = p.b0[j];
-    for (int t = 0; t < T; ++t) acc = fmaf(p.xtab[b * T + t], p.W0[j * T + t], acc);
+    for (int tt = 0; tt < T; ++tt) acc = fmaf(__ldg(p.xtab + b * T + tt), __ldg(p.W0 + j * T + tt), acc);
+    s_z[i] = acc;
     z0[i] = acc;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < Hd; j += TPB) {
-    float mean, rstd;
-    if (p.train) {
-      float s = 0.f;
-      for (int b = 0; b < B; ++b) s += z0[b * Hd + j];
-      mean = s / B;
-      float v = 0.f;
-      for (int b = 0; b < B; ++b) { const float d = z0[b * Hd + j] - mean; v = fmaf(d, d, v); }
-      const float var = v / B;
-      rstd = rsqrtf(var + p.bn_eps);
-      p.bn_rm[j] = (1.f - p.bn_momentum) * p.bn_rm[j] + p.bn_momentum * mean;
-      p.bn_rv[j] = (1.f - p.bn_momentum) * p.bn_rv[j] + p.bn_momentum * (B > 1 ? v / (B - 1) : var);
-      if (j == 0 && p.bn_nbt) *p.bn_nbt += 1;
-    } else {
-      mean = p.bn_rm[j];
-      rstd = rsqrtf(p.bn_rv[j] + p.bn_eps);
+  // BatchNorm1d statistics: thread = (feature j, batch slice); two-pass (mean, then centred sum of squares) like torch
+  const int parts = TPB / Hd > 0 ? TPB / Hd : 1;
+  const int j = t % Hd, part = t / Hd;
+  if (p.train) {
+    float sacc = 0.f;
+    if (part < parts) for (int b = part; b < B; b += parts) sacc += s_z[b * Hd + j];
+    s_part[t] = sacc;
+    __syncthreads();
+    if (t < Hd) {
+      float m = 0.f;
+      for (int q = 0; q < parts; ++q) m += s_part[q * Hd + t];
+      s_stat[t] = m / B;
     }
-    bnstat[j] = mean;
-    bnstat[Hd + j] = rstd;
+    __syncthreads();
+    float vacc = 0.f;
+    if (part < parts) {
+      const float mean = s_stat[j];
+      for (int b = part; b < B; b += parts) { const float d = s_z[b * Hd + j] - mean; vacc = fmaf(d, d, vacc); }
+    }
+    s_part[TPB + t] = vacc;
+    __syncthreads();
+    if (t < Hd) {
+      float v = 0.f;
+      for (int q = 0; q < parts; ++q) v += s_part[TPB + q * Hd + t];
+      const float mean = s_stat[t], var = v / B;
+      s_stat[Hd + t] = rsqrtf(var + p.bn_eps);
+      p.bn_rm[t] = (1.f - p.bn_momentum) * p.bn_rm[t] + p.bn_momentum * mean;
+      p.bn_rv[t] = (1.f - p.bn_momentum) * p.bn_rv[t] + p.bn_momentum * (B > 1 ? v / (B - 1) : var);
+      if (t == 0 && p.bn_nbt) *p.bn_nbt += 1;
+    }
+  } else if (t < Hd) {
+    s_stat[t] = p.bn_rm[t];
+    s_stat[Hd + t] = rsqrtf(p.bn_rv[t] + p.bn_eps);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
-    const int j = i % Hd;
-    float v = (z0[i] - bnstat[j]) * bnstat[Hd + j] * p.bn_g[j] + p.bn_b[j];
+  if (t < 2 * Hd) bnstat[t] = s_stat[t];
+  for (int i = t; i < B * Hd; i += TPB) {
+    const int jj = i % Hd;
+    float v = (s_z[i] - s_stat[jj]) * s_stat[Hd + jj] * p.bn_g[jj] + p.bn_b[jj];
     v = fmaxf(v, 0.f);
     if (p.train) v *= keep_scale(p.drop_p, seed, 1, i);
+    s_z[i] = v;
     a1[i] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < B * Hd; i += TPB) {
-    const int b = i / Hd, j = i % Hd;
-    float acc = p.b1[j];
-    for (int t = 0; t < Hd; ++t) acc = fmaf(a1[b * Hd + t], p.W1[j * Hd + t], acc);
+  for (int i = t; i < B * Hd; i += TPB) {
+    const int b = i / Hd, jj = i % Hd;
+    float acc = p.b1[jj];
+    const float* arow = s_z + b * Hd;
+    const float* wrow = s_w1 + jj * (Hd + 1);
+#pragma unroll 8
+    for (int tt = 0; tt < Hd; ++tt) acc = fmaf(arow[tt], wrow[tt], acc);
     ft[i] = fmaxf(acc, 0.f);
   }
   if (threadIdx.x == 0 && p.loss) p.loss[0] = 0.f;     // the heads kernel (next launch) accumulates into it
@@ -636,7 +666,12 @@ extern "C" int trt_tab_heads_fwd(const float* feat, const float* xtab, const flo
   p.y_hard = y_hard; p.y_soft = y_soft; p.sample_w = sample_w;
   p.logit = logit; p.reg = reg; p.loss = loss; p.dlogit = dlogit; p.dreg = dreg;
   p.scratch = scratch;
-  tab_heads_fwd_kernel<<<1, TPB, 0, stream>>>(p);
+  TRT_REQUIRE(Hd <= TPB, "trt_tab_heads_fwd: tab_hidden %d > %d not built", Hd, TPB);
+  const size_t tsmem = ((size_t)B * Hd + (size_t)Hd * (Hd + 1) + 2 * TPB + 2 * Hd) * sizeof(float);
+  TRT_REQUIRE(tsmem <= 200 * 1024, "trt_tab_heads_fwd: batch %d x hidden %d does not fit in shared memory", B, Hd);
+  static bool tattr = false;
+  if (!tattr) { TRT_CUDA(cudaFuncSetAttribute(tab_heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); tattr = true; }
+  tab_heads_fwd_kernel<<<1, TPB, tsmem, stream>>>(p);
   trt_count_launch(1);
   heads_fwd_kernel<<<B, TPB, 0, stream>>>(p);
   return trt_check_launch("trt_tab_heads_fwd");
