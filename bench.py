@@ -155,8 +155,28 @@ def time_dominant_kernel(torch, ops, pk):
     alg = (M * K + N * K + M * N) * 2
     ach = alg / t / 1e9
     return {"kernel": "gemm_kmajor_kernel (blocks.1.0.conv_pw fwd, M=802816 K=24 N=144, BN-stats epilogue)", "bound": "hbm",
-            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
-            "peak_source": pk["src"], "avg_launch_us": t * 1e6, "algorithmic_bytes_per_launch": alg}
+            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": ncu_traffic(),
+            "peak_source": pk["src"], "avg_launch_us": t * 1e6, "algorithmic_bytes_per_launch": alg,
+            "write_cap_gbs": 3880.0, "frac_of_write_floor": (M * N * 2 / 3880e9) / t,
+            "note": "write-heavy launch: its floor is bytes_written / the measured 3.88 TB/s pure-write cap (tools/ubench/bw_probe.py); "
+                    "traffic = dram read+write bytes of this launch from profiles/r01_ncu_full_top_kernels.csv (ncu --set full)"}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed ncu --set full capture (bytes)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_top_kernels.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h, units = rows[0], rows[1]
+        r = next(r for r in rows[2:] if "gemm_kmajor" in r[0])
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(k)
+            tot += float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+        return tot
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -213,7 +233,8 @@ def run_ours(args):
     e2.record()
     for i in range(args.steps):
         loss = tr.step(*host_batches[i % 2])
-        losses.append(float(loss.item()))
+        tr.prefetch(*host_batches[(i + 1) % 2])      # next step's H2D (from pinned memory) overlaps this step's kernels
+        losses.append(float(loss.item()))            # D2H read of this step's result: one sync per step
     e3.record()
     barrier()
     t_e2e = torch.tensor([e2.elapsed_time(e3) * 1e-3], device=dev)

@@ -72,6 +72,8 @@ class _FusedTrainer:
         self._graphs = None
         self._nsteps = 0
         self._static = None
+        self._stage = None
+        self._staged = None
         self.launches_per_step = None
         self.sync.sync_initial_state(self.model)
 
@@ -138,12 +140,41 @@ class _FusedTrainer:
         self._finish_comm()
         gopt.replay()
 
+    def prefetch(self, *inputs):
+        """Start the host->device copy of the NEXT step's (pinned) inputs on a copy stream, so it overlaps the step that is
+        running; the matching step() call then only does a device-to-device copy.  (What the reference gets from DataLoader
+        workers + pin_memory + non_blocking copies, train_mm_joint_dualtask.py:211,238-240.)"""
+        if self._static is None:
+            return
+        if self._stage is None:
+            self._stage = [torch.empty_like(t) for t in self._static]
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._stage_free = torch.cuda.Event()
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.dev))
+        self._copy_stream.wait_event(self._stage_free)            # the previous step has finished reading the staging set
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, inputs):
+                if src is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._stage_ready.record(self._copy_stream)
+        self._staged = tuple(id(t) for t in inputs)
+
     def _step(self, *inputs):
         if self._static is None:
             self._make_static(*inputs)
-        for dst, src in zip(self._static, inputs):
-            if src is not None:
-                dst.copy_(src, non_blocking=True)
+        if self._staged is not None and self._staged == tuple(id(t) for t in inputs):
+            main = torch.cuda.current_stream(self.dev)
+            main.wait_event(self._stage_ready)
+            for dst, src, given in zip(self._static, self._stage, inputs):
+                if given is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._stage_free.record(main)
+            self._staged = None
+        else:
+            for dst, src in zip(self._static, inputs):
+                if src is not None:
+                    dst.copy_(src, non_blocking=True)
         if self.use_graph and self._nsteps >= self.graph_warmup:
             if self._graphs is None:
                 torch.cuda.synchronize()
@@ -205,6 +236,9 @@ class DualTaskTrainer(_FusedTrainer):
         # bucket 0 = tab + heads (everything after the backbone in the flat buffer), bucket 1 = the backbone
         first_head = min(fl.offsets[k][0] for k in TAB_PARAM_KEYS)
         return [fwd_and_heads, enc_backward], self._bucket_ranges([first_head])
+
+    def prefetch(self, x_img, x_tab, y_h, y_s, w=None):
+        super().prefetch(x_img, x_tab, y_h, y_s, w)
 
     def step(self, x_img, x_tab, y_h, y_s, w=None):
         """One train step; returns the (device-resident) loss tensor — read it whenever convenient, no per-step sync."""
