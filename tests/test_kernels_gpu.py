@@ -51,6 +51,27 @@ def test_gemm_plain(ops, M, N, K):
     assert rel_err(C, ref) < 1e-2
 
 
+# Many tiles per persistent CTA (several rounds of every epilogue group / TMEM accumulator): the path on which mbarrier
+# parity aliasing or a staging-buffer race would show up as a hang or wrong rows; small shapes never reach it.
+@pytest.mark.parametrize("N,K", [(24, 24), (144, 24), (192, 32), (56, 192), (272, 160), (672, 112)])
+def test_gemm_many_tiles_per_cta(ops, N, K):
+    M = 148 * 128 * 5 + 77
+    A, B = rnd(M, K, seed=11, dtype=bf16), rnd(N, K, scale=K ** -0.5, seed=12, dtype=bf16)
+    stats = ops.new_stats(N, "cuda")
+    for _ in range(3):                       # repeated launches: the hang this guards against was intermittent
+        stats.zero_()
+        C = ops.gemm(A, B, ops.EPI_STATS, stats=stats)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    assert rel_err(C, ref) < 1e-2
+    cf = C.double()
+    tot = ops.stats_total(stats)
+    assert torch.allclose(tot[0], cf.sum(0), rtol=1e-4, atol=5e-2)
+    assert torch.allclose(tot[1], (cf * cf).sum(0), rtol=1e-4, atol=5e-2)
+    dA = ops.gemm(C, B.t().contiguous())     # dgrad orientation (K and N swap roles)
+    assert rel_err(dA, C.float() @ B.float()) < 1e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 144, 24), (647, 336, 56), (3136, 672, 112)])
 def test_gemm_epilogues(ops, M, N, K):
     A, B = rnd(M, K, seed=3, dtype=bf16), rnd(N, K, scale=K ** -0.5, seed=4, dtype=bf16)
