@@ -269,3 +269,36 @@ def test_ensembles_mirror_reference_behaviour(T, tmp_path):
         want = float(torch.sigmoid(tw(xs)))
     assert abs(prob - want) < 1e-2 and "Instances=3" in dbg
     assert me.predict(tmp_path / "empty_dir_that_does_not_exist")[0] is None
+
+
+def test_fused_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
+    """The optional fused BatchNorm finalisation (last block of the producing kernel finalises the record; off by default
+    because it measured slower) and Trainer.prefetch() must give the same training trajectory as the default path."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+
+    def run(fuse, prefetch):
+        monkeypatch.setenv("TEETHRT_FUSE_BN_FWD", fuse)
+        monkeypatch.setenv("TEETHRT_FUSE_BN_BWD", fuse)
+        torch.manual_seed(0)
+        m = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).cuda()
+        tr = DualTaskTrainer(m, t_max=10, graph=False)
+        batches = [[t.pin_memory() for t in mm_inputs(8, 96, 300 + i)] for i in range(3)]
+        losses = []
+        for i, b in enumerate(batches):
+            loss = tr.step(*b)
+            if prefetch and i + 1 < len(batches):
+                tr.prefetch(*batches[i + 1])
+            losses.append(float(loss))
+        return losses, torch.cat([p.detach().flatten() for p in m.parameters()]).double()
+
+    l0, p0 = run("0", False)
+    l0b, p0b = run("0", False)               # run-to-run noise of the default path (atomic summation order, bf16 rounding)
+    l1, p1 = run("1", False)
+    l2, p2 = run("0", True)
+    dl = lambda a, b: max(abs(x - y) for x, y in zip(a, b))
+    dp = lambda a, b: float((a - b).norm() / a.norm())
+    print("loss diffs", dl(l0, l0b), dl(l0, l1), dl(l0, l2), "param diffs", dp(p0, p0b), dp(p0, p1), dp(p0, p2))
+    tol_l, tol_p = max(1e-3, 4 * dl(l0, l0b)), max(1e-4, 4 * dp(p0, p0b))
+    assert dl(l0, l1) < tol_l and dl(l0, l2) < tol_l
+    assert dp(p0, p1) < tol_p and dp(p0, p2) < tol_p
