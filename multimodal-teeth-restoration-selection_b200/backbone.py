@@ -410,7 +410,12 @@ class _SideQueue:
             if key not in _SideQueue._streams:
                 _SideQueue._streams[key] = torch.cuda.Stream(device=dev)
             self.side = _SideQueue._streams[key]
-            self.main = torch.cuda.current_stream(dev)
+            self.dev = dev
+
+    @property
+    def main(self):
+        # looked up at every use: a backward pass split over several captured graphs sees a different capture stream in each
+        return torch.cuda.current_stream(self.dev)
 
     def wgrad(self, P, Q, out, **kw):
         if not self.enabled:
@@ -443,6 +448,15 @@ def _stem_wgrad(ctx, ds, grads, sq):
 def backward_train(enc, ctx, dfeat, grads):
     """Backward of forward_train.  `grads`: dict name -> fp32 tensor (torch layout) for every parameter of the encoder;
     1x1-conv / depthwise / stem weight gradients are ACCUMULATED (+=) — pass zeroed tensors; the others are written."""
+    for _ in backward_train_iter(enc, ctx, dfeat, grads):
+        pass
+    return grads
+
+
+def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
+    """Generator form of backward_train: yields the block name after finishing every block listed in `split_after` (reverse
+    execution order), with all side-stream work joined - the gradients of that block and of everything executed before it
+    are final, so a data-parallel trainer can start their all-reduce while the rest of the backward pass runs."""
     dev = dfeat.device
     N, Wp, REC = ctx["N"], ctx["Wp"], ctx["rec"]
     bns = dict(enc.bn_list())
@@ -566,8 +580,10 @@ def backward_train(enc, ctx, dfeat, grads):
             ds = ops.affine2(g_s, st_raw, coef_s, g_s)
             _stem_wgrad(ctx, ds, grads, sq)
             dy = None
+        if name in split_after:
+            sq.join()
+            yield name
     sq.join()
-    return grads
 
 
 class _EncoderFn(torch.autograd.Function):

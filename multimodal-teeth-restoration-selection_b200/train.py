@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .backbone import forward_train, backward_train
+from .backbone import forward_train, backward_train, backward_train_iter
 from .ddp import GradSync
 from .modules import TAB_PARAM_KEYS
 
@@ -229,13 +229,31 @@ class DualTaskTrainer(_FusedTrainer):
                               self.head_out["dreg"], self.dfeat, grads, self.scratch, True, m.drop_p, seed=self.seed,
                               step=step_ptr)
 
-        def enc_backward():
-            backward_train(enc, holder["ctx"], self.dfeat, enc_grads)
+        # bucket 0 = tab + heads (everything after the backbone in the flat buffer); the backbone is cut where the parameter
+        # mass is: the last two stages + head hold ~80 % of the weights but are the FIRST quarter of the backward pass, so
+        # their all-reduce (bucket 1) hides behind the backward of the early, activation-heavy stages (bucket 2)
+        first_head = min(fl.offsets[k][0] for k in TAB_PARAM_KEYS)
+        blocks = [n for n, _ in enc.block_list()]
+        split = None
+        if self.world > 1 and self.num_buckets >= 3 and len(enc.blocks) >= 3:
+            split = f"blocks.{len(enc.blocks) - 2}.0"           # first block of the second-to-last stage
+        if split is None:
+            def enc_backward():
+                backward_train(enc, holder["ctx"], self.dfeat, enc_grads)
+                holder.clear()
+            return [fwd_and_heads, enc_backward], self._bucket_ranges([first_head])
+
+        def enc_backward_late():
+            holder["it"] = backward_train_iter(enc, holder["ctx"], self.dfeat, enc_grads, split_after=(split,))
+            assert next(holder["it"]) == split
+
+        def enc_backward_early():
+            for _ in holder["it"]:
+                pass
             holder.clear()
 
-        # bucket 0 = tab + heads (everything after the backbone in the flat buffer), bucket 1 = the backbone
-        first_head = min(fl.offsets[k][0] for k in TAB_PARAM_KEYS)
-        return [fwd_and_heads, enc_backward], self._bucket_ranges([first_head])
+        first_split = min(o for n, (o, _, _) in fl.offsets.items() if n.startswith("backbone." + split + "."))
+        return [fwd_and_heads, enc_backward_late, enc_backward_early], self._bucket_ranges([first_head, first_split])
 
     def prefetch(self, x_img, x_tab, y_h, y_s, w=None):
         super().prefetch(x_img, x_tab, y_h, y_s, w)

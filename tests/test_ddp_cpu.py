@@ -42,6 +42,8 @@ def _worker(rank, world, port, q):
         head_start = flat.offsets["3.weight"][0]
         ranges = sync.bucket_ranges([head_start])
         assert ranges == [(head_start, flat.numel), (0, head_start)]
+        mid = flat.offsets["1.weight"][0]                  # three buckets: heads | late encoder | early encoder
+        assert sync.bucket_ranges([head_start, mid]) == [(head_start, flat.numel), (mid, head_start), (0, mid)]
         flat.g.fill_(float(rank + 1))
         for r in ranges:
             sync.reduce(r)
