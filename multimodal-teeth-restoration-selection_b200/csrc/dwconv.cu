@@ -240,8 +240,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
 template <int P>
 __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint4 (&xr4)[P], const float* __restrict__ x_rec,
                                                   uint4* __restrict__ g_out, float (&red)[2][8], const f8& sc, const f8& sh,
-                                                  const f8& mu, const f8& rs, const DwGeom& g, int n, int iy, int ixb, int cv,
-                                                  bool cvalid, int V) {
+                                                  const DwGeom& g, int n, int iy, int ixb, int cv, bool cvalid, int V) {
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const int ix = ixb + p;
@@ -258,7 +257,7 @@ __device__ __forceinline__ void bwd_data_epilogue(float (&acc)[P][8], const uint
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           red[0][i] += r.v[i];
-          red[1][i] = fmaf(r.v[i], (xr.v[i] - mu.v[i]) * rs.v[i], red[1][i]);
+          red[1][i] = fmaf(r.v[i], xr.v[i], red[1][i]);       // sum g*x; the caller turns it into sum g*xhat at the end
         }
       } else {
 #pragma unroll
@@ -306,11 +305,8 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
     ptx::tma_load_4d(smem + st * STAGE, &tm_d, &bar[st], cb * 64, q.tx * T::TOW - PAD, q.ty * TOH - PAD, q.n);
     if (x_rec) ptx::tma_load_4d(smem + st * STAGE + T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW, q.ty * TOH, q.n);
   };
-  f8 sc, sh, mu, rs;
-  if (x_rec && cvalid) {
-    sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
-    mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
-  }
+  f8 sc, sh;
+  if (x_rec && cvalid) { sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv); }
   float red[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
@@ -334,10 +330,15 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
     uint4 xr4[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) xr4[p] = x_rec ? s_x[(oy * T::TOW + oxb + p) * CL + lane] : zero4();
-    bwd_data_epilogue<P>(acc, xr4, x_rec, g_out, red, sc, sh, mu, rs, g, q.n, q.ty * TOH + oy, q.tx * T::TOW + oxb, cv, cvalid, V);
+    bwd_data_epilogue<P>(acc, xr4, x_rec, g_out, red, sc, sh, g, q.n, q.ty * TOH + oy, q.tx * T::TOW + oxb, cv, cvalid, V);
     __syncthreads();
   }
   if (x_rec && bstats) {
+    if (cvalid) {     // sum g*xhat = rstd * (sum g*x - mean * sum g): mean / rstd are not live across the tile loop
+      const f8 mu = ldf8(x_rec + 2 * g.C + 8 * cv), rs = ldf8(x_rec + 3 * g.C + 8 * cv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[1][i] = rs.v[i] * (red[1][i] - mu.v[i] * red[0][i]);
+    }
     const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
@@ -411,11 +412,8 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     ptx::tma_load_4d(smem + st * T::STAGE, &tm_d, &bar[st], cb * 64, d_origin(q.tx * T::TI, g.pad_l), d_origin(q.ty * T::TI, g.pad_t), q.n);
     if (x_rec) ptx::tma_load_4d(smem + st * T::STAGE + T::D_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TI, q.ty * T::TI, q.n);
   };
-  f8 sc, sh, mu, rs;
-  if (x_rec && cvalid) {
-    sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv);
-    mu = ldf8(x_rec + 2 * g.C + 8 * cv); rs = ldf8(x_rec + 3 * g.C + 8 * cv);
-  }
+  f8 sc, sh;
+  if (x_rec && cvalid) { sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv); }
   float red[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][i] = red[1][i] = 0.f;
@@ -468,7 +466,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             red[0][i] += rr.v[i];
-            red[1][i] = fmaf(rr.v[i], (xr.v[i] - mu.v[i]) * rs.v[i], red[1][i]);
+            red[1][i] = fmaf(rr.v[i], xr.v[i], red[1][i]);     // sum g*x, fixed up after the loop
           }
         } else {
 #pragma unroll
@@ -480,6 +478,11 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     __syncthreads();
   }
   if (x_rec && bstats) {
+    if (cvalid) {     // sum g*xhat = rstd * (sum g*x - mean * sum g): mean / rstd are not live across the tile loop
+      const f8 mu = ldf8(x_rec + 2 * g.C + 8 * cv), rs = ldf8(x_rec + 3 * g.C + 8 * cv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[1][i] = rs.v[i] * (red[1][i] - mu.v[i] * red[0][i]);
+    }
     const float total = reduce_over_pt<2>(red, reinterpret_cast<float*>(smem), lane, pt);
     if (threadIdx.x < 128) {
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);

@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (m.active) {
-    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
     const int step = gridDim.x * RY;
     for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
       uint4 da[UNR], xa[UNR];
@@ -300,11 +299,14 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             acc[i] += d.v[i];
-            acc[8 + i] = fmaf(d.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+            acc[8 + i] = fmaf(d.v[i], a.v[i], acc[8 + i]);          // sum dy*x, turned into sum dy*xhat below
           }
         }
       }
     }
+    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[8 + i] = rs.v[i] * (acc[8 + i] - mu.v[i] * acc[i]);
   }
   block_reduce_rows<16>(acc, s_red, m);
   if (m.ry == 0 && m.active) {
@@ -676,7 +678,6 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   if (m.active) {
     const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
-    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
     f8 gt, dm;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { gt.v[i] = 1.f; dm.v[i] = 0.f; }
@@ -716,11 +717,15 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             acc[i] += oq.v[i];
-            acc[8 + i] = fmaf(oq.v[i], (a.v[i] - mu.v[i]) * rs.v[i], acc[8 + i]);
+            acc[8 + i] = fmaf(oq.v[i], a.v[i], acc[8 + i]);        // sum g*x; turned into sum g*xhat after the loop
           }
         }
       }
     }
+    // sum g*xhat = rstd * (sum g*x - mean * sum g): mean / rstd are only live here, not across the streaming loop
+    const f8 mu = ldf8(rec + 2 * C + 8 * m.v), rs = ldf8(rec + 3 * C + 8 * m.v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[8 + i] = rs.v[i] * (acc[8 + i] - mu.v[i] * acc[i]);
   }
   block_reduce_rows<16>(acc, s_red, m);
   if (m.ry == 0 && m.active) {
