@@ -290,7 +290,21 @@ def forward_train(enc, x, save=True):
     x = _check_input(enc, x)
     dev = x.device
     N, _, H, W = x.shape
-    Wp = _packed_weights(enc, dev, True)
+    # the bf16 weight packing (one launch, ~70 us) runs beside the stem / first depthwise layer: its first consumer is the
+    # first 1x1 conv, which waits on the event below
+    main = torch.cuda.current_stream(dev)
+    side = _SideQueue.stream_for(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        Wp = _packed_weights(enc, dev, True)
+        packed = torch.cuda.Event()
+        packed.record(side)
+    pack_pending = [True]
+
+    def need_packed():
+        if pack_pending[0]:
+            torch.cuda.current_stream(dev).wait_event(packed)
+            pack_pending[0] = False
     bns = dict(enc.bn_list())
     total_c = sum(b.weight.numel() for b in bns.values())
     stats = _Arena(ops.STAT_REPLICAS * 2 * total_c, torch.float64, dev)
@@ -349,6 +363,7 @@ def forward_train(enc, x, save=True):
         if c["type"] == "ir":
             cm = c["mid"]
             st = stats.take(ops.STAT_REPLICAS * 2 * cm)
+            need_packed()
             e_raw = torch.empty((N * h * w, cm), device=dev, dtype=bf16)
             rec1 = bn_stage(name + ".bn1", N * h * w, st, lambda fin: _gemm_stats(cur, Wp[name + ".conv_pw"][0], st, fin, e_raw))
             dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, rec1, name + ".bn2", name + ".conv_pwl", name + ".bn3"
@@ -367,6 +382,7 @@ def forward_train(enc, x, save=True):
         s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
         a = ops.gate_apply(d_raw, rec_d, gate, torch.empty_like(d_raw), N, oh * ow)
         st = stats.take(ops.STAT_REPLICAS * 2 * c["cout"])
+        need_packed()
         p_raw = torch.empty((N * oh * ow, c["cout"]), device=dev, dtype=bf16)
         rec_o = bn_stage(bn_out, N * oh * ow, st, lambda fin: _gemm_stats(a, Wp[pw_name][0], st, fin, p_raw))
         y = ops.bn_apply(p_raw, rec_o, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0)
@@ -375,6 +391,7 @@ def forward_train(enc, x, save=True):
         ctx["blocks"].append((blk, sv))
         cur, cur_rec, h, w = y, None, oh, ow
     st = stats.take(ops.STAT_REPLICAS * 2 * enc.num_features)
+    need_packed()
     hd_raw = torch.empty((N * h * w, enc.num_features), device=dev, dtype=bf16)
     rec_h = bn_stage("bn2", N * h * w, st, lambda fin: _gemm_stats(cur, Wp["conv_head"][0], st, fin, hd_raw))
     feat = pool_arena.take(N * enc.num_features, (N, enc.num_features))
@@ -402,14 +419,18 @@ class _SideQueue:
     hand its memory to later work on the main stream."""
     _streams = {}
 
+    @staticmethod
+    def stream_for(dev):
+        key = (dev.type, dev.index)
+        if key not in _SideQueue._streams:
+            _SideQueue._streams[key] = torch.cuda.Stream(device=dev)
+        return _SideQueue._streams[key]
+
     def __init__(self, dev):
         self.enabled = os.environ.get("TEETHRT_WGRAD_STREAM", "1") != "0"
         self.keep = []
         if self.enabled:
-            key = (dev.type, dev.index)
-            if key not in _SideQueue._streams:
-                _SideQueue._streams[key] = torch.cuda.Stream(device=dev)
-            self.side = _SideQueue._streams[key]
+            self.side = _SideQueue.stream_for(dev)
             self.dev = dev
 
     @property

@@ -87,6 +87,9 @@ template <int TH, int TW>
 __device__ __forceinline__ void activate_tile(uint4* s_tile, const f8& sc, const f8& sh, int gy0, int gx0, int H, int W,
                                               int lane, int pt) {
   constexpr int NPIX = TH * TW, NL = (NPIX + NPT - 1) / NPT;
+  f8 sc2, sh2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc2.v[k] = sc.v[k] * -1.4426950408889634f; sh2.v[k] = sh.v[k] * -1.4426950408889634f; }
 #pragma unroll
   for (int j = 0; j < NL; ++j) {
     const int i = pt + NPT * j;
@@ -95,7 +98,7 @@ __device__ __forceinline__ void activate_tile(uint4* s_tile, const f8& sc, const
     if (i < NPIX && gy >= 0 && gy < H && gx >= 0 && gx < W) {
       f8 a = unpack8(s_tile[i * CL + lane]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = siluf_(fmaf(a.v[k], sc.v[k], sh.v[k]));
+      for (int k = 0; k < 8; ++k) a.v[k] = silu_affine_(a.v[k], sc.v[k], sh.v[k], sc2.v[k], sh2.v[k]);
       s_tile[i * CL + lane] = pack8(a);
     }
   }
