@@ -41,6 +41,16 @@ struct GemmParams {
   trt_bn_fin_t fin;
 };
 
+#ifdef TRT_GEMM_TIMING
+// bring-up instrumentation (never compiled into the shipped library): per-phase clock64 totals of epilogue group 0's first thread
+__device__ unsigned long long g_gemm_dbg[8];
+#define TRT_TICK(slot) do { if (threadIdx.x == 64) { const long long now__ = clock64(); atomicAdd(&g_gemm_dbg[slot], (unsigned long long)(now__ - tick__)); tick__ = now__; } } while (0)
+#define TRT_TICK_INIT long long tick__ = clock64()
+#else
+#define TRT_TICK(slot) do {} while (0)
+#define TRT_TICK_INIT do {} while (0)
+#endif
+
 struct SmemLayout {
   uint32_t a_off, b_off, c_off, cpitch, cbuf_bytes, bar_off, total;
 };
@@ -208,6 +218,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
       };
       int seq = g;                                  // index of the tile in this CTA's sequence
+      TRT_TICK_INIT;
       for (int t = blockIdx.x + g * gridDim.x; t < num_tiles; t += p.ngroups * gridDim.x, seq += p.ngroups) {
         const int m0 = (t / p.num_n_blocks) * BM;
         const int n0 = (t % p.num_n_blocks) * p.block_n;
@@ -218,8 +229,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (st_n0 >= 0) flush_stats();
           st_n0 = n0;
         }
+        TRT_TICK(0);
         ptx::mbar_wait_sleep(&tfull_bar[acc], acc_par, 32);
         ptx::tc_fence_after();
+        TRT_TICK(1);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           uint32_t r[32];
@@ -255,8 +268,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
         ptx::tc_fence_before();
+        TRT_TICK(2);
         ptx::named_bar_sync(bar_id, EPI_THREADS);            // accumulator drained + tile staged, by all four warps
         if (gt == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        TRT_TICK(3);
         if (s_active && n0 + so * 8 < p.N) {
           // store + statistics over the bf16-rounded values (rows past M are exact zeros: zero-filled A rows)
           const uint8_t* cbase = cstage + so * 16;
@@ -289,7 +304,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
         }
+        TRT_TICK(4);
         ptx::named_bar_sync(bar_id, EPI_THREADS);            // staging buffer free for the group's next tile
+        TRT_TICK(5);
       }
       if (f_stats && st_n0 >= 0) flush_stats();
       if (p.has_fin) {
