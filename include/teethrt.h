@@ -244,6 +244,22 @@ int trt_grad_sumsq(const float* g, size_t n, double* out, trt_stream_t stream); 
 int trt_adamw_step(float* p, const float* g, float* m, float* v, size_t n, const void* state, const double* normsq,
                    float* norm_out, float grad_scale, float max_norm, float eps, float weight_decay, trt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fold calibration.  Replaces TemperatureScaler + the LBFGS closure
+ * (experiments/multimodal_v1/train_mm_joint_dualtask.py:162-174, 271-287), compute_metrics (:181-186) and the 61-point
+ * F1 threshold sweep (:289-295).
+ * trt_temperature_nll : loss_grad[0] = mean BCE(logits / exp(log_T), targets), loss_grad[1] = d loss / d log_T
+ * trt_scaled_sigmoid  : prob = sigmoid(logits / T)                                  (:286-287, :336)
+ * trt_binary_metrics  : counts[t] = {tp, fp, fn, tn} of (double)prob >= thr[t] for every threshold in one launch;
+ *                       auc = {2*#(pos > neg) + #(pos == neg), #pos, #neg, #labels outside {0,1}}; ROC-AUC = auc[0] /
+ *                       (2 * auc[1] * auc[2]) (the Mann-Whitney form of sklearn.metrics.roc_auc_score, ties = 1/2)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int trt_temperature_nll(const float* logits, const float* targets, const float* log_T, float* loss_grad, int n,
+                        trt_stream_t stream);
+int trt_scaled_sigmoid(const float* logits, float T, float* prob, int n, trt_stream_t stream);
+int trt_binary_metrics(const float* prob, const float* y, int n, const double* thr, int nthr, long long* counts,
+                       long long* auc, trt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

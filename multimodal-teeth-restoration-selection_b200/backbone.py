@@ -191,8 +191,11 @@ def _packed_weights(enc, dev, transposed):
     re-homing them into a flat buffer or moving the module rebuilds the table)."""
     convs = enc.conv1x1_list()
     key = (transposed, str(dev)) + tuple(cv.weight.data_ptr() for _, cv in convs)
-    cache = enc.__dict__.get("_pack_cache")
-    if cache is None or cache["key"] != key:
+    # one table per (transposed, device, storage) key and none is ever dropped while the encoder lives: a captured train
+    # step keeps replaying into its table after an eval pass built the other one
+    caches = enc.__dict__.setdefault("_pack_cache", {})
+    cache = caches.get(key)
+    if cache is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("teethrt: run one eager step before capturing a CUDA graph (weight-pack table not built yet)")
         out, rows, tiles = {}, [], 0
@@ -204,7 +207,7 @@ def _packed_weights(enc, dev, transposed):
             rows.append([cv.weight.data_ptr(), wb.data_ptr(), wt.data_ptr() if transposed else 0, n, k, tiles])
             tiles += ((n + 31) // 32) * ((k + 31) // 32)
         cache = dict(key=key, w=out, table=torch.tensor(rows, dtype=torch.int64).to(dev), tiles=tiles)
-        enc.__dict__["_pack_cache"] = cache
+        caches[key] = cache
     ops.pack_w1x1_batch(cache["table"], cache["tiles"])
     return cache["w"]
 

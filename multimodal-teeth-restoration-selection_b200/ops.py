@@ -314,6 +314,29 @@ def adamw_step(p, g, m, v, state, normsq=None, norm_out=None, grad_scale=1.0, ma
                              grad_scale, max_norm, eps, weight_decay, stream()))
 
 
+# ------------------------------------------------------------------------------------------------ fold calibration
+def temperature_nll(logits, targets, log_T, out=None):
+    """out[0] = mean BCE(logits / exp(log_T), targets), out[1] = d/dlog_T (train_mm_joint_dualtask.py:168-170,276-281)."""
+    out = torch.empty(2, device=logits.device, dtype=torch.float32) if out is None else out
+    check(lib.trt_temperature_nll(ptr(logits), ptr(targets), ptr(log_T), ptr(out), logits.numel(), stream()))
+    return out
+
+
+def scaled_sigmoid(logits, T, out=None):
+    out = torch.empty_like(logits) if out is None else out
+    check(lib.trt_scaled_sigmoid(ptr(logits), float(T), ptr(out), logits.numel(), stream()))
+    return out
+
+
+def binary_metrics(prob, y, thr):
+    """-> (counts [nthr, 4] int64 = tp, fp, fn, tn per threshold; auc [4] int64 = 2*wins+ties, #pos, #neg, #bad labels)."""
+    nthr = 0 if thr is None else thr.numel()
+    counts = torch.empty(max(nthr, 1), 4, device=prob.device, dtype=torch.int64)
+    auc = torch.empty(4, device=prob.device, dtype=torch.int64)
+    check(lib.trt_binary_metrics(ptr(prob), ptr(y), prob.numel(), ptr(thr), nthr, ptr(counts), ptr(auc), stream()))
+    return counts[:nthr], auc
+
+
 # ------------------------------------------------------------------------------------------------ input stage
 def same_pad(i, k, s):
     total = max((math.ceil(i / s) - 1) * s + k - i, 0)

@@ -75,6 +75,9 @@ class _FusedTrainer:
         self._stage = None
         self._staged = None
         self.launches_per_step = None
+        # one plan (static inputs, scratch, captured graphs) per input shape: the last batch of an epoch is usually ragged
+        # (DataLoader(shuffle=True) without drop_last, train_mm_joint_dualtask.py:211)
+        self._plans, self._plan_key, self._plan_steps, self._plan_attrs = {}, None, 0, None
         self.sync.sync_initial_state(self.model)
 
     def _bucket_ranges(self, boundaries):
@@ -144,7 +147,7 @@ class _FusedTrainer:
         """Start the host->device copy of the NEXT step's (pinned) inputs on a copy stream, so it overlaps the step that is
         running; the matching step() call then only does a device-to-device copy.  (What the reference gets from DataLoader
         workers + pin_memory + non_blocking copies, train_mm_joint_dualtask.py:211,238-240.)"""
-        if self._static is None:
+        if self._static is None or self._plan_key != self._shape_key(inputs):
             return
         if self._stage is None:
             self._stage = [torch.empty_like(t) for t in self._static]
@@ -160,9 +163,32 @@ class _FusedTrainer:
             self._stage_ready.record(self._copy_stream)
         self._staged = tuple(id(t) for t in inputs)
 
+    @staticmethod
+    def _shape_key(inputs):
+        return tuple(None if t is None else tuple(t.shape) for t in inputs)
+
+    _BASE_PLAN_ATTRS = ("_static", "_graphs", "_stage", "_staged", "_copy_stream", "_stage_free", "_stage_ready",
+                        "_plan_steps", "launches_per_step")
+
+    def _switch_plan(self, key):
+        if self._plan_key is not None:
+            self._plans[self._plan_key] = {k: self.__dict__.get(k) for k in self._plan_attrs}
+        plan = self._plans.get(key)
+        if plan is None:
+            self._static = self._graphs = self._stage = self._staged = None
+            self._plan_steps = 0
+        else:
+            self.__dict__.update(plan)
+        self._plan_key = key
+
     def _step(self, *inputs):
+        key = self._shape_key(inputs)
+        if key != self._plan_key:
+            self._switch_plan(key)
         if self._static is None:
+            before = set(self.__dict__)
             self._make_static(*inputs)
+            self._plan_attrs = tuple(sorted(set(self._BASE_PLAN_ATTRS) | (set(self.__dict__) - before) | set(self._plan_attrs or ())))
         if self._staged is not None and self._staged == tuple(id(t) for t in inputs):
             main = torch.cuda.current_stream(self.dev)
             main.wait_event(self._stage_ready)
@@ -175,7 +201,7 @@ class _FusedTrainer:
             for dst, src in zip(self._static, inputs):
                 if src is not None:
                     dst.copy_(src, non_blocking=True)
-        if self.use_graph and self._nsteps >= self.graph_warmup:
+        if self.use_graph and self._plan_steps >= self.graph_warmup:
             if self._graphs is None:
                 torch.cuda.synchronize()
                 self._capture()
@@ -183,6 +209,7 @@ class _FusedTrainer:
         else:
             self._run_eager()
         self._nsteps += 1
+        self._plan_steps += 1
         return self.loss
 
     def lr(self):
