@@ -234,10 +234,15 @@ def run_ours(args):
     losses = []
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    pending = None
     for i in range(args.steps):
-        loss = tr.step(*host_batches[i % 2])
+        tr.step(*host_batches[i % 2])
+        ticket = tr.loss_async()                     # D2H copy of THIS step's loss into pinned memory, queued behind the step
         tr.prefetch(*host_batches[(i + 1) % 2])      # next step's H2D (from pinned memory) overlaps this step's kernels
-        losses.append(float(loss.item()))            # D2H read of this step's result: one sync per step
+        if pending is not None:
+            losses.append(tr.loss_value(pending))    # read step i-1's loss on the host while step i runs
+        pending = ticket
+    losses.append(tr.loss_value(pending))            # every step's result has been read inside the timed region
     e3.record()
     barrier()
     t_e2e = torch.tensor([e2.elapsed_time(e3) * 1e-3], device=dev)

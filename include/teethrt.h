@@ -114,6 +114,14 @@ int trt_resize_linear_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, 
 /* uint8 BGR [n,h,w,3] -> RGB planar [n,3,h,w] = (u8/255 - mean)/std; flip: 0 none, 1 W-reverse, 2 H-reverse.
  * out_bf16 != 0 writes bf16, else fp32. */
 int trt_normalize_flip_u8(const uint8_t* src, void* dst, int n, int h, int w, int flip, int out_bf16, trt_stream_t stream);
+/* Pillow-exact antialiased resampling pass over uint8 (one separable pass per call; horizontal first, then vertical, each
+ * rounding and clipping to uint8 like Pillow's ImagingResample).  Replaces the PIL resize inside the reference's eval
+ * transforms: timm create_transform(..., interpolation='bicubic') at ui/gradio_app/infer_mm.py:12-17 and
+ * torchvision Resize(512) at ui/gradio_app/infer_mil.py:116-119.  bounds[o] = {first tap, tap count}, coeffs[o][ksize] =
+ * 22-bit fixed-point weights (host-built, teethrt.preproc.pil_coeffs).  horizontal: out[y][o] from in row y;
+ * vertical: out[o][x] from in column x.  `in` points at the first row/column the tables refer to. */
+int trt_resample_u8(const uint8_t* in, size_t in_pitch_bytes, int channels, uint8_t* out, int out_rows, int out_cols,
+                    const int* bounds, const int* coeffs, int ksize, int vertical, int swap_channels, trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm / squeeze-excite / pooling kernels around the GEMMs (NHWC bf16, rows = N*H*W, C % 8 == 0).

@@ -280,7 +280,63 @@ __global__ void __launch_bounds__(256) normalize_flip_kernel(const uint8_t* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pillow-exact antialiased resampling of 8-bit images (the eval transform the reference builds with
+// timm.data.create_transform / torchvision Resize on PIL images, ui/gradio_app/infer_mm.py:12-17, infer_mil.py:116-119).
+// Pillow resamples in two separable passes (horizontal, then vertical) over uint8 with 22-bit fixed-point coefficients and
+// round-half-up + clip after EACH pass; the coefficient tables (bounds = {first tap, tap count}, coeffs = ksize ints per
+// output index) are built on the host in double precision exactly as Pillow's precompute_coeffs does (preproc.py).
+// One thread per output pixel (all channels); the tables are tiny and stay in L1/L2.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RS_PRECISION_BITS = 32 - 8 - 2;
+
+__device__ __forceinline__ uint8_t clip8_fixed(int v) {
+  v >>= RS_PRECISION_BITS;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+template <int CH, bool VERTICAL>
+__global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restrict__ in, size_t in_pitch, uint8_t* __restrict__ out,
+                                                          int out_rows, int out_cols, const int* __restrict__ bounds,
+                                                          const int* __restrict__ coeffs, int ksize, int swap_channels) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= out_cols) return;
+  const int o = VERTICAL ? y : x;
+  const int first = __ldg(bounds + 2 * o), taps = __ldg(bounds + 2 * o + 1);
+  const int* k = coeffs + (size_t)o * ksize;
+  int acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 1 << (RS_PRECISION_BITS - 1);
+  const uint8_t* p = VERTICAL ? in + (size_t)first * in_pitch + (size_t)x * CH : in + (size_t)y * in_pitch + (size_t)first * CH;
+  const size_t step = VERTICAL ? in_pitch : (size_t)CH;
+  for (int t = 0; t < taps; ++t, p += step) {
+    const int w = __ldg(k + t);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] += (int)__ldg(p + c) * w;
+  }
+  uint8_t* q = out + ((size_t)y * out_cols + x) * CH;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) q[swap_channels ? CH - 1 - c : c] = clip8_fixed(acc[c]);
+}
+
 }  // namespace
+
+extern "C" int trt_resample_u8(const uint8_t* in, size_t in_pitch_bytes, int channels, uint8_t* out, int out_rows, int out_cols,
+                               const int* bounds, const int* coeffs, int ksize, int vertical, int swap_channels,
+                               cudaStream_t stream) {
+  TRT_REQUIRE(in && out && bounds && coeffs, "trt_resample_u8: null pointer");
+  TRT_REQUIRE(out_rows > 0 && out_cols > 0 && ksize > 0, "trt_resample_u8: bad shape %d x %d, ksize %d", out_rows, out_cols, ksize);
+  TRT_REQUIRE(channels == 1 || channels == 3, "trt_resample_u8: %d channels not built (1 or 3)", channels);
+  dim3 grid((out_cols + 255) / 256, out_rows);
+#define TRT_RS(CH, V) resample_u8_kernel<CH, V><<<grid, 256, 0, stream>>>(in, in_pitch_bytes, out, out_rows, out_cols, bounds, \
+                                                                         coeffs, ksize, swap_channels)
+  if (channels == 3) { if (vertical) TRT_RS(3, true); else TRT_RS(3, false); }
+  else               { if (vertical) TRT_RS(1, true); else TRT_RS(1, false); }
+#undef TRT_RS
+  return trt_check_launch("trt_resample_u8");
+}
+
 
 extern "C" size_t trt_clahe_workspace_bytes(int n) { return (size_t)n * NT * 256 * (sizeof(uint32_t) + 1); }
 

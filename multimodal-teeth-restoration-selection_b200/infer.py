@@ -12,12 +12,11 @@ from pathlib import Path
 import numpy as np
 import torch
 from PIL import Image
-from torchvision import transforms
 
 from . import ops  # noqa: F401
 from ._lib import init
 from .modules import MMNet, MILNetTwin
-from .preproc import normalize_flip
+from .preproc import normalize_flip, resize_center_crop
 
 TAB_FEATURES = ['depth', 'width', 'enamel_cracks', 'occlusal_load', 'carious_lesion',
                 'opposing_type', 'adjacent_teeth', 'age_range', 'cervical_lesion']
@@ -55,11 +54,11 @@ class _GraphedForward:
         return self.static_out
 
 
-def eval_resize_crop(img, size):
-    """timm eval transform up to the uint8 image: Resize(floor(S/0.875), bicubic) -> CenterCrop(S) (infer_mm.py:12-17)."""
-    tf = transforms.Compose([transforms.Resize(int(np.floor(size / 0.875)), interpolation=transforms.InterpolationMode.BICUBIC),
-                             transforms.CenterCrop(size)])
-    return np.asarray(tf(img))
+def eval_resize_crop(img, size, swap_channels=False):
+    """timm eval transform up to the uint8 image: Resize(floor(S/0.875), bicubic) -> CenterCrop(S) (infer_mm.py:12-17),
+    on the device and bit-identical to the PIL path (preproc.resize_center_crop).  img: PIL image or uint8 HWC array
+    -> CUDA uint8 [S,S,3]."""
+    return resize_center_crop(np.asarray(img), int(np.floor(size / 0.875)), size, "bicubic", swap_channels=swap_channels)
 
 
 class MMEnsemble:
@@ -126,8 +125,8 @@ class MMEnsemble:
         if not self.models:
             return 0.5, "MM not loaded"
         img = Image.open(image_path).convert('RGB')
-        rgb = eval_resize_crop(img, self.img_size)
-        bgr = torch.from_numpy(np.ascontiguousarray(rgb[..., ::-1])).to(self.device)
+        with torch.cuda.device(self.device):
+            bgr = eval_resize_crop(img, self.img_size, swap_channels=True)           # full-size upload, resize on the device
         probs = self.predict_tensor(bgr, tab_dict).cpu().numpy()                     # the one sync of the prediction
         return float(np.mean(probs)), f"fold_probs={np.round(probs, 3)}"
 
@@ -162,7 +161,8 @@ class MILEnsemble:
         self.backbone = backbone
         self.num_folds = 0
         self.models = []
-        self._tfm = transforms.Compose([transforms.Resize(512), transforms.CenterCrop(480), transforms.ToTensor()])
+        # transforms.Resize(512) (PIL bilinear, antialiased) -> CenterCrop(480) -> ToTensor, on the device (infer_mil.py:116-119)
+        self._tfm = lambda im: resize_center_crop(np.asarray(im), 512, 480, "bilinear").permute(2, 0, 1).float().div(255)
         self._load_folds()
 
     def predict(self, processed_dir):
@@ -174,12 +174,14 @@ class MILEnsemble:
         bag = []
         for p in imgs:
             try:
-                bag.append(self._tfm(Image.open(p).convert("RGB")))
+                im = Image.open(p).convert("RGB")
             except Exception:
                 continue
+            with torch.cuda.device(self.device):
+                bag.append(self._tfm(im))
         if not bag:
             return None, f"MIL: failed to load images in {processed_dir}"
-        x = torch.stack(bag, dim=0).to(self.device)
+        x = torch.stack(bag, dim=0)
         with torch.no_grad():
             logits = torch.stack([m(x) for m in self.models]).cpu()                  # one sync for all folds
         logit_mean = float(logits.mean())

@@ -4,10 +4,14 @@
     centre_crop_resize(img, size)   <- src/preprocessing/pipeline.py:23-29
     normalize_flip(img_u8, flip)    <- ToTensor + Normalize (+ torch.flip) of train_mm_joint_dualtask.py:83-84,328-333
     InputStage                      <- the three chained on the device, batch at a time
+    resize_center_crop(img, R, S)   <- PIL Resize + CenterCrop of the eval transforms (infer_mm.py:12-17, infer_mil.py:116-119)
 
 Inputs may be numpy uint8 HWC arrays (the reference's type: copied to the GPU, result copied back) or CUDA uint8 tensors
 [H,W,3] / [N,H,W,3] (result stays on the device).  All arithmetic runs in libteethrt kernels; there is no OpenCV/CPU
 fallback."""
+import functools
+import math
+
 import numpy as np
 import torch
 
@@ -98,3 +102,109 @@ class InputStage:
         check(lib.trt_normalize_flip_u8(ptr(self.buf_small), ptr(self.out), n, self.size, self.size, flip,
                                         int(self.dtype == torch.bfloat16), stream()))
         return self.out
+
+
+# ------------------------------------------------------------------------------------------------ PIL-exact eval transform
+# SURVEY.md §8 row f2 (deterministic half): Resize(shorter edge -> R, antialiased PIL filter) + CenterCrop(S) on the device,
+# bit-identical to torchvision-on-PIL, which is what timm.create_transform(is_training=False) builds for the reference
+# (ui/gradio_app/infer_mm.py:12-17: bicubic, R = floor(S / 0.875); ui/gradio_app/infer_mil.py:116-119: bilinear 512 -> 480).
+_PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic_filter(x):
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def _bilinear_filter(x):
+    if x < 0.0:
+        x = -x
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+_PIL_FILTERS = {"bicubic": (_bicubic_filter, 2.0), "bilinear": (_bilinear_filter, 1.0)}
+
+
+@functools.lru_cache(maxsize=64)
+def pil_coeffs(in_size, out_size, interpolation="bicubic"):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for a full-axis resize in_size -> out_size, in the same double
+    arithmetic and evaluation order -> (bounds int32 [out,2] = first tap / tap count, coeffs int32 [out,ksize], ksize)."""
+    filt, fsupport = _PIL_FILTERS[interpolation]
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = fsupport * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    bounds = np.zeros((out_size, 2), np.int32)
+    coeffs = np.zeros((out_size, ksize), np.int32)
+    one = float(1 << _PIL_PRECISION_BITS)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        ws, ww = [], 0.0
+        for x in range(xmax):
+            w = filt((x + xmin - center + 0.5) * ss)
+            ws.append(w)
+            ww += w
+        for x in range(xmax):
+            w = ws[x] / ww if ww != 0.0 else ws[x]
+            coeffs[xx, x] = int(-0.5 + w * one) if w < 0 else int(0.5 + w * one)
+        bounds[xx] = (xmin, xmax)
+    return bounds, coeffs, ksize
+
+
+def resized_size(h, w, short):
+    """torchvision _compute_resized_output_size for Resize(int): shorter edge -> `short`, longer = int(short * long / short0)."""
+    if w <= h:
+        return int(short * h / w), short
+    return short, int(short * w / h)
+
+
+_coeff_dev = {}
+
+
+def _coeffs_on(device, in_size, out_size, interpolation, lo, hi):
+    """Device copies of the table rows [lo, hi) (the crop window), cached per geometry."""
+    key = (str(device), in_size, out_size, interpolation, lo, hi)
+    if key not in _coeff_dev:
+        b, c, ksize = pil_coeffs(in_size, out_size, interpolation)
+        b, c = b[lo:hi].copy(), c[lo:hi].copy()
+        first = int(b[:, 0].min())
+        last = int((b[:, 0] + b[:, 1]).max())
+        b[:, 0] -= first
+        if len(_coeff_dev) > 256:
+            _coeff_dev.clear()
+        _coeff_dev[key] = (torch.from_numpy(b).to(device), torch.from_numpy(c).to(device), ksize, first, last)
+    return _coeff_dev[key]
+
+
+def resize_center_crop(img_u8, short, crop, interpolation="bicubic", swap_channels=False):
+    """transforms.Resize(short, interpolation) -> transforms.CenterCrop(crop) on a uint8 [H,W,C] image (numpy or CUDA
+    tensor, C in {1,3}) -> CUDA uint8 [crop, crop, C], bit-identical to the PIL path.  Only the crop window is computed:
+    the horizontal pass runs over the source rows the cropped output rows need and the cropped columns, the vertical pass
+    over the result.  swap_channels writes the channels reversed (RGB <-> BGR)."""
+    t = torch.from_numpy(np.ascontiguousarray(img_u8)).cuda() if isinstance(img_u8, np.ndarray) else img_u8
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3) or not t.is_cuda:
+        raise ValueError("expected a uint8 image [H,W,1|3] (numpy array or CUDA tensor)")
+    t = t.contiguous()
+    h, w, ch = t.shape
+    nh, nw = resized_size(h, w, short)
+    if crop > nh or crop > nw:
+        raise ValueError(f"crop {crop} larger than the resized image {nh}x{nw} (the reference would zero-pad; not built)")
+    top, left = int(round((nh - crop) / 2.0)), int(round((nw - crop) / 2.0))
+    vb, vc, vk, r0, r1 = _coeffs_on(t.device, h, nh, interpolation, top, top + crop)
+    hb, hc, hk, c0, _ = _coeffs_on(t.device, w, nw, interpolation, left, left + crop)
+    tmp = torch.empty((r1 - r0, crop, ch), device=t.device, dtype=torch.uint8)
+    out = torch.empty((crop, crop, ch), device=t.device, dtype=torch.uint8)
+    src = t[r0:, c0:]                                                   # tables are relative to (r0, c0)
+    check(lib.trt_resample_u8(src.data_ptr(), w * ch, ch, ptr(tmp), r1 - r0, crop, ptr(hb), ptr(hc), hk, 0, 0, stream()))
+    check(lib.trt_resample_u8(ptr(tmp), crop * ch, ch, ptr(out), crop, crop, ptr(vb), ptr(vc), vk, 1, int(swap_channels), stream()))
+    return out

@@ -75,6 +75,7 @@ class _FusedTrainer:
         self._stage = None
         self._staged = None
         self.launches_per_step = None
+        self._loss_ring = None
         # one plan (static inputs, scratch, captured graphs) per input shape: the last batch of an epoch is usually ragged
         # (DataLoader(shuffle=True) without drop_last, train_mm_joint_dualtask.py:211)
         self._plans, self._plan_key, self._plan_steps, self._plan_attrs = {}, None, 0, None
@@ -214,6 +215,29 @@ class _FusedTrainer:
 
     def lr(self):
         return self.state.read()["lr"]
+
+    # ---- loss read-back without stalling the launch queue -----------------------------------------------------------
+    def loss_async(self):
+        """Queue a device->host copy of the step that was just launched into a pinned ring; -> ticket for loss_value().
+        Reading ticket i after launching step i+1 keeps one step in flight (the reference's `loss.item()` per step,
+        train_mm_joint_dualtask.py:256, drains the GPU every iteration)."""
+        if self._loss_ring is None:
+            depth = 16
+            self._loss_ring = (torch.empty(depth, dtype=torch.float32).pin_memory(), [torch.cuda.Event() for _ in range(depth)])
+            self._loss_tickets = 0
+        buf, evs = self._loss_ring
+        slot = self._loss_tickets % len(evs)
+        buf[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        evs[slot].record(torch.cuda.current_stream(self.dev))
+        self._loss_tickets += 1
+        return self._loss_tickets - 1
+
+    def loss_value(self, ticket):
+        buf, evs = self._loss_ring
+        if not 0 <= self._loss_tickets - 1 - ticket < len(evs):
+            raise ValueError(f"loss ticket {ticket} is no longer in the ring (latest {self._loss_tickets - 1}, depth {len(evs)})")
+        evs[ticket % len(evs)].synchronize()
+        return float(buf[ticket % len(evs)])
 
 
 class DualTaskTrainer(_FusedTrainer):

@@ -184,7 +184,11 @@ def test_trainer_handles_ragged_batches(cal):
         m = MMJointDualHead("tf_efficientnet_b0_ns", tab_in=9, tab_hidden=64, drop=0.0).cuda()
         m.load_state_dict(sd, strict=True)
         tr = DualTaskTrainer(m, t_max=50, graph=graph)
-        losses = [float(tr.step(*b[:5])) for b in batches]
+        losses, tickets = [], []
+        for b in batches:
+            losses.append(float(tr.step(*b[:5])))
+            tickets.append(tr.loss_async())
+        assert [tr.loss_value(t) for t in tickets] == losses          # pinned-ring read-back returns each step's own loss
         runs.append((losses, torch.cat([p.detach().flatten() for p in m.parameters()]).cpu()))
     (l0, p0), (l1, p1) = runs
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-2, (l0, l1)

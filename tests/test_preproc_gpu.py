@@ -91,3 +91,38 @@ def test_input_stage_full_size_properties(pre):
     assert torch.equal(one, a[3])
     ref = P.normalize_flip_np(P.centre_crop_resize_cv2(P.apply_clahe_cv2(imgs[3].cpu().numpy()), 224), 0)
     assert np.allclose(a[3].cpu().numpy(), ref, atol=1e-6)
+
+
+# ---- PIL-exact eval transform: the checker is Pillow/torchvision itself, i.e. what the reference calls
+RESAMPLE_CASES = [(1024, 1024, 256, 224, "bicubic"), (480, 640, 256, 224, "bicubic"), (777, 1003, 434, 380, "bicubic"),
+                  (200, 150, 256, 224, "bicubic"), (256, 300, 256, 224, "bicubic"), (1000, 1003, 512, 480, "bilinear"),
+                  (512, 512, 512, 480, "bilinear"), (300, 451, 512, 480, "bilinear"), (97, 1024, 64, 56, "bicubic"),
+                  (2048, 3072, 434, 380, "bicubic")]
+
+
+@pytest.mark.parametrize("h,w,short,crop,interp", RESAMPLE_CASES)
+def test_resize_center_crop_is_bit_identical_to_pillow(pre, h, w, short, crop, interp):
+    from PIL import Image
+    from torchvision import transforms
+    mode = {"bicubic": transforms.InterpolationMode.BICUBIC, "bilinear": transforms.InterpolationMode.BILINEAR}[interp]
+    rng = np.random.RandomState(h * 7 + w)
+    img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+    img[: h // 3] = (img[: h // 3] > 127) * 255                    # hard edges: bicubic overshoot must clip like Pillow
+    tf = transforms.Compose([transforms.Resize(short, interpolation=mode), transforms.CenterCrop(crop)])
+    want = np.asarray(tf(Image.fromarray(img)))
+    got = pre.resize_center_crop(img, short, crop, interp)
+    assert got.is_cuda and got.shape == (crop, crop, 3) and int((got.cpu().numpy() != want).sum()) == 0
+    swapped = pre.resize_center_crop(torch.from_numpy(img).cuda(), short, crop, interp, swap_channels=True)
+    assert int((swapped.cpu().numpy() != want[..., ::-1]).sum()) == 0
+    grey = pre.resize_center_crop(img[..., :1].copy(), short, crop, interp)
+    want_g = np.asarray(tf(Image.fromarray(img[..., 0])))
+    assert int((grey.cpu().numpy()[..., 0] != want_g).sum()) == 0
+
+
+def test_resize_center_crop_rejects_bad_input(pre):
+    with pytest.raises(ValueError):
+        pre.resize_center_crop(np.zeros((8, 8, 3), np.float32), 8, 4)
+    with pytest.raises(ValueError):
+        pre.resize_center_crop(np.zeros((8, 8, 2), np.uint8), 8, 4)
+    with pytest.raises(ValueError):
+        pre.resize_center_crop(np.zeros((64, 64, 3), np.uint8), 32, 48)
