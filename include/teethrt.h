@@ -258,15 +258,27 @@ int trt_adamw_step(float* p, const float* g, float* m, float* v, size_t n, const
  * F1 threshold sweep (:289-295).
  * trt_temperature_nll : loss_grad[0] = mean BCE(logits / exp(log_T), targets), loss_grad[1] = d loss / d log_T
  * trt_scaled_sigmoid  : prob = sigmoid(logits / T)                                  (:286-287, :336)
- * trt_binary_metrics  : counts[t] = {tp, fp, fn, tn} of (double)prob >= thr[t] for every threshold in one launch;
+ * trt_binary_metrics  : counts[t] = {tp, fp, fn, tn} of (double)prob >= thr[t] for every threshold in one launch
+ *                       (prob fp32, or fp64 when prob_is_f64);
  *                       auc = {2*#(pos > neg) + #(pos == neg), #pos, #neg, #labels outside {0,1}}; ROC-AUC = auc[0] /
  *                       (2 * auc[1] * auc[2]) (the Mann-Whitney form of sklearn.metrics.roc_auc_score, ties = 1/2)
  * ------------------------------------------------------------------------------------------------------------------ */
 int trt_temperature_nll(const float* logits, const float* targets, const float* log_T, float* loss_grad, int n,
                         trt_stream_t stream);
 int trt_scaled_sigmoid(const float* logits, float T, float* prob, int n, trt_stream_t stream);
-int trt_binary_metrics(const float* prob, const float* y, int n, const double* thr, int nthr, long long* counts,
-                       long long* auc, trt_stream_t stream);
+int trt_binary_metrics(const void* prob, int prob_is_f64, const float* y, int n, const double* thr, int nthr,
+                       long long* counts, long long* auc, trt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Late-fusion stacker.  Replaces sklearn LogisticRegression(max_iter=1000).fit / predict_proba over the
+ * stream probabilities (experiments/fusion_v1/stack_blend.py:245-252, ui/gradio_app/stack_meta.py:55-57,114-116); the
+ * threshold modes of choose_threshold (:49-86) run on trt_binary_metrics with fp64 scores.
+ * trt_logreg_fit: min 0.5|w|^2 + C sum log(1+exp(-s(w.x+b))), X [n,d] fp64 row-major, y in {0,1}; coef = {w[0..d), b};
+ *                 info = {Newton passes, |grad|_inf at exit, objective}.  d <= 4.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int trt_logreg_fit(const double* X, const float* y, int n, int d, double C, int max_iter, double tol, double* coef,
+                   double* info, trt_stream_t stream);
+int trt_logreg_predict(const double* X, int n, int d, const double* coef, double* prob, trt_stream_t stream);
 
 #ifdef __cplusplus
 }

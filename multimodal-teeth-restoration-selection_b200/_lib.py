@@ -80,7 +80,9 @@ _SIGS = {
     "trt_resample_u8": (i32, [vp, sz, i32, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
     "trt_temperature_nll": (i32, [vp, vp, vp, vp, i32, vp]),
     "trt_scaled_sigmoid": (i32, [vp, f32, vp, i32, vp]),
-    "trt_binary_metrics": (i32, [vp, vp, i32, vp, i32, vp, vp, vp]),
+    "trt_binary_metrics": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),
+    "trt_logreg_fit": (i32, [vp, vp, i32, i32, f64, i32, f64, vp, vp, vp]),
+    "trt_logreg_predict": (i32, [vp, i32, i32, vp, vp, vp]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -29,10 +29,14 @@ def fast_round(x, n=4):
     return float(np.round(x, n))
 
 
-def _dev(a, device):
+def _dev(a, device, keep64=False):
+    """-> flat contiguous device tensor, fp32 (fp64 scores stay fp64 when keep64: thresholds compare in double either way)."""
     if isinstance(a, torch.Tensor):
-        return a.detach().to(device=device, dtype=torch.float32).contiguous().view(-1)
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=device).view(-1)
+        dt = torch.float64 if keep64 and a.dtype == torch.float64 else torch.float32
+        return a.detach().to(device=device, dtype=dt).contiguous().view(-1)
+    a = np.asarray(a)
+    dt = np.float64 if keep64 and a.dtype == np.float64 else np.float32
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device).view(-1)
 
 
 def _device_of(*arrays):
@@ -106,7 +110,7 @@ def _auc(stat):
 def metrics_sweep(y_true, y_prob, thresholds):
     """compute_metrics at every threshold with ONE kernel launch and one read-back -> list of dicts."""
     dev = _device_of(y_prob, y_true)
-    y, p = _dev(y_true, dev), _dev(y_prob, dev)
+    y, p = _dev(y_true, dev), _dev(y_prob, dev, keep64=True)
     if y.numel() != p.numel() or y.numel() == 0:
         raise ValueError(f"y_true ({y.numel()}) and y_prob ({p.numel()}) must be non-empty and equal in length")
     thr = torch.as_tensor(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)), device=dev)

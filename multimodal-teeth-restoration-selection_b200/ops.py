@@ -333,8 +333,28 @@ def binary_metrics(prob, y, thr):
     nthr = 0 if thr is None else thr.numel()
     counts = torch.empty(max(nthr, 1), 4, device=prob.device, dtype=torch.int64)
     auc = torch.empty(4, device=prob.device, dtype=torch.int64)
-    check(lib.trt_binary_metrics(ptr(prob), ptr(y), prob.numel(), ptr(thr), nthr, ptr(counts), ptr(auc), stream()))
+    if prob.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"scores must be fp32 or fp64, got {prob.dtype}")
+    check(lib.trt_binary_metrics(ptr(prob), int(prob.dtype == torch.float64), ptr(y), prob.numel(), ptr(thr), nthr, ptr(counts),
+                                 ptr(auc), stream()))
     return counts[:nthr], auc
+
+
+def logreg_fit(X, y, C=1.0, max_iter=100, tol=None):
+    """L2 logistic regression by Newton on the device -> (coef fp64 [d+1] = w..., b ; info fp64 [3])."""
+    n, d = X.shape
+    coef = torch.empty(d + 1, device=X.device, dtype=torch.float64)
+    info = torch.empty(3, device=X.device, dtype=torch.float64)
+    tol = 1e-10 * max(1.0, C * n) if tol is None else tol
+    check(lib.trt_logreg_fit(ptr(X), ptr(y), n, d, float(C), int(max_iter), float(tol), ptr(coef), ptr(info), stream()))
+    return coef, info
+
+
+def logreg_predict(X, coef):
+    n, d = X.shape
+    out = torch.empty(n, device=X.device, dtype=torch.float64)
+    check(lib.trt_logreg_predict(ptr(X), n, d, ptr(coef), ptr(out), stream()))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ input stage

@@ -191,7 +191,7 @@ def resize_center_crop(img_u8, short, crop, interpolation="bicubic", swap_channe
     tensor, C in {1,3}) -> CUDA uint8 [crop, crop, C], bit-identical to the PIL path.  Only the crop window is computed:
     the horizontal pass runs over the source rows the cropped output rows need and the cropped columns, the vertical pass
     over the result.  swap_channels writes the channels reversed (RGB <-> BGR)."""
-    t = torch.from_numpy(np.ascontiguousarray(img_u8)).cuda() if isinstance(img_u8, np.ndarray) else img_u8
+    t = torch.from_numpy(np.array(img_u8, copy=True)).cuda() if isinstance(img_u8, np.ndarray) else img_u8
     if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3) or not t.is_cuda:
         raise ValueError("expected a uint8 image [H,W,1|3] (numpy array or CUDA tensor)")
     t = t.contiguous()
