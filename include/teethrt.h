@@ -122,6 +122,21 @@ int trt_normalize_flip_u8(const uint8_t* src, void* dst, int n, int h, int w, in
  * vertical: out[o][x] from in column x.  `in` points at the first row/column the tables refer to. */
 int trt_resample_u8(const uint8_t* in, size_t in_pitch_bytes, int channels, uint8_t* out, int out_rows, int out_cols,
                     const int* bounds, const int* coeffs, int ksize, int vertical, int swap_channels, trt_stream_t stream);
+/* Orientation normalisation, src/preprocessing/normalise.py:19-57 `deskew`, OpenCV-bit-exact stages:
+ * trt_canny_nms_bgr_u8      cvtColor(BGR2GRAY) + Sobel 3x3 + |dx|+|dy| + non-maximum suppression of cv2.Canny(gray, low, high)
+ *                           -> map[h*w]: 0 none, 1 candidate (> low), 2 strong (> high)
+ * trt_canny_hysteresis_pass one flood pass of the strong label through 8-connected candidates (complete inside 32x32 tiles,
+ *                           one tile further per pass); sets *changed (device int, caller zeroes it) if anything was promoted;
+ *                           repeat until it stays 0
+ * trt_canny_finish          edges[h*w] = 255 where map == 2 (may be NULL) and moments = {N, Sum y, Sum x, Sum yy, Sum xy,
+ *                           Sum xx} over the edge pixels (the PCA of normalise.py:31-38 needs nothing else)
+ * trt_warp_affine_linear_u8 cv2.warpAffine(src, M, (dw, dh), INTER_LINEAR, BORDER_REPLICATE); inverse_map_host = the 2x3
+ *                           dst->src matrix (HOST doubles; cv2 inverts M itself, teethrt.preproc.invert_affine does the same) */
+int trt_canny_nms_bgr_u8(const uint8_t* bgr, int h, int w, int low, int high, uint8_t* map, trt_stream_t stream);
+int trt_canny_hysteresis_pass(uint8_t* map, int h, int w, int* changed, trt_stream_t stream);
+int trt_canny_finish(const uint8_t* map, int h, int w, uint8_t* edges, long long* moments, trt_stream_t stream);
+int trt_warp_affine_linear_u8(const uint8_t* src, int h, int w, int channels, uint8_t* dst, int dh, int dw,
+                              const double* inverse_map_host, trt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm / squeeze-excite / pooling kernels around the GEMMs (NHWC bf16, rows = N*H*W, C % 8 == 0).

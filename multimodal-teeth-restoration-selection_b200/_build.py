@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libteethrt.so")
-SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu"]
+SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math_off_placeholder"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"] + os.environ.get("TEETHRT_NVCC_EXTRA", "").split()

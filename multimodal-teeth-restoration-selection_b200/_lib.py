@@ -78,6 +78,10 @@ _SIGS = {
     "trt_grad_sumsq": (i32, [vp, sz, vp, vp]),
     "trt_adamw_step": (i32, [vp, vp, vp, vp, sz, vp, vp, vp, f32, f32, f32, f32, vp]),
     "trt_resample_u8": (i32, [vp, sz, i32, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
+    "trt_canny_nms_bgr_u8": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "trt_canny_hysteresis_pass": (i32, [vp, i32, i32, vp, vp]),
+    "trt_canny_finish": (i32, [vp, i32, i32, vp, vp, vp]),
+    "trt_warp_affine_linear_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
     "trt_temperature_nll": (i32, [vp, vp, vp, vp, i32, vp]),
     "trt_scaled_sigmoid": (i32, [vp, f32, vp, i32, vp]),
     "trt_binary_metrics": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),

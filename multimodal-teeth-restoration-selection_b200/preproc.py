@@ -5,10 +5,12 @@
     normalize_flip(img_u8, flip)    <- ToTensor + Normalize (+ torch.flip) of train_mm_joint_dualtask.py:83-84,328-333
     InputStage                      <- the three chained on the device, batch at a time
     resize_center_crop(img, R, S)   <- PIL Resize + CenterCrop of the eval transforms (infer_mm.py:12-17, infer_mil.py:116-119)
+    deskew(img_bgr)                 <- src/preprocessing/normalise.py:19-57 (BGR2GRAY, Canny, PCA angle, warpAffine)
 
 Inputs may be numpy uint8 HWC arrays (the reference's type: copied to the GPU, result copied back) or CUDA uint8 tensors
 [H,W,3] / [N,H,W,3] (result stays on the device).  All arithmetic runs in libteethrt kernels; there is no OpenCV/CPU
 fallback."""
+import ctypes as C
 import functools
 import math
 
@@ -208,3 +210,94 @@ def resize_center_crop(img_u8, short, crop, interpolation="bicubic", swap_channe
     check(lib.trt_resample_u8(src.data_ptr(), w * ch, ch, ptr(tmp), r1 - r0, crop, ptr(hb), ptr(hc), hk, 0, 0, stream()))
     check(lib.trt_resample_u8(ptr(tmp), crop * ch, ch, ptr(out), crop, crop, ptr(vb), ptr(vc), vk, 1, int(swap_channels), stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ deskew
+ROT_TOLERANCE = 15        # src/config.py:17
+
+
+def canny(img_bgr, low=50, high=150, want_edges=True):
+    """cv2.Canny(cv2.cvtColor(img, COLOR_BGR2GRAY), low, high) on the device, bit-identical
+    -> (edges uint8 [H,W] CUDA tensor or None, moments int64 [6] = N, Σy, Σx, Σyy, Σxy, Σxx of the edge pixels)."""
+    x, _, batched = _to_dev(img_bgr)
+    if batched:
+        raise ValueError("canny works on one image [H,W,3]")
+    x = x[0]
+    h, w, _ = x.shape
+    label = torch.empty((h, w), device=x.device, dtype=torch.uint8)
+    changed = torch.zeros(1, device=x.device, dtype=torch.int32)
+    check(lib.trt_canny_nms_bgr_u8(ptr(x), h, w, int(low), int(high), ptr(label), stream()))
+    for _ in range(4 * (h + w)):                       # bound: a path can cross at most every tile once per pass
+        changed.zero_()
+        for _ in range(4):
+            check(lib.trt_canny_hysteresis_pass(ptr(label), h, w, ptr(changed), stream()))
+        if int(changed.item()) == 0:
+            break
+    edges = torch.empty((h, w), device=x.device, dtype=torch.uint8) if want_edges else None
+    mom = torch.empty(6, device=x.device, dtype=torch.int64)
+    check(lib.trt_canny_finish(ptr(label), h, w, ptr(edges), ptr(mom), stream()))
+    return edges, mom
+
+
+def rotation_matrix_2d(center, angle_deg, scale=1.0):
+    """cv2.getRotationMatrix2D in the same double arithmetic."""
+    a = angle_deg * (math.pi / 180)            # OpenCV: angle *= CV_PI/180 (the constant is folded first)
+    alpha, beta = math.cos(a) * scale, math.sin(a) * scale
+    return np.array([[alpha, beta, (1 - alpha) * center[0] - beta * center[1]],
+                     [-beta, alpha, beta * center[0] + (1 - alpha) * center[1]]], dtype=np.float64)
+
+
+def invert_affine(M):
+    """The inversion cv2.warpAffine applies to a forward map (no WARP_INVERSE_MAP), statement for statement."""
+    m = [float(v) for v in np.asarray(M, dtype=np.float64).ravel()]
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = m[4] * D, m[0] * D
+    m[0] = A11; m[1] *= -D; m[3] *= -D; m[4] = A22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
+
+
+def warp_affine(img_u8, M, dsize):
+    """cv2.warpAffine(img, M, (w, h), flags=INTER_LINEAR, borderMode=BORDER_REPLICATE), bit-identical; [H,W,1|3] uint8."""
+    t = torch.from_numpy(np.array(img_u8, copy=True)).cuda() if isinstance(img_u8, np.ndarray) else img_u8.contiguous()
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3):
+        raise ValueError("expected a uint8 image [H,W,1|3]")
+    dw, dh = int(dsize[0]), int(dsize[1])
+    out = torch.empty((dh, dw, t.shape[2]), device=t.device, dtype=torch.uint8)
+    inv = (C.c_double * 6)(*invert_affine(M))
+    check(lib.trt_warp_affine_linear_u8(ptr(t), t.shape[0], t.shape[1], t.shape[2], ptr(out), dh, dw, inv, stream()))
+    return out
+
+
+def edge_angle(moments):
+    """normalise.py:31-43 from the exact integer moments: covariance of the (y, x) edge coordinates (N-1 normalisation, as
+    np.cov), principal axis by np.linalg.eigh — the same LAPACK call, so the same eigenvector sign — angle in degrees."""
+    n, sy, sx, syy, sxy, sxx = (int(v) for v in moments)
+    cyy = (syy * n - sy * sy) / (n * (n - 1))           # exact integers until the final division
+    cxy = (sxy * n - sx * sy) / (n * (n - 1))
+    cxx = (sxx * n - sx * sx) / (n * (n - 1))
+    eigvals, eigvecs = np.linalg.eigh(np.array([[cyy, cxy], [cxy, cxx]], dtype=np.float64))
+    principal = eigvecs[:, np.argmax(eigvals)]
+    return float(np.rad2deg(np.arctan2(principal[0], principal[1])))
+
+
+def deskew(img_bgr):
+    """src/preprocessing/normalise.py:19-57 -> (rotated image, applied angle in degrees); numpy in -> numpy out, CUDA
+    tensor in -> CUDA tensor out.  Fewer than 10 edge points or |angle| < ROT_TOLERANCE returns the input and 0.0."""
+    was_np = isinstance(img_bgr, np.ndarray)
+    x, _, batched = _to_dev(img_bgr)
+    if batched:
+        raise ValueError("deskew works on one image [H,W,3]")
+    _, mom = canny(x[0], 50, 150, want_edges=False)
+    mom = mom.cpu().numpy()
+    if int(mom[0]) < 10:
+        return img_bgr, 0.0
+    angle = edge_angle(mom)
+    if abs(angle) < ROT_TOLERANCE:
+        return img_bgr, 0.0
+    h, w = x.shape[1], x.shape[2]
+    out = warp_affine(x[0], rotation_matrix_2d((w / 2, h / 2), angle, 1.0), (w, h))
+    return (out.cpu().numpy() if was_np else out), angle

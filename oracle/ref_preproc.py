@@ -322,3 +322,115 @@ def image_set(name, h=1024, w=1024, seed=0):
         r = (np.arange(w) * 255 // max(w - 1, 1)).astype(np.uint8)
         return np.ascontiguousarray(np.broadcast_to(r[None, :, None], (h, w, 3)))
     raise KeyError(name)
+
+
+# ------------------------------------------------------------------ deskew (src/preprocessing/normalise.py:19-57)
+ROT_TOLERANCE = 15        # src/config.py:17
+
+
+def deskew_cv2(img_bgr):
+    """The reference's own call sequence (normalise.py:19-57) -> (image, angle, edges)."""
+    gray = cv2.cvtColor(img_bgr, cv2.COLOR_BGR2GRAY)
+    edges = cv2.Canny(gray, 50, 150)
+    coords = np.column_stack(np.where(edges > 0))
+    if coords.shape[0] < 10:
+        return img_bgr, 0.0, edges
+    centered = coords - coords.mean(axis=0)
+    cov = np.cov(centered, rowvar=False)
+    eigvals, eigvecs = np.linalg.eigh(cov)
+    principal = eigvecs[:, np.argmax(eigvals)]
+    angle_deg = np.rad2deg(np.arctan2(principal[0], principal[1]))
+    if abs(angle_deg) < ROT_TOLERANCE:
+        return img_bgr, 0.0, edges
+    (h, w) = img_bgr.shape[:2]
+    M = cv2.getRotationMatrix2D((w / 2, h / 2), angle_deg, 1.0)
+    return cv2.warpAffine(img_bgr, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE), float(angle_deg), edges
+
+
+def gray_np(img):
+    """OpenCV 8-bit BGR2GRAY: 15-bit fixed point, coefficients 3735 / 19235 / 9798."""
+    b, g, r = [img[..., i].astype(np.int64) for i in range(3)]
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def canny_np(gray, low=50, high=150):
+    """cv2.Canny(gray, low, high) (aperture 3, L1 magnitude): Sobel with replicated border, magnitudes outside the image 0,
+    OpenCV's TG22 fixed-point sector test with its asymmetric comparisons, hysteresis = 8-connected components of the
+    candidates that hold a pixel above `high`."""
+    import scipy.ndimage as ndi
+    p = np.pad(gray.astype(np.int32), 1, mode='edge')
+    dx = (p[:-2, 2:] + 2 * p[1:-1, 2:] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[1:-1, :-2] + p[2:, :-2])
+    dy = (p[2:, :-2] + 2 * p[2:, 1:-1] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[:-2, 1:-1] + p[:-2, 2:])
+    m = np.abs(dx) + np.abs(dy)
+    H, W = gray.shape
+    mp = np.pad(m, 1, mode='constant')
+    c = lambda oy, ox: mp[1 + oy:1 + oy + H, 1 + ox:1 + ox + W]  # noqa: E731
+    x = np.abs(dx).astype(np.int64)
+    y = np.abs(dy).astype(np.int64) << 15
+    tg22x = x * 13573
+    tg67x = tg22x + (x << 16)
+    horiz = y < tg22x
+    vert = ~horiz & (y > tg67x)
+    diag = ~horiz & ~vert
+    nm_d = np.where((dx ^ dy) < 0, (m > c(-1, 1)) & (m > c(1, -1)), (m > c(-1, -1)) & (m > c(1, 1)))
+    cand = (m > low) & ((horiz & (m > c(0, -1)) & (m >= c(0, 1))) | (vert & (m > c(-1, 0)) & (m >= c(1, 0))) | (diag & nm_d))
+    lab, n = ndi.label(cand, structure=np.ones((3, 3)))
+    keep = np.zeros(n + 1, bool)
+    keep[np.unique(lab[cand & (m > high)])] = True
+    keep[0] = False
+    return (keep[lab] * 255).astype(np.uint8)
+
+
+def rotation_matrix_np(center, angle_deg):
+    import math
+    a = angle_deg * (math.pi / 180)            # OpenCV: angle *= CV_PI/180 (the constant is folded first)
+    alpha, beta = math.cos(a), math.sin(a)
+    return np.array([[alpha, beta, (1 - alpha) * center[0] - beta * center[1]], [-beta, alpha, beta * center[0] + (1 - alpha) * center[1]]])
+
+
+def warp_affine_np(img, M, w, h):
+    """cv2.warpAffine(img, M, (w, h), INTER_LINEAR, BORDER_REPLICATE): inverse map, 10-bit fixed-point coordinates rounded
+    half-to-even, 5-bit sub-pixel position, 15-bit weights from OpenCV's saturated short table."""
+    M = np.asarray(M, np.float64).copy().ravel()
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22
+    b1 = -M[0] * M[2] - M[1] * M[5]
+    b2 = -M[3] * M[2] - M[4] * M[5]
+    M[2] = b1; M[5] = b2
+    rnd = lambda v: np.rint(v).astype(np.int64)  # noqa: E731
+    xs, ys = np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64)
+    adelta, bdelta = rnd(M[0] * xs * 1024), rnd(M[3] * xs * 1024)
+    X0, Y0 = rnd((M[1] * ys + M[2]) * 1024) + 16, rnd((M[4] * ys + M[5]) * 1024) + 16
+    X, Y = (X0[:, None] + adelta[None, :]) >> 5, (Y0[:, None] + bdelta[None, :]) >> 5
+    sx, sy, fx, fy = X >> 5, Y >> 5, X & 31, Y & 31
+    w00, w01, w10, w11 = (32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32
+    sat = (fx == 0) & (fy == 0)
+    w00, w11 = np.where(sat, 32767, w00), np.where(sat, 1, w11)
+    H, W = img.shape[:2]
+    x0, x1, y0, y1 = np.clip(sx, 0, W - 1), np.clip(sx + 1, 0, W - 1), np.clip(sy, 0, H - 1), np.clip(sy + 1, 0, H - 1)
+    I = img.astype(np.int64)
+    out = (I[y0, x0] * w00[..., None] + I[y0, x1] * w01[..., None] + I[y1, x0] * w10[..., None] + I[y1, x1] * w11[..., None]
+           + (1 << 14)) >> 15
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def tooth_image(h, w, seed, angle):
+    """A rotated bright body with a row of bars on a dark noisy background: something Canny + PCA can orient."""
+    import math
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    cy, cx = h / 2 + rng.uniform(-20, 20), w / 2 + rng.uniform(-20, 20)
+    t = math.radians(angle)
+    u = (xx - cx) * math.cos(t) + (yy - cy) * math.sin(t)
+    v = -(xx - cx) * math.sin(t) + (yy - cy) * math.cos(t)
+    body = ((u / (0.38 * w)) ** 2 + (v / (0.16 * h)) ** 2 < 1).astype(np.float64)
+    bars = ((np.abs(v) < 0.05 * h) & (np.abs(u) < 0.3 * w) & ((u // 25) % 2 == 0)).astype(np.float64)
+    img = cv2.GaussianBlur(40 + 120 * body + 60 * bars + rng.randn(h, w) * 6, (0, 0), 1.2)
+    out = np.stack([img * 0.9, img, img * 1.05], -1) + rng.randn(h, w, 3) * 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+DESKEW_CASES = [(512, 512, 0, 17.0), (480, 640, 1, -33.0), (600, 400, 2, 71.0), (1024, 1024, 3, 5.5), (700, 900, 4, -58.0),
+                (400, 400, 5, 0.0)]

@@ -77,3 +77,60 @@ def test_oracle_equals_imported_reference():
         assert not (apply_clahe(img) != P.apply_clahe_cv2(img)).any()
         assert not (apply_clahe(img) != P.apply_clahe_np(img)).any()
         assert not (centre_crop_resize(img, 224) != P.centre_crop_resize_np(img, 224)).any()
+
+
+# ---- deskew: numpy restatements vs OpenCV, the golden fixture of the reference's own deskew, and the
+# host half of the product (angle from integer moments, rotation matrix, affine inversion)
+DESKEW_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "deskew_golden.json")))
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("idx", range(len(P.DESKEW_CASES)))
+def test_deskew_restatement_matches_cv2_and_golden(idx):
+    import cv2
+    from teethrt import preproc as pre                   # host-side helpers only; no kernel is launched here
+    h, w, seed, tilt = P.DESKEW_CASES[idx]
+    g = DESKEW_GOLD["cases"][idx]
+    img = P.tooth_image(h, w, seed, tilt)
+    assert _sha(img) == g["input"]
+    rot, angle, edges = P.deskew_cv2(img)
+    assert angle == g["angle"] and _sha(rot) == g["output"]                    # oracle == the reference's function
+    gray = P.gray_np(img)
+    assert np.array_equal(gray, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(P.canny_np(gray), edges)
+    ys, xs = np.nonzero(edges)
+    ys, xs = ys.astype(object), xs.astype(object)                              # exact Python integers
+    mom = [len(ys), ys.sum(), xs.sum(), (ys * ys).sum(), (xs * ys).sum(), (xs * xs).sum()]
+    mine = pre.edge_angle(mom)
+    ref_angle = np.rad2deg(np.arctan2(*_principal(edges)))
+    assert abs(mine - ref_angle) < 1e-9
+    if g["angle"] != 0.0:
+        M = pre.rotation_matrix_2d((w / 2, h / 2), g["angle"])
+        assert np.array_equal(M, cv2.getRotationMatrix2D((w / 2, h / 2), g["angle"], 1.0))
+        assert np.array_equal(P.rotation_matrix_np((w / 2, h / 2), g["angle"]), M)
+        assert _sha(P.warp_affine_np(img, M, w, h)) == g["output"]
+        assert np.allclose(pre.invert_affine(M), cv2.invertAffineTransform(M).ravel(), atol=1e-12)
+        assert _sha(P.warp_affine_np(img, pre.rotation_matrix_2d((w / 2, h / 2), mine), w, h)) == g["output"]
+
+
+def _principal(edges):
+    coords = np.column_stack(np.where(edges > 0))
+    centered = coords - coords.mean(axis=0)
+    vals, vecs = np.linalg.eigh(np.cov(centered, rowvar=False))
+    p = vecs[:, np.argmax(vals)]
+    return p[0], p[1]
+
+
+def test_warp_restatement_on_extreme_maps():
+    import cv2
+    img = P.image_set("noise", 97, 131)
+    for M in (np.array([[1, 0, 0.5], [0, 1, -0.25]]), np.array([[0.5, 0.1, -30], [-0.2, 1.7, 40.0]]),
+              P.rotation_matrix_np((65.5, 48.5), 180.0), np.array([[1, 0, 0], [0, 1, 0.0]]), np.array([[1, 0, 500], [0, 1, 0.0]])):
+        want = cv2.warpAffine(img, M, (131, 97), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        assert np.array_equal(P.warp_affine_np(img, M, 131, 97), want)
+        want2 = cv2.warpAffine(img, M, (200, 50), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        assert np.array_equal(P.warp_affine_np(img, M, 200, 50), want2)

@@ -126,3 +126,80 @@ def test_resize_center_crop_rejects_bad_input(pre):
         pre.resize_center_crop(np.zeros((8, 8, 2), np.uint8), 8, 4)
     with pytest.raises(ValueError):
         pre.resize_center_crop(np.zeros((64, 64, 3), np.uint8), 32, 48)
+
+
+# ---- deskew: OpenCV on the box is the reference's arithmetic itself; golden = the reference's deskew
+DESKEW_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "deskew_golden.json")))
+
+
+def _long_line(h=64, w=4096):
+    """A faint line (between the two Canny thresholds) across 128 tiles, strong only at its left end: hysteresis must carry
+    the label along the whole path, one tile per pass."""
+    img = np.full((h, w), 100, np.uint8)
+    img[31, 8:w - 8] = 120
+    img[31, 8:40] = 180
+    return np.repeat(img[..., None], 3, axis=2)
+
+
+@pytest.mark.parametrize("case", ["tooth0", "tooth1", "tooth2", "tooth4", "noise", "odd", "tiny", "long_line", "flat"])
+def test_canny_is_bit_identical_to_opencv(pre, case):
+    import cv2
+    if case.startswith("tooth"):
+        img = P.tooth_image(*P.DESKEW_CASES[int(case[5:])])
+    elif case == "long_line":
+        img = _long_line()
+    else:
+        img = {"noise": lambda: P.image_set("noise", 300, 400), "odd": lambda: P.image_set("smooth", 97, 131, seed=3),
+               "tiny": lambda: P.image_set("noise", 5, 7), "flat": lambda: P.image_set("const128", 64, 64)}[case]()
+    want = cv2.Canny(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), 50, 150)
+    edges, mom = pre.canny(img, 50, 150)
+    got = edges.cpu().numpy()
+    assert int((got != want).sum()) == 0, (case, int((got != want).sum()), int((want > 0).sum()))
+    ys, xs = np.nonzero(want)
+    ys, xs = ys.astype(np.int64), xs.astype(np.int64)
+    assert mom.cpu().tolist() == [len(ys), int(ys.sum()), int(xs.sum()), int((ys * ys).sum()), int((xs * ys).sum()), int((xs * xs).sum())]
+    if case == "long_line":
+        assert int((want > 0).sum()) > 8000              # the whole line was kept, not just the strong stub
+
+
+@pytest.mark.parametrize("ch", [3, 1])
+def test_warp_affine_is_bit_identical_to_opencv(pre, ch):
+    import cv2
+    img = P.image_set("noise", 97, 131)[..., :ch].copy()
+    big = P.tooth_image(480, 640, 1, -33.0)[..., :ch].copy()
+    maps = [np.array([[1, 0, 0.5], [0, 1, -0.25]]), np.array([[0.5, 0.1, -30], [-0.2, 1.7, 40.0]]), np.array([[1, 0, 0], [0, 1, 0.0]]),
+            np.array([[1, 0, 500], [0, 1, 0.0]]), pre.rotation_matrix_2d((65.5, 48.5), 180.0), pre.rotation_matrix_2d((65.5, 48.5), 33.3)]
+    for src in (img, big):
+        for M in maps:
+            for dsize in ((src.shape[1], src.shape[0]), (200, 50)):
+                want = cv2.warpAffine(src, M, dsize, flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE).reshape(dsize[1], dsize[0], ch)
+                got = pre.warp_affine(src, M, dsize).cpu().numpy()
+                assert int((got != want).sum()) == 0, (src.shape, M.tolist(), dsize)
+
+
+@pytest.mark.parametrize("idx", range(len(P.DESKEW_CASES)))
+def test_deskew_matches_the_reference(pre, idx):
+    import hashlib
+    h, w, seed, tilt = P.DESKEW_CASES[idx]
+    g = DESKEW_GOLD["cases"][idx]
+    img = P.tooth_image(h, w, seed, tilt)
+    rot, angle = pre.deskew(img)
+    assert isinstance(rot, np.ndarray) and abs(angle - g["angle"]) < 1e-9
+    assert hashlib.sha1(np.ascontiguousarray(rot).tobytes()).hexdigest() == g["output"]
+    want, wa, _ = P.deskew_cv2(img)
+    assert np.array_equal(rot, want) and abs(angle - wa) < 1e-9
+    dev = torch.from_numpy(img).cuda()
+    rot_d, angle_d = pre.deskew(dev)
+    assert rot_d.is_cuda and angle_d == angle and np.array_equal(rot_d.cpu().numpy(), want)
+    if g["angle"] == 0.0:
+        assert rot is img and rot_d is dev                # skipped rotation returns the input itself (normalise.py:29,46)
+
+
+def test_deskew_too_few_edges_and_bad_input(pre):
+    flat = P.image_set("const128", 64, 64)
+    out, a = pre.deskew(flat)
+    assert out is flat and a == 0.0
+    with pytest.raises(ValueError):
+        pre.deskew(np.zeros((4, 8, 8, 3), np.uint8))
+    with pytest.raises(ValueError):
+        pre.warp_affine(np.zeros((8, 8, 2), np.uint8), np.eye(2, 3), (8, 8))
