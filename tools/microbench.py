@@ -77,5 +77,57 @@ for thr in (1, os.cpu_count()):
         t0 = time.perf_counter(); P.apply_clahe_cv2(img); ts.append(time.perf_counter() - t0)
     out.append({"what": "cpu_reference_apply_clahe", "threads": thr, "ms": statistics.median(ts) * 1e3,
                 "Mpx_per_s": 1024 * 1024 / statistics.median(ts) / 1e6})
+# ---- "next" rows of SURVEY 8 (f1-f4): device path (host buffers in, result on the host where the reference returns one)
+# beside the reference's CPU path on this box's cores.  End-to-end wall clock, host->device copies included.
+def wall(fn, n=10, warm=2):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(n):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    return statistics.median(ts)
+
+
+cv2.setNumThreads(os.cpu_count())
+tooth = P.tooth_image(1024, 1024, 3, 33.0)
+tooth_dev = torch.from_numpy(tooth).cuda()
+out.append({"what": "f1_deskew_1024", "device_resident_ms": wall(lambda: preproc.deskew(tooth_dev)) * 1e3,
+            "host_in_host_out_ms": wall(lambda: preproc.deskew(tooth)) * 1e3, "cpu_reference_ms": wall(lambda: P.deskew_cv2(tooth)) * 1e3,
+            "edges_us": gpu_time(lambda: preproc.canny(tooth_dev, want_edges=False), l2flush=False) * 1e6,
+            "warp_us": gpu_time(lambda: preproc.warp_affine(tooth_dev, preproc.rotation_matrix_2d((512, 512), 33.0), (1024, 1024)), l2flush=False) * 1e6})
+from PIL import Image
+from torchvision import transforms
+pil = Image.fromarray(tooth[..., ::-1].copy())
+tfm = transforms.Compose([transforms.Resize(256, interpolation=transforms.InterpolationMode.BICUBIC), transforms.CenterCrop(224)])
+rgb = np.asarray(pil)
+out.append({"what": "f2_eval_resize_crop_1024_to_224", "host_in_device_out_ms": wall(lambda: preproc.resize_center_crop(rgb, 256, 224)) * 1e3,
+            "kernels_us": gpu_time(lambda: preproc.resize_center_crop(tooth_dev, 256, 224), l2flush=False) * 1e6,
+            "cpu_reference_pil_ms": wall(lambda: np.asarray(tfm(pil))) * 1e3})
+import ref_calib as RC
+import ref_stack as RS
+from teethrt import calib, stack
+z, yv, _ = RC.calib_cases()["large"]
+zd, yd = torch.tensor(z).cuda(), torch.tensor(yv).cuda()
+out.append({"what": "f3_calibrate_epoch_n10007", "device_ms": wall(lambda: calib.calibrate_epoch(zd, yd), n=5) * 1e3,
+            "cpu_reference_ms": wall(lambda: RC.calibrate_epoch(z, yv), n=3, warm=1) * 1e3})
+fr = RS.stream_frames(n=20000, n_test=4000)
+oof = fr["tab_oof"].rename(columns={"prob": "a"}).merge(fr["mm_oof"].rename(columns={"prob": "b"}), on=["image_name", "y"])
+X, yo = oof[["a", "b"]].values, oof["y"].values
+
+
+def dev_stack():
+    m = stack.LogisticMeta().fit(X, yo)
+    p = m.predict_proba(X)[:, 1]
+    return [stack.choose_threshold(yo, p, mode) for mode in RS.MODES]
+
+
+def cpu_stack():
+    m = RS.fit_meta(X, yo)
+    p = m.predict_proba(X)[:, 1]
+    return [RS.choose_threshold(yo, p, mode) for mode in RS.MODES]
+
+
+out.append({"what": "f4_meta_fit_plus_5_threshold_modes_n20000", "device_ms": wall(dev_stack, n=5) * 1e3,
+            "cpu_reference_ms": wall(cpu_stack, n=2, warm=1) * 1e3})
 for o in out:
     print(json.dumps(o))
