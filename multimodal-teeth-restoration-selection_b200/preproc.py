@@ -301,3 +301,24 @@ def deskew(img_bgr):
     h, w = x.shape[1], x.shape[2]
     out = warp_affine(x[0], rotation_matrix_2d((w / 2, h / 2), angle, 1.0), (w, h))
     return (out.cpu().numpy() if was_np else out), angle
+
+
+MIN_EDGE_PX = 400         # src/config.py:13
+
+
+def preprocess_image(img_bgr, rotate=True, size=OUTPUT_SIZE):
+    """The image path of Preprocessor.process_file without segmentation (src/preprocessing/pipeline.py:80-117, crop_mode
+    'none'): size check -> CLAHE -> deskew (optional) -> centre_crop_resize, chained on the device with one small read-back
+    (the edge moments).  -> (uint8 [size,size,3], info dict with the reference's keys); numpy in -> numpy out."""
+    was_np = isinstance(img_bgr, np.ndarray)
+    x, _, batched = _to_dev(img_bgr)
+    if batched:
+        raise ValueError("preprocess_image works on one image [H,W,3]")
+    if min(x.shape[1], x.shape[2]) < MIN_EDGE_PX:
+        raise ValueError("Image too small (<400 px)")
+    img = apply_clahe(x[0])
+    info = {"rotation_deg": 0.0, "crop_mode": "none"}
+    if rotate:
+        img, info["rotation_deg"] = deskew(img)
+    out = centre_crop_resize(img, size)
+    return (out.cpu().numpy() if was_np else out), info

@@ -203,3 +203,20 @@ def test_deskew_too_few_edges_and_bad_input(pre):
         pre.deskew(np.zeros((4, 8, 8, 3), np.uint8))
     with pytest.raises(ValueError):
         pre.warp_affine(np.zeros((8, 8, 2), np.uint8), np.eye(2, 3), (8, 8))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 3])
+def test_preprocess_image_chain_matches_the_reference_sequence(pre, idx):
+    """pipeline.py:80-117 without segmentation: CLAHE -> deskew -> centre_crop_resize(512), byte-identical end to end."""
+    h, w, seed, tilt = P.DESKEW_CASES[idx]
+    img = P.tooth_image(h, w, seed, tilt)
+    cl = P.apply_clahe_cv2(img)
+    rot, angle, _ = P.deskew_cv2(cl)
+    want = P.centre_crop_resize_cv2(rot, 512)
+    got, info = pre.preprocess_image(img)
+    assert info["crop_mode"] == "none" and abs(info["rotation_deg"] - angle) < 1e-9
+    assert isinstance(got, np.ndarray) and int((got != want).sum()) == 0
+    got_d, _ = pre.preprocess_image(torch.from_numpy(img).cuda(), rotate=False)
+    assert got_d.is_cuda and int((got_d.cpu().numpy() != P.centre_crop_resize_cv2(cl, 512)).sum()) == 0
+    with pytest.raises(ValueError):
+        pre.preprocess_image(img[:300])

@@ -15,4 +15,4 @@ timeout 200 python tools/prof_top.py > /dev/null 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${T}_top_kernels python tools/prof_top.py > gpurun_out/${T}_ncu_top.log 2>&1
 echo "ncu full exit=$?"; tail -1 gpurun_out/${T}_ncu_top.log
 timeout 200 python bench.py --infer --steps 20 > gpurun_out/${T}_infer.json 2>&1; tail -c 400 gpurun_out/${T}_infer.json
-timeout 300 python tools/microbench.py > gpurun_out/${T}_micro.log 2>&1; echo "micro exit=$?"
+timeout 500 python tools/microbench.py > gpurun_out/${T}_micro.log 2>&1; echo "micro exit=$?"
