@@ -188,28 +188,53 @@ def _coeffs_on(device, in_size, out_size, interpolation, lo, hi):
     return _coeff_dev[key]
 
 
+def _as_u8_image(img_u8):
+    t = torch.from_numpy(np.array(img_u8, copy=True)).cuda() if isinstance(img_u8, np.ndarray) else img_u8
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3) or not t.is_cuda:
+        raise ValueError("expected a uint8 image [H,W,1|3] (numpy array or CUDA tensor)")
+    return t.contiguous()
+
+
+def _resample_window(t, box, out_hw, window, interpolation, swap_channels):
+    """Pillow resize of the source box (top, left, h, w) of `t` to out_hw, of which only `window` (top, left, h, w in
+    output coordinates) is computed: horizontal pass over the source rows those output rows need, then vertical pass."""
+    top, left, h, w = box
+    wt, wl, wh, ww = window
+    ch, pitch = t.shape[2], t.shape[1] * t.shape[2]
+    vb, vc, vk, r0, r1 = _coeffs_on(t.device, h, out_hw[0], interpolation, wt, wt + wh)
+    hb, hc, hk, c0, _ = _coeffs_on(t.device, w, out_hw[1], interpolation, wl, wl + ww)
+    tmp = torch.empty((r1 - r0, ww, ch), device=t.device, dtype=torch.uint8)
+    out = torch.empty((wh, ww, ch), device=t.device, dtype=torch.uint8)
+    src = t[top + r0:, left + c0:]                                      # tables are relative to (r0, c0) inside the box
+    check(lib.trt_resample_u8(src.data_ptr(), pitch, ch, ptr(tmp), r1 - r0, ww, ptr(hb), ptr(hc), hk, 0, 0, stream()))
+    check(lib.trt_resample_u8(ptr(tmp), ww * ch, ch, ptr(out), wh, ww, ptr(vb), ptr(vc), vk, 1, int(swap_channels), stream()))
+    return out
+
+
 def resize_center_crop(img_u8, short, crop, interpolation="bicubic", swap_channels=False):
     """transforms.Resize(short, interpolation) -> transforms.CenterCrop(crop) on a uint8 [H,W,C] image (numpy or CUDA
     tensor, C in {1,3}) -> CUDA uint8 [crop, crop, C], bit-identical to the PIL path.  Only the crop window is computed:
     the horizontal pass runs over the source rows the cropped output rows need and the cropped columns, the vertical pass
     over the result.  swap_channels writes the channels reversed (RGB <-> BGR)."""
-    t = torch.from_numpy(np.array(img_u8, copy=True)).cuda() if isinstance(img_u8, np.ndarray) else img_u8
-    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3) or not t.is_cuda:
-        raise ValueError("expected a uint8 image [H,W,1|3] (numpy array or CUDA tensor)")
-    t = t.contiguous()
-    h, w, ch = t.shape
+    t = _as_u8_image(img_u8)
+    h, w, _ = t.shape
     nh, nw = resized_size(h, w, short)
     if crop > nh or crop > nw:
         raise ValueError(f"crop {crop} larger than the resized image {nh}x{nw} (the reference would zero-pad; not built)")
     top, left = int(round((nh - crop) / 2.0)), int(round((nw - crop) / 2.0))
-    vb, vc, vk, r0, r1 = _coeffs_on(t.device, h, nh, interpolation, top, top + crop)
-    hb, hc, hk, c0, _ = _coeffs_on(t.device, w, nw, interpolation, left, left + crop)
-    tmp = torch.empty((r1 - r0, crop, ch), device=t.device, dtype=torch.uint8)
-    out = torch.empty((crop, crop, ch), device=t.device, dtype=torch.uint8)
-    src = t[r0:, c0:]                                                   # tables are relative to (r0, c0)
-    check(lib.trt_resample_u8(src.data_ptr(), w * ch, ch, ptr(tmp), r1 - r0, crop, ptr(hb), ptr(hc), hk, 0, 0, stream()))
-    check(lib.trt_resample_u8(ptr(tmp), crop * ch, ch, ptr(out), crop, crop, ptr(vb), ptr(vc), vk, 1, int(swap_channels), stream()))
-    return out
+    return _resample_window(t, (0, 0, h, w), (nh, nw), (top, left, crop, crop), interpolation, swap_channels)
+
+
+def resized_crop(img_u8, top, left, height, width, size, interpolation="bicubic", swap_channels=False):
+    """torchvision F.resized_crop on a PIL image (= img.crop(box).resize(size)): the deterministic part of timm's
+    RandomResizedCropAndInterpolation in the train transform (train_mm_joint_dualtask.py:75-84), given the sampled box.
+    size: int or (h, w).  Bit-identical to the PIL path; the box must lie inside the image."""
+    t = _as_u8_image(img_u8)
+    H, W, _ = t.shape
+    oh, ow = (size, size) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    if top < 0 or left < 0 or height <= 0 or width <= 0 or top + height > H or left + width > W:
+        raise ValueError(f"crop box ({top}, {left}, {height}, {width}) outside the {H}x{W} image (PIL would zero-pad; not built)")
+    return _resample_window(t, (top, left, height, width), (oh, ow), (0, 0, oh, ow), interpolation, swap_channels)
 
 
 # ------------------------------------------------------------------------------------------------ deskew (SURVEY §8 row f1)

@@ -220,3 +220,20 @@ def test_preprocess_image_chain_matches_the_reference_sequence(pre, idx):
     assert got_d.is_cuda and int((got_d.cpu().numpy() != P.centre_crop_resize_cv2(cl, 512)).sum()) == 0
     with pytest.raises(ValueError):
         pre.preprocess_image(img[:300])
+
+
+@pytest.mark.parametrize("box,size,interp", [((100, 57, 640, 480), 224, "bicubic"), ((0, 0, 300, 300), 380, "bicubic"),
+                                             ((511, 13, 97, 801), (224, 224), "bilinear"), ((3, 900, 1000, 124), (96, 160), "bicubic")])
+def test_resized_crop_is_bit_identical_to_torchvision_on_pil(pre, box, size, interp):
+    from PIL import Image
+    from torchvision.transforms import functional as TF, InterpolationMode
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, (1024, 1024, 3), dtype=np.uint8)
+    top, left, h, w = box
+    sz = [size, size] if isinstance(size, int) else list(size)
+    want = np.asarray(TF.resized_crop(Image.fromarray(img), top, left, h, w, sz,
+                                      InterpolationMode.BICUBIC if interp == "bicubic" else InterpolationMode.BILINEAR))
+    got = pre.resized_crop(img, top, left, h, w, size, interp).cpu().numpy()
+    assert got.shape == want.shape and int((got != want).sum()) == 0
+    with pytest.raises(ValueError):
+        pre.resized_crop(img, 1000, 0, 100, 100, 64)
