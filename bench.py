@@ -330,11 +330,37 @@ def run_infer(args):
 
     p50a, p95a = timeit(lambda: g1(x1, t1), args.steps * 10, 50)
     p50b, p95b = timeit(ens, args.steps * 5, 20)
+    # (C) end to end through the public API: decoded 1024x1024 RGB image on the HOST -> MMEnsemble.predict_image (upload,
+    # PIL-exact eval transform, 3 TTA flips, 5 folds, calibrated probabilities) -> host numpy, wall clock
+    import tempfile
+    import time
+    import numpy as np
+    from teethrt.infer import MMEnsemble, TAB_FEATURES
+    with tempfile.TemporaryDirectory() as d:
+        for f, m in enumerate(folds):
+            torch.save({"model": m.state_dict(), "scaler_mean": np.zeros(TAB), "scaler_scale": np.ones(TAB), "thr": 0.5, "T": 2.5,
+                        "args": {"backbone": "tf_efficientnet_b4_ns", "img_size": IMG, "tab_hidden": 64, "dropout": 0.2}, "epoch": 1},
+                       os.path.join(d, f"mm_dualtask_fold{f}.pt"))
+        ens_api = MMEnsemble(d, device="cuda")
+    rgb = np.random.default_rng(0).integers(0, 256, size=(1024, 1024, 3), dtype=np.uint8)
+    tab = {k: 0.5 for k in TAB_FEATURES}
+    for _ in range(5):
+        ens_api.predict_image(rgb, tab)
+    ws = []
+    for _ in range(args.steps * 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ens_api.predict_image(rgb, tab)
+        ws.append((time.perf_counter() - t0) * 1e3)
+    ws.sort()
     print(json.dumps({"metric": "mm_batch1_infer_p50_latency", "value": p50a, "unit": "ms", "higher_is_better": False, "n_gpus": 1,
                       "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": "batch-1 MMNet forward (B4 @224 + tab), CUDA-graph replay"},
                       "single_forward": {"p50_ms": p50a, "p95_ms": p95a},
-                      "ensemble_5fold_3tta": {"p50_ms": p50b, "p95_ms": p95b}}), flush=True)
+                      "ensemble_5fold_3tta": {"p50_ms": p50b, "p95_ms": p95b},
+                      "e2e": {"value": ws[len(ws) // 2], "unit": "ms", "p95_ms": ws[int(len(ws) * 0.95)],
+                              "what": "MMEnsemble.predict_image: 1024x1024 RGB host array -> 5-fold x 3-TTA probability on the host",
+                              "h2d_bytes_per_step": int(rgb.nbytes) + 5 * 3 * TAB * 4, "d2h_bytes_per_step": 5 * 4}}), flush=True)
 
 
 def main():

@@ -120,14 +120,18 @@ class MMEnsemble:
             probs.append(torch.sigmoid(logit / T))
         return torch.cat(probs)
 
+    def predict_image(self, rgb_u8, tab_dict=None):
+        """Decoded image (PIL image or uint8 RGB [H,W,3] host array) -> per-fold probabilities (numpy): full-size upload,
+        eval transform + TTA + all folds on the device, one device->host read."""
+        with torch.cuda.device(self.device):
+            bgr = eval_resize_crop(rgb_u8, self.img_size, swap_channels=True)
+        return self.predict_tensor(bgr, tab_dict).cpu().numpy()                      # the one sync of the prediction
+
     def predict(self, image_path, tab_dict=None):
         """Return (prob_mm, debug_str)."""
         if not self.models:
             return 0.5, "MM not loaded"
-        img = Image.open(image_path).convert('RGB')
-        with torch.cuda.device(self.device):
-            bgr = eval_resize_crop(img, self.img_size, swap_channels=True)           # full-size upload, resize on the device
-        probs = self.predict_tensor(bgr, tab_dict).cpu().numpy()                     # the one sync of the prediction
+        probs = self.predict_image(Image.open(image_path).convert('RGB'), tab_dict)
         return float(np.mean(probs)), f"fold_probs={np.round(probs, 3)}"
 
 
