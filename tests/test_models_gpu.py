@@ -302,3 +302,54 @@ def test_fused_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
     tol_l, tol_p = max(1e-3, 4 * dl(l0, l0b)), max(1e-4, 4 * dp(p0, p0b))
     assert dl(l0, l1) < tol_l and dl(l0, l2) < tol_l
     assert dp(p0, p1) < tol_p and dp(p0, p2) < tol_p
+
+
+def test_config1_full_size_step_vs_oracle_on_the_gpu(T):
+    """BASELINE.json configs[1] at its full size (B4, batch 64, 224x224): one fused train step against the fp32 oracle run
+    on the same GPU (TF32 off), plus two size-independent properties — an eval batch equals the concatenation of its halves,
+    and the TTA logit equals the mean of three separately flipped forwards."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    from teethrt.infer import tta_logit
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ora = R.seeded_model("mm", seed=3, warm=1, img=64, drop=0.0).cuda().train()
+    m = MMJointDualHead(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    x, xt, yh, ys = (t.cuda() for t in mm_inputs(64, 224, 777))
+    # --- oracle step (train_mm_joint_dualtask.py:241-256 without AMP), fp32 on the device
+    opt, _ = R.make_optimizer(ora, lr=3e-4, weight_decay=1e-4)
+    loss_o, gn_o = R.mm_train_step(ora, opt, None, x, xt, yh, ys, alpha=1.0, beta=0.3, grad_clip=1.0)
+    # --- ours
+    tr = DualTaskTrainer(m, lr=3e-4, weight_decay=1e-4, t_max=0, alpha=1.0, beta=0.3, grad_clip=1.0, graph=False)
+    loss = float(tr.step(x, xt, yh, ys))
+    assert abs(loss - float(loss_o)) < 3e-2, (loss, float(loss_o))
+    assert abs(float(tr.grad_norm) - gn_o) < 0.05 * gn_o, (float(tr.grad_norm), gn_o)
+    # whole-model gradient direction (AdamW's first update is lr*sign(g) per weight, so the weights themselves only say
+    # how many noise-level gradients kept their sign; the flat gradient is the meaningful comparison)
+    go = torch.cat([p.grad.flatten() for _, p in ora.named_parameters()])
+    gm = torch.cat([tr.flat.grads[n].flatten() for n, _ in ora.named_parameters()])
+    cos_mine = float(torch.nn.functional.cosine_similarity(go, gm, dim=0))
+    # the bar for a bf16-activation path: at least as close to the fp32 gradient as torch's own bf16 autocast of the oracle
+    # (the reference trains under AMP, train_mm_joint_dualtask.py:242)
+    amp = R.seeded_model("mm", seed=3, warm=1, img=64, drop=0.0).cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        la, ra = amp(x, xt)
+        loss_a = R.dual_bce_loss(la.float(), ra.float(), yh, ys, 1.0, 0.3)
+    loss_a.backward()
+    ga = torch.cat([p.grad.flatten() for _, p in amp.named_parameters()])
+    cos_amp = float(torch.nn.functional.cosine_similarity(go, ga, dim=0))
+    assert cos_mine > 0.9 and cos_mine >= cos_amp - 0.02, (cos_mine, cos_amp)
+    del amp, ga
+    # --- eval-mode properties at full size
+    m.eval(); ora.eval()
+    with torch.no_grad():
+        full, _ = m(x, xt)
+        halves = torch.cat([m(x[:32], xt[:32])[0], m(x[32:], xt[32:])[0]])
+        assert (full - halves).abs().max() < 2e-3
+        lo, _ = ora(x, xt)
+        # the two models took one optimiser step each from the same weights: their logits still agree at bf16 level
+        assert (full - lo).abs().max() < 1e-1
+        t3 = tta_logit(m, x[:8], xt[:8])
+        sep = torch.stack([m(x[:8], xt[:8])[0], m(torch.flip(x[:8], dims=[3]), xt[:8])[0], m(torch.flip(x[:8], dims=[2]), xt[:8])[0]]).mean(0)
+        assert (t3 - sep).abs().max() < 2e-3
