@@ -248,3 +248,49 @@ def write_outputs(outdir, results):
     with open(outdir / "summary.json", "w") as f:
         json.dump(summary, f, indent=2)
     return summary
+
+
+def finalize_from_ckpts(ckpt_dir, fold_loaders, outdir, folds=5, log=print):
+    """experiments/multimodal_v1/finalize_mm_dualtask_from_ckpts.py:110-184: reload every `mm_dualtask_fold{k}.pt`, re-run the
+    TTA inference on that fold's validation and the test loader, and write `oof_val.csv`, `pred_test.csv` and the script's
+    `summary.json` ({'val_mean', 'test_mean', 'folds': [{'fold','thr','T','val','test'}]}).  `fold_loaders(fold, ckpt)` returns
+    (dl_va, dl_te) built from the checkpoint's args / scaler statistics as the script does (:122-139); batches are
+    (x_img, x_tab, y, ..., names).  Missing folds are skipped with the script's warning; no fold at all raises SystemExit."""
+    import pandas as pd
+    from .modules import MMNet
+    from .infer import TAB_FEATURES
+    device = torch.device("cuda", init())
+    outdir = Path(outdir)
+    outdir.mkdir(parents=True, exist_ok=True)
+    oof_list, test_list, fold_summ = [], [], []
+    for fold in range(folds):
+        ckpt_path = Path(ckpt_dir) / f"mm_dualtask_fold{fold}.pt"
+        if not ckpt_path.exists():
+            log(f"[WARN] missing {ckpt_path}, skipping fold {fold}")
+            continue
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+        a, thr, T = ckpt['args'], ckpt['thr'], ckpt['T']
+        model = MMNet(backbone=a['backbone'], tab_in=len(TAB_FEATURES), tab_hidden=a['tab_hidden'], drop=a['dropout']).to(device)
+        model.load_state_dict(ckpt['model'])
+        model.eval()
+        dl_va, dl_te = fold_loaders(fold, ckpt)
+        # predict_tta reads (x_img, x_tab, y_h, y_s, w, names); the finalize script's dataset yields (x_img, x_tab, y, names)
+        six = lambda dl: ((b[0], b[1], b[2], None, None, b[-1]) for b in dl)  # noqa: E731
+        _, pv, yv, nv = predict_tta(model, six(dl_va), T, device)
+        _, pt, yt, nt = predict_tta(model, six(dl_te), T, device)
+        oof_list.append(pd.DataFrame({'image_name': nv, 'y': yv, 'prob': pv}))
+        test_list.append(pd.DataFrame({'image_name': nt, 'y': yt, 'prob': pt}))
+        fold_summ.append({'fold': fold, 'thr': thr, 'T': T, 'val': compute_metrics(yv, pv, thr), 'test': compute_metrics(yt, pt, thr)})
+        log(f"[Fold {fold}] VAL {fold_summ[-1]['val']} | TEST {fold_summ[-1]['test']}")
+    if not oof_list:
+        raise SystemExit("No folds finalized. Check ckpt-dir path.")
+    pd.concat(oof_list).reset_index(drop=True).to_csv(outdir / "oof_val.csv", index=False)
+    pd.concat(test_list).reset_index(drop=True).to_csv(outdir / "pred_test.csv", index=False)
+    keys = ['auc', 'acc', 'prec', 'rec', 'f1']
+    summary = {'val_mean': {k: fast_round(np.mean([f['val'][k] for f in fold_summ])) for k in keys},
+               'test_mean': {k: fast_round(np.mean([f['test'][k] for f in fold_summ])) for k in keys}, 'folds': fold_summ}
+    with open(outdir / "summary.json", "w") as f:
+        json.dump(summary, f, indent=2)
+    log("=== VAL (mean) ===", summary['val_mean'])
+    log("=== TEST (mean) ===", summary['test_mean'])
+    return summary

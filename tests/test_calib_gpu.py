@@ -171,6 +171,26 @@ def test_run_fold_end_to_end(cal, tmp_path):
     assert same_metrics(res['val_metrics'], RC.compute_metrics(res['val_oof']['y'].to_numpy(), res['val_oof']['prob'].to_numpy(), res['thr']))
     s = cal.write_outputs(tmp_path, [res])
     assert s['fold_details'][0]['fold'] == 0 and (tmp_path / "oof_val.csv").exists()
+    # --- finalize_mm_dualtask_from_ckpts.py: reload the checkpoint written above and regenerate the prediction files
+    four = lambda dl: [(b[0], b[1], b[2], b[5]) for b in dl]        # that script's dataset yields (x_img, x_tab, y, names)
+    seen = []
+    fin = cal.finalize_from_ckpts(tmp_path, lambda fold, ck: (four(dl_va), four(dl_te)), tmp_path / "finalized", folds=3, log=lambda *a: seen.append(a))
+    assert list(fin) == ['val_mean', 'test_mean', 'folds'] and [f['fold'] for f in fin['folds']] == [0]
+    assert sum("[WARN] missing" in str(a[0]) for a in seen) == 2                 # folds 1 and 2 have no checkpoint
+    assert fin['folds'][0]['T'] == res['T'] and fin['folds'][0]['thr'] == res['thr']
+    import pandas as pd
+    oof = pd.read_csv(tmp_path / "finalized" / "oof_val.csv")
+    assert list(oof.columns) == ['image_name', 'y', 'prob'] and len(oof) == 39
+    # the checkpoint holds the BEST epoch, run_fold predicted with the LAST one (the reference's quirk): same weights only if
+    # the last epoch was the best; either way the file must equal the oracle model loaded from that checkpoint
+    ck = torch.load(tmp_path / "mm_dualtask_fold0.pt", weights_only=False)
+    ora.load_state_dict({k: v.cpu() for k, v in ck['model'].items()})
+    with torch.no_grad():
+        ls = [torch.stack([ora(x, xt)[0], ora(torch.flip(x, dims=[3]), xt)[0], ora(torch.flip(x, dims=[2]), xt)[0]]).mean(0) for (x, xt, *_r) in dl_va]
+    assert np.abs(oof['prob'].to_numpy() - torch.sigmoid(torch.cat(ls) / ck['T']).numpy()).max() < 2e-2
+    assert same_metrics(fin['folds'][0]['val'], RC.compute_metrics(oof['y'].to_numpy(), oof['prob'].to_numpy().astype(np.float32), ck['thr']))
+    with pytest.raises(SystemExit):
+        cal.finalize_from_ckpts(tmp_path / "nowhere", lambda fold, ck: ([], []), tmp_path / "x", log=lambda *a: None)
 
 
 def test_trainer_handles_ragged_batches(cal):
