@@ -250,13 +250,13 @@ def canny(img_bgr, low=50, high=150, want_edges=True):
     x = x[0]
     h, w, _ = x.shape
     label = torch.empty((h, w), device=x.device, dtype=torch.uint8)
-    changed = torch.zeros(1, device=x.device, dtype=torch.int32)
+    changed = torch.zeros(4, device=x.device, dtype=torch.int32)      # one flag per pass of a round
     check(lib.trt_canny_nms_bgr_u8(ptr(x), h, w, int(low), int(high), ptr(label), stream()))
     for _ in range(4 * (h + w)):                       # bound: a path can cross at most every tile once per pass
         changed.zero_()
-        for _ in range(4):
-            check(lib.trt_canny_hysteresis_pass(ptr(label), h, w, ptr(changed), stream()))
-        if int(changed.item()) == 0:
+        for i in range(4):
+            check(lib.trt_canny_hysteresis_pass(ptr(label), h, w, changed.data_ptr() + 4 * i, stream()))
+        if int(changed[3].item()) == 0:                # the round's last pass promoted nothing: fixed point reached
             break
     edges = torch.empty((h, w), device=x.device, dtype=torch.uint8) if want_edges else None
     mom = torch.empty(6, device=x.device, dtype=torch.int64)
