@@ -23,6 +23,18 @@ __global__ void k(float* out, const uint32_t* in, int iters) {
       if (MODE == 1) acc[i] = fhfma(a, b, acc[i], i & 1);
       if (MODE == 2) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(acc[i]));
       if (MODE == 3) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(acc[i])); asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(acc[i])); }
+      if (MODE == 4) { uint32_t h = __float_as_uint(acc[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(h)); acc[i] = __uint_as_float(h); }
+      if (MODE == 5) { uint32_t h = __float_as_uint(acc[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h)); acc[i] = __uint_as_float(h); }
+      if (MODE == 6) { uint32_t h = __float_as_uint(acc[i]); asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(h)); acc[i] = __uint_as_float(h); }
+      if (MODE == 7) {   // the candidate packed sigmoid: 2 x f32 -> f16x2, tanh, affine, back to 2 x f32 (per PAIR of elements)
+        uint32_t h; float lo = acc[i], hi = acc[(i + 1) & 15];
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+        asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(h));
+        asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(h) : "r"(0x38003800u));
+        float a, b;
+        asm volatile("{.reg .f16 l, u; mov.b32 {l, u}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, u;}" : "=f"(a), "=f"(b) : "r"(h));
+        acc[i] = a + b;
+      }
     }
   }
   float s = 0;
@@ -45,5 +57,6 @@ template <int MODE> void run(const char* name, int ops_per) {
 }
 int main() {
   run<0>("FFMA", 1); run<1>("FHFMA.BF16", 1); run<2>("MUFU.TANH", 1); run<3>("EX2+RCP", 2);
+  run<4>("TANH.F16x2", 1); run<5>("EX2.F16x2", 1); run<6>("TANH.BF16x2", 1); run<7>("sigmoid pair", 1);
   return 0;
 }
