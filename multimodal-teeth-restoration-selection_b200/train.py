@@ -121,9 +121,14 @@ class _FusedTrainer:
         graphs = []
         pool = None
         first = True
+        # the data-gradient chain is captured on a HIGH-priority stream, so its kernel nodes win the block scheduler over
+        # the weight-gradient branch (side stream, default = lowest priority) whenever both have blocks pending
+        import os
+        prio = int(os.environ.get("TEETHRT_MAIN_PRIORITY", "-1"))
+        cap = torch.cuda.Stream(device=self.dev, priority=prio) if prio != 0 else None
         for seg in segs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=cap):
                 if first:
                     self.flat.g.zero_()
                 seg()
@@ -131,7 +136,7 @@ class _FusedTrainer:
             graphs.append(g)
             first = False
         gopt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gopt, pool=pool):
+        with torch.cuda.graph(gopt, pool=pool, stream=cap):
             self._optimizer()
         self._graphs = (graphs, gopt, ranges)
         self.launches_per_step = int(lib.trt_launch_count() - c0)     # kernels recorded into the replayed graphs
