@@ -11,6 +11,7 @@
 //
 // Replaces: the cuDNN/cuBLAS dispatch behind `self.backbone(x_img)` (train_mm_joint_dualtask.py:154) and its autograd
 // backward (:248) for every conv_pw / conv_pwl / conv_head of timm's EfficientNet.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/teethrt.h"
 
@@ -605,8 +606,11 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
   p.num_q_blocks = (Cq + p.block_q - 1) / p.block_q;
   p.num_mblocks = (M + BK - 1) / BK;
   const int tiles = p.num_p_blocks * p.num_q_blocks;
-  // split the row reduction across CTAs, but keep >= 4 k-blocks per CTA: every extra split costs a full tile of atomics
-  int splits = (2 * trt_num_sms() + tiles - 1) / tiles;
+  // split the row reduction across CTAs, but keep >= 4 k-blocks per CTA: every extra split costs a full tile of atomics.
+  // One wave (1 x SMs) measured best inside the train step, where these kernels run on the low-priority side stream
+  // beside the data-gradient chain (2 x: +0.07 ms/step, 4 x: +0.16, 8 x: +0.23; tools/gpu_prio_ab.sh)
+  static const int split_mult = getenv("TEETHRT_WGRAD_SPLIT_MULT") ? atoi(getenv("TEETHRT_WGRAD_SPLIT_MULT")) : 1;
+  int splits = (split_mult * trt_num_sms() + tiles - 1) / tiles;
   if (splits > p.num_mblocks / 4) splits = p.num_mblocks / 4;
   if (splits < 1) splits = 1;
   p.mblocks_per_split = (p.num_mblocks + splits - 1) / splits;

@@ -1,7 +1,7 @@
 #!/bin/bash
-# 2-GPU sanity: the preprocessing tests on one GPU, then the data-parallel bench at N=2 (torchrun, NCCL over NVLink).
+# 2-GPU A/B of the NCCL stream priority with the data-parallel bench (torchrun, NCCL over NVLink).
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "=== $name" ; timeout ${TMO:-300} "$@" > gpurun_out/$name.log 2>&1; echo "exit=$?"; tail -n ${TAILN:-6} gpurun_out/$name.log | cut -c1-600; }
-TAILN=8 TMO=300 run pre_tests python -m pytest tests/test_preproc_gpu.py tests/test_stack_gpu.py -m gpu -q --timeout 200
-TAILN=1 TMO=400 run bench2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline
-TAILN=1 TMO=300 run ref2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1
+one() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus 2 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/ddp2_$1.log 2>&1; echo "$1 exit=$? $(tail -1 gpurun_out/ddp2_$1.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3), round(d['value'],1), 'e2e', round(d['e2e']['value'],1))")"; }
+TEETHRT_NCCL_HIPRIO=0 one nccl_default 29531
+TEETHRT_NCCL_HIPRIO=1 one nccl_high 29532
+timeout 200 python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('1gpu', round(d['ms_per_step'],3), round(d['value'],1))"
