@@ -138,6 +138,24 @@ int trt_canny_finish(const uint8_t* map, int h, int w, uint8_t* edges, long long
 int trt_warp_affine_linear_u8(const uint8_t* src, int h, int w, int channels, uint8_t* dst, int dh, int dw,
                               const double* inverse_map_host, trt_stream_t stream);
 
+/* Pillow-exact operations behind timm's RandAugment ('rand-m9-mstd0.5-inc1', the train transform of
+ * experiments/multimodal_v1/train_mm_joint_dualtask.py:75-84), one uint8 HWC image per call:
+ * trt_hist_u8 + trt_lut_build_u8  per-channel histogram -> lookup table of ImageOps.autocontrast (mode 0) / equalize (mode 1)
+ * trt_lut_apply_u8                out = lut[c][img]  (also serves invert / posterize / solarize / solarize_add with a
+ *                                 host-built table)
+ * trt_enhance_rgb_u8              ImageEnhance.{Brightness 0, Color 1, Contrast 2, Sharpness 3}(img).enhance(factor), RGB;
+ *                                 scratch = one 8-byte device word (contrast's luma sum)
+ * trt_affine_pil_u8               Image.transform(size, AFFINE, matrix, BILINEAR | BICUBIC, fillcolor) with Pillow's
+ *                                 sampler (double coordinates, truncating store); matrix / fill are HOST arrays.
+ *                                 Serves rotate, shear_x/y, translate_x/y. */
+int trt_hist_u8(const uint8_t* img, size_t n_px, int channels, long long* hist, trt_stream_t stream);
+int trt_lut_build_u8(const long long* hist, int channels, int mode, uint8_t* lut, trt_stream_t stream);
+int trt_lut_apply_u8(const uint8_t* img, const uint8_t* lut, size_t n_px, int channels, uint8_t* out, trt_stream_t stream);
+int trt_enhance_rgb_u8(const uint8_t* img, int h, int w, int mode, float factor, long long* scratch, uint8_t* out,
+                       trt_stream_t stream);
+int trt_affine_pil_u8(const uint8_t* img, int h, int w, int channels, const double* matrix_host, int bicubic,
+                      const uint8_t* fill_host, uint8_t* out, trt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm / squeeze-excite / pooling kernels around the GEMMs (NHWC bf16, rows = N*H*W, C % 8 == 0).
  * Replace timm's BatchNormAct2d, SqueezeExcite and global_pool inside `self.backbone(x_img)`

@@ -11,10 +11,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libteethrt.so")
-SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu"]
+SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu", "augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math_off_placeholder"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"] + os.environ.get("TEETHRT_NVCC_EXTRA", "").split()
+
+
+# Pillow's float / double expressions must keep their operation order: no fused multiply-add contraction in this file
+PER_FILE_FLAGS = {"augment.cu": ["--fmad=false"]}
 
 
 def _nvcc():
@@ -25,7 +29,7 @@ def _nvcc():
 
 
 def _deps_mtime():
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(PKG_DIR, "..", "include", "teethrt.h")]
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "augment_core.h"), os.path.join(PKG_DIR, "..", "include", "teethrt.h")]
     return max(os.path.getmtime(h) for h in hdrs)
 
 
@@ -34,7 +38,7 @@ def _compile(src, force):
     path = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), _deps_mtime()):
         return obj, False
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + PER_FILE_FLAGS.get(src, []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

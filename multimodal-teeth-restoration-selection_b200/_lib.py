@@ -82,6 +82,11 @@ _SIGS = {
     "trt_canny_hysteresis_pass": (i32, [vp, i32, i32, vp, vp]),
     "trt_canny_finish": (i32, [vp, i32, i32, vp, vp, vp]),
     "trt_warp_affine_linear_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "trt_hist_u8": (i32, [vp, sz, i32, vp, vp]),
+    "trt_lut_build_u8": (i32, [vp, i32, i32, vp, vp]),
+    "trt_lut_apply_u8": (i32, [vp, vp, sz, i32, vp, vp]),
+    "trt_enhance_rgb_u8": (i32, [vp, i32, i32, i32, f32, vp, vp, vp]),
+    "trt_affine_pil_u8": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp]),
     "trt_temperature_nll": (i32, [vp, vp, vp, vp, i32, vp]),
     "trt_scaled_sigmoid": (i32, [vp, f32, vp, i32, vp]),
     "trt_binary_metrics": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),

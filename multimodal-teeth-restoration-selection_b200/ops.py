@@ -361,3 +361,35 @@ def logreg_predict(X, coef):
 def same_pad(i, k, s):
     total = max((math.ceil(i / s) - 1) * s + k - i, 0)
     return total // 2, total - total // 2
+
+
+# ------------------------------------------------------------------------------------------------ Pillow-exact augment ops
+def hist_lut_u8(img, mode):
+    """ImageOps.autocontrast (mode 0) / equalize (mode 1) lookup table of a uint8 HWC image, built on the device."""
+    ch = img.shape[2]
+    hist = torch.empty(ch * 256, device=img.device, dtype=torch.int64)
+    lut = torch.empty(ch * 256, device=img.device, dtype=torch.uint8)
+    check(lib.trt_hist_u8(ptr(img), img.shape[0] * img.shape[1], ch, ptr(hist), stream()))
+    check(lib.trt_lut_build_u8(ptr(hist), ch, int(mode), ptr(lut), stream()))
+    return lut
+
+
+def lut_apply_u8(img, lut):
+    out = torch.empty_like(img)
+    check(lib.trt_lut_apply_u8(ptr(img), ptr(lut), img.shape[0] * img.shape[1], img.shape[2], ptr(out), stream()))
+    return out
+
+
+def enhance_rgb_u8(img, mode, factor):
+    out = torch.empty_like(img)
+    scratch = torch.empty(1, device=img.device, dtype=torch.int64)
+    check(lib.trt_enhance_rgb_u8(ptr(img), img.shape[0], img.shape[1], int(mode), float(factor), ptr(scratch), ptr(out), stream()))
+    return out
+
+
+def affine_pil_u8(img, matrix, bicubic, fill):
+    out = torch.empty_like(img)
+    m = (C.c_double * 6)(*[float(v) for v in matrix])
+    f = (C.c_ubyte * 4)(*([int(v) for v in fill] + [0] * (4 - len(fill))))
+    check(lib.trt_affine_pil_u8(ptr(img), img.shape[0], img.shape[1], img.shape[2], m, int(bool(bicubic)), f, ptr(out), stream()))
+    return out
