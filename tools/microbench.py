@@ -129,5 +129,18 @@ def cpu_stack():
 
 out.append({"what": "f4_meta_fit_plus_5_threshold_modes_n20000", "device_ms": wall(dev_stack, n=5) * 1e3,
             "cpu_reference_ms": wall(cpu_stack, n=2, warm=1) * 1e3})
+# f2 train transform: RandAugment operations on one 224x224 crop, device kernels beside Pillow (what timm calls) on the host
+import ref_augment as RA
+from teethrt import augment
+crop = np.random.RandomState(0).randint(0, 256, (224, 224, 3), dtype=np.uint8)
+crop_dev, crop_pil = torch.from_numpy(crop).cuda(), Image.fromarray(crop)
+for name, args in (("Rotate", (27.0,)), ("ShearX", (0.27,)), ("SharpnessIncreasing", (1.81,)), ("ContrastIncreasing", (1.81,)), ("Equalize", ())):
+    out.append({"what": "f2_randaugment_op_224", "op": name, "device_us": gpu_time(lambda: augment._OP_FN[name](crop_dev, *args), l2flush=False) * 1e6,
+                "cpu_reference_pil_us": wall(lambda: RA.OPS[name](crop_pil, *args), n=20) * 1e3})
+big = np.random.RandomState(1).randint(0, 256, (512, 512, 3), dtype=np.uint8)
+tf = augment.TrainTransform(224, seed=0)
+big_dev = torch.from_numpy(big).cuda()
+out.append({"what": "f2_train_transform_512_to_224", "device_resident_ms": wall(lambda: tf(big_dev), n=30) * 1e3,
+            "host_in_ms": wall(lambda: tf(big), n=30) * 1e3})
 for o in out:
     print(json.dumps(o))
