@@ -49,25 +49,37 @@ def equalize(img, **_):
     return ops.lut_apply_u8(img, ops.hist_lut_u8(img, 1))
 
 
+def point_table(name, arg=None, thresh=128):
+    """256-entry lookup table of the point operations (host side; the same table Pillow's ImageOps builds)."""
+    i = np.arange(256)
+    if name == "invert":
+        return (255 - i).astype(np.uint8)
+    if name == "posterize":
+        return (i & (~(2 ** (8 - arg) - 1) & 0xff)).astype(np.uint8)
+    if name == "solarize":
+        return np.where(i < arg, i, 255 - i).astype(np.uint8)
+    if name == "solarize_add":
+        return np.where(i < thresh, np.minimum(255, i + arg), i).astype(np.uint8)
+    raise KeyError(name)
+
+
 def invert(img, **_):
-    return _lut(_img(img), 255 - np.arange(256))
+    return _lut(_img(img), point_table("invert"))
 
 
 def posterize(img, bits_to_keep, **_):
     img = _img(img)
     if bits_to_keep >= 8:
         return img
-    return _lut(img, np.arange(256) & (~(2 ** (8 - bits_to_keep) - 1) & 0xff))
+    return _lut(img, point_table("posterize", bits_to_keep))
 
 
 def solarize(img, thresh, **_):
-    i = np.arange(256)
-    return _lut(_img(img), np.where(i < thresh, i, 255 - i))
+    return _lut(_img(img), point_table("solarize", thresh))
 
 
 def solarize_add(img, add, thresh=128, **_):
-    i = np.arange(256)
-    return _lut(_img(img), np.where(i < thresh, np.minimum(255, i + add), i))
+    return _lut(_img(img), point_table("solarize_add", add, thresh))
 
 
 def brightness(img, factor, **_):

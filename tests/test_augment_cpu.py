@@ -88,6 +88,20 @@ def test_host_side_pieces():
     assert A.random_resized_crop_box(10, 1000, rr, scale=(5.0, 6.0)) == (0, 493, 10, 13)        # fallback: central, ratio clamped
 
 
+def test_point_tables_equal_pillow():
+    from teethrt import augment as A
+    for a in IMGS:
+        im = Image.fromarray(a)
+        look = lambda t: t[a]  # noqa: E731
+        assert np.array_equal(look(A.point_table("invert")), np.asarray(RA.invert(im)))
+        for bits in (0, 1, 3, 4, 7):
+            assert np.array_equal(look(A.point_table("posterize", bits)), np.asarray(RA.posterize(im, bits))), bits
+        for t in (0, 26, 146, 256):
+            assert np.array_equal(look(A.point_table("solarize", t)), np.asarray(RA.solarize(im, t))), t
+        for add in (0, 47, 99, 110):
+            assert np.array_equal(look(A.point_table("solarize_add", add)), np.asarray(RA.solarize_add(im, add))), add
+
+
 def test_pillow_transpose_fast_paths_are_rot90():
     import torch
     a = IMGS[0][:97, :97].copy()
