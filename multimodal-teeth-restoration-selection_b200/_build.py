@@ -12,9 +12,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libteethrt.so")
 SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu", "augment.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--use_fast_math_off_placeholder"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"] + os.environ.get("TEETHRT_NVCC_EXTRA", "").split()
+NVCC_FLAGS = (["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+              + os.environ.get("TEETHRT_NVCC_EXTRA", "").split())
 
 
 # Pillow's float / double expressions must keep their operation order: no fused multiply-add contraction in this file

@@ -6,6 +6,7 @@ Pointers handed to the library are device pointers of torch tensors (torch is pl
 import ctypes as C
 import os
 import re
+import threading
 
 import torch
 
@@ -25,7 +26,34 @@ def _load():
     return C.CDLL(LIB_PATH)
 
 
-lib = _load()
+_cdll = _load()
+_tl = threading.local()          # .dev = ordinal of the device the most recent operand lives on (set by ptr())
+
+
+class _Lib:
+    """The loaded library.  Every entry point launches on the device its operands live on: the reference lets the caller
+    pick any device (`MMEnsemble(device='cuda:1')`), while a CUDA launch needs the CURRENT device to own the stream, so a
+    call whose operands sit on another device runs under a device guard (one process per GPU never takes that branch)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)       # AttributeError here = library/header mismatch: fail loudly
+
+        def call(*args):
+            dev = getattr(_tl, "dev", None)
+            if dev is None or dev == torch.cuda.current_device():
+                return fn(*args)
+            with torch.cuda.device(dev):
+                return fn(*args)
+        call.__name__ = name
+        call.raw = fn
+        setattr(self, name, call)
+        return call
+
+
+lib = _Lib(_cdll)
 
 vp, i32, i64, f32, f64, u64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong, C.c_size_t
 
@@ -95,7 +123,7 @@ _SIGS = {
 }
 
 for _name, (_res, _args) in _SIGS.items():
-    _fn = getattr(lib, _name)       # AttributeError here = library/header mismatch: fail loudly
+    _fn = getattr(_cdll, _name)     # AttributeError here = library/header mismatch: fail loudly
     _fn.restype = _res
     _fn.argtypes = _args
 
@@ -121,14 +149,18 @@ def header_symbols():
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL); remembers the operand's device for stream() and the launch guard."""
     if t is None:
         return None
+    if t.is_cuda:
+        _tl.dev = t.device.index
     return t.data_ptr()
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """The current stream OF THE OPERANDS' DEVICE (ptr() of every operand is evaluated before this in a call's argument
+    list), not of whatever device happens to be current."""
+    return torch.cuda.current_stream(getattr(_tl, "dev", None)).cuda_stream
 
 
 def check(rc):
@@ -146,6 +178,6 @@ def init(device=None):
     idx = None if device is None else (device if isinstance(device, int) else torch.device(device).index)
     dev = torch.cuda.current_device() if idx is None else idx
     if dev not in _inited:
-        check(lib.trt_init(dev))
+        check(_cdll.trt_init(dev))      # leaves the caller's current device as it was
         _inited.add(dev)
     return dev

@@ -167,11 +167,16 @@ class EfficientNet(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, x):
-        feat = encoder_forward(self, x)
         if self.global_pool_type == "avg":
-            return feat
-        raise NotImplementedError("teethrt EfficientNet: only global_pool='avg' features are produced on the device; "
-                                  "use forward_pooled() (the MIL twin applies its own global average pool)")
+            return encoder_forward(self, x)
+        if self.global_pool_type == "":
+            # timm's un-pooled feature map [N, F, h, w], as the MIL twin's encoder returns it (ui/gradio_app/infer_mil.py:75,
+            # 85-92).  Inference only: the twin never trains, and its own AdaptiveAvgPool2d is fused away by forward_pooled()
+            if self.training and torch.is_grad_enabled():
+                raise NotImplementedError("teethrt EfficientNet(global_pool=''): the un-pooled feature map is an inference "
+                                          "output; train with global_pool='avg'")
+            return forward_eval(self, x, pooled=False)
+        raise ValueError(f"teethrt EfficientNet: global_pool={self.global_pool_type!r} is not built ('avg' or '')")
 
     def forward_pooled(self, x):
         return encoder_forward(self, x)
@@ -212,14 +217,23 @@ def _packed_weights(enc, dev, transposed):
     return cache["w"]
 
 
+def _version_key(enc):
+    """In-place updates made through torch (an optimiser stepping while the module is in eval mode, `copy_` into a buffer)
+    bump these counters; updates made by libteethrt kernels do not, and those paths clear the cache themselves."""
+    return (enc.conv_stem.weight._version, enc.conv_head.weight._version, enc.bn1.running_mean._version,
+            enc.bn2.running_var._version, enc.bn2.weight._version)
+
+
 def _eval_cache(enc, dev):
+    if enc._eval_cache is not None and enc._eval_cache["version"] != _version_key(enc):
+        enc._eval_cache = None
     if enc._eval_cache is None:
         recs = {}
         for name, bn in enc.bn_list():
             rec = torch.empty((4, bn.weight.numel()), device=dev, dtype=torch.float32)
             ops.bn_fold_eval(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, rec, BN_EPS)
             recs[name] = rec
-        enc._eval_cache = dict(recs=recs, w=_packed_weights(enc, dev, False))
+        enc._eval_cache = dict(recs=recs, w=_packed_weights(enc, dev, False), version=_version_key(enc))
     return enc._eval_cache
 
 
@@ -244,8 +258,9 @@ def _se_gate(blk, pooled, inv_hw, N, C, dev, save):
     return s1, gate
 
 
-def forward_eval(enc, x):
-    """Inference: BN folded from running statistics; 4 launches per MBConv block (+1 for the SE MLP)."""
+def forward_eval(enc, x, pooled=True):
+    """Inference: BN folded from running statistics; 4 launches per MBConv block (+1 for the SE MLP).
+    pooled=False returns the head's feature map as [N, F, h, w] fp32 (timm's global_pool='')."""
     x = _check_input(enc, x)
     dev = x.device
     cache = _eval_cache(enc, dev)
@@ -275,6 +290,8 @@ def forward_eval(enc, x):
         h, w = oh, ow
     rec = R["bn2"]
     hd = ops.gemm(cur, Wp["conv_head"][0], ops.EPI_SCALE_SHIFT | ops.EPI_SILU, rec[0], rec[1])
+    if not pooled:
+        return hd.view(N, h, w, enc.num_features).permute(0, 3, 1, 2).float()      # layout + dtype only: NHWC bf16 -> NCHW fp32
     feat = torch.empty((N, enc.num_features), device=dev, dtype=torch.float32)
     ops.pool_act(hd, None, feat, N, h * w, act=0)
     ops.scale_f32(feat, 1.0 / (h * w))
@@ -292,6 +309,7 @@ def forward_train(enc, x, save=True):
     """Train-mode forward (batch statistics, running-stat update).  Returns (feat [N,F] fp32, ctx for backward)."""
     x = _check_input(enc, x)
     dev = x.device
+    enc._eval_cache = None          # this pass updates the running statistics (and usually precedes a parameter update)
     N, _, H, W = x.shape
     # the bf16 weight packing (one launch, ~70 us) runs beside the stem / first depthwise layer: its first consumer is the
     # first 1x1 conv, which waits on the event below

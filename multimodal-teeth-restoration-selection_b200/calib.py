@@ -107,13 +107,19 @@ def _auc(stat):
     return wins2 / (2.0 * npos * nneg) if npos and nneg else float('nan')
 
 
-def metrics_sweep(y_true, y_prob, thresholds):
+def metrics_sweep(y_true, y_prob, thresholds, weak_thresholds=False):
     """compute_metrics at every threshold with ONE kernel launch and one read-back -> list of dicts."""
     dev = _device_of(y_prob, y_true)
     y, p = _dev(y_true, dev), _dev(y_prob, dev, keep64=True)
     if y.numel() != p.numel() or y.numel() == 0:
         raise ValueError(f"y_true ({y.numel()}) and y_prob ({p.numel()}) must be non-empty and equal in length")
-    thr = torch.as_tensor(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)), device=dev)
+    thr64 = np.atleast_1d(np.asarray(thresholds, dtype=np.float64))
+    if weak_thresholds and p.dtype == torch.float32:
+        # `(y_prob >= thr)` with a float32 array and a PYTHON float compares in float32 (the scalar is "weak" under NumPy 2's
+        # promotion, and value-cast under NumPy 1): (double)p >= (double)(float)thr decides exactly like p >= (float)thr.
+        # np.float64 thresholds (the linspace sweep at :291) stay fp64 comparisons, as NumPy 2 evaluates them.
+        thr64 = thr64.astype(np.float32).astype(np.float64)
+    thr = torch.as_tensor(thr64, device=dev)
     counts, stat = ops.binary_metrics(p, y, thr)
     counts, stat = counts.cpu().numpy(), stat.cpu().numpy()
     auc = _auc(stat)
@@ -126,7 +132,8 @@ def metrics_sweep(y_true, y_prob, thresholds):
 
 
 def compute_metrics(y_true, y_prob, thr=0.5):
-    return metrics_sweep(y_true, y_prob, [thr])[0]
+    weak = isinstance(thr, float) and not isinstance(thr, np.floating)       # np.float64 subclasses float: it is NOT weak
+    return metrics_sweep(y_true, y_prob, [thr], weak_thresholds=weak)[0]
 
 
 def best_threshold(y_true, y_prob):

@@ -99,15 +99,16 @@ int trt_make_tmap_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, 
 }
 
 extern "C" int trt_init(int device) {
-  TRT_CUDA(cudaSetDevice(device));
+  // checks the device without making it current: the caller's current device (torch's, in the Python host) is not ours to move
   int major = 0, minor = 0;
   TRT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   TRT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
   if (major != 10)
     return trt_set_error(TRT_ERR_UNSUPPORTED, "libteethrt needs an sm_100a device (B200); found sm_%d%d — no fallback path exists",
                          major, minor);
-  g_num_sms = 0;
-  trt_num_sms();
+  int n = 0;
+  TRT_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (n > 0) g_num_sms = n;          // one box holds identical GPUs; grids are sized for this count
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return trt_set_error(TRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   return TRT_OK;

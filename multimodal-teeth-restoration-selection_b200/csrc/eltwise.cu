@@ -879,8 +879,8 @@ extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr
   splits = (N + npb - 1) / npb;
   const size_t smem = ((size_t)SE_CC * (rd + 1) + (size_t)npb * rd) * sizeof(float);
   TRT_REQUIRE(smem <= 96 * 1024, "trt_se_fwd: batch %d x rd %d too large for one block", N, rd);
-  static bool attr = false;
-  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(se_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  // the opt-in is per device and cheap: set on every call (a process-wide "done" flag only covered the first device used)
+  TRT_CUDA(cudaFuncSetAttribute(se_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   se_expand_kernel<<<dim3((C + SE_CC - 1) / SE_CC, splits), TPB, smem, stream>>>(s1, We, be, gate, N, C, rd, npb);
   trt_count_launch(1);
   return trt_check_launch("trt_se_fwd");
@@ -948,12 +948,8 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
     const int blocks = (C + SEB_CC - 1) / SEB_CC;
     const size_t smem1 = ((size_t)SEB_NT * rdp + (size_t)SEB_NT * SEB_CC + (size_t)SEB_CC * rdp) * sizeof(float);
     const size_t smem2 = ((size_t)SEB_NT * rdp + (size_t)rdp * SEB_CC + (size_t)SEB_NT * SEB_CC) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      TRT_CUDA(cudaFuncSetAttribute(se_bwd_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      TRT_CUDA(cudaFuncSetAttribute(se_bwd_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr = true;
-    }
+    TRT_CUDA(cudaFuncSetAttribute(se_bwd_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    TRT_CUDA(cudaFuncSetAttribute(se_bwd_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     se_bwd_k1_kernel<<<blocks, TPB, smem1, stream>>>(dgate_pre, gate, s1, We, ds2, ds1, dWe, dbe, N, C, rd);
     trt_count_launch(1);
     se_bwd_k2_kernel<<<blocks, TPB, smem2, stream>>>(ds1, s1, pooled_sum, inv_hw, Wr, dmean, dWr, dbr, N, C, rd);

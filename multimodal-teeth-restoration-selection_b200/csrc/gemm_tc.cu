@@ -1,11 +1,13 @@
 // tcgen05 / TMEM / TMA GEMMs for the 1x1 convolutions of the EfficientNet encoder (SURVEY.md K2, 92 % of the MACs).
 //
 //   trt_gemm_bf16      C[M,N] = epi(A[M,K] . B[N,K]^T)       forward (B = W[Cout,Cin]) and dgrad (B = W^T[Cin,Cout])
-//                      both operands K-major, 128B-swizzled TMA tiles, fp32 accumulators double-buffered in TMEM,
-//                      persistent CTAs (1/SM): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
-//                      Epilogue: folded-BN scale/shift, SiLU, residual add, per-channel sum/sum^2 (train-mode BN
-//                      statistics), bf16 tile staged in swizzled shared memory and written with one TMA store per
-//                      64-column chunk.
+//                      both operands K-major, 128B-swizzled TMA tiles; persistent CTAs (1/SM, 448 threads): warp 0 = TMA
+//                      producer, warp 1 = single-thread tcgen05.mma issuer, warps 2-13 = up to three independent 4-warp
+//                      epilogue groups, each draining its own fp32 accumulator from TMEM.  The weights stay resident in
+//                      shared memory for the whole CTA when one n-block fits.  Epilogue: folded-BN scale/shift, SiLU,
+//                      residual add, bf16 tile staged in padded shared memory, then ONE pass in which every 16-byte shared
+//                      read feeds a coalesced st.global and the per-channel sum / sum^2 (train-mode BN statistics).
+//                      (A TMA tensor store of the C tile was measured slower on these 48..576-byte rows: DESIGN.md 5.)
 //   trt_gemm_wgrad_bf16  O[p,q] += sum_m P[m,p] * Q[m,q]      weight gradient: both operands MN-major (the reduction
 //                      runs over rows), split over m across CTAs, fp32 red.global.add epilogue.
 //
@@ -492,7 +494,6 @@ int pick_block_n_fwd(int M, int N, int K) {
   return best;
 }
 
-bool g_attr_set = false;
 }  // namespace
 
 static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
@@ -549,11 +550,7 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   if ((rc = trt_make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
   if ((rc = trt_make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)p.block_n, BK))) return rc;
   TRT_REQUIRE((((uintptr_t)C) & 15) == 0, "trt_gemm_bf16: C must be 16-byte aligned");
-  if (!g_attr_set) {
-    TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_attr_set = true;
-  }
+  TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
   gemm_kmajor_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
@@ -634,11 +631,7 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
   int rc;
   if ((rc = trt_make_tmap_2d(&tp, P, (uint64_t)M, (uint64_t)Cp, (uint64_t)Cp, BK, 64))) return rc;
   if ((rc = trt_make_tmap_2d(&tq, Q, (uint64_t)M, (uint64_t)Cq, (uint64_t)Cq, BK, 64))) return rc;
-  if (!g_attr_set) {
-    TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_attr_set = true;
-  }
+  TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    // per device
   gemm_wgrad_kernel<<<tiles * p.splits, WGRAD_THREADS, smem_bytes, stream>>>(tp, tq, p);
   return trt_check_launch("trt_gemm_wgrad_bf16");
 }

@@ -13,7 +13,7 @@ struct OptState {               // layout mirrored by teethrt/optim.py (8 x 8 by
   unsigned long long step;      // number of optimiser steps taken
   double lr0, t_max, beta1, beta2;
   float lr, bc1, bc2, pad;      // values for the CURRENT step (written by optim_advance)
-  double reserved;
+  double skipped;               // optimiser steps skipped because the gradient norm was not finite
 };
 
 __global__ void optim_advance_kernel(OptState* s) {
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, size_t n, const OptState* __restrict__ st,
+                                                    float* __restrict__ v, size_t n, OptState* __restrict__ st,
                                                     const double* __restrict__ normsq, float* __restrict__ norm_out,
                                                     float gscale, float max_norm, float eps, float wd) {
   const float lr = st->lr, bc1 = st->bc1, bc2 = st->bc2;
@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   if (normsq) {
     const float total = sqrtf((float)normsq[0]) * gscale;     // clip_grad_norm_: norm of the (averaged) gradient
     if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = total;
+    // one inf/NaN gradient (bf16 overflow) would poison every parameter through coef: leave p/m/v untouched and count the
+    // skip, which is what the reference's GradScaler.step does under --amp (train_mm_joint_dualtask.py:249-253)
+    if (!isfinite(total)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->skipped += 1.0;
+      return;
+    }
     if (max_norm > 0.f) coef *= fminf(1.0f, max_norm / (total + 1e-6f));
   }
   const float decay = 1.0f - lr * wd, step_size = lr / bc1, rsq_bc2 = rsqrtf(bc2);
@@ -96,7 +102,7 @@ extern "C" int trt_adamw_step(float* p, const float* g, float* m, float* v, size
   int grid = (int)((n + 255) / 256);
   const int cap = 16 * trt_num_sms();
   if (grid > cap) grid = cap;
-  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, reinterpret_cast<const OptState*>(state), normsq, norm_out,
+  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, reinterpret_cast<OptState*>(const_cast<void*>(state)), normsq, norm_out,
                                          grad_scale, max_norm, eps, weight_decay);
   return trt_check_launch("trt_adamw_step");
 }

@@ -297,6 +297,7 @@ struct TabParams {
   float *dlogit, *dreg;             // [B] gradient of the loss w.r.t. the two head outputs (written when targets given)
   // scratch (global, caller provided): z0 [B,Hd], a1 [B,Hd], ft [B,Hd], bnstat [2*Hd]
   float* scratch;
+  int big;                          // 1: [B][Hd] arrays stay in the global scratch (batch too large for shared memory)
 };
 
 // Tab MLP in ONE block with the whole problem in shared memory (z0 / a1 [B][Hd] in place, W1 padded): the earlier version
@@ -305,14 +306,16 @@ struct TabParams {
 __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
   extern __shared__ __align__(16) float tsm[];
   const int B = p.B, T = p.T, Hd = p.Hd;
-  float* s_z = tsm;                        // [B][Hd]   z0, then a1 in place
-  float* s_w1 = s_z + (size_t)B * Hd;      // [Hd][Hd+1]
+  const bool big = p.big != 0;             // batch too large for shared memory: z0 / a1 are read back from the global scratch
+  float* s_w1 = tsm + (big ? 0 : (size_t)B * Hd);      // [Hd][Hd+1]
   float* s_part = s_w1 + (size_t)Hd * (Hd + 1);   // [2][TPB] partial sums of the BatchNorm1d statistics
   float* s_stat = s_part + 2 * TPB;        // mean[Hd], rstd[Hd]
   float* z0 = p.scratch;
   float* a1 = z0 + (size_t)B * Hd;
   float* ft = a1 + (size_t)B * Hd;
   float* bnstat = ft + (size_t)B * Hd;   // mean[Hd], rstd[Hd]
+  float* s_z = big ? z0 : tsm;             // [B][Hd]   z0 ...
+  float* s_a = big ? a1 : tsm;             // ... then a1 (in place when in shared memory)
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
   const int t = threadIdx.x;
   for (int i = t; i < Hd * Hd; i += TPB) s_w1[(i / Hd) * (Hd + 1) + (i % Hd)] = __ldg(p.W1 + i);
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
     float acc = p.b0[j];
     for (int tt = 0; tt < T; ++tt) acc = fmaf(__ldg(p.xtab + b * T + tt), __ldg(p.W0 + j * T + tt), acc);
     s_z[i] = acc;
-    z0[i] = acc;
+    if (!big) z0[i] = acc;
   }
   __syncthreads();
   // BatchNorm1d statistics: thread = (feature j, batch slice); two-pass (mean, then centred sum of squares) like torch
@@ -365,14 +368,14 @@ __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
     float v = (s_z[i] - s_stat[jj]) * s_stat[Hd + jj] * p.bn_g[jj] + p.bn_b[jj];
     v = fmaxf(v, 0.f);
     if (p.train) v *= keep_scale(p.drop_p, seed, 1, i);
-    s_z[i] = v;
-    a1[i] = v;
+    s_a[i] = v;
+    if (!big) a1[i] = v;
   }
   __syncthreads();
   for (int i = t; i < B * Hd; i += TPB) {
     const int b = i / Hd, jj = i % Hd;
     float acc = p.b1[jj];
-    const float* arow = s_z + b * Hd;
+    const float* arow = s_a + b * Hd;
     const float* wrow = s_w1 + jj * (Hd + 1);
 #pragma unroll 8
     for (int tt = 0; tt < Hd; ++tt) acc = fmaf(arow[tt], wrow[tt], acc);
@@ -488,19 +491,26 @@ __global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q
   const float* ft = a1 + (size_t)B * Hd;
   const float* bnstat = ft + (size_t)B * Hd;
   const float* dz1 = q.scratch2;
-  float* s_dz1 = tsm;                               // [B][Hd+1] (padded: read by column in dW1 / db1)
-  float* s_a1 = s_dz1 + (size_t)B * (Hd + 1);       // [B][Hd+1]
-  float* s_z0 = s_a1 + (size_t)B * (Hd + 1);        // [B][Hd+1]
-  float* s_da = s_z0 + (size_t)B * (Hd + 1);        // [B][Hd+1]  da1, then dz0 in place
-  float* s_w1 = s_da + (size_t)B * (Hd + 1);        // [Hd][Hd]
+  // the four [B][Hd] arrays live in shared memory (row pitch Hd+1: read by column in dW1 / db1) when the batch fits,
+  // otherwise they are used where they are in the global scratch (row pitch Hd; da1 = second half of scratch2)
+  const bool big = p.big != 0;
+  const int ld = big ? Hd : Hd + 1;
+  const size_t arr = big ? 0 : (size_t)B * (Hd + 1);
+  const float* s_dz1 = big ? dz1 : tsm;
+  const float* s_a1 = big ? a1 : tsm + arr;
+  const float* s_z0 = big ? z0 : tsm + 2 * arr;
+  float* s_da = big ? q.scratch2 + (size_t)B * Hd : tsm + 3 * arr;   // da1, then dz0 in place
+  float* s_w1 = tsm + 4 * arr;                      // [Hd][Hd]
   float* s_xt = s_w1 + (size_t)Hd * Hd;             // [B][T]
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
   const int t_ = threadIdx.x;
-  for (int i = t_; i < B * Hd; i += TPB) {
-    const int b = i / Hd, j = i - b * Hd;
-    s_dz1[b * (Hd + 1) + j] = dz1[i];
-    s_a1[b * (Hd + 1) + j] = a1[i];
-    s_z0[b * (Hd + 1) + j] = z0[i];
+  if (!big) {
+    for (int i = t_; i < B * Hd; i += TPB) {
+      const int b = i / Hd, j = i - b * Hd;
+      tsm[b * ld + j] = dz1[i];
+      tsm[arr + b * ld + j] = a1[i];
+      tsm[2 * arr + b * ld + j] = z0[i];
+    }
   }
   for (int i = t_; i < Hd * Hd; i += TPB) s_w1[i] = __ldg(p.W1 + i);
   for (int i = t_; i < B * T; i += TPB) s_xt[i] = __ldg(p.xtab + i);
@@ -509,21 +519,21 @@ __global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q
   for (int i = t_; i < Hd * Hd; i += TPB) {
     const int j = i / Hd, t = i % Hd;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(s_dz1[b * (Hd + 1) + j], s_a1[b * (Hd + 1) + t], acc);
+    for (int b = 0; b < B; ++b) acc = fmaf(s_dz1[b * ld + j], s_a1[b * ld + t], acc);
     q.dW1[i] = acc;
   }
   for (int j = t_; j < Hd; j += TPB) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += s_dz1[b * (Hd + 1) + j];
+    for (int b = 0; b < B; ++b) acc += s_dz1[b * ld + j];
     q.db1[j] = acc;
   }
   for (int i = t_; i < B * Hd; i += TPB) {
     const int b = i / Hd, t = i % Hd;
     float acc = 0.f;
-    for (int j = 0; j < Hd; ++j) acc = fmaf(s_dz1[b * (Hd + 1) + j], s_w1[j * Hd + t], acc);
+    for (int j = 0; j < Hd; ++j) acc = fmaf(s_dz1[b * ld + j], s_w1[j * Hd + t], acc);
     // through dropout and ReLU of the first layer (a1 > 0 <=> kept and positive)
     const float ks = p.train ? keep_scale(p.drop_p, seed, 1, i) : 1.f;
-    s_da[b * (Hd + 1) + t] = s_a1[b * (Hd + 1) + t] > 0.f ? acc * ks : 0.f;
+    s_da[b * ld + t] = s_a1[b * ld + t] > 0.f ? acc * ks : 0.f;
   }
   __syncthreads();
   // BatchNorm1d backward (batch statistics in train mode, plain scaling in eval) -> overwrite da1 with dz0
@@ -531,26 +541,26 @@ __global__ void __launch_bounds__(TPB) tab_heads_bwd_kernel(const TabBwdParams q
     const float mean = bnstat[j], rstd = bnstat[Hd + j], gma = p.bn_g[j];
     float s1 = 0.f, s2 = 0.f;
     for (int b = 0; b < B; ++b) {
-      const float d = s_da[b * (Hd + 1) + j], xh = (s_z0[b * (Hd + 1) + j] - mean) * rstd;
+      const float d = s_da[b * ld + j], xh = (s_z0[b * ld + j] - mean) * rstd;
       s1 += d; s2 = fmaf(d, xh, s2);
     }
     q.dbn_b[j] = s1;
     q.dbn_g[j] = s2;
     for (int b = 0; b < B; ++b) {
-      const float d = s_da[b * (Hd + 1) + j], xh = (s_z0[b * (Hd + 1) + j] - mean) * rstd;
-      s_da[b * (Hd + 1) + j] = p.train ? gma * rstd * (d - s1 / B - xh * s2 / B) : gma * rstd * d;
+      const float d = s_da[b * ld + j], xh = (s_z0[b * ld + j] - mean) * rstd;
+      s_da[b * ld + j] = p.train ? gma * rstd * (d - s1 / B - xh * s2 / B) : gma * rstd * d;
     }
   }
   __syncthreads();
   for (int i = t_; i < Hd * T; i += TPB) {
     const int j = i / T, t = i % T;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(s_da[b * (Hd + 1) + j], s_xt[b * T + t], acc);
+    for (int b = 0; b < B; ++b) acc = fmaf(s_da[b * ld + j], s_xt[b * T + t], acc);
     q.dW0[i] = acc;
   }
   for (int j = t_; j < Hd; j += TPB) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += s_da[b * (Hd + 1) + j];
+    for (int b = 0; b < B; ++b) acc += s_da[b * ld + j];
     q.db0[j] = acc;
   }
 }
@@ -639,12 +649,8 @@ extern "C" int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb
   TRT_REQUIRE((gV == nullptr) == (gU == nullptr), "trt_mil_attn_fwd: gV and gU must be given together");
   const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 0);
   TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_fwd: bag of %d x %d does not fit in shared memory", K, D);
-  static bool attr = false;
-  if (!attr) {
-    TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
+  TRT_CUDA(cudaFuncSetAttribute(mil_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // hidden slices: enough blocks for ~2 per SM on small batches, one slice (H staged once per bag) on large ones
   // hidden units per warp: the 4-unit variant (8 gate rows per shared-memory read) was measured SLOWER at B = 1024 (203
   // registers, one block per SM, exposed L2 latency on the weight rows), so the 1-unit variant serves every batch size
@@ -672,8 +678,7 @@ extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A,
   TRT_REQUIRE(B > 0 && K > 0 && D > 0 && D % 4 == 0 && hid > 0, "trt_mil_attn_bwd: bad shape");
   const size_t smem = trt_mil_attn_smem_bytes(K, D, hid, 1);
   TRT_REQUIRE(smem <= 220 * 1024, "trt_mil_attn_bwd: bag of %d x %d does not fit in shared memory", K, hid);
-  static bool attr = false;
-  if (!attr) { TRT_CUDA(cudaFuncSetAttribute(mil_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  TRT_CUDA(cudaFuncSetAttribute(mil_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   mil_bwd_gate_kernel<<<B, TPB, (size_t)K * sizeof(float), stream>>>(dM, H, A, gV, gU, ww, dVb, dUb, dww, dwb, K, D, hid);
   trt_count_launch(1);
   mil_bwd_weight_kernel<<<dim3(2 * ((hid + MW_R - 1) / MW_R), (D + MW_C - 1) / MW_C), TPB, 0, stream>>>(H, gV, gU, dVw, dUw, B * K, D, hid);
@@ -705,10 +710,11 @@ extern "C" int trt_tab_heads_fwd(const float* feat, const float* xtab, const flo
   p.logit = logit; p.reg = reg; p.loss = loss; p.dlogit = dlogit; p.dreg = dreg;
   p.scratch = scratch;
   TRT_REQUIRE(Hd <= TPB, "trt_tab_heads_fwd: tab_hidden %d > %d not built", Hd, TPB);
-  const size_t tsmem = ((size_t)B * Hd + (size_t)Hd * (Hd + 1) + 2 * TPB + 2 * Hd) * sizeof(float);
-  TRT_REQUIRE(tsmem <= 200 * 1024, "trt_tab_heads_fwd: batch %d x hidden %d does not fit in shared memory", B, Hd);
-  static bool tattr = false;
-  if (!tattr) { TRT_CUDA(cudaFuncSetAttribute(tab_heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); tattr = true; }
+  const size_t tfixed = ((size_t)Hd * (Hd + 1) + 2 * TPB + 2 * Hd) * sizeof(float);
+  size_t tsmem = tfixed + (size_t)B * Hd * sizeof(float);
+  p.big = tsmem > 200 * 1024;          // the reference has no batch limit: large batches walk the global scratch instead
+  if (p.big) tsmem = tfixed;
+  TRT_CUDA(cudaFuncSetAttribute(tab_heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   tab_heads_fwd_kernel<<<1, TPB, tsmem, stream>>>(p);
   trt_count_launch(1);
   heads_fwd_kernel<<<B, TPB, 0, stream>>>(p);
@@ -723,7 +729,7 @@ extern "C" int trt_tab_heads_bwd(const float* feat, const float* xtab, const flo
   TabBwdParams q;
   TabParams& p = q.f;
   p.B = B; p.T = T; p.Hd = Hd; p.F = F; p.train = train;
-  p.drop_p = drop_p; p.bn_eps = 1e-5f; p.bn_momentum = 0.1f; p.alpha = 0; p.beta = 0;
+  p.drop_p = drop_p; p.bn_eps = 1e-5f; p.bn_momentum = 0.1f; p.alpha = 0; p.beta = 0; p.big = 0;
   p.seed = seed; p.step = step;
   p.feat = feat; p.xtab = xtab;
   p.W0 = params_host[0]; p.b0 = params_host[1]; p.bn_g = params_host[2]; p.bn_b = params_host[3]; p.W1 = params_host[4]; p.b1 = params_host[5];
@@ -738,10 +744,12 @@ extern "C" int trt_tab_heads_bwd(const float* feat, const float* xtab, const flo
   q.scratch2 = scratch + (size_t)3 * B * Hd + 2 * Hd;
   heads_bwd_kernel<<<(F + Hd + TPB - 1) / TPB, TPB, 0, stream>>>(q);
   trt_count_launch(1);
-  const size_t bsmem = ((size_t)4 * B * (Hd + 1) + (size_t)Hd * Hd + (size_t)B * T) * sizeof(float);
-  TRT_REQUIRE(bsmem <= 200 * 1024, "trt_tab_heads_bwd: batch %d x hidden %d does not fit in shared memory", B, Hd);
-  static bool battr = false;
-  if (!battr) { TRT_CUDA(cudaFuncSetAttribute(tab_heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); battr = true; }
+  const size_t bfixed = ((size_t)Hd * Hd + (size_t)B * T) * sizeof(float);
+  size_t bsmem = bfixed + (size_t)4 * B * (Hd + 1) * sizeof(float);
+  p.big = bsmem > 200 * 1024;
+  if (p.big) bsmem = bfixed;
+  TRT_REQUIRE(bsmem <= 200 * 1024, "trt_tab_heads_bwd: batch %d x tab_in %d does not fit in shared memory", B, T);
+  TRT_CUDA(cudaFuncSetAttribute(tab_heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   tab_heads_bwd_kernel<<<1, TPB, bsmem, stream>>>(q);
   return trt_check_launch("trt_tab_heads_bwd");
 }

@@ -112,13 +112,14 @@ class MMEnsemble:
     @torch.no_grad()
     def predict_tensor(self, bgr_u8, tab_dict=None):
         """bgr_u8: CUDA uint8 [S,S,3].  Returns a device tensor of per-fold probabilities (no host sync)."""
-        x3 = torch.stack([normalize_flip(bgr_u8, f) for f in (0, 1, 2)], 0)          # TTA: identity, W-flip, H-flip
-        probs = []
-        for f, (_, T) in enumerate(self.models):
-            xt3 = self._prep_tab(tab_dict, fold=f).to(self.device, non_blocking=True).repeat(3, 1)
-            logit = self._fold_logits(f, x3, xt3).mean(0, keepdim=True)
-            probs.append(torch.sigmoid(logit / T))
-        return torch.cat(probs)
+        with torch.cuda.device(bgr_u8.device):       # graphs and side streams are made on the ensemble's device, not the current one
+            x3 = torch.stack([normalize_flip(bgr_u8, f) for f in (0, 1, 2)], 0)      # TTA: identity, W-flip, H-flip
+            probs = []
+            for f, (_, T) in enumerate(self.models):
+                xt3 = self._prep_tab(tab_dict, fold=f).to(bgr_u8.device, non_blocking=True).repeat(3, 1)
+                logit = self._fold_logits(f, x3, xt3).mean(0, keepdim=True)
+                probs.append(torch.sigmoid(logit / T))
+            return torch.cat(probs)
 
     def predict_image(self, rgb_u8, tab_dict=None):
         """Decoded image (PIL image or uint8 RGB [H,W,3] host array) -> per-fold probabilities (numpy): full-size upload,
@@ -186,7 +187,7 @@ class MILEnsemble:
         if not bag:
             return None, f"MIL: failed to load images in {processed_dir}"
         x = torch.stack(bag, dim=0)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(self.device):
             logits = torch.stack([m(x) for m in self.models]).cpu()                  # one sync for all folds
         logit_mean = float(logits.mean())
         prob = float(torch.sigmoid(torch.tensor(logit_mean)))

@@ -302,7 +302,7 @@ class OptimState:
     def read(self):
         import struct
         vals = struct.unpack("<Qddddffffd", bytes(self.buf.cpu().numpy().tobytes()))
-        return dict(step=vals[0], lr0=vals[1], t_max=vals[2], lr=vals[5], bc1=vals[6], bc2=vals[7])
+        return dict(step=vals[0], lr0=vals[1], t_max=vals[2], lr=vals[5], bc1=vals[6], bc2=vals[7], skipped=int(vals[9]))
 
 
 def grad_sumsq(g, out):

@@ -167,7 +167,7 @@ class _FusedTrainer:
                 if src is not None:
                     dst.copy_(src, non_blocking=True)
             self._stage_ready.record(self._copy_stream)
-        self._staged = tuple(id(t) for t in inputs)
+        self._staged = tuple(inputs)               # the tensors themselves: CPython recycles the id() of a freed tensor
 
     @staticmethod
     def _shape_key(inputs):
@@ -188,6 +188,10 @@ class _FusedTrainer:
         self._plan_key = key
 
     def _step(self, *inputs):
+        with torch.cuda.device(self.dev):       # streams, events and graphs below belong to the trainer's device
+            return self._step_on_device(*inputs)
+
+    def _step_on_device(self, *inputs):
         key = self._shape_key(inputs)
         if key != self._plan_key:
             self._switch_plan(key)
@@ -195,14 +199,14 @@ class _FusedTrainer:
             before = set(self.__dict__)
             self._make_static(*inputs)
             self._plan_attrs = tuple(sorted(set(self._BASE_PLAN_ATTRS) | (set(self.__dict__) - before) | set(self._plan_attrs or ())))
-        if self._staged is not None and self._staged == tuple(id(t) for t in inputs):
+        staged, self._staged = self._staged, None   # consumed or dropped: a step with other tensors never sees it again
+        if staged is not None and len(staged) == len(inputs) and all(a is b for a, b in zip(staged, inputs)):
             main = torch.cuda.current_stream(self.dev)
             main.wait_event(self._stage_ready)
             for dst, src, given in zip(self._static, self._stage, inputs):
                 if given is not None:
                     dst.copy_(src, non_blocking=True)
             self._stage_free.record(main)
-            self._staged = None
         else:
             for dst, src in zip(self._static, inputs):
                 if src is not None:
@@ -216,7 +220,15 @@ class _FusedTrainer:
             self._run_eager()
         self._nsteps += 1
         self._plan_steps += 1
+        self._invalidate_eval_caches()
         return self.loss
+
+    def _invalidate_eval_caches(self):
+        """The step rewrote the flat parameters and the BatchNorm running statistics in place: folded-BN records and
+        packed bf16 weights cached for eval are stale, whatever mode the module is in."""
+        for m in self.model.modules():
+            if hasattr(m, "_eval_cache"):
+                m._eval_cache = None
 
     def lr(self):
         return self.state.read()["lr"]

@@ -63,6 +63,17 @@ def test_fitted_temperature_follows_reference(cal, name):
     assert np.abs(p - want).max() < 1e-6
 
 
+def test_python_float_threshold_compares_in_float32(cal):
+    """float32(0.7) < 0.7: the reference's `(y_prob >= thr)` with a float32 array and a Python float is a float32 comparison,
+    so a score equal to float32(0.7) is a positive prediction (train_mm_joint_dualtask.py:182); an np.float64 threshold (the
+    linspace sweep, :291) compares in fp64 under NumPy 2 and the same score is negative."""
+    probs = np.array([np.float32(0.7), 0.1, 0.9, np.float32(0.7), 0.3], np.float32)
+    y = np.array([1, 0, 1, 0, 1], np.float32)
+    for thr in (0.7, np.float64(0.7), 0.3, np.float64(0.3)):
+        assert same_metrics(cal.compute_metrics(y, probs, thr), RC.compute_metrics(y, probs, thr)), thr
+    assert cal.compute_metrics(y, probs, 0.7) != cal.compute_metrics(y, probs, np.float64(0.7)) or np.lib.NumpyVersion(np.__version__) < "2.0.0"
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_metrics_identical_to_oracle_at_every_threshold(cal, name):
     z, y, _ = CASES[name]

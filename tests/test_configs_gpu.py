@@ -1,0 +1,224 @@
+"""GPU parity at the sizes the reference really runs, every case against the fp32 oracle executed on
+the same GPU with TF32 off:
+
+  * configs[2] MIL train step at its full size (6 bags x 16 crops @224) and at the trainer's default resolution 320
+    (experiments/vision_v2/train_mil_attention_v1.py:259);
+  * MM eval forward + one train step at img 380 (experiments/multimodal_v1/train_mm_joint_dualtask.py:368): the stage
+    resolutions are 190/95/48/24/12, so the odd 95x95 stage exercises the asymmetric TF 'same' padding at model level;
+  * configs[4]'s per-GPU batches at 2 and 4 GPUs (256 and 128) through the whole model;
+  * the un-pooled feature map of `create_model(..., global_pool='')` (ui/gradio_app/infer_mil.py:75,85-92);
+  * host-logic regressions found by the round-1 review (stale eval cache after a fused step, non-current device).
+
+Tolerances as in tests/test_models_gpu.py: loss |d| <= 3e-2, grad-norm within 5 % (MIL: 8 %), eval logits |d| <= 5e-2.
+"""
+import pytest
+import torch
+
+import ref_models as R   # oracle (checker only)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import teethrt
+    teethrt.init()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return teethrt
+
+
+def mm_inputs(B, img, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, img, img, generator=g)
+    xt = torch.randn(B, 9, generator=g)
+    yh = (torch.rand(B, generator=g) < 0.6).float()
+    ys = (yh * 0.8 + 0.2 * torch.rand(B, generator=g)).clamp(0, 1)
+    return x, xt, yh, ys
+
+
+def flat_cos(ora, grads):
+    go = torch.cat([p.grad.flatten() for _, p in ora.named_parameters()])
+    gm = torch.cat([grads[n].flatten() for n, _ in ora.named_parameters()])
+    return float(torch.nn.functional.cosine_similarity(go, gm, dim=0))
+
+
+@pytest.mark.parametrize("bags,K,img", [(6, 16, 224), (2, 16, 320)])
+def test_mil_train_step_at_reference_sizes(T, bags, K, img):
+    from teethrt.modules import MILNet
+    from teethrt.train import MILTrainer
+    ora = R.seeded_model("mil", seed=2, warm=1, img=64, drop=0.0).cuda().train()
+    m = MILNet(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    opt = torch.optim.AdamW(ora.parameters(), lr=2e-4, weight_decay=1e-4)
+    tr = MILTrainer(m, lr=2e-4, weight_decay=1e-4, t_max=0, graph=False)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(bags, K, 3, img, img, generator=gen).cuda()
+    y = (torch.rand(bags, generator=gen) < 0.5).float().cuda()
+    lo, gn = R.mil_train_step(ora, opt, None, x, y)
+    loss = float(tr.step(x, y))
+    assert abs(loss - lo) < 3e-2, (loss, lo)
+    assert abs(float(tr.grad_norm) - gn) < 0.08 * gn + 1e-3, (float(tr.grad_norm), gn)
+    cos = flat_cos(ora, tr.flat.grads)
+    assert cos > 0.9, cos
+
+
+def test_mm_img380_eval_and_train_step(T):
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    ora = R.seeded_model("mm", seed=5, warm=1, img=64, drop=0.0).cuda()
+    m = MMJointDualHead(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    x, xt, yh, ys = (t.cuda() for t in mm_inputs(4, 380, 380))
+    m.eval(); ora.eval()
+    with torch.no_grad():
+        lg, rg = m(x, xt)
+        lo, ro = ora(x, xt)
+    assert (lg - lo).abs().max() < 5e-2 and (rg - ro).abs().max() < 5e-2, ((lg - lo).abs().max(), (rg - ro).abs().max())
+    assert (torch.sigmoid(lg) - torch.sigmoid(lo)).abs().max() < 1e-2
+    ora.train()
+    opt, _ = R.make_optimizer(ora, lr=3e-4, weight_decay=1e-4)
+    loss_o, gn_o = R.mm_train_step(ora, opt, None, x, xt, yh, ys)
+    tr = DualTaskTrainer(m, lr=3e-4, weight_decay=1e-4, t_max=0, graph=False)
+    loss = float(tr.step(x, xt, yh, ys))
+    assert abs(loss - loss_o) < 3e-2, (loss, loss_o)
+    assert abs(float(tr.grad_norm) - gn_o) < 0.05 * gn_o, (float(tr.grad_norm), gn_o)
+    assert flat_cos(ora, tr.flat.grads) > 0.9
+
+
+@pytest.mark.parametrize("B", [128, 256])
+def test_mm_train_step_per_gpu_batches_of_config4(T, B):
+    """configs[4] (global batch 512) puts 256 / 128 samples on each GPU at 2 / 4 GPUs: the whole fused step at those batch
+    sizes (tab MLP beyond its shared-memory batch, SE kernels beyond one image pass, >2^31-byte activations)."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    ora = R.seeded_model("mm", seed=3, warm=1, img=64, drop=0.0).cuda().train()
+    m = MMJointDualHead(drop=0.0).cuda()
+    m.load_state_dict(ora.state_dict(), strict=True)
+    x, xt, yh, ys = (t.cuda() for t in mm_inputs(B, 224, 900 + B))
+    opt, _ = R.make_optimizer(ora, lr=3e-4, weight_decay=1e-4)
+    loss_o, gn_o = R.mm_train_step(ora, opt, None, x, xt, yh, ys)
+    tr = DualTaskTrainer(m, lr=3e-4, weight_decay=1e-4, t_max=0, graph=True)
+    loss = float(tr.step(x, xt, yh, ys))
+    assert abs(loss - loss_o) < 3e-2, (loss, loss_o)
+    assert abs(float(tr.grad_norm) - gn_o) < 0.05 * gn_o, (float(tr.grad_norm), gn_o)
+    assert flat_cos(ora, tr.flat.grads) > 0.9
+    del ora, opt
+    torch.cuda.empty_cache()
+    # the captured graph replays at this batch size and keeps training (loss finite, parameters move)
+    p0 = tr.flat.p.clone()
+    for _ in range(3):
+        loss = tr.step(x, xt, yh, ys)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and float((tr.flat.p - p0).abs().max()) > 0
+    assert tr.state.read()["skipped"] == 0
+
+
+def test_unpooled_feature_map(T):
+    """timm's global_pool='' output, the MIL twin's encoder call (infer_mil.py:75,85-92)."""
+    from teethrt.backbone import create_model
+    import timm   # oracle shim
+    ora = timm.create_model("tf_efficientnet_b0_ns", pretrained=False, num_classes=0, global_pool="")
+    torch.manual_seed(0)
+    with torch.no_grad():
+        ora.train()
+        ora(torch.randn(4, 3, 64, 64))
+    ora.eval()
+    enc = create_model("tf_efficientnet_b0_ns", pretrained=False, num_classes=0, global_pool="").cuda()
+    enc.load_state_dict(ora.state_dict(), strict=True)
+    enc.eval()
+    x = torch.randn(3, 3, 96, 128)
+    with torch.no_grad():
+        want = ora(x)
+        got = enc(x.cuda())
+        pooled = enc.forward_pooled(x.cuda())
+    assert tuple(got.shape) == tuple(want.shape) == (3, 1280, 3, 4) and got.dtype == torch.float32
+    assert (got.cpu() - want).abs().max() < 5e-2 * max(1.0, float(want.abs().max()))
+    assert (got.mean((2, 3)) - pooled).abs().max() < 2e-2
+    enc.train()
+    with pytest.raises(NotImplementedError):
+        enc(x.cuda())
+
+
+def test_eval_after_fused_step_sees_new_weights(T):
+    """eval -> trainer.step -> eval without toggling train()/eval(): the folded-BN / packed-weight cache must not survive
+    the step (round-1 advisor finding)."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+    torch.manual_seed(0)
+    m = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).cuda()
+    tr = DualTaskTrainer(m, lr=1e-2, t_max=0, graph=False)
+    x, xt, yh, ys = (t.cuda() for t in mm_inputs(8, 64, 1))
+    m.eval()
+    with torch.no_grad():
+        before = m(x, xt)[0].clone()
+    tr.step(x, xt, yh, ys)                 # forward_train / AdamW run whatever the module mode says
+    with torch.no_grad():
+        after = m(x, xt)[0]
+        m.train(); m.eval()                # the documented way to refresh: must agree with what we just got
+        fresh = m(x, xt)[0]
+    assert (after - before).abs().max() > 1e-3
+    assert (after - fresh).abs().max() < 1e-5
+    # a torch-side in-place update in eval mode is seen as well
+    with torch.no_grad():
+        m.backbone.conv_head.weight.mul_(0.5)
+        m.backbone.bn2.running_var.mul_(1.0)
+        again = m(x, xt)[0]
+    assert (again - fresh).abs().max() > 1e-4
+
+
+def test_prefetch_with_other_tensors_is_dropped(T):
+    """prefetch(a); step(b): b's data must be what trains, and a later step must not pick the stale staging set up."""
+    from teethrt.modules import MMJointDualHead
+    from teethrt.train import DualTaskTrainer
+
+    def run(use_prefetch):
+        torch.manual_seed(0)
+        m = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).cuda()
+        tr = DualTaskTrainer(m, t_max=0, graph=False)
+        a = [t.pin_memory() for t in mm_inputs(8, 64, 1)]
+        b = [t.pin_memory() for t in mm_inputs(8, 64, 2)]
+        tr.step(*a)
+        if use_prefetch:
+            tr.prefetch(*a)
+        l1 = float(tr.step(*b))
+        l2 = float(tr.step(*a))
+        return l1, l2
+    p, q = run(True), run(False)
+    assert abs(p[0] - q[0]) < 5e-3 and abs(p[1] - q[1]) < 5e-3, (p, q)
+
+
+def test_non_finite_gradient_skips_the_update(T):
+    from teethrt import ops
+    n = 4096
+    p = torch.randn(n, device="cuda"); g = torch.randn(n, device="cuda"); m_ = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    g[7] = float("inf")
+    st = ops.OptimState(torch.device("cuda"), 1e-3)
+    st.advance()
+    nsq = torch.zeros(1, device="cuda", dtype=torch.float64)
+    ops.grad_sumsq(g, nsq)
+    p0 = p.clone()
+    norm = torch.zeros(1, device="cuda")
+    ops.adamw_step(p, g, m_, v, st, nsq, norm, 1.0, 1.0)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p0) and float(m_.abs().max()) == 0 and float(v.abs().max()) == 0
+    assert st.read()["skipped"] == 1 and not torch.isfinite(norm).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_non_current_device(T):
+    """The reference lets the caller pick the device (`MMEnsemble(device='cuda:1')`): kernels must run on the operands'
+    device and stream even when cuda:0 is current."""
+    from teethrt.modules import MMJointDualHead
+    torch.manual_seed(0)
+    assert torch.cuda.current_device() == 0
+    m0 = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).eval()
+    m1 = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).eval()
+    m1.load_state_dict(m0.state_dict())
+    m0, m1 = m0.to("cuda:0"), m1.to("cuda:1")
+    x, xt, _, _ = mm_inputs(4, 64, 3)
+    with torch.no_grad():
+        a = m0(x.to("cuda:0"), xt.to("cuda:0"))[0]
+        b = m1(x.to("cuda:1"), xt.to("cuda:1"))[0]
+    assert b.device.index == 1 and torch.cuda.current_device() == 0
+    assert (a.cpu() - b.cpu()).abs().max() < 1e-5
