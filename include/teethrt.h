@@ -34,27 +34,28 @@ enum { TRT_OK = 0, TRT_ERR_INVALID = -1, TRT_ERR_CUDA = -2, TRT_ERR_UNSUPPORTED 
 #define TRT_STAT_REPLICAS 8
 int trt_stat_replicas(void);
 
-/* Fused BatchNorm finalisation.  A kernel that accumulates BN statistics can also turn them into the per-layer record: the
- * last of its blocks to finish (a device counter, ZEROED by the caller before the launch) does what trt_bn_finalize /
- * trt_bn_bwd_finalize would do in a launch of their own.  Host structs; every pointer inside is a device pointer. */
+/* Lazy BatchNorm records (consumer-side finalisation).  The kernel that PRODUCES a train-mode BatchNorm's input only
+ * accumulates its statistics; the first kernel that CONSUMES the BatchNorm derives scale/shift for its own channel slice
+ * from those statistics in its prologue, and one designated block also publishes the record (and the running statistics)
+ * for every later consumer.  That removes the 4-5 us finalise launch that used to sit between each producer and consumer
+ * (192 launches per B4 train step).  Host structs; every pointer inside is a device pointer. */
 typedef struct {
+  const double* stats;             /* [TRT_STAT_REPLICAS][2][C] {sum, sum^2} of the BatchNorm's input, complete */
   const float* gamma;              /* [C] */
   const float* beta;               /* [C] */
   float* running_mean;             /* [C] updated in place, may be NULL */
   float* running_var;              /* [C] */
   long long* num_batches_tracked;  /* may be NULL */
   float* rec;                      /* [4][C] out: scale, shift, mean, rstd */
-  unsigned int* counter;           /* one zeroed word per launch */
   double count;                    /* elements per channel */
   float eps, momentum;
 } trt_bn_fin_t;
 typedef struct {
+  const double* bstats;            /* [TRT_STAT_REPLICAS][2][C] {sum dy, sum dy*xhat}, complete */
   const float* rec;                /* [4][C] forward record of this BatchNorm */
   const float* gamma;              /* [C] */
-  float* coef;                     /* [3][C] out: dx = a*dy + b*x + c */
   float* dgamma;                   /* [C] written */
   float* dbeta;                    /* [C] written */
-  unsigned int* counter;           /* one zeroed word per launch */
   double count;
 } trt_bn_bwd_fin_t;
 
@@ -80,9 +81,6 @@ unsigned long long trt_launch_count(void);
  * block_n_override: 0 = choose. */
 int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
                   const float* shift, const void* residual, double* stats, int block_n_override, trt_stream_t stream);
-/* the same with TRT_EPI_STATS and the BatchNorm record finalised by the last epilogue group (fin_host: host struct) */
-int trt_gemm_bf16_bn(const void* A, const void* B, void* C, int M, int N, int K, double* stats,
-                     const trt_bn_fin_t* fin_host, trt_stream_t stream);
 
 /* out[p*so_p + q*so_q] (fp32) += sum_m P[m,p] * Q[m,q]   (P:[M,Cp], Q:[M,Cq] bf16 row-major; weight gradient).
  * q_store: 0 = Cq; otherwise only columns q < q_store are stored (Q zero-padded beyond, e.g. the stem's 27 of 32 taps).
@@ -173,32 +171,53 @@ int trt_bn_fold_eval(const float* gamma, const float* beta, const float* running
 /* bstats = {sum dy, sum dy*xhat} -> coef float[3][C] with dx = a*dy + b*x + c; writes dgamma, dbeta */
 int trt_bn_bwd_finalize(const double* bstats, const float* rec, const float* gamma, float* coef, float* dgamma, float* dbeta,
                         int C, double count, trt_stream_t stream);
-/* out = act(x*scale+shift) (+ residual); act: 0 none, 1 SiLU */
-int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, int rows, int C, int act,
-                 trt_stream_t stream);
-/* pooled_sum[n,c] = sum_hw act(bn(x)) (zeroed here; rec may be NULL = plain sum) — SE squeeze and global average pool */
-int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, int N, int HW, int C, int act,
-                 trt_stream_t stream);   /* zeroed != 0: pooled_sum was cleared by the caller (one arena memset per pass) */
+/* out = act(x*scale+shift) (+ residual); act: 0 none, 1 SiLU.  fin_host (optional): `rec` is not final yet - derive
+ * scale/shift from fin_host->stats and publish the record (lazy BatchNorm, above) */
+int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, const trt_bn_fin_t* fin_host, int rows, int C,
+                 int act, trt_stream_t stream);
+/* pooled_sum[n,c] = sum_hw act(bn(x)) (zeroed here; rec may be NULL = plain sum) — SE squeeze and global average pool.
+ * zeroed != 0: pooled_sum was cleared by the caller (one arena memset per pass); fin_host: lazy BatchNorm as in trt_bn_apply */
+int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, const trt_bn_fin_t* fin_host, int N, int HW,
+                 int C, int act, trt_stream_t stream);
 /* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 [N,rd] receives the pre-activation of the reduce conv */
 int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
                float* s1, float* gate, int N, int C, int rd, trt_stream_t stream);
 /* out = (rec ? silu(bn(x)) : x) * gate[n,c] */
 int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C, trt_stream_t stream);
-int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, const trt_bn_bwd_fin_t* fin_host,
-                      int rows, int C, trt_stream_t stream);   /* fin_host (optional): finalise coef/dgamma/dbeta in the same launch */
-/* out = a*dy + b*x + c */
-int trt_affine2(const void* dy, const void* x, const float* coef, void* out, int rows, int C, trt_stream_t stream);
-/* dgate_pre[n,c] = sum_hw dA * silu(bn(x)) (zeroed here) */
-int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int zeroed, int N, int HW, int C,
+/* bstats += {sum dy, sum dy*xhat} of a BatchNorm without activation (the project conv's) */
+int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C, trt_stream_t stream);
+/* out = a*dy + b*x + c.  Either coef float[3][C] = {a, b, c} is given, or fin_host: the BatchNorm-backward coefficients are
+ * derived from fin_host->bstats in the prologue (lazy, above) and dgamma / dbeta are written by one block */
+int trt_affine2(const void* dy, const void* x, const float* coef, void* out, const trt_bn_bwd_fin_t* fin_host, int rows, int C,
+                trt_stream_t stream);
+/* sums[0][n,c] = dgate_pre = sum_hw dA * silu(bn(x)) (zeroed here unless `zeroed`).  full != 0: sums is [5][N][C] and also
+ * receives S1 = sum dA*s', S2 = sum s', S3 = sum dA*s'*x, S4 = sum s'*x (s' = silu'(bn(x))): with them the BatchNorm-backward
+ * sums of the gated activation follow from [N,C]-sized arrays once the SE MLP backward has produced gate-gradient terms,
+ * so the tensor is read twice in the backward pass instead of three times (trt_se_bwd + trt_act_bwd_apply below). */
+int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* sums, int zeroed, int full, int N, int HW, int C,
                       trt_stream_t stream);
-/* SE MLP backward: ds2 [N,C], ds1 [N,rd], dmean [N,C] scratch/outputs; parameter gradients are WRITTEN (=) */
+/* BatchNorm backward of the depthwise output folded into the SE MLP backward (host struct, device pointers) */
+typedef struct {
+  const float* sums;               /* [5][N][C] from trt_se_bwd_reduce(full) */
+  const float* rec;                /* [4][C] record of the BatchNorm in front of the SiLU */
+  const float* gamma;              /* [C] */
+  float* coef;                     /* [3][C] out: dx = a*g + b*x + c */
+  float* dgamma;                   /* [C] written */
+  float* dbeta;                    /* [C] written */
+  double count;                    /* N*HW */
+} trt_se_bn_t;
+/* SE MLP backward: ds2 [N,C], ds1 [N,rd], dmean [N,C] scratch/outputs; parameter gradients are WRITTEN (=).
+ * bn_host (optional): also derive the BatchNorm-backward coefficients / dgamma / dbeta of the gated activation */
 int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
                const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr, float* dWe,
-               float* dbe, int ds1_zeroed, int N, int C, int rd, trt_stream_t stream);
+               float* dbe, int ds1_zeroed, const trt_se_bn_t* bn_host, int N, int C, int rd, trt_stream_t stream);
+/* out = a*g + b*x + c with g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * silu'(bn(x)) formed on the fly: the gradient w.r.t. the
+ * raw depthwise output in one read of (dA, x) and one write */
+int trt_act_bwd_apply(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x, const float* rec,
+                      const float* coef, void* out, int N, int HW, int C, trt_stream_t stream);
 /* g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * (act ? silu'(bn(x)) : 1); bstats += {sum g, sum g*xhat}. dA/gate/dmean may be NULL */
 int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x, const float* rec,
-                void* g_out, double* bstats, const trt_bn_bwd_fin_t* fin_host, int N, int HW, int C, int act,
-                trt_stream_t stream);
+                void* g_out, double* bstats, int N, int HW, int C, int act, trt_stream_t stream);
 /* x *= alpha (fp32; turns pooled sums into the global-average-pool features) */
 int trt_scale_f32(float* x, size_t n, float alpha, trt_stream_t stream);
 /* fp32 [N,K] -> bf16 [N,K] and (optional) bf16 [K,N] */
@@ -213,15 +232,16 @@ int trt_pack_w1x1_batch(const long long* table_dev, int count, int total_tiles, 
  * Weights and weight gradients stay in torch layout ([C,1,k,k] / [CS,3,3,3], fp32).
  * ------------------------------------------------------------------------------------------------------------------ */
 /* x: [N,H,W,C]; in_rec != NULL: input = silu(bn(x)) applied on load; out_rec != NULL (eval): out = silu(bn_out(conv)),
- * pooled_sum[n,c] (optional, zeroed here) += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output. */
+ * pooled_sum[n,c] (optional, zeroed here) += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output.
+ * in_fin_host (optional): the INPUT's BatchNorm is lazy - in_rec is derived from in_fin_host->stats and published. */
 int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec, float* pooled_sum,
-                   double* stats, const trt_bn_fin_t* fin_host, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
+                   double* stats, const trt_bn_fin_t* in_fin_host, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
 /* gy = dD, the gradient w.r.t. the RAW depthwise output (the BN-backward affine of the following BatchNorm has already been
  * applied by trt_affine2).  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1), bstats += {sum g, sum g*xhat};
  * dw[C,1,k,k] (NULL = skip) += correlation of dD with act(x) (act = silu(bn) when x_rec).  The two halves are independent:
  * a caller may issue them as two calls on two streams. */
 int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out, double* bstats,
-                   const trt_bn_bwd_fin_t* fin_host, float* dw, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
+                   float* dw, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
 /* x: NCHW [N,3,H,W] fp32 or bf16 -> out NHWC bf16 [N,ceil(H/2),ceil(W/2),CS]; CS in {32, 48} */
 int trt_stem_fwd(const void* x, int x_is_bf16, const float* w, void* out, const float* out_rec, double* stats, int N, int H,
                  int W, int CS, trt_stream_t stream);

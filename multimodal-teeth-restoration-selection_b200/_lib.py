@@ -64,7 +64,6 @@ _SIGS = {
     "trt_launch_count": (u64, []),
     "trt_stat_replicas": (i32, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
-    "trt_gemm_bf16_bn": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp]),
     "trt_clahe_workspace_bytes": (sz, [i32]),
     "trt_clahe_bgr_u8": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
@@ -73,20 +72,21 @@ _SIGS = {
     "trt_bn_finalize": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f64, f32, f32, vp]),
     "trt_bn_fold_eval": (i32, [vp, vp, vp, vp, vp, i32, f32, vp]),
     "trt_bn_bwd_finalize": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, vp]),
-    "trt_bn_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
-    "trt_pool_act": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "trt_bn_apply": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_pool_act": (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]),
     "trt_se_fwd": (i32, [vp, f32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_gate_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
-    "trt_bn_bwd_reduce": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
-    "trt_affine2": (i32, [vp, vp, vp, vp, i32, i32, vp]),
-    "trt_se_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "trt_se_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trt_bn_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "trt_affine2": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "trt_se_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "trt_act_bwd_apply": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_se_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
+    "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_scale_f32": (i32, [vp, sz, f32, vp]),
     "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),
     "trt_pack_w1x1_batch": (i32, [vp, i32, i32, vp]),
     "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
-    "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_stem_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_stem_wgrad": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
     "trt_stem_im2col": (i32, [vp, i32, vp, i32, i32, i32, vp]),
@@ -131,14 +131,20 @@ EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS = 1, 2, 4, 8
 
 
 class BnFin(C.Structure):
-    """trt_bn_fin_t (include/teethrt.h): forward BatchNorm finalisation fused into the kernel that produces the statistics."""
-    _fields_ = [("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
-                ("rec", vp), ("counter", vp), ("count", f64), ("eps", f32), ("momentum", f32)]
+    """trt_bn_fin_t (include/teethrt.h): a lazy train-mode BatchNorm - the first consumer derives scale/shift from the
+    producer's statistics and publishes the record."""
+    _fields_ = [("stats", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
+                ("rec", vp), ("count", f64), ("eps", f32), ("momentum", f32)]
 
 
 class BnBwdFin(C.Structure):
-    """trt_bn_bwd_fin_t: BatchNorm backward finalisation (coef, dgamma, dbeta) fused into the kernel that produces the sums."""
-    _fields_ = [("rec", vp), ("gamma", vp), ("coef", vp), ("dgamma", vp), ("dbeta", vp), ("counter", vp), ("count", f64)]
+    """trt_bn_bwd_fin_t: lazy BatchNorm backward - trt_affine2 derives dx = a*dy + b*x + c from the sums and writes dgamma/dbeta."""
+    _fields_ = [("bstats", vp), ("rec", vp), ("gamma", vp), ("dgamma", vp), ("dbeta", vp), ("count", f64)]
+
+
+class SeBn(C.Structure):
+    """trt_se_bn_t: BatchNorm backward of the gated depthwise activation folded into the SE MLP backward."""
+    _fields_ = [("sums", vp), ("rec", vp), ("gamma", vp), ("coef", vp), ("dgamma", vp), ("dbeta", vp), ("count", f64)]
 
 
 def header_symbols():

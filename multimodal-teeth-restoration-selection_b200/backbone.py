@@ -175,7 +175,7 @@ class EfficientNet(nn.Module):
             if self.training and torch.is_grad_enabled():
                 raise NotImplementedError("teethrt EfficientNet(global_pool=''): the un-pooled feature map is an inference "
                                           "output; train with global_pool='avg'")
-            return forward_eval(self, x, pooled=False)
+            return forward_eval(self, x, feature_map=True)
         raise ValueError(f"teethrt EfficientNet: global_pool={self.global_pool_type!r} is not built ('avg' or '')")
 
     def forward_pooled(self, x):
@@ -258,9 +258,9 @@ def _se_gate(blk, pooled, inv_hw, N, C, dev, save):
     return s1, gate
 
 
-def forward_eval(enc, x, pooled=True):
+def forward_eval(enc, x, feature_map=False):
     """Inference: BN folded from running statistics; 4 launches per MBConv block (+1 for the SE MLP).
-    pooled=False returns the head's feature map as [N, F, h, w] fp32 (timm's global_pool='')."""
+    feature_map=True returns the head's feature map as [N, F, h, w] fp32 (timm's global_pool='')."""
     x = _check_input(enc, x)
     dev = x.device
     cache = _eval_cache(enc, dev)
@@ -290,7 +290,7 @@ def forward_eval(enc, x, pooled=True):
         h, w = oh, ow
     rec = R["bn2"]
     hd = ops.gemm(cur, Wp["conv_head"][0], ops.EPI_SCALE_SHIFT | ops.EPI_SILU, rec[0], rec[1])
-    if not pooled:
+    if feature_map:
         return hd.view(N, h, w, enc.num_features).permute(0, 3, 1, 2).float()      # layout + dtype only: NHWC bf16 -> NCHW fp32
     feat = torch.empty((N, enc.num_features), device=dev, dtype=torch.float32)
     ops.pool_act(hd, None, feat, N, h * w, act=0)
@@ -298,11 +298,22 @@ def forward_eval(enc, x, pooled=True):
     return feat
 
 
-def _gemm_stats(A, B, st, fin, out):
-    """1x1 conv with BN statistics; with `fin` the last epilogue group also finalises the BatchNorm record."""
-    if fin is not None:
-        return ops.gemm_bn(A, B, st, fin, out=out)
-    return ops.gemm(A, B, ops.EPI_STATS, stats=st, out=out)
+class _LazyRec:
+    """A train-mode BatchNorm whose statistics are complete but whose record {scale, shift, mean, rstd} is not written yet:
+    the FIRST consumer kernel takes `fin()` (a host struct) and finalises it in its prologue - no finalise launch between
+    producer and consumer.  Later consumers read `rec` as usual."""
+
+    def __init__(self, rec, fin):
+        self.rec, self._fin = rec, fin
+
+    def fin(self):
+        f, self._fin = self._fin, None
+        return f
+
+
+def _lazy_bn():
+    """TEETHRT_LAZY_BN=0: separate bn_finalize / bn_bwd_finalize launches (the round-1 path; kept as the A/B switch)."""
+    return os.environ.get("TEETHRT_LAZY_BN", "1") != "0"
 
 
 def forward_train(enc, x, save=True):
@@ -332,33 +343,23 @@ def forward_train(enc, x, save=True):
     recs = _Arena(4 * total_c, torch.float32, dev)
     ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
 
-    counters = _Arena(len(bns), torch.int32, dev)       # one "blocks done" word per BatchNorm, zeroed once per pass
     pool_arena = _Arena(N * sum(blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()) + N * enc.num_features,
                         torch.float32, dev)                # every SE / global pooling target of the pass: one memset
 
-    def fin_for(bn_name, count):
-        """(rec, fin): the BatchNorm record and the host struct that makes the PRODUCER of its statistics finalise it."""
+    lazy = _lazy_bn()
+
+    def bn_stage(bn_name, count, st):
+        """The statistics `st` of BatchNorm `bn_name` have just been produced -> its (lazy) record."""
         bn = bns[bn_name]
         c = bn.weight.numel()
         rec = recs.take(4 * c, (4, c))
         ctx["rec"][bn_name] = rec
-        return rec, ops.bn_fin(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                               rec, counters.take(1), count, BN_EPS, BN_MOM)
-
-    fuse = os.environ.get("TEETHRT_FUSE_BN_FWD", "0") != "0"     # measured: the last-block tail costs more than a 4 us launch (DESIGN.md)
-
-    def bn_stage(bn_name, count, st, launch):
-        """Run the kernel that produces the statistics `st` of BatchNorm `bn_name` (launch(fin)); returns its record."""
-        rec, fin = fin_for(bn_name, count)
-        if fuse:
-            launch(fin)
-        else:
-            launch(None)
-            bn = bns[bn_name]
-            ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                            rec, count, BN_EPS, BN_MOM)
-        return rec
-
+        if lazy:
+            return _LazyRec(rec, ops.bn_fin(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                            bn.num_batches_tracked, rec, count, BN_EPS, BN_MOM))
+        ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        rec, count, BN_EPS, BN_MOM)
+        return _LazyRec(rec, None)
 
     h, w = ops.same_out(H, 2), ops.same_out(W, 2)
     cs = enc.conv_stem.weight.shape[0]
@@ -367,7 +368,8 @@ def forward_train(enc, x, save=True):
     patches = ops.stem_im2col(x, torch.empty((N * h * w, 32), device=dev, dtype=bf16))
     w_stem = ops.stem_pack_w(enc.conv_stem.weight.detach(), torch.empty((cs, 32), device=dev, dtype=bf16))
     s_raw = torch.empty((N * h * w, cs), device=dev, dtype=bf16)
-    rec_s = bn_stage("bn1", N * h * w, st, lambda fin: _gemm_stats(patches, w_stem, st, fin, s_raw))
+    ops.gemm(patches, w_stem, ops.EPI_STATS, stats=st, out=s_raw)
+    rec_s = bn_stage("bn1", N * h * w, st)
     cur, cur_rec = s_raw, rec_s                                   # lazy: (raw, pending BN+SiLU)
     ctx["stem"] = dict(raw=s_raw, h=h, w=w, patches=patches)
     for name, blk in enc.block_list():
@@ -377,7 +379,7 @@ def forward_train(enc, x, save=True):
         sv = dict(name=name, h=h, w=w, in_rec=None)
         if c["type"] == "ir" or has_skip:
             if cur_rec is not None:        # materialise the pending activation (GEMM operand / residual need a real tensor)
-                cur = ops.bn_apply(cur, cur_rec, torch.empty_like(cur), act=1)
+                cur = ops.bn_apply(cur, cur_rec.rec, torch.empty_like(cur), act=1, fin=cur_rec.fin())
                 sv["materialised_from"] = True
                 cur_rec = None
         sv["x"] = cur
@@ -386,27 +388,29 @@ def forward_train(enc, x, save=True):
             st = stats.take(ops.STAT_REPLICAS * 2 * cm)
             need_packed()
             e_raw = torch.empty((N * h * w, cm), device=dev, dtype=bf16)
-            rec1 = bn_stage(name + ".bn1", N * h * w, st, lambda fin: _gemm_stats(cur, Wp[name + ".conv_pw"][0], st, fin, e_raw))
-            dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, rec1, name + ".bn2", name + ".conv_pwl", name + ".bn3"
+            ops.gemm(cur, Wp[name + ".conv_pw"][0], ops.EPI_STATS, stats=st, out=e_raw)
+            dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, bn_stage(name + ".bn1", N * h * w, st), name + ".bn2", name + ".conv_pwl", name + ".bn3"
             sv["e_raw"] = e_raw
         else:
             cm = c["cin"]
             dw_in, dw_rec, bn_dw, pw_name, bn_out = cur, cur_rec, name + ".bn1", name + ".conv_pw", name + ".bn2"
-            sv["in_rec"] = cur_rec
+            sv["in_rec"] = None if cur_rec is None else cur_rec.rec
         oh, ow = ops.same_out(h, s), ops.same_out(w, s)
         d_raw = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         st = stats.take(ops.STAT_REPLICAS * 2 * cm)
-        rec_d = bn_stage(bn_dw, N * oh * ow, st, lambda fin: ops.dwconv_fwd(dw_in, dw_rec, blk.conv_dw.weight.detach(), d_raw, N, h,
-                                                                          w, k, s, stats=st, fin=fin))
+        ops.dwconv_fwd(dw_in, None if dw_rec is None else dw_rec.rec, blk.conv_dw.weight.detach(), d_raw, N, h, w, k, s, stats=st,
+                       in_fin=None if dw_rec is None else dw_rec.fin())
+        rec_d = bn_stage(bn_dw, N * oh * ow, st)
         pooled = pool_arena.take(N * cm, (N, cm))
-        ops.pool_act(d_raw, rec_d, pooled, N, oh * ow, act=1, zeroed=True)
+        ops.pool_act(d_raw, rec_d.rec, pooled, N, oh * ow, act=1, zeroed=True, fin=rec_d.fin())
         s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
-        a = ops.gate_apply(d_raw, rec_d, gate, torch.empty_like(d_raw), N, oh * ow)
+        a = ops.gate_apply(d_raw, rec_d.rec, gate, torch.empty_like(d_raw), N, oh * ow)
         st = stats.take(ops.STAT_REPLICAS * 2 * c["cout"])
         need_packed()
         p_raw = torch.empty((N * oh * ow, c["cout"]), device=dev, dtype=bf16)
-        rec_o = bn_stage(bn_out, N * oh * ow, st, lambda fin: _gemm_stats(a, Wp[pw_name][0], st, fin, p_raw))
-        y = ops.bn_apply(p_raw, rec_o, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0)
+        ops.gemm(a, Wp[pw_name][0], ops.EPI_STATS, stats=st, out=p_raw)
+        rec_o = bn_stage(bn_out, N * oh * ow, st)
+        y = ops.bn_apply(p_raw, rec_o.rec, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0, fin=rec_o.fin())
         sv.update(d_raw=d_raw, pooled=pooled, s1=s1, gate=gate, a=a, p_raw=p_raw, oh=oh, ow=ow, has_skip=has_skip,
                   bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out)
         ctx["blocks"].append((blk, sv))
@@ -414,9 +418,10 @@ def forward_train(enc, x, save=True):
     st = stats.take(ops.STAT_REPLICAS * 2 * enc.num_features)
     need_packed()
     hd_raw = torch.empty((N * h * w, enc.num_features), device=dev, dtype=bf16)
-    rec_h = bn_stage("bn2", N * h * w, st, lambda fin: _gemm_stats(cur, Wp["conv_head"][0], st, fin, hd_raw))
+    ops.gemm(cur, Wp["conv_head"][0], ops.EPI_STATS, stats=st, out=hd_raw)
+    rec_h = bn_stage("bn2", N * h * w, st)
     feat = pool_arena.take(N * enc.num_features, (N, enc.num_features))
-    ops.pool_act(hd_raw, rec_h, feat, N, h * w, act=1, zeroed=True)
+    ops.pool_act(hd_raw, rec_h.rec, feat, N, h * w, act=1, zeroed=True, fin=rec_h.fin())
     ops.scale_f32(feat, 1.0 / (h * w))
     ctx.update(head=dict(x=cur, raw=hd_raw, h=h, w=w))
     return feat, ctx
@@ -507,39 +512,31 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
     dfeat = dfeat.contiguous().float()
     sq = _SideQueue(dev)
 
-    counters = _Arena(len(bns), torch.int32, dev)       # one "blocks done" word per BatchNorm, zeroed once per pass
-    zeros = _Arena(sum(N * (sv["d_raw"].shape[1] + blk.cfg["rd"]) for blk, sv in ctx["blocks"]), torch.float32, dev)
+    merged = os.environ.get("TEETHRT_SE_BWD_MERGED", "1") != "0"     # 0: round-1 path (reduce, act_bwd, affine2: three passes)
+    zeros = _Arena(sum(N * ((5 if merged else 1) * sv["d_raw"].shape[1] + blk.cfg["rd"]) for blk, sv in ctx["blocks"]),
+                   torch.float32, dev)
 
-    fuse_b = os.environ.get("TEETHRT_FUSE_BN_BWD", "0") != "0"   # measured slower than separate launches
+    lazy = _lazy_bn()
 
-    def bn_back(bn_name, count, bst, launch):
-        """Run the kernel that produces the backward sums `bst` of BatchNorm `bn_name` (launch(fin)); returns its dx
-        coefficients (dgamma / dbeta land in `grads`)."""
-        coef, fin = bwd_fin(bn_name, count)
-        if fuse_b:
-            return coef, launch(fin)
-        out = launch(None)
+    def bn_dx(bn_name, count, bst, g, x_raw, out):
+        """BatchNorm backward apply: out = a*g + b*x_raw + c with the coefficients of BatchNorm `bn_name`, whose sums `bst`
+        the producer of `g` has just accumulated; also lands dgamma / dbeta in `grads`.  Lazy (default): trt_affine2 derives
+        the coefficients itself - no finalise launch in between."""
         bn = bns[bn_name]
-        ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"], count)
-        return coef, out
-
-    def bwd_fin(bn_name, count):
-        """(coef, fin): dx = a*dy + b*x + c coefficients of this BatchNorm and the host struct that makes the kernel producing
-        its backward sums finalise them (coef, dgamma, dbeta) in the same launch."""
-        bn = bns[bn_name]
-        c = bn.weight.numel()
-        coef = torch.empty((3, c), device=dev, dtype=torch.float32)
-        return coef, ops.bn_bwd_fin(REC[bn_name], bn.weight.detach(), coef, grads[bn_name + ".weight"], grads[bn_name + ".bias"],
-                                    counters.take(1), count)
+        dgm, dbt = grads[bn_name + ".weight"], grads[bn_name + ".bias"]
+        if lazy:
+            return ops.affine2(g, x_raw, None, out, fin=ops.bn_bwd_fin(bst, REC[bn_name], bn.weight.detach(), dgm, dbt, count))
+        coef = torch.empty((3, bn.weight.numel()), device=dev, dtype=torch.float32)
+        ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, dgm, dbt, count)
+        return ops.affine2(g, x_raw, coef, out)
 
     # ---- head: feat = mean_hw silu(bn2(conv_head(y)))
     hd = ctx["head"]
     hw = hd["h"] * hd["w"]
     F_ = enc.num_features
     bst = bstats.take(ops.STAT_REPLICAS * 2 * F_)
-    coef, g = bn_back("bn2", N * hw, bst, lambda fin: ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"],
-                                                                  torch.empty_like(hd["raw"]), bst, N, hw, act=1, fin=fin))
-    d_raw = ops.affine2(g, hd["raw"], coef, g)
+    g = ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"], torch.empty_like(hd["raw"]), bst, N, hw, act=1)
+    d_raw = bn_dx("bn2", N * hw, bst, g, hd["raw"], g)
     dy = ops.gemm(d_raw, Wp["conv_head"][1])
     sq.wgrad(d_raw, hd["x"], grads["conv_head.weight"])
     del g, d_raw
@@ -552,34 +549,43 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
         cm = sv["d_raw"].shape[1]
         # project conv + its BN (no activation)
         bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cout"])
-        coef, _ = bn_back(sv["bn_out"], N * ohw, bst, lambda fin: ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst, fin=fin))
-        dp = ops.affine2(dy, sv["p_raw"], coef, torch.empty_like(dy))
+        ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst)
+        dp = bn_dx(sv["bn_out"], N * ohw, bst, dy, sv["p_raw"], torch.empty_like(dy))
         dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
         sq.wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
         # squeeze-excite + activation + BN of the depthwise output
         rec_d = REC[sv["bn_dw"]]
-        dgate_pre = zeros.take(N * cm, (N, cm))
-        ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw, zeroed=True)
-        ds2, dmean = torch.empty_like(dgate_pre), torch.empty_like(dgate_pre)
+        ds2, dmean = torch.empty((N, cm), device=dev, dtype=torch.float32), torch.empty((N, cm), device=dev, dtype=torch.float32)
         ds1 = zeros.take(N * c["rd"], (N, c["rd"]))
         se = blk.se
-        ops.se_bwd(dgate_pre, sv["gate"], sv["s1"], sv["pooled"], 1.0 / ohw, se.conv_reduce.weight.detach(),
-                   se.conv_expand.weight.detach(), ds2, ds1, dmean, grads[name + ".se.conv_reduce.weight"],
-                   grads[name + ".se.conv_reduce.bias"], grads[name + ".se.conv_expand.weight"],
-                   grads[name + ".se.conv_expand.bias"], ds1_zeroed=True)
-        bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
-        coef_d, g2 = bn_back(sv["bn_dw"], N * ohw, bst, lambda fin: ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d,
-                                                                                dA, bst, N, ohw, act=1, fin=fin))
-        dD = ops.affine2(g2, sv["d_raw"], coef_d, g2)           # gradient w.r.t. the raw depthwise output
+        se_args = (sv["gate"], sv["s1"], sv["pooled"], 1.0 / ohw, se.conv_reduce.weight.detach(), se.conv_expand.weight.detach(),
+                   ds2, ds1, dmean, grads[name + ".se.conv_reduce.weight"], grads[name + ".se.conv_reduce.bias"],
+                   grads[name + ".se.conv_expand.weight"], grads[name + ".se.conv_expand.bias"])
+        if merged:
+            # two passes over (dA, d_raw) instead of three: pass 1 leaves five per-(image, channel) sums, the SE MLP backward
+            # turns them into the BatchNorm-backward coefficients, pass 2 writes dD directly (no g tensor, no affine pass)
+            sums = zeros.take(5 * N * cm, (5, N, cm))
+            ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, sums, N, ohw, zeroed=True, full=True)
+            bn = bns[sv["bn_dw"]]
+            coef_d = torch.empty((3, cm), device=dev, dtype=torch.float32)
+            ops.se_bwd(sums[0], *se_args, ds1_zeroed=True,
+                       bn=ops.se_bn(sums, rec_d, bn.weight.detach(), coef_d, grads[sv["bn_dw"] + ".weight"], grads[sv["bn_dw"] + ".bias"], N * ohw))
+            dD = ops.act_bwd_apply(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, coef_d, dA, N, ohw)
+        else:
+            dgate_pre = zeros.take(N * cm, (N, cm))
+            ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw, zeroed=True)
+            ops.se_bwd(dgate_pre, *se_args, ds1_zeroed=True)
+            bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
+            g2 = ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, dA, bst, N, ohw, act=1)
+            dD = bn_dx(sv["bn_dw"], N * ohw, bst, g2, sv["d_raw"], g2)           # gradient w.r.t. the raw depthwise output
         dw_grad = grads[name + ".conv_dw.weight"]
         if c["type"] == "ir":
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
             bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
             g1 = torch.empty_like(e_raw)
             sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), e_raw, rec1, dw_grad, N, h, w, k, s)
-            coef1, _ = bn_back(name + ".bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1,
-                                                                                         g1, bst, None, N, h, w, k, s, fin=fin))
-            de = ops.affine2(g1, e_raw, coef1, g1)
+            ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, None, N, h, w, k, s)
+            de = bn_dx(name + ".bn1", N * h * w, bst, g1, e_raw, g1)
             flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
             dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
             sq.wgrad(de, sv["x"], grads[name + ".conv_pw.weight"])
@@ -591,9 +597,8 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
                 bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
                 g_in = torch.empty_like(x_in)
                 sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), x_in, in_rec, dw_grad, N, h, w, k, s)
-                coef_s, _ = bn_back("bn1", N * h * w, bst, lambda fin: ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec,
-                                                                                      g_in, bst, None, N, h, w, k, s, fin=fin))
-                ds = ops.affine2(g_in, x_in, coef_s, g_in)
+                ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, None, N, h, w, k, s)
+                ds = bn_dx("bn1", N * h * w, bst, g_in, x_in, g_in)
                 _stem_wgrad(ctx, ds, grads, sq)
                 dy = None
             else:
@@ -608,18 +613,16 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
                     st_raw = ctx["stem"]["raw"]
                     hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
                     bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
-                    coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
-                                                                                       torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
-                    ds = ops.affine2(g_s, st_raw, coef_s, g_s)
+                    g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
+                    ds = bn_dx("bn1", N * hw0, bst, g_s, st_raw, g_s)
                     _stem_wgrad(ctx, ds, grads, sq)
                     dy = None
         if c["type"] == "ir" and sv.get("materialised_from"):
             st_raw = ctx["stem"]["raw"]
             hw0 = ctx["stem"]["h"] * ctx["stem"]["w"]
             bst = bstats.take(ops.STAT_REPLICAS * 2 * st_raw.shape[1])
-            coef_s, g_s = bn_back("bn1", N * hw0, bst, lambda fin: ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"],
-                                                                               torch.empty_like(st_raw), bst, N, hw0, act=1, fin=fin))
-            ds = ops.affine2(g_s, st_raw, coef_s, g_s)
+            g_s = ops.act_bwd(dy, None, None, 0.0, st_raw, REC["bn1"], torch.empty_like(st_raw), bst, N, hw0, act=1)
+            ds = bn_dx("bn1", N * hw0, bst, g_s, st_raw, g_s)
             _stem_wgrad(ctx, ds, grads, sq)
             dy = None
         if name in split_after:

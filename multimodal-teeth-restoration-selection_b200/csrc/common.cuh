@@ -52,6 +52,13 @@ __device__ __forceinline__ f8 ldf8(const float* p) {  // 8 consecutive fp32 (32 
   return r;
 }
 
+__device__ __forceinline__ f8 lds8(const float* p) {  // 8 consecutive fp32 in shared memory (32 B aligned)
+  f8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
 // sigmoid = rcp(1 + 2^(-x log2 e)): two MUFU ops, no range fix-ups needed (2^+big = inf -> rcp = 0; 2^-big = 0 -> rcp(1) = 1)
 __device__ __forceinline__ float sigmoidf_(float x) {
   float e, r;
@@ -88,11 +95,7 @@ __device__ __forceinline__ float warp_max(float v) {
   ((raw) + ((((uint32_t)__cvta_generic_to_shared(raw) + (uint32_t)((align) - 1)) & ~(uint32_t)((align) - 1)) - \
             (uint32_t)__cvta_generic_to_shared(raw)))
 
-// ---------------------------------------------------------------- fused BatchNorm finalisation (last block done)
-// forward: stats {sum, sum^2} (fp64) -> rec {scale, shift, mean, rstd}, running statistics (what bn_finalize_kernel does).
-// One block finalises ALL channels, so the loads are batched: FIN_CH channels per thread per round, every load of a round
-// issued before the first use (a plain strided loop is a chain of dependent L2 round trips, ~0.6 us each).
-constexpr int FIN_CH = 4;
+// ---------------------------------------------------------------- lazy BatchNorm records (consumer-side finalisation)
 // total of a replicated statistics entry: stats is [TRT_STAT_REPLICAS][2][C]; idx in [0, 2C)
 __device__ __forceinline__ double stat_total(const double* stats, int C, int idx) {
   double t = 0;
@@ -100,80 +103,67 @@ __device__ __forceinline__ double stat_total(const double* stats, int C, int idx
   for (int r = 0; r < TRT_STAT_REPLICAS; ++r) t += __ldcg(stats + (size_t)r * 2 * C + idx);
   return t;
 }
-__device__ __forceinline__ void bn_finalize_channels(const trt_bn_fin_t& f, const double* stats, int C, int tid, int nthreads) {
-  for (int c0 = tid; c0 < C; c0 += nthreads * FIN_CH) {
-    double s[FIN_CH], q[FIN_CH];
-    float gm[FIN_CH], bt[FIN_CH], rm[FIN_CH], rv[FIN_CH];
-#pragma unroll
-    for (int j = 0; j < FIN_CH; ++j) {
-      const int c = c0 + j * nthreads;
-      if (c < C) {
-        s[j] = stat_total(stats, C, c); q[j] = stat_total(stats, C, C + c);
-        gm[j] = f.gamma[c]; bt[j] = f.beta[c];
-        if (f.running_mean) { rm[j] = f.running_mean[c]; rv[j] = f.running_var[c]; }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < FIN_CH; ++j) {
-      const int c = c0 + j * nthreads;
-      if (c < C) {
-        const double mean = s[j] / f.count;
-        double var = q[j] / f.count - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)f.eps));
-        const float sc = gm[j] * rstd;
-        f.rec[c] = sc;
-        f.rec[C + c] = bt[j] - (float)mean * sc;
-        f.rec[2 * C + c] = (float)mean;
-        f.rec[3 * C + c] = rstd;
-        if (f.running_mean) {
-          const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
-          f.running_mean[c] = (1.f - f.momentum) * rm[j] + f.momentum * (float)mean;
-          f.running_var[c] = (1.f - f.momentum) * rv[j] + f.momentum * (float)unb;
-        }
-      }
-    }
-  }
-  if (tid == 0 && f.num_batches_tracked) *f.num_batches_tracked += 1;
+// One channel of a train-mode BatchNorm: fp64 {sum, sum^2} -> {scale, shift, mean, rstd}.  The ONE definition of that
+// arithmetic: bn_finalize_kernel and every lazy consumer call it, so a consumer that derives scale/shift from the
+// statistics gets bit-identical values to a later kernel that reads the published record.
+struct BnChannel { float sc, sh, mean, rstd; double var; };
+__device__ __forceinline__ BnChannel bn_channel(const double* stats, const float* gamma, const float* beta, int C, int c,
+                                                double count, float eps) {
+  BnChannel r;
+  const double mean = stat_total(stats, C, c) / count;
+  double var = stat_total(stats, C, C + c) / count - mean * mean;
+  if (var < 0) var = 0;
+  r.var = var;
+  r.rstd = (float)(1.0 / sqrt(var + (double)eps));
+  r.mean = (float)mean;
+  r.sc = gamma[c] * r.rstd;
+  r.sh = beta[c] - r.mean * r.sc;
+  return r;
 }
-// backward: bstats {sum dy, sum dy*xhat} -> coef {a, b, c} with dx = a*dy + b*x + c, dgamma, dbeta (bn_bwd_finalize_kernel)
-__device__ __forceinline__ void bn_bwd_finalize_channels(const trt_bn_bwd_fin_t& f, const double* bstats, int C, int tid, int nthreads) {
-  for (int c0 = tid; c0 < C; c0 += nthreads * FIN_CH) {
-    double sdy[FIN_CH], sdyx[FIN_CH];
-    float mean[FIN_CH], rstd[FIN_CH], gm[FIN_CH];
-#pragma unroll
-    for (int j = 0; j < FIN_CH; ++j) {
-      const int c = c0 + j * nthreads;
-      if (c < C) {
-        sdy[j] = stat_total(bstats, C, c); sdyx[j] = stat_total(bstats, C, C + c);
-        mean[j] = f.rec[2 * C + c]; rstd[j] = f.rec[3 * C + c]; gm[j] = f.gamma[c];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < FIN_CH; ++j) {
-      const int c = c0 + j * nthreads;
-      if (c < C) {
-        const float a = gm[j] * rstd[j];
-        const float m1 = (float)(sdy[j] / f.count), m2 = (float)(sdyx[j] / f.count);
-        f.coef[c] = a;
-        f.coef[C + c] = -a * rstd[j] * m2;
-        f.coef[2 * C + c] = a * (mean[j] * rstd[j] * m2 - m1);
-        f.dgamma[c] = (float)sdyx[j];
-        f.dbeta[c] = (float)sdy[j];
-      }
-    }
+__device__ __forceinline__ void bn_publish(const BnChannel& b, float* rec, float* running_mean, float* running_var, int C,
+                                           int c, double count, float momentum) {
+  rec[c] = b.sc;
+  rec[C + c] = b.sh;
+  rec[2 * C + c] = b.mean;
+  rec[3 * C + c] = b.rstd;
+  if (running_mean) {
+    const double unb = count > 1 ? b.var * count / (count - 1) : b.var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * b.mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
   }
 }
-// Called by ALL threads of a block after their global atomics: true in every thread of the last block to get here.
-__device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int expected) {
-  __shared__ int s_last_block;
-  __threadfence();
+// Called by ALL threads of a block: scale/shift of channels [c0, c0 + nch) into shared memory, straight from the producer's
+// statistics (16 independent L2 loads per channel, ~1 us, instead of a 4-5 us finalise launch between producer and
+// consumer).  The publishing block also writes the record and the running statistics for every later consumer.
+__device__ __forceinline__ void bn_lazy_block(const trt_bn_fin_t& f, int C, int c0, int nch, float* s_sc, float* s_sh,
+                                              bool publish) {
+  for (int i = threadIdx.x; i < nch; i += blockDim.x) {
+    const int c = c0 + i;
+    if (c < C) {
+      const BnChannel b = bn_channel(f.stats, f.gamma, f.beta, C, c, f.count, f.eps);
+      s_sc[i] = b.sc;
+      s_sh[i] = b.sh;
+      if (publish) bn_publish(b, f.rec, f.running_mean, f.running_var, C, c, f.count, f.momentum);
+    }
+  }
+  if (publish && c0 == 0 && threadIdx.x == 0 && f.num_batches_tracked) *f.num_batches_tracked += 1;
   __syncthreads();
-  if (threadIdx.x == 0) s_last_block = (atomicAdd(counter, 1u) == expected - 1u);
-  __syncthreads();
-  const bool last = s_last_block != 0;
-  if (last) __threadfence();
-  return last;
+}
+// backward: bstats {sum dy, sum dy*xhat} -> dx = a*dy + b*x + c for one channel (what bn_bwd_finalize_kernel publishes)
+struct BnBwdChannel { float a, b, c, dgamma, dbeta; };
+__device__ __forceinline__ BnBwdChannel bn_bwd_channel(const double* bstats, const float* rec, const float* gamma, int C, int c,
+                                                       double count) {
+  BnBwdChannel r;
+  const double sdy = stat_total(bstats, C, c), sdyx = stat_total(bstats, C, C + c);
+  const float mean = rec[2 * C + c], rstd = rec[3 * C + c];
+  const float a = gamma[c] * rstd;
+  const float m1 = (float)(sdy / count), m2 = (float)(sdyx / count);
+  r.a = a;
+  r.b = -a * rstd * m2;
+  r.c = a * (mean * rstd * m2 - m1);
+  r.dgamma = (float)sdyx;
+  r.dbeta = (float)sdy;
+  return r;
 }
 
 // ---------------------------------------------------------------- PTX: mbarrier / TMA / tcgen05

@@ -171,7 +171,13 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
     ptx::tma_load_4d(smem + st * T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW * S - g.pad_l, q.ty * TOH * S - g.pad_t, q.n);
   };
   f8 sc, sh, osc, osh;
-  if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + g.C + 8 * cv); }
+  if (has_fin) {
+    // lazy BatchNorm on the input: scale/shift of this block's 64 channels straight from the producer's statistics; the
+    // first block of each channel group publishes the record (the backward pass reads it)
+    __shared__ __align__(16) float s_ss[2][64];
+    bn_lazy_block(fin, g.C, cb * 64, 64, s_ss[0], s_ss[1], blockIdx.x == 0);
+    if (cvalid) { sc = lds8(s_ss[0] + 8 * lane); sh = lds8(s_ss[1] + 8 * lane); }
+  } else if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + g.C + 8 * cv); }
   if (out_rec && cvalid) { osc = ldf8(out_rec + 8 * cv); osh = ldf8(out_rec + g.C + 8 * cv); }
   float red[2][8];
 #pragma unroll
@@ -235,7 +241,6 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(stats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
-    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_finalize_channels(fin, stats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -279,8 +284,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
                                                                     const __grid_constant__ CUtensorMap tm_x,
                                                                     const float* __restrict__ w, const float* __restrict__ x_rec,
                                                                     uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                    const DwGeom g, const int has_fin,
-                                                                    const trt_bn_bwd_fin_t fin) {
+                                                                    const DwGeom g) {
   using T = FwdTile<K, 1, P>;
   constexpr int STAGE = T::IN_BYTES + T::OUT_BYTES;
   constexpr int PAD = (K - 1) / 2;
@@ -347,7 +351,6 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
-    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -385,8 +388,7 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tm_x,
                                                                     const float* __restrict__ w, const float* __restrict__ x_rec,
                                                                     uint4* __restrict__ g_out, double* __restrict__ bstats,
-                                                                    const DwGeom g, const int has_fin,
-                                                                    const trt_bn_bwd_fin_t fin) {
+                                                                    const DwGeom g) {
   using T = S2Tile<K>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
@@ -491,7 +493,6 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
       const int k = threadIdx.x / 64, c = cb * 64 + (threadIdx.x % 64);
       if (c < g.C) atomicAdd(bstats + ((size_t)(blockIdx.x % TRT_STAT_REPLICAS) * 2 + k) * g.C + c, (double)total);
     }
-    if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y)) bn_bwd_finalize_channels(fin, bstats, g.C, threadIdx.x, TPB);
   }
 }
 
@@ -625,8 +626,8 @@ int persistent_blocks(Kern kern, size_t smem, int cblocks, int items, int* out) 
   int occ = -1;
   for (int i = 0; i < g_occ_n; ++i)
     if (g_occ[i].fn == key) occ = g_occ[i].occ;
+  TRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: every call
   if (occ < 0) {
-    TRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem));
     if (occ < 1) return trt_set_error(TRT_ERR_CUDA, "depthwise kernel does not fit on an SM (smem %zu)", smem);
     if (g_occ_n < 32) { g_occ[g_occ_n].fn = key; g_occ[g_occ_n].occ = occ; ++g_occ_n; }
@@ -643,8 +644,8 @@ int persistent_blocks(Kern kern, size_t smem, int cblocks, int items, int* out) 
 extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec,
                               float* pooled_sum, double* stats, const trt_bn_fin_t* fin_host, int N, int H, int W, int C,
                               int k, int s, cudaStream_t stream) {
-  TRT_REQUIRE(!fin_host || (stats && fin_host->gamma && fin_host->beta && fin_host->rec && fin_host->counter),
-              "trt_dwconv_fwd: incomplete finalisation record");
+  TRT_REQUIRE(!fin_host || (in_rec && fin_host->stats && fin_host->gamma && fin_host->beta && fin_host->rec == in_rec && fin_host->count > 0),
+              "trt_dwconv_fwd: incomplete lazy BatchNorm record for the input (rec must be in_rec)");
   trt_bn_fin_t fin = {};
   if (fin_host) fin = *fin_host;
   const int has_fin = fin_host ? 1 : 0;
@@ -682,13 +683,7 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
 }
 
 extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw, const float* x_rec, void* g_out,
-                              double* bstats, const trt_bn_bwd_fin_t* fin_host, float* dw, int N, int H, int W, int C, int k,
-                              int s, cudaStream_t stream) {
-  TRT_REQUIRE(!fin_host || (g_out && x_rec && bstats && fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->counter),
-              "trt_dwconv_bwd: incomplete finalisation record");
-  trt_bn_bwd_fin_t fin = {};
-  if (fin_host) fin = *fin_host;
-  const int has_fin = fin_host ? 1 : 0;
+                              double* bstats, float* dw, int N, int H, int W, int C, int k, int s, cudaStream_t stream) {
   TRT_REQUIRE(gy && w && x_raw && (dw || g_out) && N > 0 && C > 0 && C % 8 == 0, "trt_dwconv_bwd: bad argument");
   TRT_REQUIRE((k == 3 || k == 5) && (s == 1 || s == 2), "trt_dwconv_bwd: only k in {3,5}, s in {1,2}");
   DwGeom g;
@@ -713,7 +708,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
     if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TOW, TOH))) return rc;                             \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_bwd_data_s1_kernel<KK, PP>, smem, cblocks, items, &G))) return rc;          \
-    dwconv_bwd_data_s1_kernel<KK, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g, has_fin, fin); \
+    dwconv_bwd_data_s1_kernel<KK, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)
       if (k == 3) { if (p == 4) LAUNCH_BD_S1(3, 4); else LAUNCH_BD_S1(3, 2); }
       else { if (p == 4) LAUNCH_BD_S1(5, 4); else LAUNCH_BD_S1(5, 2); }
@@ -732,7 +727,7 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
     if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, T::TI, T::TI))) return rc;                            \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_bwd_data_s2_kernel<KK>, smem, cblocks, items, &G))) return rc;              \
-    dwconv_bwd_data_s2_kernel<KK><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g, has_fin, fin); \
+    dwconv_bwd_data_s2_kernel<KK><<<dim3(G, cblocks), TPB, smem, stream>>>(td, tx, w, x_rec, (uint4*)g_out, bstats, g); \
   } while (0)
       if (k == 3) LAUNCH_BD_S2(3); else LAUNCH_BD_S2(5);
 #undef LAUNCH_BD_S2

@@ -70,20 +70,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  const double mean = stat_total(stats, C, c) / count;
-  double var = stat_total(stats, C, C + c) / count - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[c] * rstd;
-  rec[c] = sc;
-  rec[C + c] = beta[c] - (float)mean * sc;
-  rec[2 * C + c] = (float)mean;
-  rec[3 * C + c] = rstd;
-  if (running_mean) {
-    const double unb = count > 1 ? var * count / (count - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
-  }
+  bn_publish(bn_channel(stats, gamma, beta, C, c, count, eps), rec, running_mean, running_var, C, c, count, momentum);
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -105,24 +92,30 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bstats, const 
                                        float* __restrict__ dbeta, int C, double count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double sdy = stat_total(bstats, C, c), sdyx = stat_total(bstats, C, C + c);
-  const float mean = rec[2 * C + c], rstd = rec[3 * C + c];
-  const float a = gamma[c] * rstd;
-  const float m1 = (float)(sdy / count), m2 = (float)(sdyx / count);
-  coef[c] = a;
-  coef[C + c] = -a * rstd * m2;
-  coef[2 * C + c] = a * (mean * rstd * m2 - m1);
-  dgamma[c] = (float)sdyx;
-  dbeta[c] = (float)sdy;
+  const BnBwdChannel b = bn_bwd_channel(bstats, rec, gamma, C, c, count);
+  coef[c] = b.a;
+  coef[C + c] = b.b;
+  coef[2 * C + c] = b.c;
+  dgamma[c] = b.dgamma;
+  dbeta[c] = b.dbeta;
 }
+
+// shared-memory scale/shift of a block's channel slab (VX vectors = up to TPB*8 channels): filled by bn_lazy_block when the
+// BatchNorm is lazy, otherwise the record is read directly
+constexpr int SLAB_CH = TPB * 8;
 
 // ------------------------------------------------------------------------------------------------ y = act(bn(x)) (+res)
 __global__ void __launch_bounds__(TPB) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
                                                        const uint4* __restrict__ res, uint4* __restrict__ out, int rows,
-                                                       int C, int V, int VX, int RY, int act) {
+                                                       int C, int V, int VX, int RY, int act, const int has_fin,
+                                                       const trt_bn_fin_t fin) {
+  __shared__ __align__(16) float s_ss[2][SLAB_CH];
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
+  if (has_fin) bn_lazy_block(fin, C, blockIdx.y * VX * 8, VX * 8, s_ss[0], s_ss[1], blockIdx.x == 0);
   if (!m.active) return;
-  const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
+  f8 sc, sh;
+  if (has_fin) { sc = lds8(s_ss[0] + 8 * m.vl); sh = lds8(s_ss[1] + 8 * m.vl); }
+  else { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
   const int step = gridDim.x * RY;
   for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
     uint4 xa[UNR], xr[UNR];
@@ -155,14 +148,17 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const uint4* __restrict__
 // ------------------------------------------------------------------------------------------------ pooled[n,c] += sum_hw act(bn(x))
 __global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
                                                        float* __restrict__ pooled, int HW, int C, int V, int VX, int RY,
-                                                       int act) {
+                                                       int act, const int has_fin, const trt_bn_fin_t fin) {
   __shared__ float s_red[8 * TPB];
+  __shared__ __align__(16) float s_ss[2][SLAB_CH];
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   const int n = blockIdx.y;
+  if (has_fin) bn_lazy_block(fin, C, blockIdx.z * VX * 8, VX * 8, s_ss[0], s_ss[1], blockIdx.x == 0 && blockIdx.y == 0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
     f8 sc, sh;
-    if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
+    if (has_fin) { sc = lds8(s_ss[0] + 8 * m.vl); sh = lds8(s_ss[1] + 8 * m.vl); }
+    else if (rec) { sc = ldf8(rec + 8 * m.v); sh = ldf8(rec + C + 8 * m.v); }
     const int step = gridDim.x * RY;
     for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
       uint4 xa[UNR];
@@ -274,8 +270,7 @@ __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict
 // bstats[0][c] += sum dy ; bstats[1][c] += sum dy * xhat
 __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                                             const float* __restrict__ rec, double* __restrict__ bstats,
-                                                            int rows, int C, int V, int VX, int RY, const int has_fin,
-                                                            const trt_bn_bwd_fin_t fin) {
+                                                            int rows, int C, int V, int VX, int RY) {
   __shared__ float s_red[16 * TPB];
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
   float acc[16];
@@ -317,16 +312,33 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const uint4* __restr
       atomicAdd(rep + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
-  if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);
 }
 
 // out = a*dy + b*x + c (per channel)   [BN backward apply]
 __global__ void __launch_bounds__(TPB) affine2_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                                       const float* __restrict__ coef, uint4* __restrict__ out, int rows,
-                                                      int C, int V, int VX, int RY) {
+                                                      int C, int V, int VX, int RY, const int has_fin,
+                                                      const trt_bn_bwd_fin_t fin) {
+  __shared__ __align__(16) float s_abc[3][SLAB_CH];
   const RowMap m = row_map(V, VX, RY, blockIdx.y);
+  if (has_fin) {
+    // lazy BatchNorm backward: the producer of `dy` only accumulated {sum dy, sum dy*xhat}; every block turns them into the
+    // coefficients of its channel slab, block 0 of the slab also writes dgamma / dbeta
+    const int c0 = blockIdx.y * VX * 8;
+    for (int i = threadIdx.x; i < VX * 8; i += TPB) {
+      const int c = c0 + i;
+      if (c < C) {
+        const BnBwdChannel b = bn_bwd_channel(fin.bstats, fin.rec, fin.gamma, C, c, fin.count);
+        s_abc[0][i] = b.a; s_abc[1][i] = b.b; s_abc[2][i] = b.c;
+        if (blockIdx.x == 0) { fin.dgamma[c] = b.dgamma; fin.dbeta[c] = b.dbeta; }
+      }
+    }
+    __syncthreads();
+  }
   if (!m.active) return;
-  const f8 ca = ldf8(coef + 8 * m.v), cb = ldf8(coef + C + 8 * m.v), cc = ldf8(coef + 2 * C + 8 * m.v);
+  f8 ca, cb, cc;
+  if (has_fin) { ca = lds8(s_abc[0] + 8 * m.vl); cb = lds8(s_abc[1] + 8 * m.vl); cc = lds8(s_abc[2] + 8 * m.vl); }
+  else { ca = ldf8(coef + 8 * m.v); cb = ldf8(coef + C + 8 * m.v); cc = ldf8(coef + 2 * C + 8 * m.v); }
   const int step = gridDim.x * RY;
   for (int r = blockIdx.x * RY + m.ry; r < rows; r += UNR * step) {
     uint4 da[UNR], xa[UNR];
@@ -351,14 +363,27 @@ __global__ void __launch_bounds__(TPB) affine2_kernel(const uint4* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ SE backward, pass 1
-// dgate_pre[n,c] += sum_hw dA * silu(bn(x))
+// dgate_pre[n,c] += sum_hw dA * silu(bn(x)).
+// FULL: four more per-(image, channel) sums in the same pass, from which the BatchNorm-backward sums of the gated
+// activation follow WITHOUT another pass over the tensor.  With z = bn(x), s' = silu'(z) and the upstream gradient of the
+// BatchNorm output g = (dA*gate[n,c] + dmean[n,c]/HW) * s':
+//     sum_{n,hw} g     = sum_n gate*S1 + dmean/HW*S2        S1 = sum_hw dA*s'      S2 = sum_hw s'
+//     sum_{n,hw} g*x   = sum_n gate*S3 + dmean/HW*S4        S3 = sum_hw dA*s'*x    S4 = sum_hw s'*x
+// (gate and dmean only exist after the SE MLP backward, which needs dgate_pre first; the old path made a second pass to
+// write g and a third to apply the BatchNorm-backward affine).  sums layout: [5][N][C], slot 0 = dgate_pre.
+template <bool FULL>
 __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ x,
-                                                            const float* __restrict__ rec, float* __restrict__ dgate_pre,
-                                                            int HW, int C, int V, int VX, int RY) {
+                                                            const float* __restrict__ rec, float* __restrict__ sums,
+                                                            int HW, int C, int V, int VX, int RY, size_t NC) {
+  constexpr int NS = FULL ? 5 : 1;
   __shared__ float s_red[8 * TPB];
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   const int n = blockIdx.y;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[NS][8];
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
   if (m.active) {
     const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
     const int step = gridDim.x * RY;
@@ -376,15 +401,72 @@ __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restr
         if (r + u * step < HW) {
           const f8 d = unpack8(da[u]), a = unpack8(xa[u]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(d.v[i], siluf_(fmaf(a.v[i], sc.v[i], sh.v[i])), acc[i]);
+          for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(a.v[i], sc.v[i], sh.v[i]);
+            const float sg = sigmoidf_(z);
+            acc[0][i] = fmaf(d.v[i], z * sg, acc[0][i]);
+            if (FULL) {
+              const float sp = sg * (1.0f + z * (1.0f - sg));      // silu'(z)
+              const float t = d.v[i] * sp;
+              acc[1][i] += t;
+              acc[2][i] += sp;
+              acc[3][i] = fmaf(t, a.v[i], acc[3][i]);
+              acc[4][i] = fmaf(sp, a.v[i], acc[4][i]);
+            }
+          }
         }
       }
     }
   }
-  block_reduce_rows<8>(acc, s_red, m);
-  if (m.ry == 0 && m.active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dgate_pre + (size_t)n * C + 8 * m.v + i, acc[i]);
+  for (int k = 0; k < NS; ++k) {
+    block_reduce_rows<8>(acc[k], s_red, m);
+    if (m.ry == 0 && m.active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(sums + k * NC + (size_t)n * C + 8 * m.v + i, acc[k][i]);
+    }
+  }
+}
+
+// pass 2 of the merged path: dD = a*g + b*x + c with g = (dA*gate[n,c] + dmean[n,c]/HW) * silu'(bn(x)) formed on the fly -
+// the gradient w.r.t. the raw depthwise output in ONE read of (dA, x) and one write (no g tensor, no separate affine pass)
+__global__ void __launch_bounds__(TPB) act_bwd_apply_kernel(const uint4* __restrict__ dA, const float* __restrict__ gate,
+                                                            const float* __restrict__ dmean, float inv_hw,
+                                                            const uint4* __restrict__ x, const float* __restrict__ rec,
+                                                            const float* __restrict__ coef, uint4* __restrict__ out, int HW,
+                                                            int C, int V, int VX, int RY) {
+  const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  if (!m.active) return;
+  const int n = blockIdx.y;
+  const f8 sc = ldf8(rec + 8 * m.v), sh = ldf8(rec + C + 8 * m.v);
+  const f8 ca = ldf8(coef + 8 * m.v), cb = ldf8(coef + C + 8 * m.v), cc = ldf8(coef + 2 * C + 8 * m.v);
+  f8 gt = ldf8(gate + (size_t)n * C + 8 * m.v), dm = ldf8(dmean + (size_t)n * C + 8 * m.v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gt.v[i] *= ca.v[i]; dm.v[i] *= inv_hw * ca.v[i]; }      // a folded into the upstream factors
+  const int step = gridDim.x * RY;
+  for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+    uint4 da[UNR], xa[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (r + u * step < HW) {
+        const size_t idx = ((size_t)n * HW + r + u * step) * V + m.v;
+        xa[u] = __ldg(x + idx);
+        da[u] = __ldg(dA + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (r + u * step < HW) {
+        const f8 a = unpack8(xa[u]), d = unpack8(da[u]);
+        f8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float up = fmaf(d.v[i], gt.v[i], dm.v[i]);
+          o.v[i] = fmaf(up, silu_gradf_(fmaf(a.v[i], sc.v[i], sh.v[i])), fmaf(cb.v[i], a.v[i], cc.v[i]));
+        }
+        out[((size_t)n * HW + r + u * step) * V + m.v] = pack8(o);
+      }
+    }
   }
 }
 
@@ -581,10 +663,19 @@ __global__ void __launch_bounds__(TPB) se_bwd_k1_kernel(const float* __restrict_
   if (t < SEB_CC && c0 + t < C) dbe[c0 + t] = acc_b;
 }
 
+struct SeBn {                  // device view of trt_se_bn_t (+ the gate): BatchNorm backward of the gated activation
+  const float* sums;           // [5][N][C] from se_bwd_reduce_kernel<true>; null = not requested
+  const float* gate;           // [N][C]
+  const float* rec;            // [4][C]
+  const float* gamma;
+  float *coef, *dgamma, *dbeta;
+  double count;
+};
+
 __global__ void __launch_bounds__(TPB) se_bwd_k2_kernel(const float* __restrict__ ds1_acc, const float* __restrict__ s1,
                                                         const float* __restrict__ pooled, float inv_hw,
                                                         const float* __restrict__ Wr, float* __restrict__ dmean, float* __restrict__ dWr,
-                                                        float* __restrict__ dbr, int N, int C, int rd) {
+                                                        float* __restrict__ dbr, int N, int C, int rd, const SeBn bn) {
   extern __shared__ __align__(16) float s_mem[];
   const int rdp = (rd + 3) & ~3;
   float* s_d1 = s_mem;                         // [SEB_NT][rdp]
@@ -600,6 +691,7 @@ __global__ void __launch_bounds__(TPB) se_bwd_k2_kernel(const float* __restrict_
   const bool w_active = t / (SEB_CC / 4) < rgroups;
   float acc_w[4][4] = {};
   float acc_b = 0.f;                            // dbr: block 0, threads 0..rd-1
+  double bn_g[4] = {0, 0, 0, 0}, bn_gx[4] = {0, 0, 0, 0};     // sum g, sum g*x of this thread's 4 channels over its images
   for (int n0 = 0; n0 < N; n0 += SEB_NT) {
     const int nn = min(SEB_NT, N - n0);
     __syncthreads();
@@ -635,6 +727,30 @@ __global__ void __launch_bounds__(TPB) se_bwd_k2_kernel(const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (dn + i < nn && c0 + dc + j < C) dmean[(size_t)(n0 + dn + i) * C + c0 + dc + j] = acc[i][j];
+      if (bn.sums) {
+        // BatchNorm-backward sums of the gated activation from the per-(image, channel) sums of pass 1 (C % 8 == 0 and dc is
+        // a multiple of 4, so the four channels are all inside or all outside the tensor)
+        const size_t NC = (size_t)N * C;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (dn + i < nn && c0 + dc < C) {
+            const size_t o = (size_t)(n0 + dn + i) * C + c0 + dc;
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(bn.gate + o));
+            const float4 q1 = __ldcg(reinterpret_cast<const float4*>(bn.sums + NC + o));
+            const float4 q2 = __ldcg(reinterpret_cast<const float4*>(bn.sums + 2 * NC + o));
+            const float4 q3 = __ldcg(reinterpret_cast<const float4*>(bn.sums + 3 * NC + o));
+            const float4 q4 = __ldcg(reinterpret_cast<const float4*>(bn.sums + 4 * NC + o));
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w}, v2[4] = {q2.x, q2.y, q2.z, q2.w};
+            const float v3[4] = {q3.x, q3.y, q3.z, q3.w}, v4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float dm = acc[i][j] * inv_hw;
+              bn_g[j] += (double)fmaf(gv[j], v1[j], dm * v2[j]);
+              bn_gx[j] += (double)fmaf(gv[j], v3[j], dm * v4[j]);
+            }
+          }
+        }
+      }
     }
     if (w_active) {
 #pragma unroll 4
@@ -659,6 +775,35 @@ __global__ void __launch_bounds__(TPB) se_bwd_k2_kernel(const float* __restrict_
         if (wr + i < rd && c0 + wc + j < C) dWr[(size_t)(wr + i) * C + c0 + wc + j] = acc_w[i][j];
   }
   if (blockIdx.x == 0 && t < rd) dbr[t] = acc_b;
+  if (bn.sums) {
+    // combine the (SEB_NT / 2) image-pair threads of every channel quad, then one thread per channel writes the
+    // coefficients of dx = a*g + b*x + c and the affine gradients (what bn_bwd_finalize does from fp64 sums)
+    __syncthreads();
+    double* s_d = reinterpret_cast<double*>(s_mem);               // [2][SEB_NT/2][SEB_CC] doubles = 8 KB <= the tiles
+    const int quad = t % (SEB_CC / 4), pair = t / (SEB_CC / 4);
+    if (pair < SEB_NT / 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s_d[pair * SEB_CC + quad * 4 + j] = bn_g[j];
+        s_d[(SEB_NT / 2 + pair) * SEB_CC + quad * 4 + j] = bn_gx[j];
+      }
+    }
+    __syncthreads();
+    if (t < SEB_CC && c0 + t < C) {
+      double sg = 0, sgx = 0;
+      for (int q = 0; q < SEB_NT / 2; ++q) { sg += s_d[q * SEB_CC + t]; sgx += s_d[(SEB_NT / 2 + q) * SEB_CC + t]; }
+      const int c = c0 + t;
+      const float mean = bn.rec[2 * C + c], rstd = bn.rec[3 * C + c];
+      const double sgxh = (double)rstd * (sgx - (double)mean * sg);   // sum g*xhat
+      const float a = bn.gamma[c] * rstd;
+      const float m1 = (float)(sg / bn.count), m2 = (float)(sgxh / bn.count);
+      bn.coef[c] = a;
+      bn.coef[C + c] = -a * rstd * m2;
+      bn.coef[2 * C + c] = a * (mean * rstd * m2 - m1);
+      bn.dgamma[c] = (float)sgxh;
+      bn.dbeta[c] = (float)sg;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ activation backward
@@ -668,8 +813,7 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
                                                       const float* __restrict__ dmean, float inv_hw,
                                                       const uint4* __restrict__ x, const float* __restrict__ rec,
                                                       uint4* __restrict__ g_out, double* __restrict__ bstats, int HW, int C,
-                                                      int V, int VX, int RY, int act, const int has_fin,
-                                                      const trt_bn_bwd_fin_t fin) {
+                                                      int V, int VX, int RY, int act) {
   __shared__ float s_red[16 * TPB];
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   const int n = blockIdx.y;
@@ -736,7 +880,6 @@ __global__ void __launch_bounds__(TPB) act_bwd_kernel(const uint4* __restrict__ 
       atomicAdd(rep + C + 8 * m.v + i, (double)acc[8 + i]);
     }
   }
-  if (has_fin && last_block_done(fin.counter, gridDim.x * gridDim.y * gridDim.z)) bn_bwd_finalize_channels(fin, bstats, C, threadIdx.x, TPB);
 }
 
 // fp32 [N, K] weight -> bf16 [N, K] and bf16 [K, N] (transposed copy for dgrad)
@@ -846,27 +989,41 @@ extern "C" int trt_bn_bwd_finalize(const double* bstats, const float* rec, const
   return trt_check_launch("trt_bn_bwd_finalize");
 }
 
-extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, int rows, int C, int act,
-                            cudaStream_t stream) {
+static int check_fin(const trt_bn_fin_t* f, const char* who) {
+  if (f && !(f->stats && f->gamma && f->beta && f->rec && f->count > 0))
+    return trt_set_error(TRT_ERR_INVALID, "%s: incomplete lazy BatchNorm record", who);
+  return TRT_OK;
+}
+
+extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, const trt_bn_fin_t* fin_host,
+                            int rows, int C, int act, cudaStream_t stream) {
   CHECK_C(C);
-  TRT_REQUIRE(x && rec && out && rows > 0, "trt_bn_apply: bad argument");
+  TRT_REQUIRE(x && (rec || fin_host) && out && rows > 0, "trt_bn_apply: bad argument");
+  int rc;
+  if ((rc = check_fin(fin_host, "trt_bn_apply"))) return rc;
+  trt_bn_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
   bn_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, (const uint4*)residual, (uint4*)out, rows, C, L.V, L.VX,
-                                            L.RY, act);
+                                            L.RY, act, fin_host ? 1 : 0, fin);
   return trt_check_launch("trt_bn_apply");
 }
 
-extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, int N, int HW, int C, int act,
-                            cudaStream_t stream) {
+extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, const trt_bn_fin_t* fin_host, int N,
+                            int HW, int C, int act, cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(x && pooled_sum && N > 0 && HW > 0, "trt_pool_act: bad argument");
+  int rc;
+  if ((rc = check_fin(fin_host, "trt_pool_act"))) return rc;
+  trt_bn_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   if (!zeroed) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
-  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act);
+  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act, fin_host ? 1 : 0, fin);
   return trt_check_launch("trt_pool_act");
 }
 
@@ -898,63 +1055,89 @@ extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate
   return trt_check_launch("trt_gate_apply");
 }
 
-extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats,
-                                 const trt_bn_bwd_fin_t* fin_host, int rows, int C, cudaStream_t stream) {
+extern "C" int trt_bn_bwd_reduce(const void* dy, const void* x, const float* rec, double* bstats, int rows, int C,
+                                 cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(dy && x && rec && bstats && rows > 0, "trt_bn_bwd_reduce: bad argument");
-  TRT_REQUIRE(!fin_host || (fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->dgamma && fin_host->dbeta && fin_host->counter),
-              "trt_bn_bwd_reduce: incomplete finalisation record");
-  trt_bn_bwd_fin_t fin = {};
-  if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, red_blocks((size_t)rows * C * 4)), L.slabs);
-  bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY,
-                                                 fin_host ? 1 : 0, fin);
+  bn_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, rec, bstats, rows, C, L.V, L.VX, L.RY);
   return trt_check_launch("trt_bn_bwd_reduce");
 }
 
-extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, void* out, int rows, int C,
-                           cudaStream_t stream) {
+extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, void* out, const trt_bn_bwd_fin_t* fin_host,
+                           int rows, int C, cudaStream_t stream) {
   CHECK_C(C);
-  TRT_REQUIRE(dy && x && coef && out && rows > 0, "trt_affine2: bad argument");
+  TRT_REQUIRE(dy && x && (coef || fin_host) && out && rows > 0, "trt_affine2: bad argument");
+  TRT_REQUIRE(!fin_host || (fin_host->bstats && fin_host->rec && fin_host->gamma && fin_host->dgamma && fin_host->dbeta &&
+                            fin_host->count > 0), "trt_affine2: incomplete lazy BatchNorm-backward record");
+  trt_bn_bwd_fin_t fin = {};
+  if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
-  affine2_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, coef, (uint4*)out, rows, C, L.V, L.VX, L.RY);
+  affine2_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, coef, (uint4*)out, rows, C, L.V, L.VX, L.RY,
+                                           fin_host ? 1 : 0, fin);
   return trt_check_launch("trt_affine2");
 }
 
-extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* dgate_pre, int zeroed, int N, int HW,
-                                 int C, cudaStream_t stream) {
+extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec, float* sums, int zeroed, int full, int N,
+                                 int HW, int C, cudaStream_t stream) {
   CHECK_C(C);
-  TRT_REQUIRE(dA && x && rec && dgate_pre && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
+  TRT_REQUIRE(dA && x && rec && sums && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
   const Launch L = plan(C);
-  if (!zeroed) TRT_CUDA(cudaMemsetAsync(dgate_pre, 0, (size_t)N * C * sizeof(float), stream));
+  const size_t NC = (size_t)N * C;
+  if (!zeroed) TRT_CUDA(cudaMemsetAsync(sums, 0, (full ? 5 : 1) * NC * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
-  se_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, dgate_pre, HW, C, L.V, L.VX, L.RY);
+  if (full) se_bwd_reduce_kernel<true><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
+  else se_bwd_reduce_kernel<false><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
   return trt_check_launch("trt_se_bwd_reduce");
+}
+
+extern "C" int trt_act_bwd_apply(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x,
+                                 const float* rec, const float* coef, void* out, int N, int HW, int C, cudaStream_t stream) {
+  CHECK_C(C);
+  TRT_REQUIRE(dA && gate && dmean && x && rec && coef && out && N > 0 && HW > 0, "trt_act_bwd_apply: bad argument");
+  const Launch L = plan(C);
+  int target = 6 * trt_num_sms() / (N * L.slabs);
+  if (target < 1) target = 1;
+  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
+  act_bwd_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, coef, (uint4*)out,
+                                                 HW, C, L.V, L.VX, L.RY);
+  return trt_check_launch("trt_act_bwd_apply");
 }
 
 extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
                           const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr,
-                          float* dWe, float* dbe, int ds1_zeroed, int N, int C, int rd, cudaStream_t stream) {
+                          float* dWe, float* dbe, int ds1_zeroed, const trt_se_bn_t* bn_host, int N, int C, int rd,
+                          cudaStream_t stream) {
   TRT_REQUIRE(dgate_pre && gate && s1 && pooled_sum && Wr && We && ds2 && ds1 && dmean && dWr && dbr && dWe && dbe,
               "trt_se_bwd: null pointer");
+  SeBn bn = {};
+  if (bn_host) {
+    TRT_REQUIRE(bn_host->sums && bn_host->rec && bn_host->gamma && bn_host->coef && bn_host->dgamma && bn_host->dbeta && bn_host->count > 0,
+                "trt_se_bwd: incomplete BatchNorm-backward record");
+    TRT_REQUIRE(rd <= SEB_RD, "trt_se_bwd: the BatchNorm-backward tail needs rd <= %d (got %d)", SEB_RD, rd);
+    bn.sums = bn_host->sums; bn.gate = gate; bn.rec = bn_host->rec; bn.gamma = bn_host->gamma; bn.coef = bn_host->coef;
+    bn.dgamma = bn_host->dgamma; bn.dbeta = bn_host->dbeta; bn.count = bn_host->count;
+  }
   if (rd <= SEB_RD && (SEB_NT / 4) * ((rd + 3) / 4) >= 1) {
     // fused path: ds1 (scratch) accumulates K1's per-chunk partial sums of ds2.We (zeroed here); K2 applies silu' on load
     const int rdp = (rd + 3) & ~3;
     if (!ds1_zeroed) TRT_CUDA(cudaMemsetAsync(ds1, 0, (size_t)N * rd * sizeof(float), stream));
     const int blocks = (C + SEB_CC - 1) / SEB_CC;
     const size_t smem1 = ((size_t)SEB_NT * rdp + (size_t)SEB_NT * SEB_CC + (size_t)SEB_CC * rdp) * sizeof(float);
-    const size_t smem2 = ((size_t)SEB_NT * rdp + (size_t)rdp * SEB_CC + (size_t)SEB_NT * SEB_CC) * sizeof(float);
+    size_t smem2 = ((size_t)SEB_NT * rdp + (size_t)rdp * SEB_CC + (size_t)SEB_NT * SEB_CC) * sizeof(float);
+    if (bn.sums && smem2 < (size_t)SEB_NT * SEB_CC * sizeof(double)) smem2 = (size_t)SEB_NT * SEB_CC * sizeof(double);   // the tail's fp64 scratch
     TRT_CUDA(cudaFuncSetAttribute(se_bwd_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     TRT_CUDA(cudaFuncSetAttribute(se_bwd_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     se_bwd_k1_kernel<<<blocks, TPB, smem1, stream>>>(dgate_pre, gate, s1, We, ds2, ds1, dWe, dbe, N, C, rd);
     trt_count_launch(1);
-    se_bwd_k2_kernel<<<blocks, TPB, smem2, stream>>>(ds1, s1, pooled_sum, inv_hw, Wr, dmean, dWr, dbr, N, C, rd);
+    se_bwd_k2_kernel<<<blocks, TPB, smem2, stream>>>(ds1, s1, pooled_sum, inv_hw, Wr, dmean, dWr, dbr, N, C, rd, bn);
     return trt_check_launch("trt_se_bwd");
   }
+  TRT_REQUIRE(!bn.sums, "trt_se_bwd: the BatchNorm-backward tail is only built into the fused path");
   se_bwd_a_kernel<<<dim3(rd, (N + 7) / 8), TPB, (size_t)C * sizeof(float), stream>>>(dgate_pre, gate, s1, We, ds2, ds1, N, C, rd);
   {
     int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
@@ -969,20 +1152,15 @@ extern "C" int trt_se_bwd(const float* dgate_pre, const float* gate, const float
 }
 
 extern "C" int trt_act_bwd(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x,
-                           const float* rec, void* g_out, double* bstats, const trt_bn_bwd_fin_t* fin_host, int N, int HW,
-                           int C, int act, cudaStream_t stream) {
+                           const float* rec, void* g_out, double* bstats, int N, int HW, int C, int act, cudaStream_t stream) {
   CHECK_C(C);
-  TRT_REQUIRE(!fin_host || (fin_host->rec && fin_host->gamma && fin_host->coef && fin_host->dgamma && fin_host->dbeta && fin_host->counter),
-              "trt_act_bwd: incomplete finalisation record");
-  trt_bn_bwd_fin_t fin = {};
-  if (fin_host) fin = *fin_host;
   TRT_REQUIRE(x && rec && g_out && bstats && N > 0 && HW > 0 && (dA || dmean), "trt_act_bwd: bad argument");
   const Launch L = plan(C);
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   act_bwd_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, (uint4*)g_out,
-                                           bstats, HW, C, L.V, L.VX, L.RY, act, fin_host ? 1 : 0, fin);
+                                           bstats, HW, C, L.V, L.VX, L.RY, act);
   return trt_check_launch("trt_act_bwd");
 }
 

@@ -39,9 +39,7 @@ struct GemmParams {
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
-  double* stats;  // [2][N]
-  int has_fin;    // 1: the last epilogue group of the grid finalises the BatchNorm record from the statistics
-  trt_bn_fin_t fin;
+  double* stats;  // [TRT_STAT_REPLICAS][2][N]
 };
 
 #ifdef TRT_GEMM_TIMING
@@ -312,19 +310,6 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         TRT_TICK(5);
       }
       if (f_stats && st_n0 >= 0) flush_stats();
-      if (p.has_fin) {
-        // every group of every CTA checks in (also the ones that had no tile); the last one turns the statistics into
-        // the BatchNorm record, saving the launch of a finalise kernel
-        int* s_last_group = reinterpret_cast<int*>(tmem_slot + 1);    // 3 words left in the 256-byte barrier block
-        __threadfence();
-        ptx::named_bar_sync(bar_id, EPI_THREADS);
-        if (gt == 0) s_last_group[g] = (atomicAdd(p.fin.counter, 1u) == (unsigned)(gridDim.x * p.ngroups) - 1u);
-        ptx::named_bar_sync(bar_id, EPI_THREADS);
-        if (s_last_group[g]) {
-          __threadfence();
-          bn_finalize_channels(p.fin, p.stats, p.N, gt, EPI_THREADS);
-        }
-      }
     }
   }
 
@@ -497,8 +482,7 @@ int pick_block_n_fwd(int M, int N, int K) {
 }  // namespace
 
 static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
-                       const float* shift, const void* residual, double* stats, int block_n_override,
-                       const trt_bn_fin_t* fin, cudaStream_t stream) {
+                       const float* shift, const void* residual, double* stats, int block_n_override, cudaStream_t stream) {
   TRT_REQUIRE(A && B && C, "trt_gemm_bf16: null operand");
   TRT_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "trt_gemm_bf16: M,N,K must be >0 and N,K multiples of 8 (got %d %d %d)", M, N, K);
   TRT_REQUIRE(!(flags & TRT_EPI_SCALE_SHIFT) || (scale && shift), "trt_gemm_bf16: scale/shift missing");
@@ -519,8 +503,6 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.stats = stats;
-  p.has_fin = fin ? 1 : 0;
-  if (fin) p.fin = *fin;
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   const int b_stage = p.block_n * 128;
   p.b_resident = (p.num_n_blocks == 1 && p.num_k_blocks * b_stage <= 64 * 1024) ? 1 : 0;
@@ -560,14 +542,7 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
 extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
                              const float* shift, const void* residual, double* stats, int block_n_override,
                              cudaStream_t stream) {
-  return gemm_launch(A, B, C, M, N, K, flags, scale, shift, residual, stats, block_n_override, nullptr, stream);
-}
-
-extern "C" int trt_gemm_bf16_bn(const void* A, const void* B, void* C, int M, int N, int K, double* stats,
-                                const trt_bn_fin_t* fin_host, cudaStream_t stream) {
-  TRT_REQUIRE(fin_host && fin_host->gamma && fin_host->beta && fin_host->rec && fin_host->counter && fin_host->count > 0,
-              "trt_gemm_bf16_bn: incomplete finalisation record");
-  return gemm_launch(A, B, C, M, N, K, TRT_EPI_STATS, nullptr, nullptr, nullptr, stats, 0, fin_host, stream);
+  return gemm_launch(A, B, C, M, N, K, flags, scale, shift, residual, stats, block_n_override, stream);
 }
 
 #ifdef TRT_GEMM_TIMING

@@ -6,7 +6,7 @@ import math
 
 import torch
 
-from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS, BnFin, BnBwdFin  # noqa: F401
+from ._lib import lib, check, ptr, stream, EPI_SCALE_SHIFT, EPI_SILU, EPI_RESIDUAL, EPI_STATS, BnFin, BnBwdFin, SeBn  # noqa: F401
 
 bf16 = torch.bfloat16
 
@@ -49,28 +49,19 @@ def gemm(A, B, flags=0, scale=None, shift=None, residual=None, stats=None, out=N
     return out
 
 
-def bn_fin(gamma, beta, rm, rv, nbt, rec, counter, count, eps, momentum=0.1):
-    """Host record for a BatchNorm finalisation fused into the producing kernel (`counter`: one zeroed int32 element)."""
-    return BnFin(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), ptr(counter), float(count), eps, momentum)
+def bn_fin(stats, gamma, beta, rm, rv, nbt, rec, count, eps, momentum=0.1):
+    """Host record of a LAZY train-mode BatchNorm: `stats` are complete, `rec` is not written yet.  Pass it to the first
+    consumer (dwconv_fwd / pool_act / bn_apply): that kernel derives scale/shift itself and publishes rec + running stats."""
+    return BnFin(ptr(stats), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), float(count), eps, momentum)
 
 
-def bn_bwd_fin(rec, gamma, coef, dgamma, dbeta, counter, count):
-    return BnBwdFin(ptr(rec), ptr(gamma), ptr(coef), ptr(dgamma), ptr(dbeta), ptr(counter), float(count))
+def bn_bwd_fin(bstats, rec, gamma, dgamma, dbeta, count):
+    """Lazy BatchNorm backward: pass to affine2 instead of a coefficient tensor."""
+    return BnBwdFin(ptr(bstats), ptr(rec), ptr(gamma), ptr(dgamma), ptr(dbeta), float(count))
 
 
 def _ref(st):
     return None if st is None else C.byref(st)
-
-
-def gemm_bn(A, B, stats, fin, out=None):
-    """C = A @ B^T with BN statistics in the epilogue AND the BatchNorm record finalised by the last epilogue group."""
-    _c(A, bf16), _c(B, bf16)
-    M, K = A.shape
-    N = B.shape[0]
-    if out is None:
-        out = torch.empty((M, N), device=A.device, dtype=bf16)
-    check(lib.trt_gemm_bf16_bn(ptr(A), ptr(B), ptr(out), M, N, K, ptr(stats), C.byref(fin), stream()))
-    return out
 
 
 def gemm_wgrad(P, Q, out, so_p=None, so_q=None, lbo=0, sbo=0, kstep=0, q_store=0):
@@ -109,14 +100,14 @@ def bn_bwd_finalize(bstats, rec, gamma, coef, dgamma, dbeta, count):
                                   float(count), stream()))
 
 
-def bn_apply(x, rec, out, residual=None, act=0):
+def bn_apply(x, rec, out, residual=None, act=0, fin=None):
     rows, Cc = x.shape
-    check(lib.trt_bn_apply(ptr(x), ptr(rec), ptr(residual), ptr(out), rows, Cc, act, stream()))
+    check(lib.trt_bn_apply(ptr(x), ptr(rec), ptr(residual), ptr(out), _ref(fin), rows, Cc, act, stream()))
     return out
 
 
-def pool_act(x, rec, pooled, N, HW, act=1, zeroed=False):
-    check(lib.trt_pool_act(ptr(x), ptr(rec), ptr(pooled), int(zeroed), N, HW, x.shape[-1], act, stream()))
+def pool_act(x, rec, pooled, N, HW, act=1, zeroed=False, fin=None):
+    check(lib.trt_pool_act(ptr(x), ptr(rec), ptr(pooled), int(zeroed), _ref(fin), N, HW, x.shape[-1], act, stream()))
     return pooled
 
 
@@ -136,44 +127,57 @@ def scale_f32(x, alpha):
     return x
 
 
-def bn_bwd_reduce(dy, x, rec, bstats, fin=None):
+def bn_bwd_reduce(dy, x, rec, bstats):
     rows, Cc = x.shape
-    check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), _ref(fin), rows, Cc, stream()))
+    check(lib.trt_bn_bwd_reduce(ptr(dy), ptr(x), ptr(rec), ptr(bstats), rows, Cc, stream()))
 
 
-def affine2(dy, x, coef, out):
+def affine2(dy, x, coef, out, fin=None):
+    """out = a*dy + b*x + c with coef [3,C], or (coef None) the lazy BatchNorm-backward record `fin`."""
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    check(lib.trt_affine2(ptr(dy), ptr(x), ptr(coef), ptr(out), rows, Cc, stream()))
+    check(lib.trt_affine2(ptr(dy), ptr(x), ptr(coef), ptr(out), _ref(fin), rows, Cc, stream()))
     return out
 
 
-def se_bwd_reduce(dA, x, rec, dgate_pre, N, HW, zeroed=False):
-    check(lib.trt_se_bwd_reduce(ptr(dA), ptr(x), ptr(rec), ptr(dgate_pre), int(zeroed), N, HW, x.shape[-1], stream()))
+def se_bwd_reduce(dA, x, rec, sums, N, HW, zeroed=False, full=False):
+    """sums: [N,C] (dgate_pre) or, with full=True, [5,N,C] (dgate_pre + the four sums the merged backward needs)."""
+    check(lib.trt_se_bwd_reduce(ptr(dA), ptr(x), ptr(rec), ptr(sums), int(zeroed), int(full), N, HW, x.shape[-1], stream()))
 
 
-def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe, ds1_zeroed=False):
+def se_bn(sums, rec, gamma, coef, dgamma, dbeta, count):
+    return SeBn(ptr(sums), ptr(rec), ptr(gamma), ptr(coef), ptr(dgamma), ptr(dbeta), float(count))
+
+
+def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe, ds1_zeroed=False, bn=None):
     N, Cc = gate.shape
     check(lib.trt_se_bwd(ptr(dgate_pre), ptr(gate), ptr(s1), ptr(pooled), inv_hw, ptr(Wr), ptr(We), ptr(ds2), ptr(ds1),
-                         ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), int(ds1_zeroed), N, Cc, Wr.shape[0], stream()))
+                         ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), int(ds1_zeroed), _ref(bn), N, Cc, Wr.shape[0], stream()))
 
 
-def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1, fin=None):
-    check(lib.trt_act_bwd(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(g_out), ptr(bstats), _ref(fin), N, HW,
+def act_bwd_apply(dA, gate, dmean, inv_hw, x, rec, coef, out, N, HW):
+    check(lib.trt_act_bwd_apply(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(coef), ptr(out), N, HW, x.shape[-1],
+                                stream()))
+    return out
+
+
+def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1):
+    check(lib.trt_act_bwd(ptr(dA), ptr(gate), ptr(dmean), inv_hw, ptr(x), ptr(rec), ptr(g_out), ptr(bstats), N, HW,
                           x.shape[-1], act, stream()))
     return g_out
 
 
 # ------------------------------------------------------------------------------------------------ spatial convs
-def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, fin=None):
-    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), _ref(fin), N, H, W,
+def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, in_fin=None):
+    """in_fin: lazy BatchNorm record of the INPUT (in_rec is derived from its statistics and published by this launch)."""
+    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), _ref(in_fin), N, H, W,
                              x.shape[-1], k, s, stream()))
     return out
 
 
-def dwconv_bwd(dD, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s, fin=None):
+def dwconv_bwd(dD, w, x_raw, x_rec, g_out, bstats, dw, N, H, W, k, s):
     """dD: gradient w.r.t. the raw depthwise output (BN-backward affine already applied, see affine2)."""
-    check(lib.trt_dwconv_bwd(ptr(dD), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats), _ref(fin), ptr(dw), N, H, W,
+    check(lib.trt_dwconv_bwd(ptr(dD), ptr(w), ptr(x_raw), ptr(x_rec), ptr(g_out), ptr(bstats), ptr(dw), N, H, W,
                              x_raw.shape[-1], k, s, stream()))
 
 

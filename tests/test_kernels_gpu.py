@@ -180,10 +180,86 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd):
     dx = ops.affine2(g, x2, coef, torch.empty_like(x2))
     assert rel_err(dgamma, g_.grad) < 2e-2 and rel_err(dbeta, b_.grad) < 2e-2
     assert rel_err(dx, xt.grad.reshape(N * HW, C)) < 2e-2
+    # merged path: pass 1 leaves five per-(image, channel) sums, the SE MLP backward derives the BatchNorm-backward
+    # coefficients from them, pass 2 writes dx directly (two passes over the tensor instead of three)
+    sums = torch.empty(5, N, C, device="cuda")
+    ops.se_bwd_reduce(dA.view(N * HW, C), x2, rec, sums, N, HW, full=True)
+    assert torch.allclose(sums[0], dgate_pre, rtol=1e-4, atol=1e-3)
+    ds2b, ds1b, dmeanb = torch.empty_like(ds2), torch.empty_like(ds1), torch.empty_like(dmean)
+    gW = [torch.empty_like(t) for t in (dWr, dbr, dWe, dbe)]
+    coef2, dgamma2, dbeta2 = torch.empty(3, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.se_bwd(sums[0], gate, s1, pooled, 1.0 / HW, Wr, We, ds2b, ds1b, dmeanb, *gW,
+               bn=ops.se_bn(sums, rec, gamma, coef2, dgamma2, dbeta2, N * HW))
+    assert rel_err(dmeanb, dmean) < 1e-3 and rel_err(gW[0], dWr) < 1e-3 and rel_err(gW[2], dWe) < 1e-3
+    dx2 = ops.act_bwd_apply(dA.view(N * HW, C), gate, dmeanb, 1.0 / HW, x2, rec, coef2, torch.empty_like(x2), N, HW)
+    assert rel_err(dgamma2, g_.grad) < 2e-2 and rel_err(dbeta2, b_.grad) < 2e-2
+    assert rel_err(dx2, xt.grad.reshape(N * HW, C)) < 2e-2
+    assert rel_err(dx2, dx) < 1e-2 and rel_err(coef2, coef) < 1e-2
     # standalone reduce == the fused sums
     bs2 = torch.zeros_like(bstats)
     ops.bn_bwd_reduce(g, x2, rec, bs2)
     assert torch.allclose(ops.stats_total(bs2), ops.stats_total(bstats), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,H,W,C", [(3, 14, 14, 144), (2, 9, 7, 2688), (5, 6, 6, 24), (2, 5, 5, 4352)])
+def test_lazy_batchnorm_records(ops, N, H, W, C):
+    """Consumer-side finalisation: dwconv_fwd / pool_act / bn_apply given the producer's statistics (trt_bn_fin_t) must
+    (a) compute what they compute from a finalised record, bit for bit, and (b) publish the same record and running
+    statistics trt_bn_finalize writes; affine2 given the backward sums (trt_bn_bwd_fin_t) must equal bn_bwd_finalize + affine2."""
+    HW = H * W
+    x = rnd(N, H, W, C, seed=41, dtype=bf16) * 1.3 + 0.4
+    gamma, beta = rnd(C, seed=42) * 0.1 + 1, rnd(C, seed=43) * 0.1
+    x2 = x.view(N * HW, C)
+    xd = x2.double()
+    stats = ops.new_stats(C, "cuda")
+    # spread the sums over the replicas the way producers do
+    for r in range(ops.STAT_REPLICAS):
+        part = xd[r::ops.STAT_REPLICAS]
+        stats[r] = torch.stack([part.sum(0), (part * part).sum(0)])
+
+    def fresh():
+        return (torch.full((C,), 0.25, device="cuda"), torch.full((C,), 2.0, device="cuda"), torch.zeros((), device="cuda", dtype=torch.int64),
+                torch.zeros(4, C, device="cuda"))
+    rm0, rv0, nbt0, rec0 = fresh()
+    ops.bn_finalize(stats, gamma, beta, rm0, rv0, nbt0, rec0, N * HW, 1e-3)
+
+    def check_published(rm, rv, nbt, rec):
+        assert torch.equal(rec, rec0) and torch.equal(rm, rm0) and torch.equal(rv, rv0) and int(nbt) == 1
+
+    # bn_apply (with residual)
+    res = rnd(N * HW, C, seed=44, dtype=bf16)
+    want = ops.bn_apply(x2, rec0, torch.empty_like(x2), residual=res, act=1)
+    rm, rv, nbt, rec = fresh()
+    got = ops.bn_apply(x2, rec, torch.empty_like(x2), residual=res, act=1,
+                       fin=ops.bn_fin(stats, gamma, beta, rm, rv, nbt, rec, N * HW, 1e-3))
+    assert torch.equal(got, want)
+    check_published(rm, rv, nbt, rec)
+    # pool_act
+    want = ops.pool_act(x2, rec0, torch.empty(N, C, device="cuda"), N, HW, act=1)
+    rm, rv, nbt, rec = fresh()
+    got = ops.pool_act(x2, rec, torch.empty(N, C, device="cuda"), N, HW, act=1, fin=ops.bn_fin(stats, gamma, beta, rm, rv, nbt, rec, N * HW, 1e-3))
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)       # atomics: summation order differs between launches
+    check_published(rm, rv, nbt, rec)
+    # dwconv_fwd with a lazy input BatchNorm
+    if C <= 2688:
+        w = rnd(C, 1, 3, 3, seed=45, scale=1 / 3)
+        st_a, st_b = ops.new_stats(C, "cuda"), ops.new_stats(C, "cuda")
+        want = ops.dwconv_fwd(x, rec0, w, torch.empty_like(x), N, H, W, 3, 1, stats=st_a)
+        rm, rv, nbt, rec = fresh()
+        got = ops.dwconv_fwd(x, rec, w, torch.empty_like(x), N, H, W, 3, 1, stats=st_b,
+                             in_fin=ops.bn_fin(stats, gamma, beta, rm, rv, nbt, rec, N * HW, 1e-3))
+        assert torch.equal(got, want)
+        check_published(rm, rv, nbt, rec)
+    # backward: affine2 with lazy coefficients
+    g = rnd(N * HW, C, seed=46, dtype=bf16)
+    bst = ops.new_stats(C, "cuda")
+    ops.bn_bwd_reduce(g, x2, rec0, bst)
+    coef, dg0, db0 = torch.empty(3, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd_finalize(bst, rec0, gamma, coef, dg0, db0, N * HW)
+    want = ops.affine2(g, x2, coef, torch.empty_like(x2))
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    got = ops.affine2(g, x2, None, torch.empty_like(x2), fin=ops.bn_bwd_fin(bst, rec0, gamma, dg, db, N * HW))
+    assert torch.equal(got, want) and torch.equal(dg, dg0) and torch.equal(db, db0)
 
 
 def test_bn_fold_eval_and_act0(ops):

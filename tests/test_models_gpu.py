@@ -271,15 +271,16 @@ def test_ensembles_mirror_reference_behaviour(T, tmp_path):
     assert me.predict(tmp_path / "empty_dir_that_does_not_exist")[0] is None
 
 
-def test_fused_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
-    """The optional fused BatchNorm finalisation (last block of the producing kernel finalises the record; off by default
-    because it measured slower) and Trainer.prefetch() must give the same training trajectory as the default path."""
+def test_separate_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
+    """The default path finalises every BatchNorm in the prologue of its first consumer (lazy records).  The round-1 path
+    (one finalise launch per BatchNorm, TEETHRT_LAZY_BN=0; three-pass SE/BatchNorm backward, TEETHRT_SE_BWD_MERGED=0) and
+    Trainer.prefetch() must give the same training trajectory."""
     from teethrt.modules import MMJointDualHead
     from teethrt.train import DualTaskTrainer
 
     def run(fuse, prefetch):
-        monkeypatch.setenv("TEETHRT_FUSE_BN_FWD", fuse)
-        monkeypatch.setenv("TEETHRT_FUSE_BN_BWD", fuse)
+        monkeypatch.setenv("TEETHRT_LAZY_BN", fuse)
+        monkeypatch.setenv("TEETHRT_SE_BWD_MERGED", fuse)
         torch.manual_seed(0)
         m = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).cuda()
         tr = DualTaskTrainer(m, t_max=10, graph=False)
@@ -292,10 +293,10 @@ def test_fused_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
             losses.append(float(loss))
         return losses, torch.cat([p.detach().flatten() for p in m.parameters()]).double()
 
-    l0, p0 = run("0", False)
-    l0b, p0b = run("0", False)               # run-to-run noise of the default path (atomic summation order, bf16 rounding)
-    l1, p1 = run("1", False)
-    l2, p2 = run("0", True)
+    l0, p0 = run("1", False)
+    l0b, p0b = run("1", False)               # run-to-run noise of the default path (atomic summation order, bf16 rounding)
+    l1, p1 = run("0", False)
+    l2, p2 = run("1", True)
     dl = lambda a, b: max(abs(x - y) for x, y in zip(a, b))
     dp = lambda a, b: float((a - b).norm() / a.norm())
     print("loss diffs", dl(l0, l0b), dl(l0, l1), dl(l0, l2), "param diffs", dp(p0, p0b), dp(p0, p1), dp(p0, p2))
