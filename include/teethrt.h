@@ -37,8 +37,10 @@ int trt_stat_replicas(void);
 /* Lazy BatchNorm records (consumer-side finalisation).  The kernel that PRODUCES a train-mode BatchNorm's input only
  * accumulates its statistics; the first kernel that CONSUMES the BatchNorm derives scale/shift for its own channel slice
  * from those statistics in its prologue, and one designated block also publishes the record (and the running statistics)
- * for every later consumer.  That removes the 4-5 us finalise launch that used to sit between each producer and consumer
- * (192 launches per B4 train step).  Host structs; every pointer inside is a device pointer. */
+ * for every later consumer.  That removes the 4-5 us finalise launch that used to sit between producer and consumer where
+ * the tensor is large; on small tensors the redundant per-block reads of the statistics would cost more than the launch, so
+ * the streaming entry points fall back to enqueueing the finalise kernel themselves (same arithmetic, same results).
+ * Host structs; every pointer inside is a device pointer. */
 typedef struct {
   const double* stats;             /* [TRT_STAT_REPLICAS][2][C] {sum, sum^2} of the BatchNorm's input, complete */
   const float* gamma;              /* [C] */
@@ -56,6 +58,8 @@ typedef struct {
   const float* gamma;              /* [C] */
   float* dgamma;                   /* [C] written */
   float* dbeta;                    /* [C] written */
+  float* coef;                     /* [3][C] scratch (optional): lets the callee finalise with a launch of its own when the
+                                      in-prologue form would cost more than it saves (small tensors, many blocks) */
   double count;
 } trt_bn_bwd_fin_t;
 

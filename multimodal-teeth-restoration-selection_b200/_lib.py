@@ -139,7 +139,7 @@ class BnFin(C.Structure):
 
 class BnBwdFin(C.Structure):
     """trt_bn_bwd_fin_t: lazy BatchNorm backward - trt_affine2 derives dx = a*dy + b*x + c from the sums and writes dgamma/dbeta."""
-    _fields_ = [("bstats", vp), ("rec", vp), ("gamma", vp), ("dgamma", vp), ("dbeta", vp), ("count", f64)]
+    _fields_ = [("bstats", vp), ("rec", vp), ("gamma", vp), ("dgamma", vp), ("dbeta", vp), ("coef", vp), ("count", f64)]
 
 
 class SeBn(C.Structure):

@@ -100,15 +100,23 @@ class _IRBlock(nn.Module):
 
 
 class _Arena:
-    """Bump allocator over one pre-zeroed tensor (per-BN statistics: one memset per pass instead of one per layer)."""
+    """Bump allocator over one pre-zeroed tensor (per-BN statistics: one memset per pass instead of one per layer).
+    Every slot starts on a 32-byte boundary (the kernels read them with 16- and 32-byte vector loads); `sizes` lists the
+    slots that will be taken, so the padding is part of the allocation."""
+    ALIGN = 8
 
-    def __init__(self, n, dtype, device):
-        self.buf = torch.zeros(n, dtype=dtype, device=device)
+    @classmethod
+    def _pad(cls, n):
+        return (n + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+
+    def __init__(self, sizes, dtype, device):
+        self.buf = torch.zeros(sum(self._pad(int(n)) for n in sizes), dtype=dtype, device=device)
         self.off = 0
 
     def take(self, n, shape=None):
         v = self.buf[self.off:self.off + n]
-        self.off += n
+        assert v.numel() == n, "teethrt: arena overflow (slot list and takes disagree)"
+        self.off += self._pad(n)
         return v.view(shape) if shape else v
 
 
@@ -312,8 +320,10 @@ class _LazyRec:
 
 
 def _lazy_bn():
-    """TEETHRT_LAZY_BN=0: separate bn_finalize / bn_bwd_finalize launches (the round-1 path; kept as the A/B switch)."""
-    return os.environ.get("TEETHRT_LAZY_BN", "1") != "0"
+    """TEETHRT_LAZY_BN bit mask: 1 = depthwise conv consumes its input's BatchNorm lazily, 2 = the streaming forward
+    consumers (pool_act / bn_apply), 4 = affine2 in the backward pass.  0 = one finalise launch per BatchNorm (round-1
+    path; the A/B switch).  Default 7: the library decides per call whether the in-prologue form pays."""
+    return int(os.environ.get("TEETHRT_LAZY_BN", "7"))
 
 
 def forward_train(enc, x, save=True):
@@ -339,22 +349,24 @@ def forward_train(enc, x, save=True):
             pack_pending[0] = False
     bns = dict(enc.bn_list())
     total_c = sum(b.weight.numel() for b in bns.values())
-    stats = _Arena(ops.STAT_REPLICAS * 2 * total_c, torch.float64, dev)
-    recs = _Arena(4 * total_c, torch.float32, dev)
+    chans = [b.weight.numel() for b in bns.values()]
+    stats = _Arena([ops.STAT_REPLICAS * 2 * c for c in chans], torch.float64, dev)
+    recs = _Arena([4 * c for c in chans], torch.float32, dev)
     ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
 
-    pool_arena = _Arena(N * sum(blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()) + N * enc.num_features,
+    pool_arena = _Arena([N * blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()] + [N * enc.num_features],
                         torch.float32, dev)                # every SE / global pooling target of the pass: one memset
 
     lazy = _lazy_bn()
 
-    def bn_stage(bn_name, count, st):
-        """The statistics `st` of BatchNorm `bn_name` have just been produced -> its (lazy) record."""
+    def bn_stage(bn_name, count, st, consumer=2):
+        """The statistics `st` of BatchNorm `bn_name` have just been produced -> its (lazy) record.  consumer: which kind
+        of kernel reads it first (1 = depthwise conv, 2 = pool_act / bn_apply)."""
         bn = bns[bn_name]
         c = bn.weight.numel()
         rec = recs.take(4 * c, (4, c))
         ctx["rec"][bn_name] = rec
-        if lazy:
+        if lazy & consumer:
             return _LazyRec(rec, ops.bn_fin(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                             bn.num_batches_tracked, rec, count, BN_EPS, BN_MOM))
         ops.bn_finalize(st, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.num_batches_tracked,
@@ -369,7 +381,9 @@ def forward_train(enc, x, save=True):
     w_stem = ops.stem_pack_w(enc.conv_stem.weight.detach(), torch.empty((cs, 32), device=dev, dtype=bf16))
     s_raw = torch.empty((N * h * w, cs), device=dev, dtype=bf16)
     ops.gemm(patches, w_stem, ops.EPI_STATS, stats=st, out=s_raw)
-    rec_s = bn_stage("bn1", N * h * w, st)
+    first = enc.block_list()[0][1].cfg
+    stem_to_dw = first["type"] == "ds" and not (first["s"] == 1 and first["cin"] == first["cout"])     # stem BN consumed by a depthwise conv
+    rec_s = bn_stage("bn1", N * h * w, st, 1 if stem_to_dw else 2)
     cur, cur_rec = s_raw, rec_s                                   # lazy: (raw, pending BN+SiLU)
     ctx["stem"] = dict(raw=s_raw, h=h, w=w, patches=patches)
     for name, blk in enc.block_list():
@@ -389,7 +403,7 @@ def forward_train(enc, x, save=True):
             need_packed()
             e_raw = torch.empty((N * h * w, cm), device=dev, dtype=bf16)
             ops.gemm(cur, Wp[name + ".conv_pw"][0], ops.EPI_STATS, stats=st, out=e_raw)
-            dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, bn_stage(name + ".bn1", N * h * w, st), name + ".bn2", name + ".conv_pwl", name + ".bn3"
+            dw_in, dw_rec, bn_dw, pw_name, bn_out = e_raw, bn_stage(name + ".bn1", N * h * w, st, 1), name + ".bn2", name + ".conv_pwl", name + ".bn3"
             sv["e_raw"] = e_raw
         else:
             cm = c["cin"]
@@ -508,12 +522,12 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
     N, Wp, REC = ctx["N"], ctx["Wp"], ctx["rec"]
     bns = dict(enc.bn_list())
     total_c = sum(b.weight.numel() for b in bns.values())
-    bstats = _Arena(ops.STAT_REPLICAS * 2 * total_c, torch.float64, dev)
+    bstats = _Arena([ops.STAT_REPLICAS * 2 * b.weight.numel() for b in bns.values()], torch.float64, dev)
     dfeat = dfeat.contiguous().float()
     sq = _SideQueue(dev)
 
     merged = os.environ.get("TEETHRT_SE_BWD_MERGED", "1") != "0"     # 0: round-1 path (reduce, act_bwd, affine2: three passes)
-    zeros = _Arena(sum(N * ((5 if merged else 1) * sv["d_raw"].shape[1] + blk.cfg["rd"]) for blk, sv in ctx["blocks"]),
+    zeros = _Arena([n for blk, sv in ctx["blocks"] for n in (N * (5 if merged else 1) * sv["d_raw"].shape[1], N * blk.cfg["rd"])],
                    torch.float32, dev)
 
     lazy = _lazy_bn()
@@ -524,9 +538,9 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
         the coefficients itself - no finalise launch in between."""
         bn = bns[bn_name]
         dgm, dbt = grads[bn_name + ".weight"], grads[bn_name + ".bias"]
-        if lazy:
-            return ops.affine2(g, x_raw, None, out, fin=ops.bn_bwd_fin(bst, REC[bn_name], bn.weight.detach(), dgm, dbt, count))
         coef = torch.empty((3, bn.weight.numel()), device=dev, dtype=torch.float32)
+        if lazy & 4:
+            return ops.affine2(g, x_raw, None, out, fin=ops.bn_bwd_fin(bst, REC[bn_name], bn.weight.detach(), dgm, dbt, count, coef))
         ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, dgm, dbt, count)
         return ops.affine2(g, x_raw, coef, out)
 

@@ -995,6 +995,23 @@ static int check_fin(const trt_bn_fin_t* f, const char* who) {
   return TRT_OK;
 }
 
+// A lazy prologue reads 16 fp64 words (128 bytes, L2 hits) per channel IN EVERY BLOCK.  On the wide, narrow-channel layers
+// that is a few MB in total and replaces a 4-5 us launch; on the 14x14 / 7x7 layers (hundreds of blocks x up to 2048
+// channels each) it is 100+ MB of redundant L2 reads, i.e. more than the tensor itself (measured: lazy everywhere was
+// 0.18 ms/step SLOWER than separate launches).  So the entry point decides: in-prologue while the redundant bytes stay
+// under ~24 MB (about 3 us of L2 bandwidth), otherwise it enqueues the finalise kernel itself in front of the consumer -
+// same arithmetic, same results either way.  TEETHRT_LAZY_FORCE=1 / 0 pins the choice (tests, A/B runs).
+static bool lazy_pays(long long blocks, int ch_per_block) {
+  const char* e = getenv("TEETHRT_LAZY_FORCE");
+  if (e && *e) return *e != '0';
+  return (size_t)blocks * (size_t)ch_per_block * 128u <= ((size_t)24 << 20);
+}
+static void finalize_now(const trt_bn_fin_t& f, int C, cudaStream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(f.stats, f.gamma, f.beta, f.running_mean, f.running_var,
+                                                          f.num_batches_tracked, f.rec, C, f.count, f.eps, f.momentum);
+  trt_count_launch(1);
+}
+
 extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residual, void* out, const trt_bn_fin_t* fin_host,
                             int rows, int C, int act, cudaStream_t stream) {
   CHECK_C(C);
@@ -1005,8 +1022,14 @@ extern "C" int trt_bn_apply(const void* x, const float* rec, const void* residua
   if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
+  int lazy = fin_host ? 1 : 0;
+  if (lazy && !lazy_pays((long long)grid.x * grid.y, L.VX * 8)) {
+    finalize_now(fin, C, stream);
+    rec = fin.rec;
+    lazy = 0;
+  }
   bn_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, (const uint4*)residual, (uint4*)out, rows, C, L.V, L.VX,
-                                            L.RY, act, fin_host ? 1 : 0, fin);
+                                            L.RY, act, lazy, fin);
   return trt_check_launch("trt_bn_apply");
 }
 
@@ -1023,7 +1046,13 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
-  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act, fin_host ? 1 : 0, fin);
+  int lazy = fin_host ? 1 : 0;
+  if (lazy && !lazy_pays((long long)grid.x * grid.y * grid.z, L.VX * 8)) {
+    finalize_now(fin, C, stream);
+    rec = fin.rec;
+    lazy = 0;
+  }
+  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act, lazy, fin);
   return trt_check_launch("trt_pool_act");
 }
 
@@ -1075,8 +1104,15 @@ extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, voi
   if (fin_host) fin = *fin_host;
   const Launch L = plan(C);
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
+  int lazy = fin_host ? 1 : 0;
+  if (lazy && fin.coef && !lazy_pays((long long)grid.x * grid.y, L.VX * 8)) {
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(fin.bstats, fin.rec, fin.gamma, fin.coef, fin.dgamma, fin.dbeta, C, fin.count);
+    trt_count_launch(1);
+    coef = fin.coef;
+    lazy = 0;
+  }
   affine2_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dy, (const uint4*)x, coef, (uint4*)out, rows, C, L.V, L.VX, L.RY,
-                                           fin_host ? 1 : 0, fin);
+                                           lazy, fin);
   return trt_check_launch("trt_affine2");
 }
 

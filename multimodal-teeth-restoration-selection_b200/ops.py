@@ -55,9 +55,10 @@ def bn_fin(stats, gamma, beta, rm, rv, nbt, rec, count, eps, momentum=0.1):
     return BnFin(ptr(stats), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), float(count), eps, momentum)
 
 
-def bn_bwd_fin(bstats, rec, gamma, dgamma, dbeta, count):
-    """Lazy BatchNorm backward: pass to affine2 instead of a coefficient tensor."""
-    return BnBwdFin(ptr(bstats), ptr(rec), ptr(gamma), ptr(dgamma), ptr(dbeta), float(count))
+def bn_bwd_fin(bstats, rec, gamma, dgamma, dbeta, count, coef=None):
+    """Lazy BatchNorm backward: pass to affine2 instead of a coefficient tensor.  coef: optional [3,C] scratch that lets the
+    library finalise with its own launch where that is cheaper (small tensors)."""
+    return BnBwdFin(ptr(bstats), ptr(rec), ptr(gamma), ptr(dgamma), ptr(dbeta), ptr(coef), float(count))
 
 
 def _ref(st):

@@ -201,11 +201,14 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd):
     assert torch.allclose(ops.stats_total(bs2), ops.stats_total(bstats), rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("force", ["1", "0"])
 @pytest.mark.parametrize("N,H,W,C", [(3, 14, 14, 144), (2, 9, 7, 2688), (5, 6, 6, 24), (2, 5, 5, 4352)])
-def test_lazy_batchnorm_records(ops, N, H, W, C):
+def test_lazy_batchnorm_records(ops, N, H, W, C, force, monkeypatch):
     """Consumer-side finalisation: dwconv_fwd / pool_act / bn_apply given the producer's statistics (trt_bn_fin_t) must
     (a) compute what they compute from a finalised record, bit for bit, and (b) publish the same record and running
-    statistics trt_bn_finalize writes; affine2 given the backward sums (trt_bn_bwd_fin_t) must equal bn_bwd_finalize + affine2."""
+    statistics trt_bn_finalize writes; affine2 given the backward sums (trt_bn_bwd_fin_t) must equal bn_bwd_finalize + affine2.
+    force = 1: the in-prologue form; force = 0: the entry point's own finalise launch (what it picks for small tensors)."""
+    monkeypatch.setenv("TEETHRT_LAZY_FORCE", force)
     HW = H * W
     x = rnd(N, H, W, C, seed=41, dtype=bf16) * 1.3 + 0.4
     gamma, beta = rnd(C, seed=42) * 0.1 + 1, rnd(C, seed=43) * 0.1
@@ -258,7 +261,7 @@ def test_lazy_batchnorm_records(ops, N, H, W, C):
     ops.bn_bwd_finalize(bst, rec0, gamma, coef, dg0, db0, N * HW)
     want = ops.affine2(g, x2, coef, torch.empty_like(x2))
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    got = ops.affine2(g, x2, None, torch.empty_like(x2), fin=ops.bn_bwd_fin(bst, rec0, gamma, dg, db, N * HW))
+    got = ops.affine2(g, x2, None, torch.empty_like(x2), fin=ops.bn_bwd_fin(bst, rec0, gamma, dg, db, N * HW, torch.empty(3, C, device="cuda")))
     assert torch.equal(got, want) and torch.equal(dg, dg0) and torch.equal(db, db0)
 
 
