@@ -158,6 +158,27 @@ int trt_enhance_rgb_u8(const uint8_t* img, int h, int w, int mode, float factor,
 int trt_affine_pil_u8(const uint8_t* img, int h, int w, int channels, const double* matrix_host, int bicubic,
                       const uint8_t* fill_host, uint8_t* out, trt_stream_t stream);
 
+/* Batched train transform (one DataLoader batch per call; experiments/multimodal_v1/train_mm_joint_dualtask.py:72-85 runs
+ * the same transform image by image inside DataLoader workers).  Job tables are DEVICE arrays the host fills after sampling:
+ *   crop job  : int32[8]  {top, left, h, w, flip, 0, 0, 0}  crop box inside the source image; flip mirrors the output
+ *   aug job   : 88 bytes  {i64 src, i64 dst, i32 op, i32 mode, f32 factor, i32 bicubic, f64 m[6], i32 slot, u8 fill[4]}
+ *               op 0 = lookup table luts[slot] (host-built: invert, posterize, solarize, solarize_add), 1 = histogram LUT
+ *               (mode 0 autocontrast, 1 equalize; built on the device into luts[slot]), 2 = ImageEnhance blend (mode 0..3 =
+ *               brightness, color, contrast, sharpness), 3 = Image.transform(AFFINE, m)
+ *   fin job   : 32 bytes  {i64 src, i32 top, left, eh, ew, i64 noise}  erase box (eh = 0: none) filled from fp32 noise[3][S][S]
+ * trt_crop_resize_batch_u8: src [n,h,w,3] -> out [n,size,size,3] = img.crop(box).resize(size) (+ horizontal flip), Pillow-exact;
+ *   bounds int32 [n][2][size][2], coeffs int32 [n][2][size][kmax], tmp uint8 [n][hmax][size][3] are caller scratch
+ *   (kmax = 2*ceil(support * max(1, hmax_or_wmax / size)) + 1, hmax >= every crop height).
+ * trt_aug_layer_batch_u8: one RandAugment layer over `njobs` images (S x S x 3 each); hist u64 [njobs][768] and luma u64
+ *   [njobs] must be zeroed by the caller when need_stats (some job is op 1 or contrast).
+ * trt_normalize_erase_batch: ToTensor + Normalize (+ RandomErasing 'pixel') -> dst [n,3,S,S] fp32 or bf16. */
+int trt_crop_resize_batch_u8(const uint8_t* src, int n, int h, int w, const void* crop_jobs, int size, int bicubic, int kmax,
+                             int hmax, int* bounds, int* coeffs, uint8_t* tmp, uint8_t* out, trt_stream_t stream);
+int trt_aug_layer_batch_u8(const void* aug_jobs, int njobs, int size, int need_stats, unsigned long long* hist,
+                           unsigned long long* luma, uint8_t* luts, trt_stream_t stream);
+int trt_normalize_erase_batch(const void* fin_jobs, int n, int size, void* dst, int out_bf16, trt_stream_t stream);
+int trt_aug_job_bytes(void);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm / squeeze-excite / pooling kernels around the GEMMs (NHWC bf16, rows = N*H*W, C % 8 == 0).
  * Replace timm's BatchNormAct2d, SqueezeExcite and global_pool inside `self.backbone(x_img)`

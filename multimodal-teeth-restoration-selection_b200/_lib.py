@@ -115,6 +115,10 @@ _SIGS = {
     "trt_lut_apply_u8": (i32, [vp, vp, sz, i32, vp, vp]),
     "trt_enhance_rgb_u8": (i32, [vp, i32, i32, i32, f32, vp, vp, vp]),
     "trt_affine_pil_u8": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp]),
+    "trt_crop_resize_batch_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "trt_aug_layer_batch_u8": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
+    "trt_normalize_erase_batch": (i32, [vp, i32, i32, vp, i32, vp]),
+    "trt_aug_job_bytes": (i32, []),
     "trt_temperature_nll": (i32, [vp, vp, vp, vp, i32, vp]),
     "trt_scaled_sigmoid": (i32, [vp, f32, vp, i32, vp]),
     "trt_binary_metrics": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),

@@ -259,3 +259,234 @@ class TrainTransform:
                 x[:, top:top + eh, left:left + ew] = torch.empty((c, eh, ew), device=x.device, dtype=torch.float32).normal_(generator=self.gen).to(x.dtype)
                 break
         return x
+
+
+# ================================================================================================= batched transform
+# The reference runs the transform above image by image inside DataLoader workers (train_mm_joint_dualtask.py:72-85,211).
+# At 5,000+ images/s per GPU that is the bottleneck again, so the batch form below takes one uint8 batch [B,H,W,3] on the
+# device and runs every stage as ONE launch over the images that need it: the host only samples (vectorised numpy) and
+# fills three small job tables that are uploaded in one copy.  The kernels call the same per-pixel code as the
+# single-image path, so `apply(batch, plan)` equals running `TrainTransform`'s operations image by image with the same
+# draws (tests/test_augment_gpu.py) - and that path is pinned to Pillow.  Sampling parity with timm stays UNPINNED.
+_AUG_JOB = np.dtype([("src", "<i8"), ("dst", "<i8"), ("op", "<i4"), ("mode", "<i4"), ("factor", "<f4"), ("bicubic", "<i4"),
+                     ("m", "<f8", (6,)), ("slot", "<i4"), ("fill", "u1", (4,))], align=True)
+_FIN_JOB = np.dtype([("src", "<i8"), ("top", "<i4"), ("left", "<i4"), ("eh", "<i4"), ("ew", "<i4"), ("noise", "<i8")], align=True)
+_ENHANCE_MODE = {"BrightnessIncreasing": 0, "ColorIncreasing": 1, "ContrastIncreasing": 2, "SharpnessIncreasing": 3}
+_POINT = {"Invert": "invert", "PosterizeIncreasing": "posterize", "SolarizeIncreasing": "solarize", "SolarizeAdd": "solarize_add"}
+
+
+class BatchPlan:
+    """Everything random about one batch, drawn on the host: crop boxes + flips, per layer (op, args) or None, erase boxes."""
+
+    def __init__(self, boxes, flips, layers, erase):
+        self.boxes, self.flips, self.layers, self.erase = boxes, flips, layers, erase
+
+
+class BatchTrainTransform:
+    """timm's training transform for a whole batch: uint8 RGB [B,H,W,3] (CUDA tensor, or numpy / pinned tensor that is
+    uploaded) -> normalised [B,3,S,S] fp32 / bf16 CUDA tensor."""
+
+    def __init__(self, img_size, re_prob=0.2, dtype=torch.bfloat16, seed=None, magnitude=9.0, magnitude_std=0.5, num_layers=2,
+                 prob=0.5, scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0)):
+        from ._lib import lib
+        assert _AUG_JOB.itemsize == lib.trt_aug_job_bytes(), "AugJob layout out of sync with augment.cu"
+        self.size, self.re_prob, self.dtype = int(img_size), float(re_prob), dtype
+        self.magnitude, self.magnitude_std, self.num_layers, self.prob = magnitude, magnitude_std, num_layers, prob
+        self.scale, self.ratio = scale, ratio
+        self.rng = np.random.RandomState(seed)
+        self.gen, self.seed = None, seed
+        self._bufs = {}
+
+    # ---- sampling: one vectorised pass over the batch -------------------------------------------------------------
+    def sample(self, B, H, W):
+        r = self.rng
+        S = self.size
+        # RandomResizedCropAndInterpolation.get_params: first of 10 attempts that fits, else the central fallback
+        area = H * W
+        ta = r.uniform(self.scale[0], self.scale[1], (B, 10)) * area
+        asp = np.exp(r.uniform(math.log(self.ratio[0]), math.log(self.ratio[1]), (B, 10)))
+        cw = np.rint(np.sqrt(ta * asp)).astype(np.int64)
+        ch = np.rint(np.sqrt(ta / asp)).astype(np.int64)
+        ok = (cw <= W) & (ch <= H) & (cw > 0) & (ch > 0)
+        first = np.where(ok.any(1), ok.argmax(1), -1)
+        in_ratio = W / H
+        if in_ratio < min(self.ratio):
+            fw, fh = W, int(round(W / min(self.ratio)))
+        elif in_ratio > max(self.ratio):
+            fh, fw = H, int(round(H * max(self.ratio)))
+        else:
+            fw, fh = W, H
+        idx = np.arange(B)
+        bw = np.where(first >= 0, cw[idx, np.maximum(first, 0)], fw)
+        bh = np.where(first >= 0, ch[idx, np.maximum(first, 0)], fh)
+        top = np.where(first >= 0, np.floor(r.uniform(0, 1, B) * (H - bh + 1)).astype(np.int64), (H - bh) // 2)
+        left = np.where(first >= 0, np.floor(r.uniform(0, 1, B) * (W - bw + 1)).astype(np.int64), (W - bw) // 2)
+        boxes = np.stack([top, left, bh, bw], 1).astype(np.int32)
+        flips = r.uniform(0, 1, B) < 0.5
+        # RandAugment 'rand-m9-mstd0.5-inc1'
+        names = r.choice(len(RAND_INCREASING_TRANSFORMS), (B, self.num_layers), replace=True)
+        applied = r.uniform(0, 1, (B, self.num_layers)) <= self.prob if self.prob < 1.0 else np.ones((B, self.num_layers), bool)
+        mags = np.clip(r.normal(self.magnitude, self.magnitude_std, (B, self.num_layers)) if self.magnitude_std > 0
+                       else np.full((B, self.num_layers), self.magnitude), 0.0, _LEVEL_DENOM)
+        signs = r.uniform(0, 1, (B, self.num_layers))
+
+        class _Sign:                                   # _level_args draws the sign through rng.random()
+            def __init__(self, v):
+                self.v = v
+
+            def random(self):
+                return self.v
+        layers = []
+        for l in range(self.num_layers):
+            layer = []
+            for b in range(B):
+                if not applied[b, l]:
+                    layer.append(None)
+                    continue
+                name = RAND_INCREASING_TRANSFORMS[names[b, l]]
+                layer.append((name, _level_args(name, float(mags[b, l]), _Sign(float(signs[b, l])))))
+            layers.append(layer)
+        # RandomErasing(p, mode='pixel', one box, 10 attempts)
+        erase = np.zeros((B, 4), np.int32)
+        do = r.uniform(0, 1, B) <= self.re_prob
+        et = r.uniform(0.02, 1 / 3, (B, 10)) * (S * S)
+        ea = np.exp(r.uniform(math.log(0.3), math.log(1 / 0.3), (B, 10)))
+        eh = np.rint(np.sqrt(et * ea)).astype(np.int64)
+        ew = np.rint(np.sqrt(et / ea)).astype(np.int64)
+        eok = (ew < S) & (eh < S)
+        ef = np.where(eok.any(1), eok.argmax(1), -1)
+        u1, u2 = r.uniform(0, 1, B), r.uniform(0, 1, B)
+        for b in np.nonzero(do & (ef >= 0))[0]:
+            h_, w_ = int(eh[b, ef[b]]), int(ew[b, ef[b]])
+            erase[b] = (int(u1[b] * (S - h_ + 1)), int(u2[b] * (S - w_ + 1)), h_, w_)
+        return BatchPlan(boxes, flips, layers, erase)
+
+    # ---- execution ------------------------------------------------------------------------------------------------
+    def _scratch(self, dev, B, H, S, kmax):
+        key = (str(dev), B, H, S, kmax)
+        if key not in self._bufs:
+            u8 = lambda *s: torch.empty(s, device=dev, dtype=torch.uint8)
+            self._bufs = {key: dict(bounds=torch.empty((B, 2, S, 2), device=dev, dtype=torch.int32),
+                                    coeffs=torch.empty((B, 2, S, kmax), device=dev, dtype=torch.int32),
+                                    tmp=u8(B, H, S, 3), a=u8(B, S, S, 3), b=u8(B, S, S, 3),
+                                    luts=u8(2 * B, 768), stats=torch.zeros(2 * B * 769, device=dev, dtype=torch.int64))}
+        return self._bufs[key]
+
+    def apply(self, imgs, plan):
+        from ._lib import lib, check, stream as cur_stream
+        if isinstance(imgs, np.ndarray):
+            imgs = torch.from_numpy(imgs)
+        imgs = imgs.cuda(non_blocking=True) if not imgs.is_cuda else imgs
+        if imgs.dtype != torch.uint8 or imgs.dim() != 4 or imgs.shape[3] != 3:
+            raise ValueError("expected a uint8 RGB batch [B,H,W,3]")
+        imgs = imgs.contiguous()
+        B, H, W, _ = imgs.shape
+        S, dev = self.size, imgs.device
+        hmax, wmax = int(plan.boxes[:, 2].max()), int(plan.boxes[:, 3].max())
+        kmax = int(math.ceil(2.0 * max(1.0, max(hmax, wmax) / S))) * 2 + 1
+        sc = self._scratch(dev, B, H, S, kmax)
+        bufs = (sc["a"], sc["b"])
+        cur = np.zeros(B, np.int64)                                        # which buffer holds image b right now
+        base = [t.data_ptr() for t in bufs]
+        img_bytes = S * S * 3
+        # ---- job tables (host), one upload
+        crop = np.zeros((B, 8), np.int32)
+        crop[:, :4] = plan.boxes
+        crop[:, 4] = plan.flips
+        layer_jobs, luts_host, fallbacks = [], np.zeros((2 * B, 768), np.uint8), []
+        slot = 0
+        for l, layer in enumerate(plan.layers):
+            jobs, need_stats = [], False
+            for b, item in enumerate(layer):
+                if item is None:
+                    continue
+                name, args = item
+                j = np.zeros((), _AUG_JOB)
+                j["slot"] = slot
+                if name in _POINT:
+                    if name == "PosterizeIncreasing" and args[0] >= 8:
+                        continue                                           # Pillow returns the image unchanged
+                    j["op"] = 0
+                    luts_host[slot] = np.tile(point_table(_POINT[name], *args), 3)
+                elif name in ("AutoContrast", "Equalize"):
+                    j["op"], j["mode"], need_stats = 1, int(name == "Equalize"), True
+                elif name in _ENHANCE_MODE:
+                    j["op"], j["mode"], j["factor"] = 2, _ENHANCE_MODE[name], args[0]
+                    need_stats |= name == "ContrastIncreasing"
+                else:
+                    if name == "Rotate":
+                        m = rotation_matrix(S, S, args[0])
+                        if m is None:                                      # exact multiples of 90 degrees: Pillow's transpose paths
+                            fallbacks.append((l, b, args[0]))
+                            continue
+                    elif name == "ShearX":
+                        m = (1, args[0], 0, 0, 1, 0)
+                    elif name == "ShearY":
+                        m = (1, 0, 0, args[0], 1, 0)
+                    elif name == "TranslateXRel":
+                        m = (1, 0, args[0] * S, 0, 1, 0)
+                    else:
+                        m = (1, 0, 0, 0, 1, args[0] * S)
+                    j["op"], j["bicubic"], j["m"] = 3, 1, m
+                    j["fill"][:3] = IMG_MEAN_FILL
+                j["src"] = base[cur[b]] + b * img_bytes
+                cur[b] ^= 1
+                j["dst"] = base[cur[b]] + b * img_bytes
+                jobs.append((b, j))
+                slot += 1
+            layer_jobs.append((jobs, need_stats))
+        # erase noise only for the images that erase
+        er = np.nonzero(plan.erase[:, 2] > 0)[0]
+        noise = None
+        if len(er):
+            if self.gen is None:
+                self.gen = torch.Generator(device=dev)
+                if self.seed is not None:
+                    self.gen.manual_seed(self.seed + 2)
+            noise = torch.empty((len(er), 3, S, S), device=dev, dtype=torch.float32).normal_(generator=self.gen)
+        # rotate fast paths are rare (the magnitude is continuous): run them between the layers on the single-image op
+        table = [crop.tobytes()] + [b"".join(j.tobytes() for _, j in jobs) for jobs, _ in layer_jobs]
+        offs = np.cumsum([0] + [len(t) for t in table])
+        fin_off = int(offs[-1])
+        blob = torch.empty(fin_off + B * _FIN_JOB.itemsize, dtype=torch.uint8).pin_memory()
+        host = blob.numpy()
+        for t, o in zip(table, offs[:-1]):
+            host[o:o + len(t)] = np.frombuffer(t, np.uint8)
+        # the fin jobs depend on the final buffer of every image (known now that all layers are planned)
+        for l, b, deg in fallbacks:
+            cur[b] ^= 1
+        fin = np.zeros(B, _FIN_JOB)
+        fin["src"] = [base[cur[b]] + b * img_bytes for b in range(B)]
+        fin["top"], fin["left"], fin["eh"], fin["ew"] = plan.erase.T
+        for i, b in enumerate(er):
+            fin["noise"][b] = noise[i].data_ptr()
+        host[fin_off:] = np.frombuffer(fin.tobytes(), np.uint8)
+        dblob = blob.to(dev, non_blocking=True)
+        dluts = sc["luts"]
+        dluts.copy_(torch.from_numpy(luts_host), non_blocking=True)
+        p0 = dblob.data_ptr()
+        st = cur_stream()
+        check(lib.trt_crop_resize_batch_u8(imgs.data_ptr(), B, H, W, p0, S, 1, kmax, hmax, sc["bounds"].data_ptr(),
+                                           sc["coeffs"].data_ptr(), sc["tmp"].data_ptr(), sc["a"].data_ptr(), st))
+        state = np.zeros(B, np.int64)
+        for l, (jobs, need_stats) in enumerate(layer_jobs):
+            if jobs:
+                if need_stats:
+                    sc["stats"].zero_()
+                hist, luma = sc["stats"].data_ptr(), sc["stats"].data_ptr() + 2 * B * 768 * 8
+                check(lib.trt_aug_layer_batch_u8(p0 + int(offs[1 + l]), len(jobs), S, int(need_stats), hist, luma, dluts.data_ptr(), st))
+                for b, _ in jobs:
+                    state[b] ^= 1
+            for fl, b, deg in fallbacks:
+                if fl == l:
+                    src = bufs[state[b]][b]
+                    state[b] ^= 1
+                    bufs[state[b]][b].copy_(rotate(src, deg))
+        out = torch.empty((B, 3, S, S), device=dev, dtype=self.dtype)
+        check(lib.trt_normalize_erase_batch(p0 + fin_off, B, S, out.data_ptr(), int(self.dtype == torch.bfloat16), st))
+        self._keep = (dblob, noise, imgs)             # alive until the next call: the launches above read them asynchronously
+        return out
+
+    def __call__(self, imgs):
+        B, H, W = imgs.shape[:3]
+        return self.apply(imgs, self.sample(B, H, W))

@@ -107,3 +107,44 @@ TRT_HD void pil_equalize_lut(const long long* h, uint8_t* lut) {
     n += h[i];
   }
 }
+
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc (Resample.c) for ONE output index of an axis resize in_size -> out_size:
+// the taps [*first, *first + n) and their 22-bit fixed-point weights k[0..n), k[n..kmax) = 0.  Same double arithmetic and
+// evaluation order as the C source (and as teethrt.preproc.pil_coeffs, which is pinned to Pillow).  Returns n.
+TRT_HD double pil_filter(double x, int bicubic) {
+  if (x < 0.0) x = -x;
+  if (bicubic) {
+    const double a = -0.5;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+  }
+  return x < 1.0 ? 1.0 - x : 0.0;
+}
+TRT_HD int pil_resample_taps(int in_size, int out_size, int bicubic, int xx, int kmax, int* first, int* k) {
+  const double scale = (double)in_size / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = (bicubic ? 2.0 : 1.0) * filterscale;
+  const double ss = 1.0 / filterscale;
+  const double center = (xx + 0.5) * scale;
+  int xmin = (int)(center - support + 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)(center + support + 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  if (xmax > kmax) xmax = kmax;                     // cannot happen when kmax = ceil(support) * 2 + 1
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) ww += pil_filter((x + xmin - center + 0.5) * ss, bicubic);
+  const double one = (double)(1 << 22);
+  for (int x = 0; x < kmax; ++x) {
+    if (x < xmax) {
+      double w = pil_filter((x + xmin - center + 0.5) * ss, bicubic);
+      if (ww != 0.0) w = w / ww;
+      k[x] = w < 0 ? (int)(-0.5 + w * one) : (int)(0.5 + w * one);
+    } else {
+      k[x] = 0;
+    }
+  }
+  *first = xmin;
+  return xmax;
+}

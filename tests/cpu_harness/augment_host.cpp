@@ -37,3 +37,8 @@ void h_hist_lut(const uint8_t* img, long n_px, int ch, int mode, uint8_t* lut) {
   }
 }
 }
+
+// Pillow's resampling taps of one output index (the device builds the batched crop tables with this function)
+extern "C" int h_resample_taps(int in_size, int out_size, int bicubic, int xx, int kmax, int* first, int* k) {
+  return pil_resample_taps(in_size, out_size, bicubic, xx, kmax, first, k);
+}

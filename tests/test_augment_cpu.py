@@ -109,3 +109,19 @@ def test_pillow_transpose_fast_paths_are_rot90():
     for deg in (90.0, 180.0, 270.0, -90.0):
         k = int(round((deg % 360.0) / 90.0))
         assert np.array_equal(torch.rot90(torch.from_numpy(a), k, dims=(0, 1)).numpy(), np.asarray(im.rotate(deg, Image.BICUBIC, fillcolor=RA.FILL)))
+
+
+def test_device_coefficient_routine_equals_pillow_tables(host):
+    """The batched crop+resize builds its per-image coefficient tables ON THE DEVICE with pil_resample_taps (augment_core.h).
+    Compiled for the host it must reproduce teethrt.preproc.pil_coeffs, the table builder that tests/test_pil_resample_cpu.py
+    pins to Pillow's own resize, for up- and down-scaling and both filters."""
+    import teethrt  # noqa: F401  (import alias)
+    from teethrt.preproc import pil_coeffs
+    host.h_resample_taps.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for in_size, out_size in [(512, 224), (433, 224), (97, 160), (224, 224), (1024, 224), (60, 224), (354, 96), (7, 3)]:
+        for interp in ("bicubic", "bilinear"):
+            b, c, ks = pil_coeffs(in_size, out_size, interp)
+            first, k = C.c_int(), (C.c_int * ks)()
+            for xx in range(out_size):
+                n = host.h_resample_taps(in_size, out_size, int(interp == "bicubic"), xx, ks, C.byref(first), k)
+                assert (first.value, n) == tuple(b[xx]) and list(k) == list(c[xx]), (in_size, out_size, interp, xx)

@@ -79,3 +79,43 @@ def test_randaugment_policy_and_train_transform(A):
     assert erased >= 25
     bf = A.TrainTransform(96, dtype=torch.bfloat16, seed=1)(img)
     assert bf.dtype == torch.bfloat16 and bf.shape == (3, 96, 96)
+
+
+@pytest.mark.parametrize("B,H,W,S", [(12, 300, 451, 224), (7, 512, 512, 96), (5, 130, 97, 160)])
+def test_batched_train_transform_equals_the_per_image_path(A, B, H, W, S):
+    """One launch per stage over the whole batch must give, bit for bit, what the single-image operations (pinned to Pillow
+    above) give when they replay the same draws: crop + resize, flip, two RandAugment layers, ToTensor + Normalize; inside an
+    erase box the pixels are the noise, outside they are untouched."""
+    from teethrt.preproc import resized_crop, normalize_flip
+    rng = np.random.RandomState(B)
+    imgs = rng.randint(0, 256, (B, H, W, 3), dtype=np.uint8)
+    imgs[0] = (np.add.outer(np.arange(H), np.arange(W))[:, :, None] % 256).astype(np.uint8)      # a smooth image: LUT / equalize paths
+    seen = set()
+    for seed in range(6):
+        tf = A.BatchTrainTransform(S, re_prob=0.5, dtype=torch.float32, seed=seed)
+        plan = tf.sample(B, H, W)
+        out = tf.apply(imgs, plan)
+        assert out.shape == (B, 3, S, S) and out.dtype == torch.float32 and torch.isfinite(out).all()
+        for b in range(B):
+            top, left, ch, cw = (int(v) for v in plan.boxes[b])
+            x = resized_crop(imgs[b], top, left, ch, cw, S, "bicubic")
+            if plan.flips[b]:
+                x = torch.flip(x, dims=[1]).contiguous()
+            for layer in plan.layers:
+                if layer[b] is not None:
+                    name, args = layer[b]
+                    seen.add(name)
+                    x = A._OP_FN[name](x, *args, resample="bicubic", fillcolor=A.IMG_MEAN_FILL)
+            want = normalize_flip(torch.flip(x, dims=[2]).contiguous(), 0, dtype=torch.float32)
+            et, el, eh, ew = (int(v) for v in plan.erase[b])
+            mask = torch.ones(S, S, dtype=torch.bool, device="cuda")
+            mask[et:et + eh, el:el + ew] = False
+            assert torch.equal(out[b][:, mask], want[:, mask]), (seed, b, plan.layers[0][b], plan.layers[1][b])
+            if eh:
+                box = out[b][:, et:et + eh, el:el + ew]
+                assert not torch.equal(box, want[:, et:et + eh, el:el + ew]) and float(box.std()) > 0.5
+    assert len(seen) >= 12
+    # determinism, dtype, device-tensor input
+    a = A.BatchTrainTransform(S, seed=3)(torch.from_numpy(imgs).cuda())
+    b_ = A.BatchTrainTransform(S, seed=3)(imgs)
+    assert a.dtype == torch.bfloat16 and torch.equal(a, b_)

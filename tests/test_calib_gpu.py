@@ -223,8 +223,10 @@ def test_trainer_handles_ragged_batches(cal):
         runs.append((losses, torch.cat([p.detach().flatten() for p in m.parameters()]).cpu()))
     (l0, p0), (l1, p1) = runs
     # same trajectory: tight while the runs are still close, loose once atomics-order noise has been amplified by 13
-    # tiny-batch BatchNorm steps
-    assert max(abs(a - b) for a, b in zip(l0[:5], l1[:5])) < 1e-2 and max(abs(a - b) for a, b in zip(l0, l1)) < 6e-2, (l0, l1)
+    # tiny-batch BatchNorm steps.  (Steps 0 and 1 are eager in BOTH runs and already differ by up to 3e-3 - two eager runs of
+    # a B0 at 64 px, whose last stages normalise 32 values per channel, are that far apart; measured up to 1.2e-2 at step 2.)
+    assert abs(l0[0] - l1[0]) < 2e-3, (l0[0], l1[0])
+    assert max(abs(a - b) for a, b in zip(l0[:5], l1[:5])) < 2.5e-2 and max(abs(a - b) for a, b in zip(l0, l1)) < 6e-2, (l0, l1)
     # AdamW moves a weight by up to lr per step whatever the gradient's size, so single weights whose gradient is pure
     # atomics-order noise differ by up to 2*lr*steps; the bulk must agree far better than that
     assert (p0 - p1).abs().mean() < 5e-4 and (p0 - p1).abs().max() <= 2 * 3e-4 * len(batches)

@@ -142,5 +142,38 @@ tf = augment.TrainTransform(224, seed=0)
 big_dev = torch.from_numpy(big).cuda()
 out.append({"what": "f2_train_transform_512_to_224", "device_resident_ms": wall(lambda: tf(big_dev), n=30) * 1e3,
             "host_in_ms": wall(lambda: tf(big), n=30) * 1e3})
+# f2, batched: one DataLoader batch (64 images, 512x512 uint8, the size src/preprocessing writes) per call, every stage one
+# launch; beside (a) the per-image device path above looped over the batch and (b) the same transform on PIL images on the
+# host (RandomResizedCrop bicubic + flip + the policy's Pillow ops + ToTensor/Normalize: what timm's transform does per image
+# inside a DataLoader worker), one host thread
+batch = np.random.RandomState(2).randint(0, 256, (64, 512, 512, 3), dtype=np.uint8)
+batch_pin = torch.from_numpy(batch).pin_memory()
+batch_dev = batch_pin.cuda()
+btf = augment.BatchTrainTransform(224, seed=0)
+plan = btf.sample(64, 512, 512)
+t_sample = wall(lambda: btf.sample(64, 512, 512), n=20)
+t_dev = wall(lambda: btf(batch_dev), n=20)
+t_host = wall(lambda: btf(batch_pin), n=20)
+t_loop = wall(lambda: [tf(batch_dev[i]) for i in range(64)], n=3, warm=1)
+from torchvision.transforms import functional as TF
+
+
+def pil_one(i):
+    im = Image.fromarray(batch[i])
+    top, left, ch, cw = (int(v) for v in plan.boxes[i])
+    im = TF.resized_crop(im, top, left, ch, cw, [224, 224], interpolation=transforms.InterpolationMode.BICUBIC)
+    if plan.flips[i]:
+        im = TF.hflip(im)
+    for layer in plan.layers:
+        if layer[i] is not None:
+            im = RA.OPS[layer[i][0]](im, *layer[i][1])
+    return TF.normalize(TF.to_tensor(im), (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+
+
+t_pil = wall(lambda: [pil_one(i) for i in range(16)], n=3, warm=1) * 4
+out.append({"what": "f2_train_transform_batch64_512_to_224", "device_resident_ms": t_dev * 1e3, "pinned_host_in_ms": t_host * 1e3,
+            "host_sampling_ms": t_sample * 1e3, "images_per_s_device_resident": 64 / t_dev, "images_per_s_host_in": 64 / t_host,
+            "per_image_device_loop_ms": t_loop * 1e3, "cpu_reference_pil_one_thread_ms": t_pil * 1e3,
+            "h2d_bytes": int(batch.nbytes), "note": "sampling parity with timm unpinned; pixels Pillow-exact"})
 for o in out:
     print(json.dumps(o))
