@@ -359,6 +359,54 @@ def run_ours(args):
         timed_steps += n_sus
     del dev_batches
 
+    # ---- end to end from uint8 images (N = 1): pinned uint8 batch -> H2D -> batched train transform on the device
+    # (RandomResizedCrop + flip + RandAugment + normalise + erase, teethrt.augment.BatchTrainTransform) -> step -> D2H loss.
+    # What the reference's DataLoader workers do on the host per image (train_mm_joint_dualtask.py:72-85) runs here as ~10
+    # launches per batch, and the copy is 12.6 MB of uint8 instead of 38.5 MB of fp32.
+    e2e_u8 = None
+    if world == 1 and not args.no_u8:
+        from teethrt.augment import BatchTrainTransform
+        import numpy as np
+        SRC = 256
+        rs = np.random.RandomState(7)
+        u8_batches = [torch.from_numpy(rs.randint(0, 256, (per_gpu, SRC, SRC, 3), dtype=np.uint8)).pin_memory() for _ in range(2)]
+        small = [[t.pin_memory() for t in synth_batch(per_gpu, 3000 + i)[1:]] for i in range(2)]
+        btf = BatchTrainTransform(IMG, dtype=torch.bfloat16, seed=11)
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def u8_step(i):
+            with torch.cuda.stream(copy_stream):
+                raw = u8_batches[i % 2].to(dev, non_blocking=True)
+                rest = [t.to(dev, non_blocking=True) for t in small[i % 2]]
+            main = torch.cuda.current_stream(dev)
+            main.wait_stream(copy_stream)
+            for t in [raw] + rest:
+                t.record_stream(main)            # allocated on the copy stream, read on the main stream
+            x = btf(raw)
+            tr.step(x, *rest)
+            return tr.loss_async()
+        for i in range(4):                      # new input dtype (bf16) -> its own plan: eager warm-up + capture
+            tr.loss_value(u8_step(i))
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        pending = None
+        for i in range(args.steps):
+            ticket = u8_step(i)
+            if pending is not None:
+                last_u8 = tr.loss_value(pending)
+            pending = ticket
+        last_u8 = tr.loss_value(pending)
+        e5.record()
+        barrier()
+        t_u8 = e4.elapsed_time(e5) * 1e-3
+        e2e_u8 = {"value": per_gpu * args.steps / t_u8, "unit": "images/s", "ms_per_step": t_u8 / args.steps * 1e3,
+                  "h2d_bytes_per_step": int(u8_batches[0].numel()) + sum(t.numel() * 4 for t in small[0]), "d2h_bytes_per_step": 4,
+                  "last_loss": last_u8,
+                  "what": f"pinned uint8 [{per_gpu},{SRC},{SRC},3] -> H2D -> BatchTrainTransform({IMG}) on the device -> DualTaskTrainer.step -> loss "
+                          "read back; transform sampling on the host (vectorised), pixels Pillow-exact, sampling parity with timm unpinned"}
+        timed_steps += args.steps
+
     # ---- weak-scaling arm of round 1 (64 per GPU at every N), when the main line ran another per-GPU batch
     weak = None
     if world > 1 and per_gpu != BATCH and args.batch <= 0:
@@ -423,6 +471,8 @@ def run_ours(args):
             "cpu_baseline": cpu}
     if sustained is not None:
         line["sustained"] = sustained
+    if e2e_u8 is not None:
+        line["e2e_u8_transform"] = e2e_u8
     if weak is not None:
         line["weak_scaling"] = weak
     if ddp_identical is not None:
@@ -545,6 +595,7 @@ def main():
     ap.add_argument("--infer", action="store_true", help="batch-1 inference latency instead of the train step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true", help="skip the batch-1 inference leg of the default line (N=1)")
+    ap.add_argument("--no-u8", action="store_true", help="skip the uint8 -> device train transform -> step end-to-end leg (N=1)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: 64 at N=1, 512/N at N>1)")
     ap.add_argument("--sustain-seconds", type=float, default=5.0, help="length of the sustained arm at N=1 (0 = skip)")
     args = ap.parse_args()
