@@ -257,10 +257,12 @@ int trt_pack_w1x1_batch(const long long* table_dev, int count, int total_tiles, 
  * Weights and weight gradients stay in torch layout ([C,1,k,k] / [CS,3,3,3], fp32).
  * ------------------------------------------------------------------------------------------------------------------ */
 /* x: [N,H,W,C]; in_rec != NULL: input = silu(bn(x)) applied on load; out_rec != NULL (eval): out = silu(bn_out(conv)),
- * pooled_sum[n,c] (optional, zeroed here) += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output.
+ * pooled_sum[n,c] (optional; zeroed here unless pooled_zeroed: one arena memset per forward instead of one per block)
+ * += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output.
  * in_fin_host (optional): the INPUT's BatchNorm is lazy - in_rec is derived from in_fin_host->stats and published. */
 int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec, float* pooled_sum,
-                   double* stats, const trt_bn_fin_t* in_fin_host, int N, int H, int W, int C, int k, int s, trt_stream_t stream);
+                   int pooled_zeroed, double* stats, const trt_bn_fin_t* in_fin_host, int N, int H, int W, int C, int k, int s,
+                   trt_stream_t stream);
 /* gy = dD, the gradient w.r.t. the RAW depthwise output (the BN-backward affine of the following BatchNorm has already been
  * applied by trt_affine2).  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1), bstats += {sum g, sum g*xhat};
  * dw[C,1,k,k] (NULL = skip) += correlation of dD with act(x) (act = silu(bn) when x_rec).  The two halves are independent:

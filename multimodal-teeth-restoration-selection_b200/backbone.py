@@ -275,6 +275,9 @@ def forward_eval(enc, x, feature_map=False):
     R, Wp = cache["recs"], cache["w"]
     N, _, H, W = x.shape
     h, w = ops.same_out(H, 2), ops.same_out(W, 2)
+    # every SE pooling target of the pass in one zeroed arena: one memset node instead of one per block (and no memset
+    # between two kernels, so the whole chain can use programmatic dependent launch)
+    pool_arena = _Arena([N * blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()], torch.float32, dev)
     cur = torch.empty((N * h * w, enc.conv_stem.weight.shape[0]), device=dev, dtype=bf16)
     ops.stem_fwd(x, enc.conv_stem.weight.detach(), cur, out_rec=R["bn1"])
     for name, blk in enc.block_list():
@@ -289,8 +292,8 @@ def forward_eval(enc, x, feature_map=False):
             e, cm, dwrec, pw, outrec = cur, c["cin"], R[name + ".bn1"], Wp[name + ".conv_pw"][0], R[name + ".bn2"]
         oh, ow = ops.same_out(h, s), ops.same_out(w, s)
         d = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
-        pooled = torch.empty((N, cm), device=dev, dtype=torch.float32)
-        ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled)
+        pooled = pool_arena.take(N * cm, (N, cm))
+        ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled, pooled_zeroed=True)
         _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)
         ops.gate_apply(d, None, gate, d, N, oh * ow)
         flags = ops.EPI_SCALE_SHIFT | (ops.EPI_RESIDUAL if skip is not None else 0)

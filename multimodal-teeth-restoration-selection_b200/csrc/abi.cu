@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/teethrt.h"
 
@@ -29,6 +30,11 @@ int trt_check_launch(const char* what) {
 extern "C" const char* trt_last_error_string(void) { return g_err; }
 extern "C" int trt_version(void) { return TEETHRT_VERSION; }
 extern "C" int trt_stat_replicas(void) { return TRT_STAT_REPLICAS; }
+
+bool trt_pdl_enabled() {
+  static const int on = [] { const char* e = getenv("TEETHRT_PDL"); return (e && *e) ? (*e != '0') : 1; }();
+  return on != 0;
+}
 
 static int g_num_sms = 0;
 int trt_num_sms() {

@@ -21,6 +21,28 @@ void trt_count_launch(int n);             // extra launches of entry points that
 
 int trt_num_sms();
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The batch-1 forward is ~200 dependent kernels of a few microseconds each: launch latency, not work.  A kernel launched
+// through trt_launch() with TEETHRT_PDL != 0 carries cudaLaunchAttributeProgrammaticStreamSerialization: it may start while
+// its predecessor in the stream is still draining, runs its prologue (barrier init, descriptor prefetch, index math) and
+// blocks in pdl_wait() until the predecessor has completed and its writes are visible.  Every kernel launched this way calls
+// pdl_launch_dependents() first (so ITS successor can be staged early) and pdl_wait() before touching global memory; both are
+// no-ops in a launch without the attribute.  Works inside stream capture (programmatic graph edges).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool trt_pdl_enabled();   // abi.cu: TEETHRT_PDL (default on)
+template <typename... KArgs, typename... Args>
+inline cudaError_t trt_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = trt_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- small device utilities
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

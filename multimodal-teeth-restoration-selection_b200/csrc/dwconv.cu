@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
     ptx::mbar_init(&bar[1], 1);
     ptx::fence_barrier_init();
   }
+  pdl_launch_dependents();
+  pdl_wait();
   load_weights<K>(s_w, w, cb, g.C, false);
   __syncthreads();
   const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
@@ -642,8 +644,8 @@ int persistent_blocks(Kern kern, size_t smem, int cblocks, int items, int* out) 
 }  // namespace
 
 extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec,
-                              float* pooled_sum, double* stats, const trt_bn_fin_t* fin_host, int N, int H, int W, int C,
-                              int k, int s, cudaStream_t stream) {
+                              float* pooled_sum, int pooled_zeroed, double* stats, const trt_bn_fin_t* fin_host, int N, int H,
+                              int W, int C, int k, int s, cudaStream_t stream) {
   TRT_REQUIRE(!fin_host || (in_rec && fin_host->stats && fin_host->gamma && fin_host->beta && fin_host->rec == in_rec && fin_host->count > 0),
               "trt_dwconv_fwd: incomplete lazy BatchNorm record for the input (rec must be in_rec)");
   trt_bn_fin_t fin = {};
@@ -659,7 +661,7 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
   g.tiles_x = (g.OW + 4 * p - 1) / (4 * p);
   g.tiles_y = (g.OH + TOH - 1) / TOH;
   set_magic(g);
-  if (pooled_sum) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
+  if (pooled_sum && !pooled_zeroed) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
   const int cblocks = (C / 8 + CL - 1) / CL;
   const int items = N * g.tiles_x * g.tiles_y;
   TRT_REQUIRE((long long)items * g.tiles_x * g.tiles_y < (1ll << 32), "trt_dwconv_fwd: too many tiles");
@@ -672,7 +674,7 @@ extern "C" int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w
     if ((rc = trt_make_tmap_nhwc(&tm, x, N, H, W, C, 64, T::IW, T::IH))) return rc;                                \
     int G;                                                                                                         \
     if ((rc = persistent_blocks(dwconv_fwd_kernel<KK, SS, PP>, smem, cblocks, items, &G))) return rc;              \
-    dwconv_fwd_kernel<KK, SS, PP><<<dim3(G, cblocks), TPB, smem, stream>>>(tm, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g, has_fin, fin); \
+    TRT_CUDA(trt_launch(dwconv_fwd_kernel<KK, SS, PP>, dim3(G, cblocks), dim3(TPB), smem, stream, tm, in_rec, w, (uint4*)out, out_rec, pooled_sum, stats, g, has_fin, fin)); \
   } while (0)
   if (k == 3 && s == 1) { if (p == 4) LAUNCH_DW(3, 1, 4); else LAUNCH_DW(3, 1, 2); }
   else if (k == 5 && s == 1) { if (p == 4) LAUNCH_DW(5, 1, 4); else LAUNCH_DW(5, 1, 2); }

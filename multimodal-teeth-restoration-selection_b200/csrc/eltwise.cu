@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__
   __shared__ __align__(16) float s_ss[2][SLAB_CH];
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
   const int n = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   if (has_fin) bn_lazy_block(fin, C, blockIdx.z * VX * 8, VX * 8, s_ss[0], s_ss[1], blockIdx.x == 0 && blockIdx.y == 0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(TPB) se_reduce_kernel(const float* __restrict_
                                                         float* __restrict__ s1, int N, int C, int rd) {
   extern __shared__ float s_mem[];   // [C] one row of Wr, pre-scaled by 1/HW
   const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int c = threadIdx.x; c < C; c += TPB) s_mem[c] = __ldg(Wr + (size_t)r * C + c) * inv_hw;
   __syncthreads();
   const float bias = br[r];
@@ -219,6 +223,8 @@ __global__ void __launch_bounds__(TPB) se_expand_kernel(const float* __restrict_
   float* s_a1 = s_mem + SE_CC * (rd + 1);      // [n_per_block][rd]
   const int c0 = blockIdx.x * SE_CC, n0 = blockIdx.y * n_per_block;
   const int nn = min(n_per_block, N - n0);
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < SE_CC * rd; i += TPB) {
     const int cl = i / rd, r = i - cl * rd;
     s_we[cl * (rd + 1) + r] = (c0 + cl < C) ? __ldg(We + (size_t)(c0 + cl) * rd + r) : 0.f;
@@ -243,6 +249,8 @@ __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict
                                                          const float* __restrict__ gate, uint4* __restrict__ out, int HW,
                                                          int C, int V, int VX, int RY) {
   const RowMap m = row_map(V, VX, RY, blockIdx.z);
+  pdl_launch_dependents();
+  pdl_wait();
   if (!m.active) return;
   const int n = blockIdx.y;
   f8 sc, sh;
@@ -944,6 +952,8 @@ __global__ void pack_w_batch_kernel(const long long* __restrict__ table, int cou
 }
 
 __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= alpha;
 }
 
@@ -1052,14 +1062,14 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
     rec = fin.rec;
     lazy = 0;
   }
-  pool_act_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act, lazy, fin);
+  TRT_CUDA(trt_launch(pool_act_kernel, grid, dim3(TPB), 0, stream, (const uint4*)x, rec, pooled_sum, HW, C, L.V, L.VX, L.RY, act, lazy, fin));
   return trt_check_launch("trt_pool_act");
 }
 
 extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We,
                           const float* be, float* s1, float* gate, int N, int C, int rd, cudaStream_t stream) {
   TRT_REQUIRE(pooled_sum && Wr && br && We && be && s1 && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
-  se_reduce_kernel<<<dim3(rd, (N + 7) / 8), TPB, (size_t)C * sizeof(float), stream>>>(pooled_sum, inv_hw, Wr, br, s1, N, C, rd);
+  TRT_CUDA(trt_launch(se_reduce_kernel, dim3(rd, (N + 7) / 8), dim3(TPB), (size_t)C * sizeof(float), stream, pooled_sum, inv_hw, Wr, br, s1, N, C, rd));
   int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
   const int npb = (N + splits - 1) / splits;
   splits = (N + npb - 1) / npb;
@@ -1067,7 +1077,7 @@ extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr
   TRT_REQUIRE(smem <= 96 * 1024, "trt_se_fwd: batch %d x rd %d too large for one block", N, rd);
   // the opt-in is per device and cheap: set on every call (a process-wide "done" flag only covered the first device used)
   TRT_CUDA(cudaFuncSetAttribute(se_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  se_expand_kernel<<<dim3((C + SE_CC - 1) / SE_CC, splits), TPB, smem, stream>>>(s1, We, be, gate, N, C, rd, npb);
+  TRT_CUDA(trt_launch(se_expand_kernel, dim3((C + SE_CC - 1) / SE_CC, splits), dim3(TPB), smem, stream, s1, We, be, gate, N, C, rd, npb));
   trt_count_launch(1);
   return trt_check_launch("trt_se_fwd");
 }
@@ -1080,7 +1090,7 @@ extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate
   int target = 6 * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
-  gate_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)x, rec, gate, (uint4*)out, HW, C, L.V, L.VX, L.RY);
+  TRT_CUDA(trt_launch(gate_apply_kernel, grid, dim3(TPB), 0, stream, (const uint4*)x, rec, gate, (uint4*)out, HW, C, L.V, L.VX, L.RY));
   return trt_check_launch("trt_gate_apply");
 }
 
@@ -1217,6 +1227,6 @@ extern "C" int trt_scale_f32(float* x, size_t n, float alpha, cudaStream_t strea
   TRT_REQUIRE(x && n > 0, "trt_scale_f32: bad argument");
   int grid = (int)((n + 255) / 256);
   if (grid > 4 * trt_num_sms()) grid = 4 * trt_num_sms();
-  scale_f32_kernel<<<grid, 256, 0, stream>>>(x, n, alpha);
+  TRT_CUDA(trt_launch(scale_f32_kernel, dim3(grid), dim3(256), 0, stream, x, n, alpha));
   return trt_check_launch("trt_scale_f32");
 }

@@ -103,6 +103,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
+  pdl_launch_dependents();
+  pdl_wait();                      // everything above (barriers, descriptor prefetch) overlapped the previous kernel's tail
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
@@ -535,7 +537,7 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
-  gemm_kmajor_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+  TRT_CUDA(trt_launch(gemm_kmajor_kernel, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p));
   return trt_check_launch("trt_gemm_bf16");
 }
 

@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(TPB) tab_heads_fwd_kernel(const TabParams p) {
   float* bnstat = ft + (size_t)B * Hd;   // mean[Hd], rstd[Hd]
   float* s_z = big ? z0 : tsm;             // [B][Hd]   z0 ...
   float* s_a = big ? a1 : tsm;             // ... then a1 (in place when in shared memory)
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
   const int t = threadIdx.x;
   for (int i = t; i < Hd * Hd; i += TPB) s_w1[(i / Hd) * (Hd + 1) + (i % Hd)] = __ldg(p.W1 + i);
@@ -389,6 +391,8 @@ __global__ void __launch_bounds__(TPB) heads_fwd_kernel(const TabParams p) {
   const int B = p.B, Hd = p.Hd, F = p.F, b = blockIdx.x;
   const float* ft = p.scratch + (size_t)2 * B * Hd;
   __shared__ float s_c[TPB / 32], s_r[TPB / 32];
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned long long seed = p.seed + (p.step ? *p.step * 0x9E3779B97F4A7C15ull : 0ull);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float lc = 0.f, lr = 0.f;
@@ -715,9 +719,9 @@ extern "C" int trt_tab_heads_fwd(const float* feat, const float* xtab, const flo
   p.big = tsmem > 200 * 1024;          // the reference has no batch limit: large batches walk the global scratch instead
   if (p.big) tsmem = tfixed;
   TRT_CUDA(cudaFuncSetAttribute(tab_heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  tab_heads_fwd_kernel<<<1, TPB, tsmem, stream>>>(p);
+  TRT_CUDA(trt_launch(tab_heads_fwd_kernel, dim3(1), dim3(TPB), tsmem, stream, p));
   trt_count_launch(1);
-  heads_fwd_kernel<<<B, TPB, 0, stream>>>(p);
+  TRT_CUDA(trt_launch(heads_fwd_kernel, dim3(B), dim3(TPB), 0, stream, p));
   return trt_check_launch("trt_tab_heads_fwd");
 }
 

@@ -169,10 +169,10 @@ def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1):
 
 
 # ------------------------------------------------------------------------------------------------ spatial convs
-def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, in_fin=None):
+def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, in_fin=None, pooled_zeroed=False):
     """in_fin: lazy BatchNorm record of the INPUT (in_rec is derived from its statistics and published by this launch)."""
-    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), ptr(stats), _ref(in_fin), N, H, W,
-                             x.shape[-1], k, s, stream()))
+    check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), int(pooled_zeroed), ptr(stats),
+                             _ref(in_fin), N, H, W, x.shape[-1], k, s, stream()))
     return out
 
 
