@@ -5,6 +5,7 @@
 //
 // Replaces: src/preprocessing/normalise.py:10-16 (apply_clahe), src/preprocessing/pipeline.py:23-29
 // (centre_crop_resize), and ToTensor/Normalize/flip of experiments/multimodal_v1/train_mm_joint_dualtask.py:83-84,328-333.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -225,6 +226,173 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restr
   }
 }
 
+// ---------------------------------------------------------------- fast path (no padding, tile width a multiple of 32)
+// Round-2 rewrite of both passes for the shapes the pipeline really sees (512^2 / 1024^2 radiographs).  What ncu and the
+// instruction count said about the kernels above: (1) abToXZ (147 KB) was gathered from global memory twice per pixel - it
+// is pure integer arithmetic and is now computed (abxz_at); (2) the apply pass staged all 64 tile LUTs (16 KB) per block
+// and looked four of them up per pixel - a block now works inside ONE interpolation cell (the square between four tile
+// centres), where the four LUTs are fixed, and packs them into one 256-entry uint32 table: one lookup per pixel;
+// (3) pixels were read with byte loads - a thread now owns 16 consecutive pixels = three 16-byte loads / stores;
+// (4) the sRGB gamma table (3 lookups per pixel, 128 words) is replicated per lane so those lookups can never conflict;
+// (5) the constant tables are staged once per persistent block, not once per 16 rows.  Bit-exactness is unchanged: the
+// per-pixel arithmetic is the same sequence of integer / non-contracted fp32 operations.
+constexpr int MIN_AB = -8145;
+// abToXZ_b[i - MIN_AB] of OpenCV's Lab2RGBinteger, computed instead of looked up (checked against the
+// table entry by entry on the host: tests/test_oracle_preproc.py)
+__device__ __forceinline__ int abxz_at(int i) {
+  if (i <= 3390) return (i * 108) / 841 - 290;                  // C division truncates toward zero, like the table builder
+  return (int)((((unsigned)(i * i)) >> 14) * (unsigned)i >> 14);
+}
+
+struct FastTables {            // shared-memory copies used by the fast kernels
+  uint32_t* gamma32;           // [128][32] lane-private copies of the packed u16 gamma table
+  const uint16_t* cbrt;        // [3072]
+  const int2* yf;              // [256] (y, ify)
+  const uint8_t* inv;          // [4096]
+};
+__device__ __forceinline__ int gamma_at(const uint32_t* g32, int v, int lane) {
+  const uint32_t w = g32[(v >> 1) * 32 + lane];
+  return (v & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+}
+__device__ __forceinline__ void stage_gamma(uint32_t* g32, const uint16_t* gamma) {
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(gamma);
+  for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) g32[i] = __ldg(g + (i >> 5));
+}
+
+// pass A: grid = (NT * bands, N); block = one band of one tile, thread = 16 consecutive pixels of a row
+__global__ void __launch_bounds__(256) clahe_hist_fast_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ hist,
+                                                              const void* __restrict__ tables, int H, int W, int th, int tw,
+                                                              int bands) {
+  __shared__ uint32_t s_gamma32[128 * 32];
+  __shared__ uint16_t s_cbrt[3072];
+  __shared__ uint32_t s_hist[8][256];
+  const LabTables T = table_views(tables);
+  stage_gamma(s_gamma32, T.gamma);
+  for (int i = threadIdx.x; i < 3072 / 2; i += 256) reinterpret_cast<uint32_t*>(s_cbrt)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.cbrt) + i);
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int tile = blockIdx.x / bands, band = blockIdx.x % bands;
+  const int ty = tile / GRID, tx = tile % GRID;
+  const int rows_per_band = (th + bands - 1) / bands;
+  const int y_begin = band * rows_per_band, y_end = min(th, y_begin + rows_per_band);
+  const uint8_t* img = src + (size_t)blockIdx.y * H * W * 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = tw >> 4;                                   // 16-pixel groups per tile row
+  const int items = (y_end - y_begin) * groups;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int yy = y_begin + i / groups, g = i % groups;
+    const uint4* p = reinterpret_cast<const uint4*>(img + ((size_t)(ty * th + yy) * W + tx * tw + g * 16) * 3);
+    uint32_t w[12];
+    *reinterpret_cast<uint4*>(w) = __ldg(p);
+    *reinterpret_cast<uint4*>(w + 4) = __ldg(p + 1);
+    *reinterpret_cast<uint4*>(w + 8) = __ldg(p + 2);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int B = gamma_at(s_gamma32, b[3 * j], lane), G = gamma_at(s_gamma32, b[3 * j + 1], lane), R = gamma_at(s_gamma32, b[3 * j + 2], lane);
+      const int fY = s_cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
+      atomicAdd(&s_hist[warp][clamp_u8(descale(296 * fY - 1336934, 15))], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* out = hist + ((size_t)blockIdx.y * NT + tile) * 256;
+  uint32_t v = 0;
+#pragma unroll
+  for (int wv = 0; wv < 8; ++wv) v += s_hist[wv][threadIdx.x];
+  if (v) atomicAdd(out + threadIdx.x, v);
+}
+
+// pass B: persistent blocks over (image, cell, 32-row band) items; a cell is the region between four tile centres
+constexpr int CELLS = GRID + 1;
+constexpr int BAND = 32;      // rows per item: 8 threads x 16 pixels cover a 128-pixel cell row, 32 rows per 256 threads
+__global__ void __launch_bounds__(256) clahe_apply_fast_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                               const uint8_t* __restrict__ luts, const void* __restrict__ tables,
+                                                               int H, int W, int th, int tw, float inv_th, float inv_tw,
+                                                               int bands_per_cell, int n_items) {
+  __shared__ uint32_t s_gamma32[128 * 32];
+  __shared__ uint16_t s_cbrt[3072];
+  __shared__ int2 s_yf[256];
+  __shared__ __align__(16) uint8_t s_inv[4096];
+  __shared__ uint32_t s_comb[2][256];
+  const LabTables T = table_views(tables);
+  stage_gamma(s_gamma32, T.gamma);
+  for (int i = threadIdx.x; i < 3072 / 2; i += 256) reinterpret_cast<uint32_t*>(s_cbrt)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.cbrt) + i);
+  s_yf[threadIdx.x] = make_int2(T.yf[2 * threadIdx.x], T.yf[2 * threadIdx.x + 1]);
+  for (int i = threadIdx.x; i < 1024; i += 256) reinterpret_cast<uint32_t*>(s_inv)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.invgamma) + i);
+  const int lane = threadIdx.x & 31;
+  const int per_img = CELLS * CELLS * bands_per_cell;
+  int buf = 0;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, buf ^= 1) {
+    const int n = it / per_img, r0 = it - n * per_img;
+    const int cell = r0 / bands_per_cell, band = r0 - cell * bands_per_cell;
+    const int cy = cell / CELLS, cx = cell - cy * CELLS;
+    // cell geometry: cells 1..GRID-1 span [half + (c-1)*t, half + c*t); cell 0 = [0, half); cell GRID = [size - half, size)
+    const int hx = tw >> 1, hy = th >> 1;
+    const int x_lo = cx == 0 ? 0 : hx + (cx - 1) * tw, x_hi = cx == 0 ? hx : min(W, hx + cx * tw);
+    const int y_lo = cy == 0 ? 0 : hy + (cy - 1) * th, y_hi = cy == 0 ? hy : min(H, hy + cy * th);
+    const int tx1 = max(cx - 1, 0), tx2 = min(cx, GRID - 1), ty1 = max(cy - 1, 0), ty2 = min(cy, GRID - 1);
+    // the four LUTs of the cell packed per grey level (double-buffered: the previous item's readers may still be in flight)
+    {
+      const uint8_t* L = luts + (size_t)n * NT * 256 + threadIdx.x;
+      s_comb[buf][threadIdx.x] = (uint32_t)__ldg(L + (ty1 * GRID + tx1) * 256) | ((uint32_t)__ldg(L + (ty1 * GRID + tx2) * 256) << 8) |
+                                 ((uint32_t)__ldg(L + (ty2 * GRID + tx1) * 256) << 16) | ((uint32_t)__ldg(L + (ty2 * GRID + tx2) * 256) << 24);
+    }
+    __syncthreads();
+    const uint32_t* comb = s_comb[buf];
+    const int groups = (x_hi - x_lo) >> 4;                      // 16-pixel groups per cell row (4 or 8)
+    const int rows = min(BAND, y_hi - (y_lo + band * BAND));
+    const size_t img_off = (size_t)n * H * W * 3;
+    for (int i = threadIdx.x; i < rows * groups; i += 256) {
+      const int yy = i / groups, g = i - yy * groups;
+      const int y = y_lo + band * BAND + yy, x0 = x_lo + g * 16;
+      int t1, t2;
+      float ya, ya1;
+      tile_coord(y, inv_th, t1, t2, ya, ya1);
+      const size_t off = img_off + ((size_t)y * W + x0) * 3;
+      const uint4* p = reinterpret_cast<const uint4*>(src + off);
+      uint32_t w[12], o[12];
+      *reinterpret_cast<uint4*>(w) = __ldg(p);
+      *reinterpret_cast<uint4*>(w + 4) = __ldg(p + 1);
+      *reinterpret_cast<uint4*>(w + 8) = __ldg(p + 2);
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(w);
+      uint8_t* ob = reinterpret_cast<uint8_t*>(o);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int B = gamma_at(s_gamma32, b[3 * j], lane), G = gamma_at(s_gamma32, b[3 * j + 1], lane), R = gamma_at(s_gamma32, b[3 * j + 2], lane);
+        const int fX = s_cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
+        const int fY = s_cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
+        const int fZ = s_cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
+        const int L = clamp_u8(descale(296 * fY - 1336934, 15));
+        const int a = clamp_u8(descale(500 * (fX - fY) + 128 * 32768, 15));
+        const int bb = clamp_u8(descale(200 * (fY - fZ) + 128 * 32768, 15));
+        // CLAHE interpolation (fp32, written order, no FMA contraction - OpenCV CLAHE_Interpolation_Body)
+        int u1, u2;
+        float xa, xa1;
+        tile_coord(x0 + j, inv_tw, u1, u2, xa, xa1);
+        const uint32_t c4 = comb[L];
+        const float l11 = (float)(c4 & 255u), l12 = (float)((c4 >> 8) & 255u), l21 = (float)((c4 >> 16) & 255u), l22 = (float)(c4 >> 24);
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        const int L2 = clamp_u8(__float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya))));
+        // Lab -> BGR
+        constexpr int BASE = 16384;
+        const int2 yv = s_yf[L2];
+        const int adiv = ((5 * a * 53687 + 128) >> 13) - 128 * BASE / 500;
+        const int bdiv = ((bb * 41943 + 16) >> 9) - 128 * BASE / 200 + 1;
+        const int X = abxz_at(yv.y + adiv), Z = abxz_at(yv.y - bdiv);
+        const int ro = min(max(descale(12615 * X - 6296 * yv.x - 2223 * Z, 14), 0), 4095);
+        const int go = min(max(descale(-3773 * X + 7684 * yv.x + 185 * Z, 14), 0), 4095);
+        const int bo = min(max(descale(217 * X - 836 * yv.x + 4715 * Z, 14), 0), 4095);
+        ob[3 * j] = s_inv[bo]; ob[3 * j + 1] = s_inv[go]; ob[3 * j + 2] = s_inv[ro];
+      }
+      uint4* q = reinterpret_cast<uint4*>(dst + off);
+      q[0] = *reinterpret_cast<uint4*>(o);
+      q[1] = *reinterpret_cast<uint4*>(o + 4);
+      q[2] = *reinterpret_cast<uint4*>(o + 8);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- centre crop + cv2.resize(INTER_LINEAR) (App. A.4)
 __device__ __forceinline__ void axis_coef(int d, double scale, int ssize, bool zero_edges, int& s, int& w0, int& w1) {
   float f = (float)(((double)d + 0.5) * scale - 0.5);
@@ -360,11 +528,29 @@ extern "C" int trt_clahe_bgr_u8(const uint8_t* src, uint8_t* dst, int n, int h, 
   TRT_CUDA(cudaMemsetAsync(hist, 0, (size_t)n * NT * 256 * sizeof(uint32_t), stream));
   int bands = 1;
   while (bands < 8 && n * NT * bands < 4 * trt_num_sms() && th / (bands * 2) >= 8) bands *= 2;
-  clahe_hist_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
-  clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
-  const int vec_ok = (w % 4 == 0) && (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 3) == 0);
-  dim3 grid((w + 1023) / 1024, (h + APPLY_ROWS - 1) / APPLY_ROWS, n);
-  clahe_apply_kernel<<<grid, 256, 0, stream>>>(src, dst, luts, tables, h, w, inv_th, inv_tw, vec_ok);
+  // fast path: no reflect padding, 16-pixel groups never straddle a tile or cell boundary, 16-byte aligned rows
+  const char* slow = getenv("TEETHRT_CLAHE_SLOW");
+  // tile sizes must be powers of two: then p * (1 / tile) is exact in fp32 and OpenCV's floor(p / tile - 0.5) changes exactly
+  // at the integer cell boundaries the fast kernel uses (with e.g. 96-pixel tiles the rounded product can put a boundary
+  // pixel in the neighbouring cell)
+  const bool pow2 = (tw & (tw - 1)) == 0 && (th & (th - 1)) == 0;
+  const bool fast = hp == h && wp == w && pow2 && tw >= 32 && th >= 2 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 &&
+                    !(slow && *slow == '1');
+  if (fast) {
+    clahe_hist_fast_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
+    clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
+    const int bands_per_cell = (th + BAND - 1) / BAND;            // edge cells are half as tall: their upper bands are empty
+    const long long items = (long long)n * CELLS * CELLS * bands_per_cell;
+    TRT_REQUIRE(items < (1ll << 31), "trt_clahe_bgr_u8: too many items");
+    const int blocks = (int)(items < 4ll * trt_num_sms() ? items : 4ll * trt_num_sms());
+    clahe_apply_fast_kernel<<<blocks, 256, 0, stream>>>(src, dst, luts, tables, h, w, th, tw, inv_th, inv_tw, bands_per_cell, (int)items);
+  } else {
+    clahe_hist_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
+    clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
+    const int vec_ok = (w % 4 == 0) && (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 3) == 0);
+    dim3 grid((w + 1023) / 1024, (h + APPLY_ROWS - 1) / APPLY_ROWS, n);
+    clahe_apply_kernel<<<grid, 256, 0, stream>>>(src, dst, luts, tables, h, w, inv_th, inv_tw, vec_ok);
+  }
   trt_count_launch(2);
   return trt_check_launch("trt_clahe_bgr_u8");
 }

@@ -134,3 +134,20 @@ def test_warp_restatement_on_extreme_maps():
         assert np.array_equal(P.warp_affine_np(img, M, 131, 97), want)
         want2 = cv2.warpAffine(img, M, (200, 50), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
         assert np.array_equal(P.warp_affine_np(img, M, 200, 50), want2)
+
+
+def test_ab_to_xz_table_is_pure_integer_arithmetic():
+    """The CLAHE fast path computes OpenCV's abToXZ_b entries instead of gathering them from a 147 KB table
+    (csrc/preproc.cu abxz_at): the closed form must reproduce the digest-checked table entry by entry, in int32 range."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("lab_tables", os.path.join(os.path.dirname(__file__), "..",
+                                                  "multimodal-teeth-restoration-selection_b200", "lab_tables.py"))
+    lt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lt)
+    table = lt._abxz()
+    i = np.arange(-8145, -8145 + 36864, dtype=np.int64)
+    lo = np.sign(i * 108) * (np.abs(i * 108) // 841) - 290          # C truncating division, as in `(i * 108) / 841 - 290`
+    hi = (((i * i) >> 14) * i) >> 14
+    assert int((i * i).max()) < 2 ** 31 and int((((i * i) >> 14) * i).max()) < 2 ** 31
+    assert np.array_equal(np.where(i <= 3390, lo, hi), table)

@@ -55,6 +55,20 @@ def test_clahe_small_and_ragged_shapes(pre, h, w):
     assert int((pre.apply_clahe(img) != P.apply_clahe_cv2(img)).sum()) == 0
 
 
+@pytest.mark.parametrize("h,w,kind", [(1024, 1024, "radiograph"), (512, 512, "noise"), (256, 1024, "smooth"), (1024, 256, "noise"), (2048, 512, "ramp")])
+def test_clahe_fast_path_equals_opencv_and_the_general_kernels(pre, h, w, kind, monkeypatch):
+    """Power-of-two tiles take the round-2 kernels (one interpolation cell per block, packed four-LUT table, computed abToXZ,
+    16-pixel vector loads): byte-identical to OpenCV and to the general kernels (TEETHRT_CLAHE_SLOW=1), batched."""
+    imgs = np.stack([P.image_set(kind, h, w, seed=s) for s in range(3)])
+    dev = torch.from_numpy(imgs).cuda()
+    fast = pre.apply_clahe(dev).cpu().numpy()
+    monkeypatch.setenv("TEETHRT_CLAHE_SLOW", "1")
+    slow = pre.apply_clahe(dev).cpu().numpy()
+    assert int((fast != slow).sum()) == 0
+    for i in range(3):
+        assert int((fast[i] != P.apply_clahe_cv2(imgs[i])).sum()) == 0
+
+
 def test_batched_device_path_and_idempotent_buffers(pre):
     imgs = np.stack([P.image_set(n, 256, 256, seed=i) for i, n in enumerate(["noise", "smooth", "radiograph", "ramp"])])
     dev = torch.from_numpy(imgs).cuda()
