@@ -226,48 +226,45 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restr
   }
 }
 
-// ---------------------------------------------------------------- fast path (no padding, tile width a multiple of 32)
-// Round-2 rewrite of both passes for the shapes the pipeline really sees (512^2 / 1024^2 radiographs).  What ncu and the
-// instruction count said about the kernels above: (1) abToXZ (147 KB) was gathered from global memory twice per pixel - it
-// is pure integer arithmetic and is now computed (abxz_at); (2) the apply pass staged all 64 tile LUTs (16 KB) per block
-// and looked four of them up per pixel - a block now works inside ONE interpolation cell (the square between four tile
-// centres), where the four LUTs are fixed, and packs them into one 256-entry uint32 table: one lookup per pixel;
-// (3) pixels were read with byte loads - a thread now owns 16 consecutive pixels = three 16-byte loads / stores;
-// (4) the sRGB gamma table (3 lookups per pixel, 128 words) is replicated per lane so those lookups can never conflict;
-// (5) the constant tables are staged once per persistent block, not once per 16 rows.  Bit-exactness is unchanged: the
-// per-pixel arithmetic is the same sequence of integer / non-contracted fp32 operations.
+// ---------------------------------------------------------------- fast path (no padding, power-of-two tiles)
+// Round-2 rewrite of both passes for the shapes the pipeline really sees (512^2 / 1024^2 radiographs).  ncu on the kernels
+// above (profiles/r02_ncu_full_small_kernels.csv, 64 x 1024^2): histogram pass 72 thread-instructions per pixel at 72 %
+// issue, apply pass 129 per pixel at 60 % issue with 46 M shared-memory bank-conflict cycles and two random global gathers
+// per pixel - the path is INTEGER-ISSUE-bound (201 instructions per pixel = 0.45 ms of issue slots at 100 %), nowhere near
+// HBM.  So the rewrite removes instructions, not bytes:
+//   (1) BGR -> Lab is computed ONCE: pass A writes the Lab image into `dst` while it histograms L, pass B converts `dst` in
+//       place (6 more bytes per pixel of traffic, ~50 fewer instructions per pixel);
+//   (2) abToXZ (147 KB, gathered from global memory twice per pixel) is pure integer arithmetic and is computed (abxz_at);
+//   (3) a block of pass B works inside ONE interpolation cell (the square between four tile centres), where the four LUTs
+//       are fixed, and packs them into one 256-entry uint32 table: one lookup per pixel instead of four, 1 KB instead of 16;
+//   (4) a thread owns 16 consecutive pixels = three 16-byte loads / stores, and its 16 horizontal interpolation weights live
+//       in registers across all its rows;
+//   (5) the sRGB gamma table (3 lookups per pixel) is replicated per lane (32 KB) so those lookups never conflict;
+//   (6) constant tables are staged once per persistent block.
+// Bit-exactness is unchanged: per pixel it is the same sequence of integer / non-contracted fp32 operations.
 constexpr int MIN_AB = -8145;
 // abToXZ_b[i - MIN_AB] of OpenCV's Lab2RGBinteger, computed instead of looked up (checked against the
-// table entry by entry on the host: tests/test_oracle_preproc.py)
+// digest-verified table entry by entry: tests/test_oracle_preproc.py)
 __device__ __forceinline__ int abxz_at(int i) {
   if (i <= 3390) return (i * 108) / 841 - 290;                  // C division truncates toward zero, like the table builder
   return (int)((((unsigned)(i * i)) >> 14) * (unsigned)i >> 14);
 }
 
-struct FastTables {            // shared-memory copies used by the fast kernels
-  uint32_t* gamma32;           // [128][32] lane-private copies of the packed u16 gamma table
-  const uint16_t* cbrt;        // [3072]
-  const int2* yf;              // [256] (y, ify)
-  const uint8_t* inv;          // [4096]
-};
-__device__ __forceinline__ int gamma_at(const uint32_t* g32, int v, int lane) {
-  const uint32_t w = g32[(v >> 1) * 32 + lane];
-  return (v & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
-}
-__device__ __forceinline__ void stage_gamma(uint32_t* g32, const uint16_t* gamma) {
-  const uint32_t* g = reinterpret_cast<const uint32_t*>(gamma);
-  for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) g32[i] = __ldg(g + (i >> 5));
+// lane-private gamma table: entry v of lane l at word v * 32 + l, so a warp's 32 lookups hit 32 different banks whatever v is
+__device__ __forceinline__ void stage_gamma32(uint32_t* g32, const uint16_t* gamma) {
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) g32[i] = __ldg(gamma + (i >> 5));
 }
 
-// pass A: grid = (NT * bands, N); block = one band of one tile, thread = 16 consecutive pixels of a row
-__global__ void __launch_bounds__(256) clahe_hist_fast_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ hist,
-                                                              const void* __restrict__ tables, int H, int W, int th, int tw,
-                                                              int bands) {
-  __shared__ uint32_t s_gamma32[128 * 32];
+// pass A: grid = (NT * bands, N); block = one band of one tile, thread = 16 consecutive pixels of a row.
+// Writes the Lab image (L, a, b interleaved like the input) to `lab` and the per-tile histogram of L.
+__global__ void __launch_bounds__(256) clahe_lab_hist_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ lab,
+                                                             uint32_t* __restrict__ hist, const void* __restrict__ tables, int H,
+                                                             int W, int th, int tw, int bands) {
+  __shared__ uint32_t s_gamma32[256 * 32];
   __shared__ uint16_t s_cbrt[3072];
   __shared__ uint32_t s_hist[8][256];
   const LabTables T = table_views(tables);
-  stage_gamma(s_gamma32, T.gamma);
+  stage_gamma32(s_gamma32, T.gamma);
   for (int i = threadIdx.x; i < 3072 / 2; i += 256) reinterpret_cast<uint32_t*>(s_cbrt)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.cbrt) + i);
   for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
   __syncthreads();
@@ -275,24 +272,37 @@ __global__ void __launch_bounds__(256) clahe_hist_fast_kernel(const uint8_t* __r
   const int ty = tile / GRID, tx = tile % GRID;
   const int rows_per_band = (th + bands - 1) / bands;
   const int y_begin = band * rows_per_band, y_end = min(th, y_begin + rows_per_band);
-  const uint8_t* img = src + (size_t)blockIdx.y * H * W * 3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t img_off = (size_t)blockIdx.y * H * W * 3;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t* gl = s_gamma32 + (threadIdx.x & 31);
   const int groups = tw >> 4;                                   // 16-pixel groups per tile row
   const int items = (y_end - y_begin) * groups;
   for (int i = threadIdx.x; i < items; i += 256) {
     const int yy = y_begin + i / groups, g = i % groups;
-    const uint4* p = reinterpret_cast<const uint4*>(img + ((size_t)(ty * th + yy) * W + tx * tw + g * 16) * 3);
-    uint32_t w[12];
+    const size_t off = img_off + ((size_t)(ty * th + yy) * W + tx * tw + g * 16) * 3;
+    const uint4* p = reinterpret_cast<const uint4*>(src + off);
+    uint32_t w[12], o[12];
     *reinterpret_cast<uint4*>(w) = __ldg(p);
     *reinterpret_cast<uint4*>(w + 4) = __ldg(p + 1);
     *reinterpret_cast<uint4*>(w + 8) = __ldg(p + 2);
     const uint8_t* b = reinterpret_cast<const uint8_t*>(w);
+    uint8_t* ob = reinterpret_cast<uint8_t*>(o);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int B = gamma_at(s_gamma32, b[3 * j], lane), G = gamma_at(s_gamma32, b[3 * j + 1], lane), R = gamma_at(s_gamma32, b[3 * j + 2], lane);
+      const int B = (int)gl[b[3 * j] * 32], G = (int)gl[b[3 * j + 1] * 32], R = (int)gl[b[3 * j + 2] * 32];
+      const int fX = s_cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
       const int fY = s_cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
-      atomicAdd(&s_hist[warp][clamp_u8(descale(296 * fY - 1336934, 15))], 1u);
+      const int fZ = s_cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
+      const int L = clamp_u8(descale(296 * fY - 1336934, 15));
+      ob[3 * j] = (uint8_t)L;
+      ob[3 * j + 1] = (uint8_t)clamp_u8(descale(500 * (fX - fY) + 128 * 32768, 15));
+      ob[3 * j + 2] = (uint8_t)clamp_u8(descale(200 * (fY - fZ) + 128 * 32768, 15));
+      atomicAdd(&s_hist[warp][L], 1u);
     }
+    uint4* q = reinterpret_cast<uint4*>(lab + off);
+    q[0] = *reinterpret_cast<uint4*>(o);
+    q[1] = *reinterpret_cast<uint4*>(o + 4);
+    q[2] = *reinterpret_cast<uint4*>(o + 8);
   }
   __syncthreads();
   uint32_t* out = hist + ((size_t)blockIdx.y * NT + tile) * 256;
@@ -302,24 +312,18 @@ __global__ void __launch_bounds__(256) clahe_hist_fast_kernel(const uint8_t* __r
   if (v) atomicAdd(out + threadIdx.x, v);
 }
 
-// pass B: persistent blocks over (image, cell, 32-row band) items; a cell is the region between four tile centres
+// pass B: persistent blocks over (image, cell, 32-row band) items; converts the Lab image IN PLACE to the CLAHE'd BGR image
 constexpr int CELLS = GRID + 1;
 constexpr int BAND = 32;      // rows per item: 8 threads x 16 pixels cover a 128-pixel cell row, 32 rows per 256 threads
-__global__ void __launch_bounds__(256) clahe_apply_fast_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                               const uint8_t* __restrict__ luts, const void* __restrict__ tables,
-                                                               int H, int W, int th, int tw, float inv_th, float inv_tw,
-                                                               int bands_per_cell, int n_items) {
-  __shared__ uint32_t s_gamma32[128 * 32];
-  __shared__ uint16_t s_cbrt[3072];
+__global__ void __launch_bounds__(256) clahe_apply_lab_kernel(uint8_t* __restrict__ img, const uint8_t* __restrict__ luts,
+                                                              const void* __restrict__ tables, int H, int W, int th, int tw,
+                                                              float inv_th, float inv_tw, int bands_per_cell, int n_items) {
   __shared__ int2 s_yf[256];
   __shared__ __align__(16) uint8_t s_inv[4096];
   __shared__ uint32_t s_comb[2][256];
   const LabTables T = table_views(tables);
-  stage_gamma(s_gamma32, T.gamma);
-  for (int i = threadIdx.x; i < 3072 / 2; i += 256) reinterpret_cast<uint32_t*>(s_cbrt)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.cbrt) + i);
   s_yf[threadIdx.x] = make_int2(T.yf[2 * threadIdx.x], T.yf[2 * threadIdx.x + 1]);
   for (int i = threadIdx.x; i < 1024; i += 256) reinterpret_cast<uint32_t*>(s_inv)[i] = __ldg(reinterpret_cast<const uint32_t*>(T.invgamma) + i);
-  const int lane = threadIdx.x & 31;
   const int per_img = CELLS * CELLS * bands_per_cell;
   int buf = 0;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, buf ^= 1) {
@@ -339,40 +343,39 @@ __global__ void __launch_bounds__(256) clahe_apply_fast_kernel(const uint8_t* __
     }
     __syncthreads();
     const uint32_t* comb = s_comb[buf];
-    const int groups = (x_hi - x_lo) >> 4;                      // 16-pixel groups per cell row (4 or 8)
+    const int groups = (x_hi - x_lo) >> 4;                      // 16-pixel groups per cell row: a power of two <= 256
     const int rows = min(BAND, y_hi - (y_lo + band * BAND));
     const size_t img_off = (size_t)n * H * W * 3;
-    for (int i = threadIdx.x; i < rows * groups; i += 256) {
-      const int yy = i / groups, g = i - yy * groups;
-      const int y = y_lo + band * BAND + yy, x0 = x_lo + g * 16;
+    // 256 % groups == 0: a thread keeps its column group for all its rows, so its horizontal weights are computed once
+    const int g = threadIdx.x & (groups - 1), x0 = x_lo + g * 16;
+    float xa[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int u1, u2;
+      float a1;
+      tile_coord(x0 + j, inv_tw, u1, u2, xa[j], a1);
+    }
+    for (int yy = threadIdx.x / groups; yy < rows; yy += 256 / groups) {
+      const int y = y_lo + band * BAND + yy;
       int t1, t2;
       float ya, ya1;
       tile_coord(y, inv_th, t1, t2, ya, ya1);
-      const size_t off = img_off + ((size_t)y * W + x0) * 3;
-      const uint4* p = reinterpret_cast<const uint4*>(src + off);
+      uint4* p = reinterpret_cast<uint4*>(img + img_off + ((size_t)y * W + x0) * 3);
       uint32_t w[12], o[12];
-      *reinterpret_cast<uint4*>(w) = __ldg(p);
-      *reinterpret_cast<uint4*>(w + 4) = __ldg(p + 1);
-      *reinterpret_cast<uint4*>(w + 8) = __ldg(p + 2);
+      *reinterpret_cast<uint4*>(w) = p[0];
+      *reinterpret_cast<uint4*>(w + 4) = p[1];
+      *reinterpret_cast<uint4*>(w + 8) = p[2];
       const uint8_t* b = reinterpret_cast<const uint8_t*>(w);
       uint8_t* ob = reinterpret_cast<uint8_t*>(o);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int B = gamma_at(s_gamma32, b[3 * j], lane), G = gamma_at(s_gamma32, b[3 * j + 1], lane), R = gamma_at(s_gamma32, b[3 * j + 2], lane);
-        const int fX = s_cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
-        const int fY = s_cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
-        const int fZ = s_cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
-        const int L = clamp_u8(descale(296 * fY - 1336934, 15));
-        const int a = clamp_u8(descale(500 * (fX - fY) + 128 * 32768, 15));
-        const int bb = clamp_u8(descale(200 * (fY - fZ) + 128 * 32768, 15));
+        const int L = b[3 * j], a = b[3 * j + 1], bb = b[3 * j + 2];
         // CLAHE interpolation (fp32, written order, no FMA contraction - OpenCV CLAHE_Interpolation_Body)
-        int u1, u2;
-        float xa, xa1;
-        tile_coord(x0 + j, inv_tw, u1, u2, xa, xa1);
+        const float xa1 = __fsub_rn(1.0f, xa[j]);
         const uint32_t c4 = comb[L];
         const float l11 = (float)(c4 & 255u), l12 = (float)((c4 >> 8) & 255u), l21 = (float)((c4 >> 16) & 255u), l22 = (float)(c4 >> 24);
-        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa[j]));
+        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa[j]));
         const int L2 = clamp_u8(__float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya))));
         // Lab -> BGR
         constexpr int BASE = 16384;
@@ -385,10 +388,9 @@ __global__ void __launch_bounds__(256) clahe_apply_fast_kernel(const uint8_t* __
         const int bo = min(max(descale(217 * X - 836 * yv.x + 4715 * Z, 14), 0), 4095);
         ob[3 * j] = s_inv[bo]; ob[3 * j + 1] = s_inv[go]; ob[3 * j + 2] = s_inv[ro];
       }
-      uint4* q = reinterpret_cast<uint4*>(dst + off);
-      q[0] = *reinterpret_cast<uint4*>(o);
-      q[1] = *reinterpret_cast<uint4*>(o + 4);
-      q[2] = *reinterpret_cast<uint4*>(o + 8);
+      p[0] = *reinterpret_cast<uint4*>(o);
+      p[1] = *reinterpret_cast<uint4*>(o + 4);
+      p[2] = *reinterpret_cast<uint4*>(o + 8);
     }
   }
 }
@@ -534,16 +536,16 @@ extern "C" int trt_clahe_bgr_u8(const uint8_t* src, uint8_t* dst, int n, int h, 
   // at the integer cell boundaries the fast kernel uses (with e.g. 96-pixel tiles the rounded product can put a boundary
   // pixel in the neighbouring cell)
   const bool pow2 = (tw & (tw - 1)) == 0 && (th & (th - 1)) == 0;
-  const bool fast = hp == h && wp == w && pow2 && tw >= 32 && th >= 2 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 &&
+  const bool fast = hp == h && wp == w && pow2 && tw >= 32 && tw <= 4096 && th >= 2 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 &&
                     !(slow && *slow == '1');
   if (fast) {
-    clahe_hist_fast_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
+    clahe_lab_hist_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, dst, hist, tables, h, w, th, tw, bands);
     clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
     const int bands_per_cell = (th + BAND - 1) / BAND;            // edge cells are half as tall: their upper bands are empty
     const long long items = (long long)n * CELLS * CELLS * bands_per_cell;
     TRT_REQUIRE(items < (1ll << 31), "trt_clahe_bgr_u8: too many items");
-    const int blocks = (int)(items < 4ll * trt_num_sms() ? items : 4ll * trt_num_sms());
-    clahe_apply_fast_kernel<<<blocks, 256, 0, stream>>>(src, dst, luts, tables, h, w, th, tw, inv_th, inv_tw, bands_per_cell, (int)items);
+    const int blocks = (int)(items < 6ll * trt_num_sms() ? items : 6ll * trt_num_sms());
+    clahe_apply_lab_kernel<<<blocks, 256, 0, stream>>>(dst, luts, tables, h, w, th, tw, inv_th, inv_tw, bands_per_cell, (int)items);
   } else {
     clahe_hist_kernel<<<dim3(NT * bands, n), 256, 0, stream>>>(src, hist, tables, h, w, th, tw, bands);
     clahe_lut_kernel<<<dim3(NT, n), 256, 0, stream>>>(hist, luts, clip_limit, lut_scale);
