@@ -67,6 +67,10 @@ int trt_version(void);
 const char* trt_last_error_string(void);
 /* Select the device, verify it is sm_100, resolve cuTensorMapEncodeTiled. Call once per process/device. */
 int trt_init(int device);
+/* Launch mode of the kernels that support programmatic dependent launch (the inference chain): on != 0 lets each start
+ * while its predecessor in the stream drains and wait on the device (griddepcontrol).  Returns the previous setting; the
+ * Python host turns it on around eval forwards only (it measured slower inside the train step).  Process-wide. */
+int trt_set_pdl(int on);
 /* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long trt_launch_count(void);
 
@@ -80,6 +84,7 @@ unsigned long long trt_launch_count(void);
 #define TRT_EPI_SILU 2        /* y = silu(y) */
 #define TRT_EPI_RESIDUAL 4    /* y += residual[m, n]  (bf16) */
 #define TRT_EPI_STATS 8       /* stats[0][n] += sum_m y, stats[1][n] += sum_m y^2  (fp64; train-mode BN batch statistics) */
+#define TRT_EPI_MILGATE 16    /* internal: gated-attention score epilogue of trt_mil_attn_fwd_tc (no C output) */
 
 /* C[M,N] (bf16) = epi( A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major) ), fp32 accumulate in TMEM.
  * block_n_override: 0 = choose. */
@@ -289,6 +294,13 @@ int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb, const flo
                      trt_stream_t stream);
 /* parameter gradients are ACCUMULATED (+=): zero them first.  gV / gU (the gate activations saved by the forward) are
  * CONSUMED: they are overwritten with the gate gradients dv / du, which the weight-gradient and dH kernels then read. */
+/* The same forward with the score projection on the tensor cores (tcgen05 GEMM over split-bf16 operands, fp32-level
+ * accuracy: hi.Whi + lo.Whi + hi.Wlo; gate math in the epilogue).  workspace: trt_mil_attn_tc_workspace_bytes(B, K, D, hid)
+ * bytes, 256-byte aligned; needs D % 64 == 0 and hid % 8 == 0 (1280 / 128 and 256 in the reference). */
+size_t trt_mil_attn_tc_workspace_bytes(int B, int K, int D, int hid);
+int trt_mil_attn_fwd_tc(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub, const float* ww,
+                        const float* wb, float* M, float* A, float* gV, float* gU, int B, int K, int D, int hid, void* workspace,
+                        size_t workspace_bytes, trt_stream_t stream);
 int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, float* gV, float* gU, const float* Vw,
                      const float* Uw, const float* ww, float* dH, float* dVw, float* dVb, float* dUw, float* dUb, float* dww,
                      float* dwb, int B, int K, int D, int hid, trt_stream_t stream);

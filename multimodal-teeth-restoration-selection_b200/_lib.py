@@ -62,6 +62,7 @@ _SIGS = {
     "trt_last_error_string": (C.c_char_p, []),
     "trt_init": (i32, [i32]),
     "trt_launch_count": (u64, []),
+    "trt_set_pdl": (i32, [i32]),
     "trt_stat_replicas": (i32, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp]),
@@ -94,6 +95,8 @@ _SIGS = {
     "trt_mil_attn_smem_bytes": (sz, [i32, i32, i32, i32]),
     "trt_mil_attn_fwd": (i32, [vp] * 11 + [i32, i32, i32, i32, vp]),
     "trt_mil_attn_bwd": (i32, [vp] * 15 + [i32, i32, i32, i32, vp]),
+    "trt_mil_attn_tc_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "trt_mil_attn_fwd_tc": (i32, [vp] * 11 + [i32, i32, i32, i32, vp, sz, vp]),
     "trt_linear1_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, u64, vp, vp]),
     "trt_linear1_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, vp, vp]),
     "trt_bce_logits": (i32, [vp, vp, vp, vp, vp, i32, vp]),

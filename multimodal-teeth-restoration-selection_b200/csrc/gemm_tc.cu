@@ -40,6 +40,13 @@ struct GemmParams {
   const float* shift;
   const __nv_bfloat16* residual;
   double* stats;  // [TRT_STAT_REPLICAS][2][N]
+  int a_kblocks;  // > 0: A has only this many k-blocks; k-block kb of the product reads A k-block kb % a_kblocks (split operands)
+  // TRT_EPI_MILGATE: columns come in (V_j, U_j) pairs; score[m] += sum_j w[j] * tanh(acc[2j] + bias[2j]) * sigmoid(acc[2j+1] + bias[2j+1])
+  const float* mil_bias;   // [N] interleaved (Vb_j, Ub_j)
+  const float* mil_w;      // [N/2]
+  float* mil_score;        // [M] accumulated (atomicAdd): zeroed by the caller
+  float* mil_gv;           // [M][N/2] tanh(.) (optional, with mil_gu)
+  float* mil_gu;           // [M][N/2] sigmoid(.)
 };
 
 #ifdef TRT_GEMM_TIMING
@@ -55,7 +62,7 @@ __device__ unsigned long long g_gemm_dbg[8];
 struct SmemLayout {
   uint32_t a_off, b_off, c_off, cpitch, cbuf_bytes, bar_off, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int block_n, int stages, int ngroups, int b_slots) {
+__host__ __device__ inline SmemLayout make_layout(int block_n, int stages, int ngroups, int b_slots, int nostage = 0) {
   SmemLayout L;
   uint32_t b_stage = (uint32_t)block_n * 128u;
   L.a_off = 0;
@@ -66,6 +73,7 @@ __host__ __device__ inline SmemLayout make_layout(int block_n, int stages, int n
   L.cpitch = (((uint32_t)block_n >> 3) | 1u) * 16u;
   L.cbuf_bytes = (BM * L.cpitch + 1023u) & ~1023u;
   if (L.cbuf_bytes < 16384u) L.cbuf_bytes = 16384u;       // also the scratch of the statistics flush
+  if (nostage) L.cbuf_bytes = 1024u;                      // epilogues that keep everything in registers (gated-attention scores)
   L.bar_off = L.c_off + (uint32_t)ngroups * L.cbuf_bytes;
   L.total = L.bar_off + 256;
   return L;
@@ -76,7 +84,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 1024);
-  const SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages);
+  const SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages,
+                                   (p.flags & TRT_EPI_MILGATE) ? 1 : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;     // [nacc] accumulator complete (MMA -> epilogue group)
@@ -132,7 +141,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes));
-          ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage],
+                           (p.a_kblocks > 0 ? kb % p.a_kblocks : kb) * BK, m0);
           if (!p.b_resident) ptx::tma_load_2d(smem + L.b_off + stage * b_stage_bytes, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -237,6 +247,36 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::tc_fence_after();
         TRT_TICK(1);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+        if (p.flags & TRT_EPI_MILGATE) {
+          // gated-attention scores straight from the accumulator: a thread owns one instance row, its (V_j, U_j) pairs are
+          // adjacent columns; nothing is staged or stored except the optional gate activations the backward pass needs
+          float part = 0.f;
+          const int hid = p.N >> 1;
+          for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld32(taddr + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = n0 + c0 + 2 * i;
+              if (col < p.N) {
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(p.mil_bias + col));
+                const float v = __uint_as_float(r[2 * i]) + bb.x, u = __uint_as_float(r[2 * i + 1]) + bb.y;
+                const float tv = 2.0f * sigmoidf_(2.0f * v) - 1.0f, su = sigmoidf_(u);      // tanh(v) = 2 sigmoid(2v) - 1
+                part = fmaf(__ldg(p.mil_w + (col >> 1)) * tv, su, part);
+                if (p.mil_gv && row < p.M) {
+                  p.mil_gv[(size_t)row * hid + (col >> 1)] = tv;
+                  p.mil_gu[(size_t)row * hid + (col >> 1)] = su;
+                }
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::named_bar_sync(bar_id, EPI_THREADS);          // accumulator drained by all four warps
+          if (gt == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          if (row < p.M) atomicAdd(p.mil_score + row, part);
+          continue;
+        }
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           uint32_t r[32];
           const bool full = c0 + 32 <= p.block_n;    // the tile may end on a 16-column boundary
@@ -483,9 +523,12 @@ int pick_block_n_fwd(int M, int N, int K) {
 
 }  // namespace
 
+struct MilEpi { int a_kblocks; const float* bias; const float* w; float* score; float* gv; float* gu; };
+
 static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
-                       const float* shift, const void* residual, double* stats, int block_n_override, cudaStream_t stream) {
-  TRT_REQUIRE(A && B && C, "trt_gemm_bf16: null operand");
+                       const float* shift, const void* residual, double* stats, int block_n_override, cudaStream_t stream,
+                       const MilEpi* mil = nullptr) {
+  TRT_REQUIRE(A && B && (C || mil), "trt_gemm_bf16: null operand");
   TRT_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "trt_gemm_bf16: M,N,K must be >0 and N,K multiples of 8 (got %d %d %d)", M, N, K);
   TRT_REQUIRE(!(flags & TRT_EPI_SCALE_SHIFT) || (scale && shift), "trt_gemm_bf16: scale/shift missing");
   TRT_REQUIRE(!(flags & TRT_EPI_RESIDUAL) || residual, "trt_gemm_bf16: residual missing");
@@ -505,12 +548,18 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.stats = stats;
+  p.a_kblocks = 0;
+  p.mil_bias = p.mil_w = nullptr; p.mil_score = p.mil_gv = p.mil_gu = nullptr;
+  if (mil) {
+    p.a_kblocks = mil->a_kblocks; p.mil_bias = mil->bias; p.mil_w = mil->w; p.mil_score = mil->score; p.mil_gv = mil->gv; p.mil_gu = mil->gu;
+  }
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   const int b_stage = p.block_n * 128;
   p.b_resident = (p.num_n_blocks == 1 && p.num_k_blocks * b_stage <= 64 * 1024) ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage);
   const int fixed_bytes = (p.b_resident ? p.num_k_blocks * b_stage : 0) + 2048;
-  const int cbuf_bytes = (int)make_layout(p.block_n, 2, 1, 2).cbuf_bytes;
+  const int nostage = (flags & TRT_EPI_MILGATE) ? 1 : 0;
+  const int cbuf_bytes = (int)make_layout(p.block_n, 2, 1, 2, nostage).cbuf_bytes;
   // as many epilogue groups (one staging buffer each) as fit beside min(k-blocks + 1, 4) pipeline stages
   const int want_stages = p.num_k_blocks + 1 < 3 ? p.num_k_blocks + 1 : 3;
   // Several groups must each be the ONLY consumer of "their" accumulator barrier (mbarrier parity waits alias if a waiter can
@@ -526,14 +575,17 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages);
+  SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages, nostage);
   size_t smem_bytes = (size_t)L.total + 1024;      // slack for the manual 1024B alignment
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // > half an SM's smem: exactly one persistent CTA per SM
   CUtensorMap ta, tb;
   int rc;
-  if ((rc = trt_make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BM, BK))) return rc;
+  const uint64_t a_cols = p.a_kblocks > 0 ? (uint64_t)p.a_kblocks * BK : (uint64_t)K;     // physical width of A
+  if ((rc = trt_make_tmap_2d(&ta, A, (uint64_t)M, a_cols, a_cols, BM, BK))) return rc;
   if ((rc = trt_make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)p.block_n, BK))) return rc;
   TRT_REQUIRE((((uintptr_t)C) & 15) == 0, "trt_gemm_bf16: C must be 16-byte aligned");
+  TRT_REQUIRE(!(flags & TRT_EPI_MILGATE) || (mil && mil->bias && mil->w && mil->score && (N % 2) == 0 && (mil->gv == nullptr) == (mil->gu == nullptr)),
+              "trt_gemm_bf16: incomplete gated-attention epilogue");
   TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
@@ -611,4 +663,16 @@ extern "C" int trt_gemm_wgrad_bf16(const void* P, const void* Q, float* out, int
   TRT_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    // per device
   gemm_wgrad_kernel<<<tiles * p.splits, WGRAD_THREADS, smem_bytes, stream>>>(tp, tq, p);
   return trt_check_launch("trt_gemm_wgrad_bf16");
+}
+
+// internal (small.cu): A' = [hi | lo | hi] (physically [M, 2*D] bf16), B' = [Whi | Whi | Wlo] ([2*hid, 3*D] bf16, rows
+// interleaved V_j, U_j) -> gated-attention scores; see trt_mil_attn_fwd_tc
+int trt_gemm_mil_scores(const void* A_split, const void* W_split, int M, int hid, int D, const float* bias2, const float* w,
+                        float* score, float* gv, float* gu, cudaStream_t stream) {
+  MilEpi mil = {2 * D / BK, bias2, w, score, gv, gu};
+  // few instance rows (6 training bags = one 128-row tile): narrow n-blocks put more SMs on the weight stream; partial
+  // scores of the n-blocks meet in the atomicAdd
+  const int m_tiles = (M + BM - 1) / BM;
+  const int bn = (2 * hid) % 64 == 0 && m_tiles * ((2 * hid + 255) / 256) < 32 ? 64 : 0;
+  return gemm_launch(A_split, W_split, nullptr, M, 2 * hid, 3 * D, TRT_EPI_MILGATE, nullptr, nullptr, nullptr, nullptr, bn, stream, &mil);
 }

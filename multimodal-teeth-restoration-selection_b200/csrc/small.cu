@@ -87,6 +87,42 @@ __global__ void __launch_bounds__(TPB) mil_score_kernel(const float* __restrict_
   for (int k = threadIdx.x; k < K; k += TPB) atomicAdd(score + (size_t)b * K + k, s_sc[k]);
 }
 
+// ---- tensor-core path of the score pass: the [B*K, D] x [D, 2*hid] projection is a dense contraction.
+// fp32 accuracy is kept by splitting both operands into bf16 pairs x = hi + lo and taking three of the four products,
+//     x.w ~ hi.Whi + lo.Whi + hi.Wlo      (error ~2^-18 relative per product, the dropped lo.Wlo term)
+// as ONE tcgen05 GEMM over a 3*D-long reduction: A' = [hi | lo | hi] (stored once as [hi | lo]; the third segment re-reads
+// the first through the TMA coordinates), B' = [Whi | Whi | Wlo], weight rows interleaved (V_j, U_j) so the epilogue sees a
+// gate's two pre-activations in adjacent accumulator columns and reduces tanh * sigmoid * w to one score per instance.
+__global__ void __launch_bounds__(TPB) mil_split_h_kernel(const float4* __restrict__ H, uint2* __restrict__ out, size_t rows, int D4) {
+  // out row layout: [hi (D bf16) | lo (D bf16)]; one thread = 4 consecutive features
+  for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < rows * D4; i += (size_t)gridDim.x * TPB) {
+    const size_t r = i / D4;
+    const int d = (int)(i - r * D4);
+    const float4 x = __ldg(H + i);
+    const float h0 = bf16_round(x.x), h1 = bf16_round(x.y), h2 = bf16_round(x.z), h3 = bf16_round(x.w);
+    uint2 hi, lo;
+    hi.x = pack_bf16(h0, h1); hi.y = pack_bf16(h2, h3);
+    lo.x = pack_bf16(x.x - h0, x.y - h1); lo.y = pack_bf16(x.z - h2, x.w - h3);
+    out[r * 2 * D4 + d] = hi;
+    out[r * 2 * D4 + D4 + d] = lo;
+  }
+}
+// W' [2*hid][3*D] bf16: row 2j = V_j, row 2j+1 = U_j, columns [Whi | Whi | Wlo]; bias2[2j] = Vb_j, bias2[2j+1] = Ub_j
+__global__ void __launch_bounds__(TPB) mil_split_w_kernel(const float* __restrict__ Vw, const float* __restrict__ Uw,
+                                                          const float* __restrict__ Vb, const float* __restrict__ Ub,
+                                                          __nv_bfloat16* __restrict__ out, float* __restrict__ bias2, int hid, int D) {
+  const int n = blockIdx.x, j = n >> 1;
+  const float* w = (n & 1) ? Uw + (size_t)j * D : Vw + (size_t)j * D;
+  __nv_bfloat16* o = out + (size_t)n * 3 * D;
+  for (int d = threadIdx.x; d < D; d += TPB) {
+    const float x = __ldg(w + d), h = bf16_round(x);
+    o[d] = __float2bfloat16_rn(h);
+    o[D + d] = __float2bfloat16_rn(h);
+    o[2 * D + d] = __float2bfloat16_rn(x - h);
+  }
+  if (threadIdx.x == 0) bias2[n] = (n & 1) ? Ub[j] : Vb[j];
+}
+
 // A holds the raw scores on entry and the softmax weights on exit
 __global__ void __launch_bounds__(TPB) mil_pool_kernel(const float* __restrict__ H, const float* __restrict__ wb,
                                                        float* __restrict__ A, float* __restrict__ M, int K, int D) {
@@ -671,6 +707,42 @@ extern "C" int trt_mil_attn_fwd(const float* H, const float* Vw, const float* Vb
   trt_count_launch(1);
   mil_pool_kernel<<<B, TPB, (size_t)K * sizeof(float), stream>>>(H, wb, A, M, K, D);
   return trt_check_launch("trt_mil_attn_fwd");
+}
+
+int trt_gemm_mil_scores(const void* A_split, const void* W_split, int M, int hid, int D, const float* bias2, const float* w,
+                        float* score, float* gv, float* gu, cudaStream_t stream);     // gemm_tc.cu
+
+extern "C" size_t trt_mil_attn_tc_workspace_bytes(int B, int K, int D, int hid) {
+  const size_t hs = (size_t)B * K * 2 * D * 2, wsz = (size_t)2 * hid * 3 * D * 2, bs = (size_t)2 * hid * 4;
+  return ((hs + 255) & ~(size_t)255) + ((wsz + 255) & ~(size_t)255) + bs;
+}
+
+extern "C" int trt_mil_attn_fwd_tc(const float* H, const float* Vw, const float* Vb, const float* Uw, const float* Ub,
+                                   const float* ww, const float* wb, float* M, float* A, float* gV, float* gU, int B, int K,
+                                   int D, int hid, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  TRT_REQUIRE(H && Vw && Vb && Uw && Ub && ww && wb && M && A && workspace, "trt_mil_attn_fwd_tc: null pointer");
+  TRT_REQUIRE(B > 0 && K > 0 && D > 0 && D % 64 == 0 && hid > 0 && hid % 8 == 0 && 2 * hid <= 4096, "trt_mil_attn_fwd_tc: bad shape (D %% 64, hid %% 8)");
+  TRT_REQUIRE((gV == nullptr) == (gU == nullptr), "trt_mil_attn_fwd_tc: gV and gU must be given together");
+  TRT_REQUIRE(workspace_bytes >= trt_mil_attn_tc_workspace_bytes(B, K, D, hid) && (((uintptr_t)workspace) & 255) == 0,
+              "trt_mil_attn_fwd_tc: workspace too small or not 256-byte aligned");
+  TRT_REQUIRE((size_t)K * sizeof(float) <= 48 * 1024, "trt_mil_attn_fwd_tc: bag too large");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const size_t rows = (size_t)B * K;
+  const size_t hs = (rows * 2 * D * 2 + 255) & ~(size_t)255, wsz = ((size_t)2 * hid * 3 * D * 2 + 255) & ~(size_t)255;
+  __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(ws + hs);
+  float* bias2 = reinterpret_cast<float*>(ws + hs + wsz);
+  TRT_CUDA(cudaMemsetAsync(A, 0, rows * sizeof(float), stream));                // A accumulates the raw scores first
+  size_t blocks = (rows * (D / 4) + TPB - 1) / TPB;
+  if (blocks > (size_t)8 * trt_num_sms()) blocks = (size_t)8 * trt_num_sms();
+  mil_split_h_kernel<<<(int)blocks, TPB, 0, stream>>>(reinterpret_cast<const float4*>(H), reinterpret_cast<uint2*>(Hs), rows, D / 4);
+  trt_count_launch(1);
+  mil_split_w_kernel<<<2 * hid, TPB, 0, stream>>>(Vw, Uw, Vb, Ub, Ws, bias2, hid, D);
+  trt_count_launch(1);
+  int rc = trt_gemm_mil_scores(Hs, Ws, (int)rows, hid, D, bias2, ww, A, gV, gU, stream);
+  if (rc) return rc;
+  mil_pool_kernel<<<B, TPB, (size_t)K * sizeof(float), stream>>>(H, wb, A, M, K, D);
+  return trt_check_launch("trt_mil_attn_fwd_tc");
 }
 
 extern "C" int trt_mil_attn_bwd(const float* dM, const float* H, const float* A, float* gV, float* gU,

@@ -3,6 +3,7 @@ device pointers + the current CUDA stream to libteethrt and returns the output t
 Activations: NHWC bf16 viewed as [rows, C]; parameters/gradients fp32."""
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -208,7 +209,10 @@ def stem_wgrad(x, ds, dw):
 
 
 # ------------------------------------------------------------------------------------------------ MIL pooling
-def mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False):
+_mil_ws = {}
+
+
+def mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False, tensor_core=None):
     B, K, D = H.shape
     hid = Vw.shape[0]
     M = torch.empty((B, D), device=H.device, dtype=torch.float32)
@@ -217,8 +221,20 @@ def mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False):
     if save:
         gV = torch.empty((B, K, hid), device=H.device, dtype=torch.float32)
         gU = torch.empty_like(gV)
-    check(lib.trt_mil_attn_fwd(ptr(H), ptr(Vw), ptr(Vb), ptr(Uw), ptr(Ub), ptr(ww), ptr(wb), ptr(M), ptr(A), ptr(gV),
-                               ptr(gU), B, K, D, hid, stream()))
+    if tensor_core is None:
+        tensor_core = D % 64 == 0 and hid % 8 == 0 and os.environ.get("TEETHRT_MIL_TC", "1") != "0"
+    if tensor_core:
+        nbytes = int(lib.trt_mil_attn_tc_workspace_bytes(B, K, D, hid))
+        key = (str(H.device), nbytes)
+        ws = _mil_ws.get(key)
+        if ws is None:           # one per shape, never dropped: a captured train step keeps replaying into its workspace
+            ws = _mil_ws[key] = torch.empty(nbytes + 256, device=H.device, dtype=torch.uint8)
+        off = (-ws.data_ptr()) % 256
+        check(lib.trt_mil_attn_fwd_tc(ptr(H), ptr(Vw), ptr(Vb), ptr(Uw), ptr(Ub), ptr(ww), ptr(wb), ptr(M), ptr(A), ptr(gV),
+                                      ptr(gU), B, K, D, hid, ws.data_ptr() + off, nbytes, stream()))
+    else:
+        check(lib.trt_mil_attn_fwd(ptr(H), ptr(Vw), ptr(Vb), ptr(Uw), ptr(Ub), ptr(ww), ptr(wb), ptr(M), ptr(A), ptr(gV),
+                                   ptr(gU), B, K, D, hid, stream()))
     return M, A, gV, gU
 
 

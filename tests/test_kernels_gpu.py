@@ -390,8 +390,12 @@ def test_stem_forward_wgrad(ops, CS, N, H, W, dt):
 
 
 # ------------------------------------------------------------------------------------------------ MIL pooling
-@pytest.mark.parametrize("B,K,D,hid", [(6, 16, 1280, 128), (1, 5, 1280, 256), (3, 12, 64, 32), (2, 31, 1280, 128), (160, 7, 64, 40)])
-def test_mil_attention_forward_backward(ops, B, K, D, hid):
+@pytest.mark.parametrize("tc", [True, False], ids=["tcgen05", "cuda-cores"])
+@pytest.mark.parametrize("B,K,D,hid", [(6, 16, 1280, 128), (1, 5, 1280, 256), (3, 12, 64, 32), (2, 31, 1280, 128), (160, 7, 64, 40),
+                                       (70, 16, 1280, 128), (9, 16, 1280, 256)])
+def test_mil_attention_forward_backward(ops, B, K, D, hid, tc):
+    """tc: the score projection as a tcgen05 GEMM over split-bf16 operands (fp32-level accuracy) with the gate math in the
+    epilogue; otherwise the round-1 CUDA-core kernel.  Same tolerances for both."""
     H = rnd(B, K, D, seed=41)
     Vw, Vb = rnd(hid, D, seed=42, scale=D ** -0.5), rnd(hid, seed=43, scale=0.1)
     Uw, Ub = rnd(hid, D, seed=44, scale=D ** -0.5), rnd(hid, seed=45, scale=0.1)
@@ -401,8 +405,11 @@ def test_mil_attention_forward_backward(ops, B, K, D, hid):
     g = torch.tanh(Ht @ Vw_.t() + Vb_) * torch.sigmoid(Ht @ Uw_.t() + Ub_)
     a = torch.softmax(g @ ww_ + wb_, dim=1)
     M_ref = torch.einsum('bkd,bk->bd', Ht, a)
-    M, A, gV, gU = ops.mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=True)
+    M, A, gV, gU = ops.mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=True, tensor_core=tc)
     assert torch.allclose(M, M_ref, atol=1e-4, rtol=1e-4) and torch.allclose(A, a, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(gV, torch.tanh(Ht @ Vw_.t() + Vb_).detach(), atol=2e-5) and torch.allclose(gU, torch.sigmoid(Ht @ Uw_.t() + Ub_).detach(), atol=2e-5)
+    M2, A2, _, _ = ops.mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False, tensor_core=tc)          # inference flavour: no gate tensors
+    assert torch.allclose(M2, M, atol=1e-6) and torch.allclose(A2, A, atol=1e-6)
     dM = rnd(B, D, seed=48)
     M_ref.backward(dM)
     grads = [torch.zeros_like(t) for t in (Vw, Vb, Uw, Ub, ww, wb)]

@@ -39,6 +39,10 @@ for B in (6, 64, 1024):
     alg = B * (K * D * 4 + D * 4 + K * 4) + 2 * hid * D * 4
     out.append({"what": "mil_attn_fwd", "B": B, "K": K, "D": D, "hid": hid, "us": t * 1e6, "bags_per_s": B / t,
                 "algorithmic_GBps": alg / t / 1e9, "hbm_frac": alg / t / 1e9 / PK["hbm_gbs"], "gflops": B * 10.5e6 / t / 1e9})
+if "--only-mil" in sys.argv:
+    for o in out:
+        print(json.dumps(o))
+    sys.exit(0)
 # ---- MIL train step (B=6 bags x 16 instances @224, B0 encoder)
 torch.manual_seed(0)
 m = MILNet().cuda()
