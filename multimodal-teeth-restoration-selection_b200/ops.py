@@ -222,7 +222,10 @@ def mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False, tensor_core=None):
         gV = torch.empty((B, K, hid), device=H.device, dtype=torch.float32)
         gU = torch.empty_like(gV)
     if tensor_core is None:
-        tensor_core = D % 64 == 0 and hid % 8 == 0 and os.environ.get("TEETHRT_MIL_TC", "1") != "0"
+        # measured (profiles/r02_microbench.jsonl): 6 bags x 16 = 96 instance rows are one 128-row tile - the CUDA-core kernel
+        # (45 us) beats split + GEMM + pool (72 us, launch-bound); from 64 bags on the tensor-core path wins (70 vs 115 us,
+        # 128 vs 942 us at 1024 bags)
+        tensor_core = B * K >= 512 and D % 64 == 0 and hid % 8 == 0 and os.environ.get("TEETHRT_MIL_TC", "1") != "0"
     if tensor_core:
         nbytes = int(lib.trt_mil_attn_tc_workspace_bytes(B, K, D, hid))
         key = (str(H.device), nbytes)

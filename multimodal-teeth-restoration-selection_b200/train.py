@@ -261,7 +261,7 @@ class DualTaskTrainer(_FusedTrainer):
     """MMJointDualHead + dual BCE + clip + AdamW + cosine (train_mm_joint_dualtask.py:217-256)."""
 
     def __init__(self, model, lr=3e-4, weight_decay=1e-4, t_max=0, alpha=1.0, beta=0.3, grad_clip=1.0,
-                 use_sample_weights=False, graph=True, process_group=None, num_buckets=3, seed=0):
+                 use_sample_weights=False, graph=True, process_group=None, num_buckets=4, seed=0):
         super().__init__(model, lr, weight_decay, t_max, grad_clip, graph, process_group, num_buckets)
         self.alpha, self.beta, self.use_w, self.seed = float(alpha), float(beta), bool(use_sample_weights), int(seed)
 
@@ -299,29 +299,38 @@ class DualTaskTrainer(_FusedTrainer):
 
         # bucket 0 = tab + heads (everything after the backbone in the flat buffer); the backbone is cut where the parameter
         # mass is: the last two stages + head hold ~80 % of the weights but are the FIRST quarter of the backward pass, so
-        # their all-reduce (bucket 1) hides behind the backward of the early, activation-heavy stages (bucket 2)
+        # their all-reduce (bucket 1) hides behind the backward of the early, activation-heavy stages.  With 4 buckets those
+        # are cut once more in front of stage 2: the LAST bucket (stem + stages 0-1, ~1 % of the weights) is the only
+        # all-reduce nothing can hide, so it should be a latency-sized message (round 1: 14 MB exposed, 0.24 ms/step at N=8)
         first_head = min(fl.offsets[k][0] for k in TAB_PARAM_KEYS)
-        blocks = [n for n, _ in enc.block_list()]
-        split = None
+        splits = []
         if self.world > 1 and self.num_buckets >= 3 and len(enc.blocks) >= 3:
-            split = f"blocks.{len(enc.blocks) - 2}.0"           # first block of the second-to-last stage
-        if split is None:
+            splits.append(f"blocks.{len(enc.blocks) - 2}.0")    # first block of the second-to-last stage
+            if self.num_buckets >= 4 and len(enc.blocks) >= 5:
+                splits.append("blocks.2.0")                     # first block of stage 2
+        if not splits:
             def enc_backward():
                 backward_train(enc, holder["ctx"], self.dfeat, enc_grads)
                 holder.clear()
             return [fwd_and_heads, enc_backward], self._bucket_ranges([first_head])
 
-        def enc_backward_late():
-            holder["it"] = backward_train_iter(enc, holder["ctx"], self.dfeat, enc_grads, split_after=(split,))
-            assert next(holder["it"]) == split
+        def first_segment():
+            holder["it"] = backward_train_iter(enc, holder["ctx"], self.dfeat, enc_grads, split_after=tuple(splits))
+            assert next(holder["it"]) == splits[0]
 
-        def enc_backward_early():
+        def middle_segment(expected):
+            def run():
+                assert next(holder["it"]) == expected
+            return run
+
+        def last_segment():
             for _ in holder["it"]:
                 pass
             holder.clear()
 
-        first_split = min(o for n, (o, _, _) in fl.offsets.items() if n.startswith("backbone." + split + "."))
-        return [fwd_and_heads, enc_backward_late, enc_backward_early], self._bucket_ranges([first_head, first_split])
+        segs = [fwd_and_heads, first_segment] + [middle_segment(sp) for sp in splits[1:]] + [last_segment]
+        cuts = [min(o for n, (o, _, _) in fl.offsets.items() if n.startswith("backbone." + sp + ".")) for sp in splits]
+        return segs, self._bucket_ranges([first_head] + cuts)
 
     def prefetch(self, x_img, x_tab, y_h, y_s, w=None):
         super().prefetch(x_img, x_tab, y_h, y_s, w)

@@ -407,7 +407,7 @@ def test_mil_attention_forward_backward(ops, B, K, D, hid, tc):
     M_ref = torch.einsum('bkd,bk->bd', Ht, a)
     M, A, gV, gU = ops.mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=True, tensor_core=tc)
     assert torch.allclose(M, M_ref, atol=1e-4, rtol=1e-4) and torch.allclose(A, a, atol=1e-5, rtol=1e-4)
-    assert torch.allclose(gV, torch.tanh(Ht @ Vw_.t() + Vb_).detach(), atol=2e-5) and torch.allclose(gU, torch.sigmoid(Ht @ Uw_.t() + Ub_).detach(), atol=2e-5)
+    assert torch.allclose(gV, torch.tanh(Ht @ Vw_.t() + Vb_).detach(), atol=1e-4) and torch.allclose(gU, torch.sigmoid(Ht @ Uw_.t() + Ub_).detach(), atol=1e-4)
     M2, A2, _, _ = ops.mil_attn_fwd(H, Vw, Vb, Uw, Ub, ww, wb, save=False, tensor_core=tc)          # inference flavour: no gate tensors
     assert torch.allclose(M2, M, atol=1e-6) and torch.allclose(A2, A, atol=1e-6)
     dM = rnd(B, D, seed=48)

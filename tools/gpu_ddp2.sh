@@ -1,7 +1,9 @@
 #!/bin/bash
-# 2-GPU A/B of the NCCL stream priority with the data-parallel bench (torchrun, NCCL over NVLink).
+# 2 GPUs: configs[4] as written (global batch 512 -> 256 per GPU) through torchrun + NCCL, the cross-rank parameter check,
+# the weak-scaling arm, the reference arm launched the same way, and the non-current-device test.
 mkdir -p gpurun_out
-one() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus 2 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/ddp2_$1.log 2>&1; echo "$1 exit=$? $(tail -1 gpurun_out/ddp2_$1.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3), round(d['value'],1), 'e2e', round(d['e2e']['value'],1))")"; }
-TEETHRT_NCCL_HIPRIO=0 one nccl_default 29531
-TEETHRT_NCCL_HIPRIO=1 one nccl_high 29532
-timeout 200 python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('1gpu', round(d['ms_per_step'],3), round(d['value'],1))"
+T=${TAG:-r02}
+N=${N:-2}
+run() { name=$1; shift; echo "=== $name" ; timeout ${TMO:-400} "$@" > gpurun_out/${T}_$name.log 2>&1; echo "exit=$?"; tail -n ${TAILN:-3} gpurun_out/${T}_$name.log | cut -c1-${CUT:-2500}; }
+TAILN=1 run ddp$N python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 20 --warmup 3
+TAILN=4 CUT=300 run dev1_test python -m pytest tests/test_configs_gpu.py -q -k non_current_device
