@@ -24,7 +24,7 @@ for row in csv.DictReader(lines):
 have_adv = any(o["op"] == "optim_advance" for o in ops)
 ours = [(n, t) for n, t in kern if "at::" not in n and "elementwise" not in n and "Memset" not in n
         and (have_adv or "optim_advance" not in n)]
-ops = [o for o in ops if o["op"] not in ("bn_fin", "bn_bwd_fin")]
+ops = [o for o in ops if o["op"] not in ("bn_fin", "bn_bwd_fin", "se_bn")]
 need = sum(o["launches"] for o in ops)
 print(f"# {len(kern)} launches in the csv, {len(ours)} from libteethrt, op log expects {need}")
 if len(ours) != need:

@@ -56,7 +56,7 @@ def wrap(name, fn):
 for n in dir(ops):
     f = getattr(ops, n)
     if callable(f) and getattr(f, "__module__", None) == ops.__name__ and not n.startswith("_") and n not in (
-            "same_out", "same_pad", "tab_heads_scratch", "OptimState", "bn_fin", "bn_bwd_fin", "new_stats", "stats_total"):
+            "same_out", "same_pad", "tab_heads_scratch", "OptimState", "bn_fin", "bn_bwd_fin", "se_bn", "new_stats", "stats_total"):
         setattr(ops, n, wrap(n, f))
 
 ops.OptimState.advance = wrap("optim_advance", ops.OptimState.advance)     # a method, not a module-level op
