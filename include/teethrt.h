@@ -61,6 +61,7 @@ typedef struct {
   float* coef;                     /* [3][C] scratch (optional): lets the callee finalise with a launch of its own when the
                                       in-prologue form would cost more than it saves (small tensors, many blocks) */
   double count;
+  int raw_x;                       /* 1: bstats[1] holds sum dy*x (trt_gemm_bf16_bnbwd); converted with the record's mean / rstd */
 } trt_bn_bwd_fin_t;
 
 int trt_version(void);
@@ -85,11 +86,19 @@ unsigned long long trt_launch_count(void);
 #define TRT_EPI_RESIDUAL 4    /* y += residual[m, n]  (bf16) */
 #define TRT_EPI_STATS 8       /* stats[0][n] += sum_m y, stats[1][n] += sum_m y^2  (fp64; train-mode BN batch statistics) */
 #define TRT_EPI_MILGATE 16    /* internal: gated-attention score epilogue of trt_mil_attn_fwd_tc (no C output) */
+#define TRT_EPI_BNBWD 32      /* with TRT_EPI_STATS: stats[1][n] += sum_m y * bn_x[m,n] instead of sum_m y^2 (trt_gemm_bf16_bnbwd) */
 
 /* C[M,N] (bf16) = epi( A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major) ), fp32 accumulate in TMEM.
  * block_n_override: 0 = choose. */
 int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
                   const float* shift, const void* residual, double* stats, int block_n_override, trt_stream_t stream);
+
+/* Data-gradient GEMM that also accumulates the backward sums of the BatchNorm its OUTPUT feeds next in the backward pass:
+ * C = A . B^T (+ residual); bstats[0][n] += sum_m C[m,n], bstats[1][n] += sum_m C[m,n] * bn_x[m,n]  (bn_x = the raw input
+ * of that BatchNorm; the sums are over the bf16-rounded C that is stored).  Saves the separate trt_bn_bwd_reduce pass over
+ * (C, bn_x); trt_affine2 is told through trt_bn_bwd_fin_t.raw_x that the second sum is sum dy*x, not sum dy*xhat. */
+int trt_gemm_bf16_bnbwd(const void* A, const void* B, void* C, int M, int N, int K, int flags, const void* residual,
+                        const void* bn_x, double* bstats, trt_stream_t stream);
 
 /* out[p*so_p + q*so_q] (fp32) += sum_m P[m,p] * Q[m,q]   (P:[M,Cp], Q:[M,Cq] bf16 row-major; weight gradient).
  * q_store: 0 = Cq; otherwise only columns q < q_store are stored (Q zero-padded beyond, e.g. the stem's 27 of 32 taps).

@@ -65,6 +65,7 @@ _SIGS = {
     "trt_set_pdl": (i32, [i32]),
     "trt_stat_replicas": (i32, []),
     "trt_gemm_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+    "trt_gemm_bf16_bnbwd": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "trt_gemm_wgrad_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp]),
     "trt_clahe_workspace_bytes": (sz, [i32]),
     "trt_clahe_bgr_u8": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, sz, vp]),
@@ -146,7 +147,7 @@ class BnFin(C.Structure):
 
 class BnBwdFin(C.Structure):
     """trt_bn_bwd_fin_t: lazy BatchNorm backward - trt_affine2 derives dx = a*dy + b*x + c from the sums and writes dgamma/dbeta."""
-    _fields_ = [("bstats", vp), ("rec", vp), ("gamma", vp), ("dgamma", vp), ("dbeta", vp), ("coef", vp), ("count", f64)]
+    _fields_ = [("bstats", vp), ("rec", vp), ("gamma", vp), ("dgamma", vp), ("dbeta", vp), ("coef", vp), ("count", f64), ("raw_x", i32)]
 
 
 class SeBn(C.Structure):

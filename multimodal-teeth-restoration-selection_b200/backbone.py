@@ -544,7 +544,11 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
 
     lazy = _lazy_bn()
 
-    def bn_dx(bn_name, count, bst, g, x_raw, out):
+    # the data-gradient GEMM that produces a block's input gradient also accumulates the backward sums of the BatchNorm that
+    # gradient flows into next (the previous block's project BN): no separate pass over (dy, p_raw).  Needs the lazy affine2.
+    fuse_bnbwd = bool(lazy & 4) and os.environ.get("TEETHRT_GEMM_BNBWD", "1") != "0"
+
+    def bn_dx(bn_name, count, bst, g, x_raw, out, raw_x=False):
         """BatchNorm backward apply: out = a*g + b*x_raw + c with the coefficients of BatchNorm `bn_name`, whose sums `bst`
         the producer of `g` has just accumulated; also lands dgamma / dbeta in `grads`.  Lazy (default): trt_affine2 derives
         the coefficients itself - no finalise launch in between."""
@@ -552,7 +556,8 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
         dgm, dbt = grads[bn_name + ".weight"], grads[bn_name + ".bias"]
         coef = torch.empty((3, bn.weight.numel()), device=dev, dtype=torch.float32)
         if lazy & 4:
-            return ops.affine2(g, x_raw, None, out, fin=ops.bn_bwd_fin(bst, REC[bn_name], bn.weight.detach(), dgm, dbt, count, coef))
+            return ops.affine2(g, x_raw, None, out, fin=ops.bn_bwd_fin(bst, REC[bn_name], bn.weight.detach(), dgm, dbt, count, coef, raw_x))
+        assert not raw_x
         ops.bn_bwd_finalize(bst, REC[bn_name], bn.weight.detach(), coef, dgm, dbt, count)
         return ops.affine2(g, x_raw, coef, out)
 
@@ -563,20 +568,36 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
     bst = bstats.take(ops.STAT_REPLICAS * 2 * F_)
     g = ops.act_bwd(None, None, dfeat, 1.0 / hw, hd["raw"], REC["bn2"], torch.empty_like(hd["raw"]), bst, N, hw, act=1)
     d_raw = bn_dx("bn2", N * hw, bst, g, hd["raw"], g)
-    dy = ops.gemm(d_raw, Wp["conv_head"][1])
+    blocks = ctx["blocks"]
+
+    def dgrad(A, Wt, idx, residual=None):
+        """dx of the GEMM whose output is the input gradient of block `idx` - i.e. the output gradient of block idx - 1, whose
+        project BatchNorm consumes it next.  -> (dx, bst of that BatchNorm or None)."""
+        if fuse_bnbwd and idx >= 1:
+            psv = blocks[idx - 1][1]
+            bst_prev = bstats.take(ops.STAT_REPLICAS * 2 * psv["p_raw"].shape[1])
+            return ops.gemm_bnbwd(A, Wt, psv["p_raw"], bst_prev, residual=residual), bst_prev
+        return ops.gemm(A, Wt, ops.EPI_RESIDUAL if residual is not None else 0, residual=residual), None
+
+    dy, dy_bst = dgrad(d_raw, Wp["conv_head"][1], len(blocks))
     sq.wgrad(d_raw, hd["x"], grads["conv_head.weight"])
     del g, d_raw
 
-    for blk, sv in reversed(ctx["blocks"]):
+    for bidx in range(len(blocks) - 1, -1, -1):
+        blk, sv = blocks[bidx]
         c, name = blk.cfg, sv["name"]
         k, s = c["k"], c["s"]
         h, w, oh, ow = sv["h"], sv["w"], sv["oh"], sv["ow"]
         ohw = oh * ow
         cm = sv["d_raw"].shape[1]
         # project conv + its BN (no activation)
-        bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cout"])
-        ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst)
-        dp = bn_dx(sv["bn_out"], N * ohw, bst, dy, sv["p_raw"], torch.empty_like(dy))
+        if dy_bst is not None:        # the GEMM that produced dy already summed {dy, dy * p_raw}
+            dp = bn_dx(sv["bn_out"], N * ohw, dy_bst, dy, sv["p_raw"], torch.empty_like(dy), raw_x=True)
+        else:
+            bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cout"])
+            ops.bn_bwd_reduce(dy, sv["p_raw"], REC[sv["bn_out"]], bst)
+            dp = bn_dx(sv["bn_out"], N * ohw, bst, dy, sv["p_raw"], torch.empty_like(dy))
+        dy_bst = None
         dA = ops.gemm(dp, Wp[sv["pw_name"]][1])
         sq.wgrad(dp, sv["a"], grads[sv["pw_name"] + ".weight"])
         # squeeze-excite + activation + BN of the depthwise output
@@ -612,8 +633,7 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
             sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), e_raw, rec1, dw_grad, N, h, w, k, s)
             ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, None, N, h, w, k, s)
             de = bn_dx(name + ".bn1", N * h * w, bst, g1, e_raw, g1)
-            flags = ops.EPI_RESIDUAL if sv["has_skip"] else 0
-            dx = ops.gemm(de, Wp[name + ".conv_pw"][1], flags, residual=dy if sv["has_skip"] else None)
+            dx, dy_bst = dgrad(de, Wp[name + ".conv_pw"][1], bidx, residual=dy if sv["has_skip"] else None)
             sq.wgrad(de, sv["x"], grads[name + ".conv_pw.weight"])
             dy = dx
         else:

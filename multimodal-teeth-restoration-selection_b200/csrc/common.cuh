@@ -174,10 +174,12 @@ __device__ __forceinline__ void bn_lazy_block(const trt_bn_fin_t& f, int C, int 
 // backward: bstats {sum dy, sum dy*xhat} -> dx = a*dy + b*x + c for one channel (what bn_bwd_finalize_kernel publishes)
 struct BnBwdChannel { float a, b, c, dgamma, dbeta; };
 __device__ __forceinline__ BnBwdChannel bn_bwd_channel(const double* bstats, const float* rec, const float* gamma, int C, int c,
-                                                       double count) {
+                                                       double count, int raw_x = 0) {
   BnBwdChannel r;
-  const double sdy = stat_total(bstats, C, c), sdyx = stat_total(bstats, C, C + c);
   const float mean = rec[2 * C + c], rstd = rec[3 * C + c];
+  const double sdy = stat_total(bstats, C, c);
+  double sdyx = stat_total(bstats, C, C + c);
+  if (raw_x) sdyx = (double)rstd * (sdyx - (double)mean * sdy);      // the producer summed dy * x: -> sum dy * xhat
   const float a = gamma[c] * rstd;
   const float m1 = (float)(sdy / count), m2 = (float)(sdyx / count);
   r.a = a;

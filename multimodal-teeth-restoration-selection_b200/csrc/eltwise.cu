@@ -89,10 +89,10 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 // coef[0]=a, [1]=b, [2]=c with dx = a*dy + b*x + c ; also dgamma / dbeta (written, not accumulated)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bstats, const float* __restrict__ rec,
                                        const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int C, double count) {
+                                       float* __restrict__ dbeta, int C, double count, int raw_x) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const BnBwdChannel b = bn_bwd_channel(bstats, rec, gamma, C, c, count);
+  const BnBwdChannel b = bn_bwd_channel(bstats, rec, gamma, C, c, count, raw_x);
   coef[c] = b.a;
   coef[C + c] = b.b;
   coef[2 * C + c] = b.c;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TPB) affine2_kernel(const uint4* __restrict__ 
     for (int i = threadIdx.x; i < VX * 8; i += TPB) {
       const int c = c0 + i;
       if (c < C) {
-        const BnBwdChannel b = bn_bwd_channel(fin.bstats, fin.rec, fin.gamma, C, c, fin.count);
+        const BnBwdChannel b = bn_bwd_channel(fin.bstats, fin.rec, fin.gamma, C, c, fin.count, fin.raw_x);
         s_abc[0][i] = b.a; s_abc[1][i] = b.b; s_abc[2][i] = b.c;
         if (blockIdx.x == 0) { fin.dgamma[c] = b.dgamma; fin.dbeta[c] = b.dbeta; }
       }
@@ -995,7 +995,7 @@ extern "C" int trt_bn_fold_eval(const float* gamma, const float* beta, const flo
 extern "C" int trt_bn_bwd_finalize(const double* bstats, const float* rec, const float* gamma, float* coef, float* dgamma,
                                    float* dbeta, int C, double count, cudaStream_t stream) {
   TRT_REQUIRE(bstats && rec && gamma && coef && dgamma && dbeta && C > 0, "trt_bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(bstats, rec, gamma, coef, dgamma, dbeta, C, count);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(bstats, rec, gamma, coef, dgamma, dbeta, C, count, 0);
   return trt_check_launch("trt_bn_bwd_finalize");
 }
 
@@ -1116,7 +1116,7 @@ extern "C" int trt_affine2(const void* dy, const void* x, const float* coef, voi
   dim3 grid(row_blocks((rows + UNR - 1) / UNR, L.RY, L.slabs, 6 * trt_num_sms()), L.slabs);
   int lazy = fin_host ? 1 : 0;
   if (lazy && fin.coef && !lazy_pays((long long)grid.x * grid.y, L.VX * 8)) {
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(fin.bstats, fin.rec, fin.gamma, fin.coef, fin.dgamma, fin.dbeta, C, fin.count);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(fin.bstats, fin.rec, fin.gamma, fin.coef, fin.dgamma, fin.dbeta, C, fin.count, fin.raw_x);
     trt_count_launch(1);
     coef = fin.coef;
     lazy = 0;

@@ -40,6 +40,7 @@ struct GemmParams {
   const float* shift;
   const __nv_bfloat16* residual;
   double* stats;  // [TRT_STAT_REPLICAS][2][N]
+  const __nv_bfloat16* bn_x;   // TRT_EPI_BNBWD: [M,N] input of the BatchNorm whose backward sums this launch accumulates
   int a_kblocks;  // > 0: A has only this many k-blocks; k-block kb of the product reads A k-block kb % a_kblocks (split operands)
   // TRT_EPI_MILGATE: columns come in (V_j, U_j) pairs; score[m] += sum_j w[j] * tanh(acc[2j] + bias[2j]) * sigmoid(acc[2j+1] + bias[2j+1])
   const float* mil_bias;   // [N] interleaved (Vb_j, Ub_j)
@@ -195,6 +196,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int gt = threadIdx.x - 64 - g * EPI_THREADS;   // 0..127 inside the group
       const bool f_ss = p.flags & TRT_EPI_SCALE_SHIFT, f_silu = p.flags & TRT_EPI_SILU;
       const bool f_res = p.flags & TRT_EPI_RESIDUAL, f_stats = p.flags & TRT_EPI_STATS;
+      const bool f_bnbwd = p.flags & TRT_EPI_BNBWD;     // second sum = sum y * bn_x instead of sum y^2 (BatchNorm backward)
       const uint32_t cpitch = L.cpitch;
       uint8_t* cstage = smem + L.c_off + g * L.cbuf_bytes;
       const int n_oct = p.block_n >> 3;             // 8-column octets per tile row
@@ -321,11 +323,15 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           __nv_bfloat16* gbase = p.C + (size_t)m0 * p.N + n0 + so * 8;
           const int rows_here = min(BM, p.M - m0);
           const uint32_t one2 = 0x3f803f80u;                  // bf16x2 {1, 1}
+          const __nv_bfloat16* xbase = f_bnbwd ? p.bn_x + (size_t)m0 * p.N + n0 + so * 8 : nullptr;
           for (int r0 = srg; r0 < rows_here; r0 += 4 * rg_count) {
-            uint4 w[4];
+            uint4 w[4], xq[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              if (r0 + u * rg_count < rows_here) w[u] = *reinterpret_cast<const uint4*>(cbase + (r0 + u * rg_count) * cpitch);
+              if (r0 + u * rg_count < rows_here) {
+                w[u] = *reinterpret_cast<const uint4*>(cbase + (r0 + u * rg_count) * cpitch);
+                if (f_bnbwd) xq[u] = ldg16(xbase + (size_t)(r0 + u * rg_count) * p.N);
+              }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               if (r0 + u * rg_count < rows_here) *reinterpret_cast<uint4*>(gbase + (size_t)(r0 + u * rg_count) * p.N) = w[u];
@@ -334,13 +340,15 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               for (int u = 0; u < 4; ++u) {
                 if (r0 + u * rg_count < rows_here) {
                   const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+                  const uint32_t xs[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     const uint16_t lo = (uint16_t)(ws[i] & 0xffffu), hi = (uint16_t)(ws[i] >> 16);
+                    const uint16_t qlo = f_bnbwd ? (uint16_t)(xs[i] & 0xffffu) : lo, qhi = f_bnbwd ? (uint16_t)(xs[i] >> 16) : hi;
                     st_s[2 * i] = ptx::fhfma(lo, (uint16_t)(one2 & 0xffffu), st_s[2 * i]);
                     st_s[2 * i + 1] = ptx::fhfma(hi, (uint16_t)(one2 >> 16), st_s[2 * i + 1]);
-                    st_q[2 * i] = ptx::fhfma(lo, lo, st_q[2 * i]);
-                    st_q[2 * i + 1] = ptx::fhfma(hi, hi, st_q[2 * i + 1]);
+                    st_q[2 * i] = ptx::fhfma(lo, qlo, st_q[2 * i]);
+                    st_q[2 * i + 1] = ptx::fhfma(hi, qhi, st_q[2 * i + 1]);
                   }
                 }
               }
@@ -527,7 +535,7 @@ struct MilEpi { int a_kblocks; const float* bias; const float* w; float* score; 
 
 static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,
                        const float* shift, const void* residual, double* stats, int block_n_override, cudaStream_t stream,
-                       const MilEpi* mil = nullptr) {
+                       const MilEpi* mil = nullptr, const void* bn_x = nullptr) {
   TRT_REQUIRE(A && B && (C || mil), "trt_gemm_bf16: null operand");
   TRT_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 8) == 0 && (K % 8) == 0, "trt_gemm_bf16: M,N,K must be >0 and N,K multiples of 8 (got %d %d %d)", M, N, K);
   TRT_REQUIRE(!(flags & TRT_EPI_SCALE_SHIFT) || (scale && shift), "trt_gemm_bf16: scale/shift missing");
@@ -548,6 +556,9 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.stats = stats;
+  p.bn_x = reinterpret_cast<const __nv_bfloat16*>(bn_x);
+  TRT_REQUIRE(!(flags & TRT_EPI_BNBWD) || ((flags & TRT_EPI_STATS) && bn_x && (((uintptr_t)bn_x) & 15) == 0),
+              "trt_gemm_bf16: the BatchNorm-backward sums need TRT_EPI_STATS and a 16-byte aligned bn_x");
   p.a_kblocks = 0;
   p.mil_bias = p.mil_w = nullptr; p.mil_score = p.mil_gv = p.mil_gu = nullptr;
   if (mil) {
@@ -591,6 +602,12 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
   TRT_CUDA(trt_launch(gemm_kmajor_kernel, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p));
   return trt_check_launch("trt_gemm_bf16");
+}
+
+extern "C" int trt_gemm_bf16_bnbwd(const void* A, const void* B, void* C, int M, int N, int K, int flags, const void* residual,
+                                   const void* bn_x, double* bstats, cudaStream_t stream) {
+  return gemm_launch(A, B, C, M, N, K, (flags & TRT_EPI_RESIDUAL) | TRT_EPI_STATS | TRT_EPI_BNBWD, nullptr, nullptr, residual, bstats,
+                     0, stream, nullptr, bn_x);
 }
 
 extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int flags, const float* scale,

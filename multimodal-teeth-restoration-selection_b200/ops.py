@@ -56,10 +56,24 @@ def bn_fin(stats, gamma, beta, rm, rv, nbt, rec, count, eps, momentum=0.1):
     return BnFin(ptr(stats), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(rec), float(count), eps, momentum)
 
 
-def bn_bwd_fin(bstats, rec, gamma, dgamma, dbeta, count, coef=None):
+def gemm_bnbwd(A, B, bn_x, bstats, residual=None, out=None):
+    """Data-gradient GEMM C = A @ B^T (+ residual) that also accumulates {sum C, sum C * bn_x} per output channel: the
+    backward sums of the BatchNorm (input bn_x) that C flows into next (pass raw_x=True to bn_bwd_fin)."""
+    _c(A, bf16), _c(B, bf16), _c(bn_x, bf16)
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K and tuple(bn_x.shape) == (M, N)
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=bf16)
+    check(lib.trt_gemm_bf16_bnbwd(ptr(A), ptr(B), ptr(out), M, N, K, EPI_RESIDUAL if residual is not None else 0, ptr(residual),
+                                  ptr(bn_x), ptr(bstats), stream()))
+    return out
+
+
+def bn_bwd_fin(bstats, rec, gamma, dgamma, dbeta, count, coef=None, raw_x=False):
     """Lazy BatchNorm backward: pass to affine2 instead of a coefficient tensor.  coef: optional [3,C] scratch that lets the
     library finalise with its own launch where that is cheaper (small tensors)."""
-    return BnBwdFin(ptr(bstats), ptr(rec), ptr(gamma), ptr(dgamma), ptr(dbeta), ptr(coef), float(count))
+    return BnBwdFin(ptr(bstats), ptr(rec), ptr(gamma), ptr(dgamma), ptr(dbeta), ptr(coef), float(count), int(raw_x))
 
 
 def _ref(st):

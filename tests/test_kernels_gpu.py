@@ -94,6 +94,34 @@ def test_gemm_epilogues(ops, M, N, K):
     assert torch.allclose(tot[1], (cf * cf).sum(0), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K,res", [(3136, 448, 2688, True), (50176, 56, 336, False), (200, 24, 144, True), (12544, 160, 960, True)])
+def test_gemm_with_batchnorm_backward_sums(ops, M, N, K, res):
+    """Data-gradient GEMM whose epilogue also accumulates {sum C, sum C * x} per output channel over the stored (bf16) C: the
+    backward sums of the BatchNorm (input x) that C flows into next - equal to the separate bn_bwd_reduce pass, and through
+    the lazy affine2 (raw_x) equal to bn_bwd_reduce + bn_bwd_finalize + affine2."""
+    A, B = rnd(M, K, seed=61, dtype=bf16), rnd(N, K, seed=62, dtype=bf16, scale=K ** -0.5)
+    x = rnd(M, N, seed=63, dtype=bf16) * 1.5 + 0.4
+    r = rnd(M, N, seed=64, dtype=bf16) if res else None
+    bst = ops.new_stats(N, "cuda")
+    C = ops.gemm_bnbwd(A, B, x, bst, residual=r)
+    want = ops.gemm(A, B, ops.EPI_RESIDUAL if res else 0, residual=r)
+    assert torch.equal(C, want)
+    Cd, xd = C.double(), x.double()
+    tot = ops.stats_total(bst)
+    assert torch.allclose(tot[0], Cd.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(tot[1], (Cd * xd).sum(0), rtol=1e-4, atol=5e-2)
+    # through the lazy BatchNorm-backward apply
+    gamma, beta = rnd(N, seed=65) * 0.1 + 1, rnd(N, seed=66) * 0.1
+    rec, _, _, _ = make_rec(ops, x, gamma, beta)
+    bs2 = ops.new_stats(N, "cuda")
+    ops.bn_bwd_reduce(C, x, rec, bs2)
+    coef, dg0, db0 = torch.empty(3, N, device="cuda"), torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    ops.bn_bwd_finalize(bs2, rec, gamma, coef, dg0, db0, M)
+    ref = ops.affine2(C, x, coef, torch.empty_like(C))
+    dg, db = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    got = ops.affine2(C, x, None, torch.empty_like(C), fin=ops.bn_bwd_fin(bst, rec, gamma, dg, db, M, torch.empty(3, N, device="cuda"), raw_x=True))
+    assert rel_err(got, ref) < 2e-3 and rel_err(dg, dg0) < 2e-3 and rel_err(db, db0) < 1e-4
+
+
 @pytest.mark.parametrize("M,Cp,Cq", [(4096, 144, 24), (1000, 24, 144), (50000, 32, 192), (3136, 448, 2688), (777, 1632, 272),
                                      (64, 48, 24)])
 def test_gemm_wgrad(ops, M, Cp, Cq):
