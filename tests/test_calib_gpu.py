@@ -224,8 +224,9 @@ def test_trainer_handles_ragged_batches(cal):
     (l0, p0), (l1, p1) = runs
     # same trajectory: tight while the runs are still close, loose once atomics-order noise has been amplified by 13
     # tiny-batch BatchNorm steps.  (Steps 0 and 1 are eager in BOTH runs and already differ by up to 3e-3 - two eager runs of
-    # a B0 at 64 px, whose last stages normalise 32 values per channel, are that far apart; measured up to 1.2e-2 at step 2.)
-    assert abs(l0[0] - l1[0]) < 2e-3, (l0[0], l1[0])
+    # a B0 at 64 px, whose last stages normalise 32 values per channel, are that far apart (fp32 atomics order -> a bf16 rounding flips -> 32-sample batch statistics amplify it); up to
+    # 1.2e-2 measured at step 2.)
+    assert abs(l0[0] - l1[0]) < 1e-2, (l0[0], l1[0])       # same weights, same batch, both eager: 3e-4 .. 3e-3 observed
     assert max(abs(a - b) for a, b in zip(l0[:5], l1[:5])) < 2.5e-2 and max(abs(a - b) for a, b in zip(l0, l1)) < 6e-2, (l0, l1)
     # AdamW moves a weight by up to lr per step whatever the gradient's size, so single weights whose gradient is pure
     # atomics-order noise differ by up to 2*lr*steps; the bulk must agree far better than that
