@@ -37,6 +37,27 @@ inline Launch plan(int C) {
   L.RY = TPB / L.VX;
   return L;
 }
+// Per-image reductions (SE squeeze, SE backward sums) on SMALL feature maps: a block takes a narrow channel slab and ALL rows of
+// one image in a single pass (RY row-lanes x UNR rows in flight >= HW), so the per-(image, channel) results are plain stores
+// - no atomics, no zeroed target, no serial row loop.  Measured need (profiles/r02_step_per_op.txt): with full-width slabs
+// the 7x7 / 14x14 layers spent 15-28 us on 10-50 MB tensors, most of it in fp32 atomics (five sums x every row block).
+// Large maps keep full-width slabs with several row blocks per image.
+inline Launch plan_img(int C, int HW) {
+  Launch L = plan(C);
+  const int lanes = (HW + UNR - 1) / UNR;
+  const char* off = getenv("TEETHRT_NARROW_SLABS");       // "0": round-1 geometry everywhere (A/B switch)
+  if (lanes > TPB / 4 || (off && *off == '0')) return L;
+  int ry = 1;
+  while (ry < lanes) ry <<= 1;
+  const int vx = TPB / ry;                 // 4 .. 256, a power of two
+  if (vx >= L.V) return L;                 // the whole channel range fits one narrow slab anyway
+  L.VX = vx;
+  L.RY = ry;
+  L.slabs = (L.V + vx - 1) / vx;
+  return L;
+}
+inline bool one_pass(const Launch& L, int HW) { return (size_t)L.RY * UNR >= (size_t)HW; }
+
 inline int row_blocks(int rows, int RY, int slabs, int target_blocks) {
   int nb = (rows + RY - 1) / RY;
   int cap = target_blocks / slabs;
@@ -57,6 +78,35 @@ __device__ __forceinline__ void block_reduce_rows(float (&acc)[NV], float* s_red
     for (int r = 1; r < m.RY; ++r) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) acc[i] += s_red[(size_t)i * TPB + r * m.VX + m.vl];
+    }
+  }
+}
+
+// The same for 8 values when the block was planned by plan_img (VX a power of two <= 32: a warp holds 32 / VX whole rows):
+// rows inside a warp meet in shuffles, the 8 warps meet in 8 KB of shared memory - two barriers instead of an RY-long walk.
+// Falls back to block_reduce_rows for full-width slabs.  Result valid for ry == 0.
+__device__ __forceinline__ void reduce_rows8(float (&acc)[8], float* s_red, const RowMap& m) {
+  if (m.VX > 32 || (m.VX & (m.VX - 1)) != 0) {
+    block_reduce_rows<8>(acc, s_red, m);
+    return;
+  }
+  for (int o = 16; o >= m.VX; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane < m.VX) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[(warp * m.VX + lane) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (m.ry == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+      for (int w = 0; w < TPB / 32; ++w) t += s_red[(w * m.VX + m.vl) * 8 + i];
+      acc[i] = t;
     }
   }
 }
@@ -177,10 +227,16 @@ __global__ void __launch_bounds__(TPB) pool_act_kernel(const uint4* __restrict__
       }
     }
   }
-  block_reduce_rows<8>(acc, s_red, m);
+  reduce_rows8(acc, s_red, m);
   if (m.ry == 0 && m.active) {
+    float* o = pooled + (size_t)n * C + 8 * m.v;
+    if (gridDim.x == 1) {                  // this block saw every row of the image: plain stores
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(pooled + (size_t)n * C + 8 * m.v + i, acc[i]);
+      for (int i = 0; i < 8; ++i) o[i] = acc[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, acc[i]);
+    }
   }
 }
 
@@ -428,10 +484,16 @@ __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restr
   }
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
-    block_reduce_rows<8>(acc[k], s_red, m);
+    reduce_rows8(acc[k], s_red, m);
     if (m.ry == 0 && m.active) {
+      float* o = sums + k * NC + (size_t)n * C + 8 * m.v;
+      if (gridDim.x == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(sums + k * NC + (size_t)n * C + 8 * m.v + i, acc[k][i]);
+        for (int i = 0; i < 8; ++i) o[i] = acc[k][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(o + i, acc[k][i]);
+      }
     }
   }
 }
@@ -1051,11 +1113,12 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   if ((rc = check_fin(fin_host, "trt_pool_act"))) return rc;
   trt_bn_fin_t fin = {};
   if (fin_host) fin = *fin_host;
-  const Launch L = plan(C);
-  if (!zeroed) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
+  const Launch L = plan_img(C, HW);
+  const bool single = one_pass(L, HW);
+  if (!zeroed && !single) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
-  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
+  dim3 grid(single ? 1 : row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   int lazy = fin_host ? 1 : 0;
   if (lazy && !lazy_pays((long long)grid.x * grid.y * grid.z, L.VX * 8)) {
     finalize_now(fin, C, stream);
@@ -1130,12 +1193,13 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
                                  int HW, int C, cudaStream_t stream) {
   CHECK_C(C);
   TRT_REQUIRE(dA && x && rec && sums && N > 0 && HW > 0, "trt_se_bwd_reduce: bad argument");
-  const Launch L = plan(C);
+  const Launch L = plan_img(C, HW);
+  const bool single = one_pass(L, HW);
   const size_t NC = (size_t)N * C;
-  if (!zeroed) TRT_CUDA(cudaMemsetAsync(sums, 0, (full ? 5 : 1) * NC * sizeof(float), stream));
+  if (!zeroed && !single) TRT_CUDA(cudaMemsetAsync(sums, 0, (full ? 5 : 1) * NC * sizeof(float), stream));
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
-  dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
+  dim3 grid(single ? 1 : row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   if (full) se_bwd_reduce_kernel<true><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
   else se_bwd_reduce_kernel<false><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
   return trt_check_launch("trt_se_bwd_reduce");

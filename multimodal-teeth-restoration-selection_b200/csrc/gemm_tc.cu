@@ -80,13 +80,16 @@ __host__ __device__ inline SmemLayout make_layout(int block_n, int stages, int n
   return L;
 }
 
+// MODE 0: the standard epilogue; 1: + BatchNorm-backward sums (TRT_EPI_BNBWD); 2: gated-attention scores (TRT_EPI_MILGATE).
+// A template parameter, not a flag: the extra live registers of modes 1 / 2 would otherwise spill the standard epilogue
+// (128 registers at 448 threads).
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 1024);
-  const SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages,
-                                   (p.flags & TRT_EPI_MILGATE) ? 1 : 0);
+  const SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages, MODE == 2 ? 1 : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;     // [nacc] accumulator complete (MMA -> epilogue group)
@@ -143,7 +146,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes));
           ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage],
-                           (p.a_kblocks > 0 ? kb % p.a_kblocks : kb) * BK, m0);
+                           (MODE == 2 && p.a_kblocks > 0 ? kb % p.a_kblocks : kb) * BK, m0);
           if (!p.b_resident) ptx::tma_load_2d(smem + L.b_off + stage * b_stage_bytes, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -196,7 +199,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int gt = threadIdx.x - 64 - g * EPI_THREADS;   // 0..127 inside the group
       const bool f_ss = p.flags & TRT_EPI_SCALE_SHIFT, f_silu = p.flags & TRT_EPI_SILU;
       const bool f_res = p.flags & TRT_EPI_RESIDUAL, f_stats = p.flags & TRT_EPI_STATS;
-      const bool f_bnbwd = p.flags & TRT_EPI_BNBWD;     // second sum = sum y * bn_x instead of sum y^2 (BatchNorm backward)
+      constexpr bool f_bnbwd = MODE == 1;               // second sum = sum y * bn_x instead of sum y^2 (BatchNorm backward)
       const uint32_t cpitch = L.cpitch;
       uint8_t* cstage = smem + L.c_off + g * L.cbuf_bytes;
       const int n_oct = p.block_n >> 3;             // 8-column octets per tile row
@@ -249,7 +252,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::tc_fence_after();
         TRT_TICK(1);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-        if (p.flags & TRT_EPI_MILGATE) {
+        if constexpr (MODE == 2) {
           // gated-attention scores straight from the accumulator: a thread owns one instance row, its (V_j, U_j) pairs are
           // adjacent columns; nothing is staged or stored except the optional gate activations the backward pass needs
           float part = 0.f;
@@ -597,10 +600,17 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   TRT_REQUIRE((((uintptr_t)C) & 15) == 0, "trt_gemm_bf16: C must be 16-byte aligned");
   TRT_REQUIRE(!(flags & TRT_EPI_MILGATE) || (mil && mil->bias && mil->w && mil->score && (N % 2) == 0 && (mil->gv == nullptr) == (mil->gu == nullptr)),
               "trt_gemm_bf16: incomplete gated-attention epilogue");
-  TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
-  TRT_CUDA(trt_launch(gemm_kmajor_kernel, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p));
+#define TRT_GEMM_GO(MODE)                                                                                                          \
+  do {                                                                                                                             \
+    TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); /* per device */ \
+    TRT_CUDA(trt_launch(gemm_kmajor_kernel<MODE>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p));               \
+  } while (0)
+  if (flags & TRT_EPI_MILGATE) TRT_GEMM_GO(2);
+  else if (flags & TRT_EPI_BNBWD) TRT_GEMM_GO(1);
+  else TRT_GEMM_GO(0);
+#undef TRT_GEMM_GO
   return trt_check_launch("trt_gemm_bf16");
 }
 

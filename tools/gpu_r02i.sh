@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T=${TAG:-r02i}
+run() { name=$1; shift; echo "=== $name" ; timeout ${TMO:-300} "$@" > gpurun_out/${T}_$name.log 2>&1; echo "exit=$?"; tail -n ${TAILN:-6} gpurun_out/${T}_$name.log | cut -c1-${CUT:-400}; }
+TAILN=10 TMO=900 run gpu_tests python -m pytest tests -m gpu -q --timeout 600
+Q="--steps 40 --warmup 3 --no-infer --no-cpu-baseline --sustain-seconds 0 --no-u8"
+for i in 1 2; do
+TAILN=1 CUT=330 run ab_default_$i python bench.py $Q
+TEETHRT_NARROW_SLABS=0 TAILN=1 CUT=330 run ab_wide_$i python bench.py $Q
+done
+TEETHRT_GEMM_BNBWD=0 TAILN=1 CUT=330 run ab_nobnbwd python bench.py $Q
