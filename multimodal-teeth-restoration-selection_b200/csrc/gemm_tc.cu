@@ -133,11 +133,14 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       if (p.b_resident) {
-        // thin GEMMs are bound by the TMA unit's box-row rate (~8 cycles per <=128-byte row, measured): the weights are the
-        // same for every tile of the CTA, so their rows are fetched once instead of once per tile
+        // these GEMMs are bound by the TMA unit's box-row rate (~7 cycles per <=128-byte row, measured): the weights of the
+        // CTA's n-block are the same for every tile it computes, so their rows are fetched once instead of once per tile.
+        // With several n-blocks the grid is a multiple of their number, so a CTA's tiles t = blockIdx.x + i * gridDim.x all
+        // share the n-block blockIdx.x % num_n_blocks (host: gemm_launch)
+        const int n_res = (blockIdx.x % p.num_n_blocks) * p.block_n;
         ptx::mbar_expect_tx(bres_bar, (uint32_t)p.num_k_blocks * b_stage_bytes);
         for (int kb = 0; kb < p.num_k_blocks; ++kb)
-          ptx::tma_load_2d(smem + L.b_off + kb * b_stage_bytes, &tmap_b, bres_bar, kb * BK, 0);
+          ptx::tma_load_2d(smem + L.b_off + kb * b_stage_bytes, &tmap_b, bres_bar, kb * BK, n_res);
       }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / p.num_n_blocks) * BM;
@@ -490,6 +493,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
   if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// TEETHRT_GEMM_RES_TILED=0: weights stay resident only when the whole N fits one n-block (the round-1 rule; A/B switch)
+const int g_res_tiled_n = [] { const char* e = getenv("TEETHRT_GEMM_RES_TILED"); return (e && *e == '0') ? 0 : 1; }();
+
 int pow2_cols(int c) {
   int v = 32;
   while (v < c) v <<= 1;
@@ -522,8 +528,9 @@ int pick_block_n_fwd(int M, int N, int K) {
   for (int i = 0; i < nc; ++i) {
     const int bn = cand[i], nb = (N + bn - 1) / bn;
     const long long tiles = (long long)mb * nb;
-    const long long waves = (tiles + sms - 1) / sms;
-    const bool resident = nb == 1 && kb * bn * 128 <= 64 * 1024;
+    long long waves = (tiles + sms - 1) / sms;
+    const bool resident = kb * bn * 128 <= 64 * 1024 && nb <= sms / 2 && (nb == 1 || g_res_tiled_n);
+    if (resident && nb > 1) waves = (tiles + (sms / nb * nb) - 1) / (sms / nb * nb);
     double rows = (double)waves * kb * (128 + (resident ? 0 : bn)) + (resident ? (double)kb * bn : 0.0);
     rows += 600.0 * waves * (bn <= 160 ? 1.0 : 1.5);         // per-tile epilogue (three groups fit up to ~160 columns)
     rows *= 1.0 + 0.15 * ((double)(nb * bn - N) / N);        // padded columns are wasted MMA + epilogue work
@@ -569,7 +576,9 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   }
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   const int b_stage = p.block_n * 128;
-  p.b_resident = (p.num_n_blocks == 1 && p.num_k_blocks * b_stage <= 64 * 1024) ? 1 : 0;
+  const int sms = trt_num_sms();
+  p.b_resident = (p.num_k_blocks * b_stage <= 64 * 1024 && p.num_n_blocks <= sms / 2 && !(flags & TRT_EPI_MILGATE) &&
+                  g_res_tiled_n >= (p.num_n_blocks > 1 ? 1 : 0)) ? 1 : 0;
   const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage);
   const int fixed_bytes = (p.b_resident ? p.num_k_blocks * b_stage : 0) + 2048;
   const int nostage = (flags & TRT_EPI_MILGATE) ? 1 : 0;
@@ -601,7 +610,8 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   TRT_REQUIRE(!(flags & TRT_EPI_MILGATE) || (mil && mil->bias && mil->w && mil->score && (N % 2) == 0 && (mil->gv == nullptr) == (mil->gu == nullptr)),
               "trt_gemm_bf16: incomplete gated-attention epilogue");
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < trt_num_sms() ? tiles : trt_num_sms();
+  int grid = tiles < sms ? tiles : sms;
+  if (p.b_resident && p.num_n_blocks > 1) grid = grid / p.num_n_blocks * p.num_n_blocks;     // every CTA keeps ONE n-block
 #define TRT_GEMM_GO(MODE)                                                                                                          \
   do {                                                                                                                             \
     TRT_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); /* per device */ \

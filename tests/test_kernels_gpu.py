@@ -39,7 +39,9 @@ def rnd(*shape, scale=1.0, seed=0, dtype=torch.float32):
 
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMMs
 GEMM_SHAPES = [(256, 144, 24), (1000, 32, 144), (647, 336, 56), (3136, 1792, 448), (64, 24, 144), (12544, 48, 24),
-               (130, 272, 960), (49, 448, 2688), (8192, 256, 64)]
+               (130, 272, 960), (49, 448, 2688), (8192, 256, 64),
+               # several n-blocks with the weights of ONE n-block resident per CTA (grid = a multiple of the n-block count)
+               (12544, 960, 160), (3136, 1632, 272), (3136, 2688, 448), (50176, 336, 56), (19000, 672, 112), (129, 1000, 72)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
@@ -53,7 +55,7 @@ def test_gemm_plain(ops, M, N, K):
 
 # Many tiles per persistent CTA (several rounds of every epilogue group / TMEM accumulator): the path on which mbarrier
 # parity aliasing or a staging-buffer race would show up as a hang or wrong rows; small shapes never reach it.
-@pytest.mark.parametrize("N,K", [(24, 24), (144, 24), (192, 32), (56, 192), (272, 160), (672, 112)])
+@pytest.mark.parametrize("N,K", [(24, 24), (144, 24), (192, 32), (56, 192), (272, 160), (672, 112), (960, 160)])
 def test_gemm_many_tiles_per_cta(ops, N, K):
     M = 148 * 128 * 5 + 77
     A, B = rnd(M, K, seed=11, dtype=bf16), rnd(N, K, scale=K ** -0.5, seed=12, dtype=bf16)
@@ -72,7 +74,7 @@ def test_gemm_many_tiles_per_cta(ops, N, K):
     assert rel_err(dA, C.float() @ B.float()) < 1e-2
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 144, 24), (647, 336, 56), (3136, 672, 112)])
+@pytest.mark.parametrize("M,N,K", [(1000, 144, 24), (647, 336, 56), (3136, 672, 112), (12544, 960, 160), (3136, 1632, 272)])
 def test_gemm_epilogues(ops, M, N, K):
     A, B = rnd(M, K, seed=3, dtype=bf16), rnd(N, K, scale=K ** -0.5, seed=4, dtype=bf16)
     sc, sh = rnd(N, seed=5) * 0.2 + 1.0, rnd(N, seed=6) * 0.3

@@ -7,5 +7,7 @@ Q="--steps 40 --warmup 3 --no-infer --no-cpu-baseline --sustain-seconds 0 --no-u
 for i in 1 2; do
 TAILN=1 CUT=330 run ab_default_$i python bench.py $Q
 TEETHRT_NARROW_SLABS=0 TAILN=1 CUT=330 run ab_wide_$i python bench.py $Q
+TEETHRT_GEMM_RES_TILED=0 TAILN=1 CUT=330 run ab_nores_$i python bench.py $Q
 done
 TEETHRT_GEMM_BNBWD=0 TAILN=1 CUT=330 run ab_nobnbwd python bench.py $Q
+TAILN=1 CUT=700 run infer python bench.py --infer --steps 20
