@@ -544,9 +544,12 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
 
     lazy = _lazy_bn()
 
-    # the data-gradient GEMM that produces a block's input gradient also accumulates the backward sums of the BatchNorm that
-    # gradient flows into next (the previous block's project BN): no separate pass over (dy, p_raw).  Needs the lazy affine2.
-    fuse_bnbwd = bool(lazy & 4) and os.environ.get("TEETHRT_GEMM_BNBWD", "1") != "0"
+    # Optional (TEETHRT_GEMM_BNBWD=1): the data-gradient GEMM that produces a block's input gradient also accumulates the
+    # backward sums of the BatchNorm that gradient flows into next (the previous block's project BN), so the separate pass
+    # over (dy, p_raw) disappears.  Measured neutral: the 31 reduce launches (0.30 ms serialised) go away, the GEMM epilogue
+    # (an extra 16-byte global load per store, spills at 128 registers) gets 0.3-0.4 ms slower - 11.69 ms/step with it,
+    # 11.52-11.70 without (A/B on one box).  Off by default; needs the lazy affine2.
+    fuse_bnbwd = bool(lazy & 4) and os.environ.get("TEETHRT_GEMM_BNBWD", "0") != "0"
 
     def bn_dx(bn_name, count, bst, g, x_raw, out, raw_x=False):
         """BatchNorm backward apply: out = a*g + b*x_raw + c with the coefficients of BatchNorm `bn_name`, whose sums `bst`

@@ -45,8 +45,11 @@ inline Launch plan(int C) {
 inline Launch plan_img(int C, int HW) {
   Launch L = plan(C);
   const int lanes = (HW + UNR - 1) / UNR;
-  const char* off = getenv("TEETHRT_NARROW_SLABS");       // "0": round-1 geometry everywhere (A/B switch)
-  if (lanes > TPB / 4 || (off && *off == '0')) return L;
+  // Opt-in (TEETHRT_NARROW_SLABS=1).  Per kernel the narrow geometry wins on the 7x7 / 14x14 layers, but at the step level
+  // it measured 11.69 / 11.69 ms against 11.69 / 11.56 ms for full-width slabs: these kernels overlap the weight-gradient
+  // branch on the side stream, so their latency is not on the critical path while the extra blocks are.
+  const char* on = getenv("TEETHRT_NARROW_SLABS");
+  if (lanes > TPB / 4 || !(on && *on == '1')) return L;
   int ry = 1;
   while (ry < lanes) ry <<= 1;
   const int vx = TPB / ry;                 // 4 .. 256, a power of two

@@ -446,7 +446,9 @@ def test_mil_attention_forward_backward(ops, B, K, D, hid, tc):
     dH = ops.mil_attn_bwd(dM, H, A, gV, gU, Vw, Uw, ww, *grads)
     assert rel_err(dH, Ht.grad) < 1e-4
     for got, want in zip(grads, (Vw_.grad, Vb_.grad, Uw_.grad, Ub_.grad, ww_.grad, wb_.grad)):
-        assert close(got, want, 1e-3)
+        # the last one (scalar bias in front of the softmax) is mathematically zero: what is left is the rounding noise of
+        # B * K terms, so its floor grows with the batch
+        assert close(got, want, 1e-3, atol=1e-5 * max(1.0, B * K / 96))
 
 
 # ------------------------------------------------------------------------------------------------ tab MLP + heads + loss

@@ -281,7 +281,8 @@ def test_separate_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
     def run(fuse, prefetch):
         monkeypatch.setenv("TEETHRT_LAZY_BN", fuse)
         monkeypatch.setenv("TEETHRT_SE_BWD_MERGED", fuse)
-        monkeypatch.setenv("TEETHRT_GEMM_BNBWD", fuse)
+        monkeypatch.setenv("TEETHRT_GEMM_BNBWD", "1" if (fuse == "1" and prefetch) else "0")      # opt-in variants ride along with one arm
+        monkeypatch.setenv("TEETHRT_NARROW_SLABS", "1" if (fuse == "1" and prefetch) else "0")
         torch.manual_seed(0)
         m = MMJointDualHead("tf_efficientnet_b0_ns", 9, 64, 0.0).cuda()
         tr = DualTaskTrainer(m, t_max=10, graph=False)
