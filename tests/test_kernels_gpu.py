@@ -160,7 +160,9 @@ def make_rec(ops, xr, gamma, beta, eps=1e-3):
 
 
 @pytest.mark.parametrize("N,HW,C,rd", [(4, 49, 144, 6), (3, 196, 24, 6), (2, 64, 2688, 112), (5, 33, 336, 14), (70, 9, 48, 12), (96, 4, 1632, 68)])
-def test_bn_se_block_forward_backward(ops, N, HW, C, rd):
+@pytest.mark.parametrize("narrow", ["0", "1"], ids=["full-width", "narrow-slabs"])
+def test_bn_se_block_forward_backward(ops, N, HW, C, rd, narrow, monkeypatch):
+    monkeypatch.setenv("TEETHRT_NARROW_SLABS", narrow)      # opt-in geometry of the per-image reductions (one pass, plain stores)
     x_raw = rnd(N, HW, C, seed=11, dtype=bf16) * 1.5 + 0.3
     gamma, beta = rnd(C, seed=12) * 0.1 + 1, rnd(C, seed=13) * 0.1
     Wr, br = rnd(rd, C, seed=14, scale=C ** -0.5), rnd(rd, seed=15, scale=0.1)
