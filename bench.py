@@ -167,13 +167,13 @@ def time_dominant_kernel(torch, ops, pk):
             "peak_source": pk["src"], "avg_launch_us": t * 1e6, "algorithmic_bytes_per_launch": alg,
             "write_cap_gbs": 3880.0, "frac_of_write_floor": (M * N * 2 / 3880e9) / t,
             "note": "write-heavy launch: its floor is bytes_written / the measured 3.88 TB/s pure-write cap (tools/ubench/bw_probe.py); "
-                    "traffic = dram read+write bytes of this launch from profiles/r01_ncu_full_top_kernels.csv (ncu --set full)"}
+                    "traffic = dram read+write bytes of this launch from profiles/r02_ncu_full_top_kernels.csv (ncu --set full)"}
 
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed ncu --set full capture (bytes)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_top_kernels.csv")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_full_top_kernels.csv")
     try:
         rows = list(csv.reader(open(p)))
         h, units = rows[0], rows[1]
