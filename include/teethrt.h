@@ -218,9 +218,11 @@ int trt_bn_apply(const void* x, const float* rec, const void* residual, void* ou
  * zeroed != 0: pooled_sum was cleared by the caller (one arena memset per pass); fin_host: lazy BatchNorm as in trt_bn_apply */
 int trt_pool_act(const void* x, const float* rec, float* pooled_sum, int zeroed, const trt_bn_fin_t* fin_host, int N, int HW,
                  int C, int act, trt_stream_t stream);
-/* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 [N,rd] receives the pre-activation of the reduce conv */
+/* gate[n,c] = sigmoid(We . silu(Wr . mean + br) + be); s1 [N,rd] receives the pre-activation of the reduce conv.
+ * apply_x (optional, bf16 [N*HW, C], in place): x[n,hw,c] *= gate[n,c] in the same launch - for the small feature maps of a
+ * batch-1 / TTA inference forward, where a separate trt_gate_apply launch is pure latency (x must already be activated) */
 int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
-               float* s1, float* gate, int N, int C, int rd, trt_stream_t stream);
+               float* s1, float* gate, void* apply_x, int HW, int N, int C, int rd, trt_stream_t stream);
 /* out = (rec ? silu(bn(x)) : x) * gate[n,c] */
 int trt_gate_apply(const void* x, const float* rec, const float* gate, void* out, int N, int HW, int C, trt_stream_t stream);
 /* bstats += {sum dy, sum dy*xhat} of a BatchNorm without activation (the project conv's) */

@@ -76,7 +76,7 @@ _SIGS = {
     "trt_bn_bwd_finalize": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, vp]),
     "trt_bn_apply": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_pool_act": (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]),
-    "trt_se_fwd": (i32, [vp, f32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "trt_se_fwd": (i32, [vp, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_gate_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_bn_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, vp]),
     "trt_affine2": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),

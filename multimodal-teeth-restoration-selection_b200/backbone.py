@@ -256,13 +256,13 @@ def _check_input(enc, x):
     return x.contiguous()
 
 
-def _se_gate(blk, pooled, inv_hw, N, C, dev, save):
+def _se_gate(blk, pooled, inv_hw, N, C, dev, save, apply_x=None, HW=0):
     rd = blk.cfg["rd"]
     s1 = torch.empty((N, rd), device=dev, dtype=torch.float32)
     gate = torch.empty((N, C), device=dev, dtype=torch.float32)
     se = blk.se
     ops.se_fwd(pooled, inv_hw, se.conv_reduce.weight.detach(), se.conv_reduce.bias.detach(), se.conv_expand.weight.detach(),
-               se.conv_expand.bias.detach(), s1, gate)
+               se.conv_expand.bias.detach(), s1, gate, apply_x=apply_x, HW=HW)
     return s1, gate
 
 
@@ -303,8 +303,11 @@ def _forward_eval(enc, x, cache, feature_map):
         d = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled, pooled_zeroed=True)
-        _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)
-        ops.gate_apply(d, None, gate, d, N, oh * ow)
+        if N * oh * ow <= 1024:      # small maps (14x14 / 7x7 at batch <= 5): the SE expand launch gates the activation itself
+            _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False, apply_x=d, HW=oh * ow)
+        else:
+            _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)
+            ops.gate_apply(d, None, gate, d, N, oh * ow)
         flags = ops.EPI_SCALE_SHIFT | (ops.EPI_RESIDUAL if skip is not None else 0)
         cur = ops.gemm(d, pw, flags, outrec[0], outrec[1], residual=skip)
         h, w = oh, ow

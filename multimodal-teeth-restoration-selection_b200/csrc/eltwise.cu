@@ -276,10 +276,11 @@ __global__ void __launch_bounds__(TPB) se_reduce_kernel(const float* __restrict_
 constexpr int SE_CC = 64;   // channels per block in the expand kernels
 __global__ void __launch_bounds__(TPB) se_expand_kernel(const float* __restrict__ s1, const float* __restrict__ We,
                                                         const float* __restrict__ be, float* __restrict__ gate, int N, int C,
-                                                        int rd, int n_per_block) {
+                                                        int rd, int n_per_block, uint4* __restrict__ apply_x, int HW) {
   extern __shared__ float s_mem[];
   float* s_we = s_mem;                         // [SE_CC][rd+1]
   float* s_a1 = s_mem + SE_CC * (rd + 1);      // [n_per_block][rd]
+  float* s_g = s_a1 + n_per_block * rd;        // [n_per_block][SE_CC] gates of this block (only with apply_x)
   const int c0 = blockIdx.x * SE_CC, n0 = blockIdx.y * n_per_block;
   const int nn = min(n_per_block, N - n0);
   pdl_launch_dependents();
@@ -292,14 +293,34 @@ __global__ void __launch_bounds__(TPB) se_expand_kernel(const float* __restrict_
   __syncthreads();
   const int cl = threadIdx.x % SE_CC, nsub = threadIdx.x / SE_CC;
   const int c = c0 + cl;
-  if (c >= C) return;
-  const float bias = be[c];
-  const float* wrow = s_we + cl * (rd + 1);
-  for (int n = nsub; n < nn; n += TPB / SE_CC) {
-    float acc = bias;
-    const float* a = s_a1 + n * rd;
-    for (int r = 0; r < rd; ++r) acc = fmaf(a[r], wrow[r], acc);
-    gate[(size_t)(n0 + n) * C + c] = sigmoidf_(acc);
+  if (c < C) {
+    const float bias = be[c];
+    const float* wrow = s_we + cl * (rd + 1);
+    for (int n = nsub; n < nn; n += TPB / SE_CC) {
+      float acc = bias;
+      const float* a = s_a1 + n * rd;
+      for (int r = 0; r < rd; ++r) acc = fmaf(a[r], wrow[r], acc);
+      const float g = sigmoidf_(acc);
+      gate[(size_t)(n0 + n) * C + c] = g;
+      if (apply_x) s_g[n * SE_CC + cl] = g;
+    }
+  }
+  if (apply_x == nullptr) return;
+  // Small feature maps at inference (a few images x <= 196 pixels): this block also applies its 64 gates to the activation in
+  // place, x[n, hw, c0..c0+63] *= gate - the separate gate_apply launch is pure latency there.  One thread = one 16-byte
+  // vector (8 channels) of one pixel row.
+  __syncthreads();                                     // the block's gates are staged
+  const int vec = SE_CC / 8, V = C / 8;
+  for (int i = threadIdx.x; i < nn * HW * vec; i += TPB) {
+    const int v = i % vec, row = i / vec;              // row = n_local * HW + hw
+    const int n = row / HW;
+    if (c0 / 8 + v >= V) continue;
+    uint4* px = apply_x + ((size_t)(n0 * HW + row)) * V + c0 / 8 + v;
+    f8 a = unpack8(*px);
+    const float* g = s_g + n * SE_CC + v * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] *= g[k];
+    *px = pack8(a);
   }
 }
 
@@ -1133,17 +1154,20 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
 }
 
 extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We,
-                          const float* be, float* s1, float* gate, int N, int C, int rd, cudaStream_t stream) {
+                          const float* be, float* s1, float* gate, void* apply_x, int HW, int N, int C, int rd,
+                          cudaStream_t stream) {
   TRT_REQUIRE(pooled_sum && Wr && br && We && be && s1 && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
+  TRT_REQUIRE(!apply_x || (HW > 0 && C % 8 == 0), "trt_se_fwd: apply_x needs HW > 0 and C %% 8 == 0");
   TRT_CUDA(trt_launch(se_reduce_kernel, dim3(rd, (N + 7) / 8), dim3(TPB), (size_t)C * sizeof(float), stream, pooled_sum, inv_hw, Wr, br, s1, N, C, rd));
   int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
   const int npb = (N + splits - 1) / splits;
   splits = (N + npb - 1) / npb;
-  const size_t smem = ((size_t)SE_CC * (rd + 1) + (size_t)npb * rd) * sizeof(float);
+  const size_t smem = ((size_t)SE_CC * (rd + 1) + (size_t)npb * rd + (apply_x ? (size_t)npb * SE_CC : 0)) * sizeof(float);
   TRT_REQUIRE(smem <= 96 * 1024, "trt_se_fwd: batch %d x rd %d too large for one block", N, rd);
   // the opt-in is per device and cheap: set on every call (a process-wide "done" flag only covered the first device used)
   TRT_CUDA(cudaFuncSetAttribute(se_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  TRT_CUDA(trt_launch(se_expand_kernel, dim3((C + SE_CC - 1) / SE_CC, splits), dim3(TPB), smem, stream, s1, We, be, gate, N, C, rd, npb));
+  TRT_CUDA(trt_launch(se_expand_kernel, dim3((C + SE_CC - 1) / SE_CC, splits), dim3(TPB), smem, stream, s1, We, be, gate, N, C, rd, npb,
+                      reinterpret_cast<uint4*>(apply_x), HW));
   trt_count_launch(1);
   return trt_check_launch("trt_se_fwd");
 }

@@ -127,10 +127,11 @@ def pool_act(x, rec, pooled, N, HW, act=1, zeroed=False, fin=None):
     return pooled
 
 
-def se_fwd(pooled, inv_hw, Wr, br, We, be, s1, gate):
+def se_fwd(pooled, inv_hw, Wr, br, We, be, s1, gate, apply_x=None, HW=0):
+    """apply_x: activated bf16 [N*HW, C] tensor gated IN PLACE by the same launch (small inference feature maps)."""
     N, Cc = pooled.shape
-    check(lib.trt_se_fwd(ptr(pooled), inv_hw, ptr(Wr), ptr(br), ptr(We), ptr(be), ptr(s1), ptr(gate), N, Cc, Wr.shape[0],
-                         stream()))
+    check(lib.trt_se_fwd(ptr(pooled), inv_hw, ptr(Wr), ptr(br), ptr(We), ptr(be), ptr(s1), ptr(gate), ptr(apply_x), HW, N, Cc,
+                         Wr.shape[0], stream()))
 
 
 def gate_apply(x, rec, gate, out, N, HW):
