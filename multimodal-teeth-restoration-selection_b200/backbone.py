@@ -303,7 +303,7 @@ def _forward_eval(enc, x, cache, feature_map):
         d = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled, pooled_zeroed=True)
-        if N * oh * ow <= 1024:      # small maps (14x14 / 7x7 at batch <= 5): the SE expand launch gates the activation itself
+        if N * oh * ow <= 1024 and os.environ.get("TEETHRT_SE_APPLY", "1") != "0":      # small maps (14x14 / 7x7 at batch <= 5): the SE expand launch gates the activation itself
             _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False, apply_x=d, HW=oh * ow)
         else:
             _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)

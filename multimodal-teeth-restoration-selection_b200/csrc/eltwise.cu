@@ -522,6 +522,67 @@ __global__ void __launch_bounds__(TPB) se_bwd_reduce_kernel(const uint4* __restr
   }
 }
 
+// The FULL pass again with FOUR channels per thread (8-byte loads).  ncu on the 8-channel version: 127 registers, 25 %
+// occupancy, ~30 % issue utilisation although the instruction stream alone would need a third of the time - five FMA chains
+// behind a two-MUFU sigmoid per element need more warps in flight, and 40 accumulators per thread leave room for only 16.
+// 20 accumulators per thread fit four blocks per SM.  Same sums, same layout ([5][N][C]).
+__global__ void __launch_bounds__(TPB, 4) se_bwd_reduce5_kernel(const uint2* __restrict__ dA, const uint2* __restrict__ x,
+                                                                const float* __restrict__ rec, float* __restrict__ sums,
+                                                                int HW, int C, int V4, int VX, int RY, size_t NC) {
+  __shared__ float s_red[4 * TPB];
+  const RowMap m = row_map(V4, VX, RY, blockIdx.z);
+  const int n = blockIdx.y;
+  float acc[5][4];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+  if (m.active) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(rec) + m.v), sh = __ldg(reinterpret_cast<const float4*>(rec + C) + m.v);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const int step = gridDim.x * RY;
+    for (int r = blockIdx.x * RY + m.ry; r < HW; r += UNR * step) {
+      uint2 da[UNR], xa[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          da[u] = __ldg(dA + ((size_t)n * HW + r + u * step) * V4 + m.v);
+          xa[u] = __ldg(x + ((size_t)n * HW + r + u * step) * V4 + m.v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (r + u * step < HW) {
+          const float d[4] = {bf16_lo(da[u].x), bf16_hi(da[u].x), bf16_lo(da[u].y), bf16_hi(da[u].y)};
+          const float a[4] = {bf16_lo(xa[u].x), bf16_hi(xa[u].x), bf16_lo(xa[u].y), bf16_hi(xa[u].y)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(a[i], scv[i], shv[i]);
+            const float sg = sigmoidf_(z);
+            const float sl = z * sg;
+            const float sp = fmaf(sl, 1.0f - sg, sg);              // silu'(z) = s + silu * (1 - s)
+            const float t = d[i] * sp;
+            acc[0][i] = fmaf(d[i], sl, acc[0][i]);
+            acc[1][i] += t;
+            acc[2][i] += sp;
+            acc[3][i] = fmaf(t, a[i], acc[3][i]);
+            acc[4][i] = fmaf(sp, a[i], acc[4][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    block_reduce_rows<4>(acc[k], s_red, m);
+    if (m.ry == 0 && m.active) {
+      float* o = sums + k * NC + (size_t)n * C + 4 * m.v;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(o + i, acc[k][i]);
+    }
+  }
+}
+
 // pass 2 of the merged path: dD = a*g + b*x + c with g = (dA*gate[n,c] + dmean[n,c]/HW) * silu'(bn(x)) formed on the fly -
 // the gradient w.r.t. the raw depthwise output in ONE read of (dA, x) and one write (no g tensor, no separate affine pass)
 __global__ void __launch_bounds__(TPB) act_bwd_apply_kernel(const uint4* __restrict__ dA, const float* __restrict__ gate,
@@ -1227,7 +1288,19 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
   int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(single ? 1 : row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
-  if (full) se_bwd_reduce_kernel<true><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
+  const char* v8 = getenv("TEETHRT_SE_REDUCE_V8");          // "1": the 8-channel-per-thread version (A/B switch)
+  if (full && !single && !(v8 && *v8 == '1')) {
+    // four channels per thread: V4 = C / 4 vectors of 8 bytes
+    Launch L4;
+    L4.V = C / 4;
+    L4.slabs = (L4.V + TPB - 1) / TPB;
+    L4.VX = (L4.V + L4.slabs - 1) / L4.slabs;
+    L4.RY = TPB / L4.VX;
+    int tgt = 6 * trt_num_sms() / (N * L4.slabs);
+    if (tgt < 1) tgt = 1;
+    dim3 g4(row_blocks((HW + UNR - 1) / UNR, L4.RY, 1, tgt), N, L4.slabs);
+    se_bwd_reduce5_kernel<<<g4, TPB, 0, stream>>>((const uint2*)dA, (const uint2*)x, rec, sums, HW, C, L4.V, L4.VX, L4.RY, NC);
+  } else if (full) se_bwd_reduce_kernel<true><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
   else se_bwd_reduce_kernel<false><<<grid, TPB, 0, stream>>>((const uint4*)dA, (const uint4*)x, rec, sums, HW, C, L.V, L.VX, L.RY, NC);
   return trt_check_launch("trt_se_bwd_reduce");
 }
