@@ -303,7 +303,10 @@ def _forward_eval(enc, x, cache, feature_map):
         d = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.dwconv_fwd(e, None, blk.conv_dw.weight.detach(), d, N, h, w, k, s, out_rec=dwrec, pooled=pooled, pooled_zeroed=True)
-        if N * oh * ow <= 1024 and os.environ.get("TEETHRT_SE_APPLY", "1") != "0":      # small maps (14x14 / 7x7 at batch <= 5): the SE expand launch gates the activation itself
+        # Opt-in (TEETHRT_SE_APPLY=1): on small maps the SE expand launch can gate the activation itself.  Measured SLOWER
+        # (batch-1 forward 1.119 vs 1.067 ms, A/B on one box): the expand kernel has C/64 blocks, the separate gate_apply
+        # launch spreads the same bytes over the whole GPU and its launch latency is hidden by PDL.
+        if N * oh * ow <= 1024 and os.environ.get("TEETHRT_SE_APPLY", "0") == "1":
             _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False, apply_x=d, HW=oh * ow)
         else:
             _, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, False)
