@@ -252,6 +252,19 @@ typedef struct {
 int trt_se_bwd(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
                const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr, float* dWe,
                float* dbe, int ds1_zeroed, const trt_se_bn_t* bn_host, int N, int C, int rd, trt_stream_t stream);
+/* One-launch versions of trt_se_fwd / trt_se_bwd for training batches (timm SqueezeExcite inside `self.backbone(x_img)`,
+ * experiments/multimodal_v1/train_mm_joint_dualtask.py:154, and its backward, :248).  One block per channel chunk (at most one
+ * per SM); the contraction over channels is split across the blocks and combined behind a grid-wide barrier, so nothing is
+ * accumulated atomically.  `workspace`: trt_se_workspace_bytes(N, C, rd) bytes, 16-byte aligned, ZEROED once by the caller
+ * before its first use (the first 256 bytes hold the barrier state) and owned by one stream at a time.  Results equal the
+ * two-launch entry points up to fp32 summation order; ds2 may be NULL. */
+size_t trt_se_workspace_bytes(int N, int C, int rd);
+int trt_se_fwd_fused(const float* pooled_sum, float inv_hw, const float* Wr, const float* br, const float* We, const float* be,
+                     float* s1, float* gate, void* workspace, size_t ws_bytes, int N, int C, int rd, trt_stream_t stream);
+int trt_se_bwd_fused(const float* dgate_pre, const float* gate, const float* s1, const float* pooled_sum, float inv_hw,
+                     const float* Wr, const float* We, float* ds2, float* ds1, float* dmean, float* dWr, float* dbr, float* dWe,
+                     float* dbe, const trt_se_bn_t* bn_host, void* workspace, size_t ws_bytes, int N, int C, int rd,
+                     trt_stream_t stream);
 /* out = a*g + b*x + c with g = (dA*gate[n,c] + dmean[n,c]*inv_hw) * silu'(bn(x)) formed on the fly: the gradient w.r.t. the
  * raw depthwise output in one read of (dA, x) and one write */
 int trt_act_bwd_apply(const void* dA, const float* gate, const float* dmean, float inv_hw, const void* x, const float* rec,

@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libteethrt.so")
-SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu", "augment.cu"]
+SOURCES = ["abi.cu", "gemm_tc.cu", "eltwise.cu", "se_mlp.cu", "conv.cu", "dwconv.cu", "small.cu", "optim.cu", "preproc.cu", "calib.cu", "deskew.cu", "augment.cu"]
 NVCC_FLAGS = (["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
               + os.environ.get("TEETHRT_NVCC_EXTRA", "").split())
 

@@ -83,6 +83,9 @@ _SIGS = {
     "trt_se_bwd_reduce": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "trt_act_bwd_apply": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, vp]),
     "trt_se_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
+    "trt_se_workspace_bytes": (sz, [i32, i32, i32]),
+    "trt_se_fwd_fused": (i32, [vp, f32, vp, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
+    "trt_se_bwd_fused": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
     "trt_act_bwd": (i32, [vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_scale_f32": (i32, [vp, sz, f32, vp]),
     "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),

@@ -256,13 +256,34 @@ def _check_input(enc, x):
     return x.contiguous()
 
 
-def _se_gate(blk, pooled, inv_hw, N, C, dev, save, apply_x=None, HW=0):
+def _se_workspace(enc, N, dev):
+    """Workspace of the one-launch SE MLP kernels (ops.se_workspace), sized for the encoder's largest block at batch N.  One per
+    (device, size): captured graphs keep pointing at theirs, so a workspace is never freed or shrunk while the encoder lives.
+    Measured per layer (tools/se_probe.py, batch 64): a grid barrier costs 1.5-2 us on B200 - more than a launch boundary inside
+    a CUDA graph - so the one-launch BACKWARD only wins where the two-launch kernels are compute-bound (>= 1632 channels:
+    22.6 vs 27 us, 30.7 vs 47 us at 2688) and the one-launch FORWARD nowhere (opt-in: TEETHRT_SE_FUSED_FWD=1).
+    TEETHRT_SE_FUSED=0 keeps the two-launch kernels everywhere (A/B switch)."""
+    if os.environ.get("TEETHRT_SE_FUSED", "1") == "0" or N < 32:
+        return None
+    need = max(int(lib.trt_se_workspace_bytes(N, blk.conv_dw.weight.shape[0], blk.cfg["rd"])) for _, blk in enc.block_list())
+    cache = enc.__dict__.setdefault("_se_ws", {})
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), need)
+    if key not in cache:
+        cache[key] = torch.zeros(need, device=dev, dtype=torch.uint8)
+    return cache[key]
+
+
+def _se_fused_min_c():
+    return int(os.environ.get("TEETHRT_SE_FUSED_MIN_C", "1632"))
+
+
+def _se_gate(blk, pooled, inv_hw, N, C, dev, save, apply_x=None, HW=0, ws=None):
     rd = blk.cfg["rd"]
     s1 = torch.empty((N, rd), device=dev, dtype=torch.float32)
     gate = torch.empty((N, C), device=dev, dtype=torch.float32)
     se = blk.se
     ops.se_fwd(pooled, inv_hw, se.conv_reduce.weight.detach(), se.conv_reduce.bias.detach(), se.conv_expand.weight.detach(),
-               se.conv_expand.bias.detach(), s1, gate, apply_x=apply_x, HW=HW)
+               se.conv_expand.bias.detach(), s1, gate, apply_x=apply_x, HW=HW, ws=ws)
     return s1, gate
 
 
@@ -371,6 +392,9 @@ def forward_train(enc, x, save=True):
     stats = _Arena([ops.STAT_REPLICAS * 2 * c for c in chans], torch.float64, dev)
     recs = _Arena([4 * c for c in chans], torch.float32, dev)
     ctx = dict(x=x, N=N, Wp=Wp, rec={}, blocks=[], dims=[])
+    se_ws = _se_workspace(enc, N, dev)
+    se_fwd_fused, se_min_c = os.environ.get("TEETHRT_SE_FUSED_FWD") == "1", _se_fused_min_c()
+    ctx["se_ws"] = se_ws
 
     pool_arena = _Arena([N * blk.conv_dw.weight.shape[0] for _, blk in enc.block_list()] + [N * enc.num_features],
                         torch.float32, dev)                # every SE / global pooling target of the pass: one memset
@@ -435,7 +459,7 @@ def forward_train(enc, x, save=True):
         rec_d = bn_stage(bn_dw, N * oh * ow, st)
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.pool_act(d_raw, rec_d.rec, pooled, N, oh * ow, act=1, zeroed=True, fin=rec_d.fin())
-        s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True)
+        s1, gate = _se_gate(blk, pooled, 1.0 / (oh * ow), N, cm, dev, True, ws=se_ws if se_fwd_fused and cm >= se_min_c else None)
         a = ops.gate_apply(d_raw, rec_d.rec, gate, torch.empty_like(d_raw), N, oh * ow)
         st = stats.take(ops.STAT_REPLICAS * 2 * c["cout"])
         need_packed()
@@ -545,6 +569,7 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
     sq = _SideQueue(dev)
 
     merged = os.environ.get("TEETHRT_SE_BWD_MERGED", "1") != "0"     # 0: round-1 path (reduce, act_bwd, affine2: three passes)
+    se_min_c = _se_fused_min_c()
     zeros = _Arena([n for blk, sv in ctx["blocks"] for n in (N * (5 if merged else 1) * sv["d_raw"].shape[1], N * blk.cfg["rd"])],
                    torch.float32, dev)
 
@@ -624,13 +649,13 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
             ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, sums, N, ohw, zeroed=True, full=True)
             bn = bns[sv["bn_dw"]]
             coef_d = torch.empty((3, cm), device=dev, dtype=torch.float32)
-            ops.se_bwd(sums[0], *se_args, ds1_zeroed=True,
+            ops.se_bwd(sums[0], *se_args, ds1_zeroed=True, ws=ctx.get("se_ws") if cm >= se_min_c else None,
                        bn=ops.se_bn(sums, rec_d, bn.weight.detach(), coef_d, grads[sv["bn_dw"] + ".weight"], grads[sv["bn_dw"] + ".bias"], N * ohw))
             dD = ops.act_bwd_apply(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, coef_d, dA, N, ohw)
         else:
             dgate_pre = zeros.take(N * cm, (N, cm))
             ops.se_bwd_reduce(dA, sv["d_raw"], rec_d, dgate_pre, N, ohw, zeroed=True)
-            ops.se_bwd(dgate_pre, *se_args, ds1_zeroed=True)
+            ops.se_bwd(dgate_pre, *se_args, ds1_zeroed=True, ws=ctx.get("se_ws") if cm >= se_min_c else None)
             bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
             g2 = ops.act_bwd(dA, sv["gate"], dmean, 1.0 / ohw, sv["d_raw"], rec_d, dA, bst, N, ohw, act=1)
             dD = bn_dx(sv["bn_dw"], N * ohw, bst, g2, sv["d_raw"], g2)           # gradient w.r.t. the raw depthwise output

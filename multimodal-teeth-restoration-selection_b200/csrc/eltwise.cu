@@ -42,14 +42,16 @@ inline Launch plan(int C) {
 // - no atomics, no zeroed target, no serial row loop.  Measured need (profiles/r02_step_per_op.txt): with full-width slabs
 // the 7x7 / 14x14 layers spent 15-28 us on 10-50 MB tensors, most of it in fp32 atomics (five sums x every row block).
 // Large maps keep full-width slabs with several row blocks per image.
-inline Launch plan_img(int C, int HW) {
+inline Launch plan_img(int C, int HW, bool auto_narrow = false) {
   Launch L = plan(C);
   const int lanes = (HW + UNR - 1) / UNR;
-  // Opt-in (TEETHRT_NARROW_SLABS=1).  Per kernel the narrow geometry wins on the 7x7 / 14x14 layers, but at the step level
-  // it measured 11.69 / 11.69 ms against 11.69 / 11.56 ms for full-width slabs: these kernels overlap the weight-gradient
-  // branch on the side stream, so their latency is not on the critical path while the extra blocks are.
+  // TEETHRT_NARROW_SLABS=1 / 0 forces the narrow geometry on / off wherever it applies.  Unset: only where the isolated
+  // per-layer timings (tools/elt_probe.py, HBM-cold, inside a CUDA graph) show a win - the SE squeeze on 7x7 maps (6.6 -> 4.9,
+  // 9.6 -> 6.9, 12.5 -> 9.7 us at 960 / 1632 / 2688 channels); on 14x14 maps and for the five-sum backward pass it is a wash
+  // or a loss (more blocks, each with its own reduction tail).
   const char* on = getenv("TEETHRT_NARROW_SLABS");
-  if (lanes > TPB / 4 || !(on && *on == '1')) return L;
+  const bool want = (on && *on) ? (*on == '1') : (auto_narrow && HW <= 64);
+  if (lanes > TPB / 4 || !want) return L;
   int ry = 1;
   while (ry < lanes) ry <<= 1;
   const int vx = TPB / ry;                 // 4 .. 256, a power of two
@@ -58,6 +60,11 @@ inline Launch plan_img(int C, int HW) {
   L.RY = ry;
   L.slabs = (L.V + vx - 1) / vx;
   return L;
+}
+// grid-size multipliers (blocks per SM the per-image kernels aim for); environment overrides are bring-up knobs (tools/elt_probe.py)
+inline int env_mult(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
 }
 inline bool one_pass(const Launch& L, int HW) { return (size_t)L.RY * UNR >= (size_t)HW; }
 
@@ -1198,10 +1205,10 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   if ((rc = check_fin(fin_host, "trt_pool_act"))) return rc;
   trt_bn_fin_t fin = {};
   if (fin_host) fin = *fin_host;
-  const Launch L = plan_img(C, HW);
+  const Launch L = plan_img(C, HW, true);
   const bool single = one_pass(L, HW);
   if (!zeroed && !single) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
-  int target = 3 * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
+  int target = env_mult("TEETHRT_POOL_BLOCKS", 3) * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(single ? 1 : row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   int lazy = fin_host ? 1 : 0;
@@ -1296,7 +1303,10 @@ extern "C" int trt_se_bwd_reduce(const void* dA, const void* x, const float* rec
     L4.slabs = (L4.V + TPB - 1) / TPB;
     L4.VX = (L4.V + L4.slabs - 1) / L4.slabs;
     L4.RY = TPB / L4.VX;
-    int tgt = 6 * trt_num_sms() / (N * L4.slabs);
+    // one full wave: the kernel is compiled for 4 resident blocks per SM, and the isolated sweep (tools/gpu_elt_sweep.sh:
+    // 771 / 716 / 816 / 997 us per step at 3 / 4 / 6 / 12) has its minimum exactly there - more blocks only add reduction
+    // tails and atomics, fewer leave SMs idle
+    int tgt = env_mult("TEETHRT_SEBR_BLOCKS", 4) * trt_num_sms() / (N * L4.slabs);
     if (tgt < 1) tgt = 1;
     dim3 g4(row_blocks((HW + UNR - 1) / UNR, L4.RY, 1, tgt), N, L4.slabs);
     se_bwd_reduce5_kernel<<<g4, TPB, 0, stream>>>((const uint2*)dA, (const uint2*)x, rec, sums, HW, C, L4.V, L4.VX, L4.RY, NC);

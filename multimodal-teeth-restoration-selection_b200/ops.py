@@ -127,9 +127,19 @@ def pool_act(x, rec, pooled, N, HW, act=1, zeroed=False, fin=None):
     return pooled
 
 
-def se_fwd(pooled, inv_hw, Wr, br, We, be, s1, gate, apply_x=None, HW=0):
-    """apply_x: activated bf16 [N*HW, C] tensor gated IN PLACE by the same launch (small inference feature maps)."""
+def se_workspace(N, Cc, rd, device):
+    """Zeroed workspace of the one-launch SE MLP kernels (barrier state + split-K partials); owned by ONE stream at a time."""
+    return torch.zeros(int(lib.trt_se_workspace_bytes(N, Cc, rd)), device=device, dtype=torch.uint8)
+
+
+def se_fwd(pooled, inv_hw, Wr, br, We, be, s1, gate, apply_x=None, HW=0, ws=None):
+    """apply_x: activated bf16 [N*HW, C] tensor gated IN PLACE by the same launch (small inference feature maps).
+    ws: workspace from se_workspace() -> the one-launch kernel (training batches)."""
     N, Cc = pooled.shape
+    if ws is not None and apply_x is None:
+        check(lib.trt_se_fwd_fused(ptr(pooled), inv_hw, ptr(Wr), ptr(br), ptr(We), ptr(be), ptr(s1), ptr(gate), ptr(ws), ws.numel(),
+                                   N, Cc, Wr.shape[0], stream()))
+        return
     check(lib.trt_se_fwd(ptr(pooled), inv_hw, ptr(Wr), ptr(br), ptr(We), ptr(be), ptr(s1), ptr(gate), ptr(apply_x), HW, N, Cc,
                          Wr.shape[0], stream()))
 
@@ -166,8 +176,13 @@ def se_bn(sums, rec, gamma, coef, dgamma, dbeta, count):
     return SeBn(ptr(sums), ptr(rec), ptr(gamma), ptr(coef), ptr(dgamma), ptr(dbeta), float(count))
 
 
-def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe, ds1_zeroed=False, bn=None):
+def se_bwd(dgate_pre, gate, s1, pooled, inv_hw, Wr, We, ds2, ds1, dmean, dWr, dbr, dWe, dbe, ds1_zeroed=False, bn=None, ws=None):
     N, Cc = gate.shape
+    if ws is not None:
+        check(lib.trt_se_bwd_fused(ptr(dgate_pre), ptr(gate), ptr(s1), ptr(pooled), inv_hw, ptr(Wr), ptr(We), ptr(ds2), ptr(ds1),
+                                   ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), _ref(bn), ptr(ws), ws.numel(), N, Cc,
+                                   Wr.shape[0], stream()))
+        return
     check(lib.trt_se_bwd(ptr(dgate_pre), ptr(gate), ptr(s1), ptr(pooled), inv_hw, ptr(Wr), ptr(We), ptr(ds2), ptr(ds1),
                          ptr(dmean), ptr(dWr), ptr(dbr), ptr(dWe), ptr(dbe), int(ds1_zeroed), _ref(bn), N, Cc, Wr.shape[0], stream()))
 

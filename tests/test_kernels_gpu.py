@@ -239,6 +239,56 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd, narrow, monkeypatch):
     assert torch.allclose(ops.stats_total(bs2), ops.stats_total(bstats), rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("N,C,rd", [(64, 2688, 112), (64, 144, 6), (64, 1632, 68), (8, 48, 12), (70, 336, 14), (130, 960, 40), (256, 24, 6)])
+def test_se_mlp_one_launch_matches_two_launch(ops, N, C, rd):
+    """trt_se_fwd_fused / trt_se_bwd_fused (one launch, split-K over channel chunks behind a grid barrier) against the two-launch
+    kernels on the same inputs, and the forward against fp64 torch.  The workspace is reused for several calls in a row: the
+    barrier state must come back to a usable state by itself."""
+    HW = 49
+    pooled = (rnd(N, C, seed=51).abs() + 0.2) * HW
+    Wr, br = rnd(rd, C, seed=52, scale=C ** -0.5), rnd(rd, seed=53, scale=0.1)
+    We, be = rnd(C, rd, seed=54, scale=rd ** -0.5), rnd(C, seed=55, scale=0.1)
+    ws = ops.se_workspace(N, C, rd, "cuda")
+    s1a, ga = torch.empty(N, rd, device="cuda"), torch.empty(N, C, device="cuda")
+    ops.se_fwd(pooled, 1.0 / HW, Wr, br, We, be, s1a, ga)
+    for _ in range(3):
+        s1b, gb = torch.full((N, rd), float("nan"), device="cuda"), torch.full((N, C), float("nan"), device="cuda")
+        ops.se_fwd(pooled, 1.0 / HW, Wr, br, We, be, s1b, gb, ws=ws)
+        assert torch.allclose(s1b, s1a, rtol=1e-4, atol=1e-5) and torch.allclose(gb, ga, rtol=1e-4, atol=1e-5)
+    s1_ref = (pooled.double() / HW) @ Wr.double().t() + br.double()
+    gate_ref = torch.sigmoid(F.silu(s1_ref) @ We.double().t() + be.double())
+    assert rel_err(s1b, s1_ref.float()) < 1e-4 and rel_err(gb, gate_ref.float()) < 1e-4
+    # backward, without and with the BatchNorm tail
+    dgate_pre = rnd(N, C, seed=56)
+    sums = rnd(5, N, C, seed=57)
+    sums[0] = dgate_pre
+    rec = torch.stack([rnd(C, seed=58) * 0.1 + 1, rnd(C, seed=59) * 0.1, rnd(C, seed=60) * 0.2, rnd(C, seed=61).abs() + 0.5])
+    gamma = rnd(C, seed=62) * 0.1 + 1
+
+    def run(ws_):
+        outs = dict(ds2=torch.empty(N, C, device="cuda"), ds1=torch.zeros(N, rd, device="cuda"), dmean=torch.empty(N, C, device="cuda"),
+                    dWr=torch.empty_like(Wr), dbr=torch.empty_like(br), dWe=torch.empty_like(We), dbe=torch.empty_like(be),
+                    coef=torch.empty(3, C, device="cuda"), dgamma=torch.empty(C, device="cuda"), dbeta=torch.empty(C, device="cuda"))
+        ops.se_bwd(sums[0], ga, s1a, pooled, 1.0 / HW, Wr, We, outs["ds2"], outs["ds1"], outs["dmean"], outs["dWr"], outs["dbr"],
+                   outs["dWe"], outs["dbe"], ds1_zeroed=True,
+                   bn=ops.se_bn(sums, rec, gamma, outs["coef"], outs["dgamma"], outs["dbeta"], N * HW), ws=ws_)
+        return outs
+    want = run(None)
+    for _ in range(2):
+        got = run(ws)
+        for k in ("ds2", "dmean", "dWr", "dbr", "dWe", "dbe", "coef", "dgamma", "dbeta"):
+            assert rel_err(got[k], want[k]) < 2e-4, k
+    # ds1: the two-launch path leaves the pre-silu' accumulator in its buffer, the one-launch path the finished gradient
+    sg = torch.sigmoid(s1a.double())
+    ds1_ref = ((dgate_pre * ga * (1 - ga)).double() @ We.double()) * (sg * (1 + s1a.double() * (1 - sg)))
+    assert rel_err(got["ds1"], ds1_ref.float()) < 1e-4
+    # plain (no BatchNorm tail), ds2 not requested
+    dmean2, dWr2 = torch.empty(N, C, device="cuda"), torch.empty_like(Wr)
+    ops.se_bwd(dgate_pre, ga, s1a, pooled, 1.0 / HW, Wr, We, None, torch.empty(N, rd, device="cuda"), dmean2, dWr2,
+               torch.empty_like(br), torch.empty_like(We), torch.empty_like(be), ws=ws)
+    assert rel_err(dmean2, want["dmean"]) < 2e-4 and rel_err(dWr2, want["dWr"]) < 2e-4
+
+
 @pytest.mark.parametrize("force", ["1", "0"])
 @pytest.mark.parametrize("N,H,W,C", [(3, 14, 14, 144), (2, 9, 7, 2688), (5, 6, 6, 24), (2, 5, 5, 4352)])
 def test_lazy_batchnorm_records(ops, N, H, W, C, force, monkeypatch):

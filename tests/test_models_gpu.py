@@ -302,7 +302,9 @@ def test_separate_bn_finalise_and_prefetch_match_default_path(T, monkeypatch):
     dl = lambda a, b: max(abs(x - y) for x, y in zip(a, b))
     dp = lambda a, b: float((a - b).norm() / a.norm())
     print("loss diffs", dl(l0, l0b), dl(l0, l1), dl(l0, l2), "param diffs", dp(p0, p0b), dp(p0, p1), dp(p0, p2))
-    tol_l, tol_p = max(1e-3, 4 * dl(l0, l0b)), max(1e-4, 4 * dp(p0, p0b))
+    # floors = the noise two runs of the SAME path show on this tiny batch (loss up to 3e-3, parameters ~9e-4 relative: bf16
+    # rounding on top of atomic summation order); a single noise sample can come out 10x smaller than the next one
+    tol_l, tol_p = max(6e-3, 4 * dl(l0, l0b)), max(3e-3, 4 * dp(p0, p0b))
     assert dl(l0, l1) < tol_l and dl(l0, l2) < tol_l
     assert dp(p0, p1) < tol_p and dp(p0, p2) < tol_p
 

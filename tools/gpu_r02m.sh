@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for i in 1 2; do
+  for cfg in "TEETHRT_SE_FUSED=0" "TEETHRT_SE_FUSED_MIN_C=1632" "TEETHRT_SE_FUSED_MIN_C=960"; do
+    env $cfg timeout 300 python bench.py --steps 40 --warmup 5 --no-infer --no-u8 --no-cpu-baseline --sustain-seconds 0 2>/dev/null | tail -1 > gpurun_out/r02m_$cfg_$i.log
+    python - "$cfg" gpurun_out/r02m_$cfg_$i.log <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1]); print(sys.argv[1], round(d['ms_per_step'],3), round(d['value'],1))
+PY
+  done
+done
