@@ -61,7 +61,10 @@ inline Launch plan_img(int C, int HW, bool auto_narrow = false) {
   L.slabs = (L.V + vx - 1) / vx;
   return L;
 }
-// grid-size multipliers (blocks per SM the per-image kernels aim for); environment overrides are bring-up knobs (tools/elt_probe.py)
+// grid-size multipliers (blocks per SM the per-image kernels aim for); environment overrides are bring-up knobs.  The defaults
+// are the minima of the isolated sweeps (tools/gpu_elt_sweep.sh -> profiles/r02_elt_sweep.txt): 4 blocks per SM = one full
+// wave of these 64-register kernels; 6 (1.4 waves) cost 17 / 25 / 40 / 100 us per step more for the squeeze, the gate, the
+// activation backward and the five-sum pass.
 inline int env_mult(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
@@ -1208,7 +1211,7 @@ extern "C" int trt_pool_act(const void* x, const float* rec, float* pooled_sum, 
   const Launch L = plan_img(C, HW, true);
   const bool single = one_pass(L, HW);
   if (!zeroed && !single) TRT_CUDA(cudaMemsetAsync(pooled_sum, 0, (size_t)N * C * sizeof(float), stream));
-  int target = env_mult("TEETHRT_POOL_BLOCKS", 3) * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
+  int target = env_mult("TEETHRT_POOL_BLOCKS", 4) * trt_num_sms() / (N * L.slabs);     // per-image outputs: no cross-block contention, latency-bound when fewer
   if (target < 1) target = 1;
   dim3 grid(single ? 1 : row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   int lazy = fin_host ? 1 : 0;
@@ -1245,7 +1248,7 @@ extern "C" int trt_gate_apply(const void* x, const float* rec, const float* gate
   CHECK_C(C);
   TRT_REQUIRE(x && gate && out && N > 0 && HW > 0, "trt_gate_apply: bad argument");
   const Launch L = plan(C);
-  int target = 6 * trt_num_sms() / (N * L.slabs);
+  int target = env_mult("TEETHRT_GATE_BLOCKS", 4) * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   TRT_CUDA(trt_launch(gate_apply_kernel, grid, dim3(TPB), 0, stream, (const uint4*)x, rec, gate, (uint4*)out, HW, C, L.V, L.VX, L.RY));
@@ -1320,7 +1323,7 @@ extern "C" int trt_act_bwd_apply(const void* dA, const float* gate, const float*
   CHECK_C(C);
   TRT_REQUIRE(dA && gate && dmean && x && rec && coef && out && N > 0 && HW > 0, "trt_act_bwd_apply: bad argument");
   const Launch L = plan(C);
-  int target = 6 * trt_num_sms() / (N * L.slabs);
+  int target = env_mult("TEETHRT_ABA_BLOCKS", 4) * trt_num_sms() / (N * L.slabs);
   if (target < 1) target = 1;
   dim3 grid(row_blocks((HW + UNR - 1) / UNR, L.RY, 1, target), N, L.slabs);
   act_bwd_apply_kernel<<<grid, TPB, 0, stream>>>((const uint4*)dA, gate, dmean, inv_hw, (const uint4*)x, rec, coef, (uint4*)out,

@@ -513,28 +513,63 @@ int pick_block_n(int N) {
   return best;
 }
 
-// Forward/dgrad tile width.  These GEMMs are bound by the TMA unit's box-row rate (one <=128-byte row per ~6-8 cycles,
-// measured), so the model counts box rows on the busiest CTA: waves x k-blocks x (128 A rows + block_n B rows); a single
-// n-block whose weights fit in shared memory loads them once per CTA instead (b_resident).
+// Shared-memory plan of one tile width: is the n-block's whole weight slab resident, how many epilogue groups (one staging
+// buffer + one accumulator each) fit beside the pipeline stages, how many stages.  Used by the launcher and by the tile-width
+// model, so the model prices exactly what will be launched.
+struct TilePlan { int resident, ngroups, stages; };
+TilePlan plan_tile(int block_n, int num_k_blocks, int num_n_blocks, int nostage) {
+  TilePlan t;
+  const int b_stage = block_n * 128, sms = trt_num_sms();
+  t.resident = (num_k_blocks * b_stage <= 64 * 1024 && num_n_blocks <= sms / 2 && !nostage &&
+                g_res_tiled_n >= (num_n_blocks > 1 ? 1 : 0)) ? 1 : 0;
+  const int stage_bytes = A_STAGE_BYTES + (t.resident ? 0 : b_stage);
+  const int fixed_bytes = (t.resident ? num_k_blocks * b_stage : 0) + 2048;
+  const int cbuf_bytes = (int)make_layout(block_n, 2, 1, 2, nostage).cbuf_bytes;
+  // as many epilogue groups as fit beside min(k-blocks + 1, 3) pipeline stages.  Several groups must each be the ONLY consumer
+  // of "their" accumulator barrier (mbarrier parity waits alias if a waiter can fall two phases behind), so with G > 1 groups
+  // the accumulators are G as well: tile i -> group i % G -> accumulator i % G.
+  const int want_stages = num_k_blocks + 1 < 3 ? num_k_blocks + 1 : 3;
+  const int acc_stride = (block_n + 31) & ~31, max_acc = 512 / acc_stride;
+  t.ngroups = 1;
+  for (int gq = MAX_GROUPS < max_acc ? MAX_GROUPS : max_acc; gq >= 1; --gq)
+    if ((220 * 1024 - gq * cbuf_bytes - fixed_bytes) / stage_bytes >= (gq == 1 ? 2 : want_stages)) { t.ngroups = gq; break; }
+  int stages = (220 * 1024 - t.ngroups * cbuf_bytes - fixed_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  t.stages = stages;
+  return t;
+}
+
+// Forward/dgrad tile width: the width whose busiest CTA finishes first under a two-term model fitted to an isolated sweep of
+// every 1x1-conv shape of the encoder at batch 64 (tools/gemm_probe.py -> profiles/r02_gemm_probe.jsonl; 44 shapes x up to 5
+// widths, each timed inside a CUDA graph):
+//   load     = 7 cycles per 128-byte A box row (activations, streamed from HBM) + 2 per B row (weights: L2 hits)
+//   epilogue = 48 cycles per output column of a tile, divided by the epilogue groups that work in parallel
+//   cost     = max(load, epilogue) on the CTA with the most tiles
+// The model picks the measured optimum on all but one of those shapes (total regret 0.9 us per step; the round-1 model, which
+// charged every tile a constant epilogue and B rows like A rows, lost 106 us per step to its choices).
 int pick_block_n_fwd(int M, int N, int K) {
   const int mb = (M + BM - 1) / BM, kb = (K + BK - 1) / BK, sms = trt_num_sms();
   int cand[5], nc = 0;
   if (N <= 256) cand[nc++] = (N + 15) / 16 * 16;
-  const int tiled[3] = {192, 128, 64};
-  for (int i = 0; i < 3; ++i)
+  const int tiled[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i)
     if (tiled[i] < N) cand[nc++] = tiled[i];
   int best = cand[0];
   double best_cost = 1e30;
   for (int i = 0; i < nc; ++i) {
     const int bn = cand[i], nb = (N + bn - 1) / bn;
+    const TilePlan t = plan_tile(bn, kb, nb, 0);
     const long long tiles = (long long)mb * nb;
-    long long waves = (tiles + sms - 1) / sms;
-    const bool resident = kb * bn * 128 <= 64 * 1024 && nb <= sms / 2 && (nb == 1 || g_res_tiled_n);
-    if (resident && nb > 1) waves = (tiles + (sms / nb * nb) - 1) / (sms / nb * nb);
-    double rows = (double)waves * kb * (128 + (resident ? 0 : bn)) + (resident ? (double)kb * bn : 0.0);
-    rows += 600.0 * waves * (bn <= 160 ? 1.0 : 1.5);         // per-tile epilogue (three groups fit up to ~160 columns)
-    rows *= 1.0 + 0.15 * ((double)(nb * bn - N) / N);        // padded columns are wasted MMA + epilogue work
-    if (rows < best_cost) { best_cost = rows; best = bn; }
+    long long grid = tiles < sms ? tiles : sms;
+    if (t.resident && nb > 1) grid = grid / nb * nb;
+    const long long waves = (tiles + grid - 1) / grid;
+    const double a_rows = (double)waves * kb * 128;
+    const double b_rows = t.resident ? (double)kb * bn : (double)waves * kb * bn;
+    const double load = 7.0 * a_rows + 2.0 * b_rows;
+    const double epi = 48.0 * (double)waves * bn / t.ngroups;
+    const double cost = load > epi ? load : epi;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -575,29 +610,15 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
     p.a_kblocks = mil->a_kblocks; p.mil_bias = mil->bias; p.mil_w = mil->w; p.mil_score = mil->score; p.mil_gv = mil->gv; p.mil_gu = mil->gu;
   }
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
-  const int b_stage = p.block_n * 128;
   const int sms = trt_num_sms();
-  p.b_resident = (p.num_k_blocks * b_stage <= 64 * 1024 && p.num_n_blocks <= sms / 2 && !(flags & TRT_EPI_MILGATE) &&
-                  g_res_tiled_n >= (p.num_n_blocks > 1 ? 1 : 0)) ? 1 : 0;
-  const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage);
-  const int fixed_bytes = (p.b_resident ? p.num_k_blocks * b_stage : 0) + 2048;
   const int nostage = (flags & TRT_EPI_MILGATE) ? 1 : 0;
-  const int cbuf_bytes = (int)make_layout(p.block_n, 2, 1, 2, nostage).cbuf_bytes;
-  // as many epilogue groups (one staging buffer each) as fit beside min(k-blocks + 1, 4) pipeline stages
-  const int want_stages = p.num_k_blocks + 1 < 3 ? p.num_k_blocks + 1 : 3;
-  // Several groups must each be the ONLY consumer of "their" accumulator barrier (mbarrier parity waits alias if a waiter can
-  // fall two phases behind), so with G > 1 groups the accumulators are G as well: tile i -> group i % G -> accumulator i % G.
+  const TilePlan tp = plan_tile(p.block_n, p.num_k_blocks, p.num_n_blocks, nostage);
+  p.b_resident = tp.resident;
+  p.ngroups = tp.ngroups;
+  p.stages = tp.stages;
   const int max_acc = 512 / p.acc_stride;
-  p.ngroups = 1;
-  for (int gq = MAX_GROUPS < max_acc ? MAX_GROUPS : max_acc; gq >= 1; --gq)
-    if ((220 * 1024 - gq * cbuf_bytes - fixed_bytes) / stage_bytes >= (gq == 1 ? 2 : want_stages)) { p.ngroups = gq; break; }
   p.nacc = p.ngroups > 1 ? p.ngroups : (max_acc >= 2 ? 2 : 1);
   p.tmem_cols = pow2_cols(p.nacc * p.acc_stride);
-  const int budget = 220 * 1024 - p.ngroups * cbuf_bytes - fixed_bytes;
-  int stages = budget / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
   SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages, nostage);
   size_t smem_bytes = (size_t)L.total + 1024;      // slack for the manual 1024B alignment
   static const int smem_floor_kb = [] { const char* e = getenv("TEETHRT_GEMM_SMEM_FLOOR"); return e ? atoi(e) : 120; }();

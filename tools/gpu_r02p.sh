@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "gemm" 2>&1 | tail -3
+timeout 600 python tools/gemm_probe.py 2>&1 | tail -1
+GEMM_B=256 timeout 900 python tools/gemm_probe.py 2>&1 | tail -23 > gpurun_out/r02p_gemm_probe_b256.jsonl; tail -1 gpurun_out/r02p_gemm_probe_b256.jsonl
+for i in 1 2; do
+  for cfg in "TEETHRT_X=0"; do
+    env $cfg timeout 300 python bench.py --steps 40 --warmup 5 --no-infer --no-u8 --no-cpu-baseline --sustain-seconds 0 2>/dev/null | tail -1 > gpurun_out/r02p_tmp.log
+    python - "$cfg" gpurun_out/r02p_tmp.log <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1]); print(sys.argv[1], round(d['ms_per_step'],3), round(d['value'],1))
+PY
+  done
+done
