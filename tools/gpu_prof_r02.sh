@@ -7,7 +7,7 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench.json 2
 tail -c 400 gpurun_out/${T}_bench.json
 Q="--steps 2 --warmup 3 --no-cpu-baseline --no-infer --no-u8 --sustain-seconds 0"
 TEETHRT_NO_GRAPH=1 timeout 300 python bench.py $Q > /dev/null 2>&1 && \
-TEETHRT_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3400 -c 1500 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py $Q > gpurun_out/${T}_ncu_bench.log 2>&1
+TEETHRT_NO_GRAPH=1 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py $Q > gpurun_out/${T}_ncu_bench.log 2>&1
 echo "launch list exit=$?"
 timeout 300 python tools/step_profile.py --log gpurun_out/${T}_step_ops_plain.json > /dev/null 2>&1 && \
 TEETHRT_WGRAD_STREAM=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv --log-file gpurun_out/${T}_step_launches.csv python tools/step_profile.py --log gpurun_out/${T}_step_ops.json > gpurun_out/${T}_stepprof.log 2>&1

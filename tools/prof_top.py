@@ -1,6 +1,7 @@
 """Driver for `ncu --set full` captures of the top kernels of the train step on their largest real shapes (one launch each
 after warm-up): 1x1-conv GEMM forward (24->144 @112x112, BN-stats epilogue), its dgrad (144->24), wgrad, depthwise forward /
-data gradient / weight gradient (192 ch k3 @56x56; 144 ch k3 s2 @112x112), activation backward."""
+data gradient / weight gradient (192 ch k3 @56x56; 144 ch k3 s2 @112x112), the two SE / BatchNorm backward passes and the SE
+squeeze on 192 ch @56x56."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, teethrt
@@ -21,6 +22,7 @@ def dw_case(H, Cc, k, s):
     return dict(x=x, rec=rec, w=w, y=y, dD=dD, g=torch.empty_like(x), st=ops.new_stats(Cc, "cuda"), bst=ops.new_stats(Cc, "cuda"), dw=torch.zeros_like(w), H=H, k=k, s=s)
 c1, c2 = dw_case(56, 192, 3, 1), dw_case(112, 144, 3, 2)
 gate = torch.rand(N, 192, device="cuda"); dmean = torch.randn(N, 192, device="cuda")
+sums = torch.zeros(5, N, 192, device="cuda"); coef = torch.randn(3, 192, device="cuda") * 0.1; pooled = torch.zeros(N, 192, device="cuda")
 def run():
     ops.gemm(A, W, ops.EPI_STATS, stats=st, out=C)
     ops.gemm(C, Wt, 0, out=dA)
@@ -28,7 +30,10 @@ def run():
     for c in (c1, c2):
         ops.dwconv_fwd(c["x"], c["rec"], c["w"], c["y"], N, c["H"], c["H"], c["k"], c["s"], stats=c["st"])
         ops.dwconv_bwd(c["dD"], c["w"], c["x"], c["rec"], c["g"], c["bst"], c["dw"], N, c["H"], c["H"], c["k"], c["s"])
-    ops.act_bwd(c1["dD"].view(-1, 192), gate, dmean, 1.0 / 3136, c1["y"].view(-1, 192), c1["rec"], c1["g"].view(-1, 192), c1["bst"], N, 3136, act=1)
+    # SE / BatchNorm backward of the depthwise output, merged path: five-sum pass, then the apply pass
+    ops.se_bwd_reduce(c1["dD"].view(-1, 192), c1["y"].view(-1, 192), c1["rec"], sums, N, 3136, zeroed=False, full=True)
+    ops.act_bwd_apply(c1["dD"].view(-1, 192), gate, dmean, 1.0 / 3136, c1["y"].view(-1, 192), c1["rec"], coef, c1["g"].view(-1, 192), N, 3136)
+    ops.pool_act(c1["y"].view(-1, 192), c1["rec"], pooled, N, 3136, act=1)
 for _ in range(2):
     run()
 torch.cuda.synchronize()
