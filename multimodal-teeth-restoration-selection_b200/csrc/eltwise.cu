@@ -353,6 +353,84 @@ __global__ void __launch_bounds__(TPB) se_expand_kernel(const float* __restrict_
   }
 }
 
+// SE MLP forward for an inference batch (N <= SE_SMALL_N images: batch 1, three TTA flips).  The batched kernels above give
+// one WARP to an image and 64 threads to a channel chunk, so at one image 7 of 8 warps idle and every dot product is one long
+// dependent chain: 8.7 us per block inside the captured batch-1 forward (tools/knockout.py --infer 1: 0.28 ms of 1.09 ms).
+// Here the whole block works on every dot product: the reduce kernel splits the channels over its 256 threads, the expand
+// kernel gives each output channel 8 lanes over the reduced dimension.
+constexpr int SE_SMALL_N = 4;
+__global__ void __launch_bounds__(TPB) se_reduce_small_kernel(const float* __restrict__ pooled, float inv_hw,
+                                                              const float* __restrict__ Wr, const float* __restrict__ br,
+                                                              float* __restrict__ s1, int N, int C, int rd) {
+  __shared__ float s_part[SE_SMALL_N][TPB / 32];
+  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc[SE_SMALL_N];
+#pragma unroll
+  for (int n = 0; n < SE_SMALL_N; ++n) acc[n] = 0.f;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    const float w = __ldg(Wr + (size_t)r * C + c);
+#pragma unroll
+    for (int n = 0; n < SE_SMALL_N; ++n)
+      if (n < N) acc[n] = fmaf(__ldg(pooled + (size_t)n * C + c), w, acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < SE_SMALL_N; ++n) {
+    acc[n] = warp_sum(acc[n]);
+    if (lane == 0) s_part[n][warp] = acc[n];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < TPB / 32; ++w) t += s_part[threadIdx.x][w];
+    s1[(size_t)threadIdx.x * rd + r] = fmaf(t, inv_hw, __ldg(br + r));
+  }
+}
+
+constexpr int SE_SCC = 32;    // channels per block of the small-batch expand kernel (8 lanes per channel)
+__global__ void __launch_bounds__(TPB) se_expand_small_kernel(const float* __restrict__ s1, const float* __restrict__ We,
+                                                              const float* __restrict__ be, float* __restrict__ gate, int N,
+                                                              int C, int rd) {
+  extern __shared__ float s_mem[];
+  float* s_we = s_mem;                          // [SE_SCC][rd + 1]
+  float* s_a1 = s_mem + SE_SCC * (rd + 1);      // [SE_SMALL_N][rd]
+  const int c0 = blockIdx.x * SE_SCC;
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < SE_SCC * rd; i += TPB) {       // the weights do not depend on the previous kernel
+    const int cl = i / rd, r = i - cl * rd;
+    s_we[cl * (rd + 1) + r] = (c0 + cl < C) ? __ldg(We + (size_t)(c0 + cl) * rd + r) : 0.f;
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < N * rd; i += TPB) s_a1[i] = siluf_(s1[i]);
+  __syncthreads();
+  const int cl = threadIdx.x >> 3, q = threadIdx.x & 7;        // 8 consecutive lanes share an output channel
+  float acc[SE_SMALL_N];
+#pragma unroll
+  for (int n = 0; n < SE_SMALL_N; ++n) acc[n] = 0.f;
+  const float* wrow = s_we + cl * (rd + 1);
+  for (int r = q; r < rd; r += 8) {
+    const float w = wrow[r];
+#pragma unroll
+    for (int n = 0; n < SE_SMALL_N; ++n)
+      if (n < N) acc[n] = fmaf(s_a1[n * rd + r], w, acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < SE_SMALL_N; ++n) {
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+    acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+  }
+  const int c = c0 + cl;
+  if (q < N && c < C) {
+    float mine = acc[0];
+#pragma unroll
+    for (int n = 1; n < SE_SMALL_N; ++n) mine = q == n ? acc[n] : mine;
+    gate[(size_t)q * C + c] = sigmoidf_(mine + __ldg(be + c));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ y = act(bn(x)) * gate[n,c]
 __global__ void __launch_bounds__(TPB) gate_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ rec,
                                                          const float* __restrict__ gate, uint4* __restrict__ out, int HW,
@@ -1248,6 +1326,15 @@ extern "C" int trt_se_fwd(const float* pooled_sum, float inv_hw, const float* Wr
                           cudaStream_t stream) {
   TRT_REQUIRE(pooled_sum && Wr && br && We && be && s1 && gate && N > 0 && C > 0 && rd > 0, "trt_se_fwd: bad argument");
   TRT_REQUIRE(!apply_x || (HW > 0 && C % 8 == 0), "trt_se_fwd: apply_x needs HW > 0 and C %% 8 == 0");
+  static const int small_off = [] { const char* e = getenv("TEETHRT_SE_SMALL"); return (e && *e == '0') ? 1 : 0; }();   // A/B switch
+  if (N <= SE_SMALL_N && !apply_x && !small_off) {
+    TRT_CUDA(trt_launch(se_reduce_small_kernel, dim3(rd), dim3(TPB), 0, stream, pooled_sum, inv_hw, Wr, br, s1, N, C, rd));
+    const size_t smem_s = ((size_t)SE_SCC * (rd + 1) + (size_t)SE_SMALL_N * rd) * sizeof(float);
+    TRT_REQUIRE(smem_s <= 48 * 1024, "trt_se_fwd: rd %d too large for the small-batch expand kernel", rd);
+    TRT_CUDA(trt_launch(se_expand_small_kernel, dim3((C + SE_SCC - 1) / SE_SCC), dim3(TPB), smem_s, stream, (const float*)s1, We, be, gate, N, C, rd));
+    trt_count_launch(1);
+    return trt_check_launch("trt_se_fwd");
+  }
   TRT_CUDA(trt_launch(se_reduce_kernel, dim3(rd, (N + 7) / 8), dim3(TPB), (size_t)C * sizeof(float), stream, pooled_sum, inv_hw, Wr, br, s1, N, C, rd));
   int splits = N >= 32 ? 4 : (N >= 8 ? 2 : 1);
   const int npb = (N + splits - 1) / splits;

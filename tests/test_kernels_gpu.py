@@ -198,7 +198,7 @@ def test_bn_se_block_forward_backward(ops, N, HW, C, rd, narrow, monkeypatch):
     gated = y_only.clone()
     s1b, gate_b = torch.empty_like(s1), torch.empty_like(gate)
     ops.se_fwd(pooled, 1.0 / HW, Wr, br, We, be, s1b, gate_b, apply_x=gated, HW=HW)
-    assert torch.equal(gate_b, gate)
+    assert torch.allclose(gate_b, gate, rtol=1e-5, atol=1e-6)       # N <= 4 takes the small-batch kernels without apply_x
     assert rel_err(gated.view(N, HW, C), y_only.float().view(N, HW, C) * gate[:, None, :]) < 1e-2
     y_res = ops.bn_apply(x2, rec, torch.empty_like(x2), residual=dA.view(N * HW, C), act=0)
     ref_res = (x_raw.float() * rec[0] + rec[1] + dA.float()).view(N * HW, C)

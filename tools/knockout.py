@@ -82,14 +82,53 @@ def run(dev, steps, B=64):
     return best
 
 
+INFER_CLASSES = {
+    "gemm": ["trt_gemm_bf16"],
+    "dwconv_fwd": ["trt_dwconv_fwd"],
+    "se_fwd_mlp": ["trt_se_fwd"],
+    "gate_apply": ["trt_gate_apply"],
+    "pool_act": ["trt_pool_act"],
+    "stem": ["trt_stem_fwd"],
+    "tab_heads": ["trt_tab_heads_fwd"],
+}
+
+
+def run_infer(dev, steps, batch):
+    """p50 of the graph-replayed MMNet eval forward at `batch` images (microseconds -> returned in ms)."""
+    from teethrt.modules import MMNet
+    from teethrt.infer import _GraphedForward
+    torch.manual_seed(0)
+    m = MMNet().to(dev).eval()
+    x, t = torch.randn(batch, 3, bench.IMG, bench.IMG, device=dev), torch.randn(batch, bench.TAB, device=dev)
+    g = _GraphedForward(lambda a, b: m(a, b)[0], [x, t])
+    for _ in range(30):
+        g(x, t)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps * 5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g(x, t)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--only", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--infer", type=int, default=0, help="N > 0: the batch-N eval forward instead of the train step")
     args = ap.parse_args()
     teethrt.init(0)
     dev = torch.device("cuda", 0)
+    global run, CLASSES
+    if args.infer:
+        CLASSES = INFER_CLASSES
+        run = lambda dev_, steps_: run_infer(dev_, steps_, args.infer)  # noqa: E731
     names = [n for n in args.only.split(",") if n] or list(CLASSES)
     base = run(dev, args.steps)
     lines = [{"knockout": None, "ms_per_step": round(base, 3)}]
