@@ -52,12 +52,17 @@ struct GemmParams {
 
 #ifdef TRT_GEMM_TIMING
 // bring-up instrumentation (never compiled into the shipped library): per-phase clock64 totals of epilogue group 0's first thread
-__device__ unsigned long long g_gemm_dbg[8];
+__device__ unsigned long long g_gemm_dbg[16];
+// producer / MMA-issuer phases of CTA 0 (slots 8..11): cycles waiting for a free stage, issuing TMA, waiting for data, issuing MMAs
+#define TRT_ROLE_TICK(slot) do { if (blockIdx.x == 0) { const long long now__ = clock64(); atomicAdd(&g_gemm_dbg[slot], (unsigned long long)(now__ - rtick__)); rtick__ = now__; } } while (0)
+#define TRT_ROLE_TICK_INIT long long rtick__ = clock64()
 #define TRT_TICK(slot) do { if (threadIdx.x == 64) { const long long now__ = clock64(); atomicAdd(&g_gemm_dbg[slot], (unsigned long long)(now__ - tick__)); tick__ = now__; } } while (0)
 #define TRT_TICK_INIT long long tick__ = clock64()
 #else
 #define TRT_TICK(slot) do {} while (0)
 #define TRT_TICK_INIT do {} while (0)
+#define TRT_ROLE_TICK(slot) do {} while (0)
+#define TRT_ROLE_TICK_INIT do {} while (0)
 #endif
 
 struct SmemLayout {
@@ -129,9 +134,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {   // elect.sync, not lane == 0: ptxas then issues the uniform-datapath TMA / MMA instructions directly instead of inside a per-lane loop
       int stage = 0;
       uint32_t phase = 0;
+      TRT_ROLE_TICK_INIT;
       if (p.b_resident) {
         // these GEMMs are bound by the TMA unit's box-row rate (~7 cycles per <=128-byte row, measured): the weights of the
         // CTA's n-block are the same for every tile it computes, so their rows are fetched once instead of once per tile.
@@ -146,7 +152,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int m0 = (t / p.num_n_blocks) * BM;
         const int n0 = (t % p.num_n_blocks) * p.block_n;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          TRT_ROLE_TICK(9);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          TRT_ROLE_TICK(8);
           ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (p.b_resident ? 0u : b_stage_bytes));
           ptx::tma_load_2d(smem + L.a_off + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage],
                            (MODE == 2 && p.a_kblocks > 0 ? kb % p.a_kblocks : kb) * BK, m0);
@@ -157,30 +165,41 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::instr_desc_bf16(BM, p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      TRT_ROLE_TICK_INIT;
       if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          TRT_ROLE_TICK(11);
           ptx::mbar_wait(&full_bar[stage], phase);
+          TRT_ROLE_TICK(10);
           ptx::tc_fence_after();
+          TRT_ROLE_TICK(12);
           const uint32_t a_addr = ptx::smem_u32(smem + L.a_off + stage * A_STAGE_BYTES);
           const uint32_t b_addr = ptx::smem_u32(smem + L.b_off + (p.b_resident ? kb : stage) * b_stage_bytes);
           const int k_rem = p.K - kb * BK;
           const int nk = k_rem >= BK ? BK / UK : (k_rem + UK - 1) / UK;
-          for (int k = 0; k < nk; ++k) {
+#ifdef TRT_GEMM_TIMING
+          const int nk_dbg = (p.flags & (1 << 21)) ? 1 : nk;       // ablation: one MMA per k-block (wrong result, timing only)
+#else
+          const int nk_dbg = nk;
+#endif
+          for (int k = 0; k < nk_dbg; ++k) {
             const uint64_t da = ptx::smem_desc(a_addr + k * (UK * 2), 0, 1024);
             const uint64_t db = ptx::smem_desc(b_addr + k * (UK * 2), 0, 1024);
             ptx::umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
+          TRT_ROLE_TICK(13);
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          TRT_ROLE_TICK(14);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
@@ -425,7 +444,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < nmb; ++i) {
         const int r0 = (mb_begin + i) * BK;
@@ -439,7 +458,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::instr_desc_bf16(BM, p.block_q, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < nmb; ++i) {
@@ -660,8 +679,8 @@ extern "C" int trt_gemm_bf16(const void* A, const void* B, void* C, int M, int N
 
 #ifdef TRT_GEMM_TIMING
 extern "C" int trt_debug_gemm_timing(unsigned long long* out8, int reset) {
-  if (out8) cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_gemm_dbg, z, sizeof(z)); }
+  if (out8) cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_gemm_dbg, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -74,7 +74,9 @@ def test_gemm_many_tiles_per_cta(ops, N, K):
     assert rel_err(dA, C.float() @ B.float()) < 1e-2
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 144, 24), (647, 336, 56), (3136, 672, 112), (12544, 960, 160), (3136, 1632, 272)])
+@pytest.mark.parametrize("M,N,K", [(1000, 144, 24), (647, 336, 56), (3136, 672, 112), (12544, 960, 160), (3136, 1632, 272),
+                                   # M <= 64 (batch-1 7x7 maps): half-height A box unless the epilogue takes statistics
+                                   (49, 272, 1632), (64, 160, 960), (17, 112, 672)])
 def test_gemm_epilogues(ops, M, N, K):
     A, B = rnd(M, K, seed=3, dtype=bf16), rnd(N, K, scale=K ** -0.5, seed=4, dtype=bf16)
     sc, sh = rnd(N, seed=5) * 0.2 + 1.0, rnd(N, seed=6) * 0.3
