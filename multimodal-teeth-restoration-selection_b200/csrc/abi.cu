@@ -34,11 +34,11 @@ extern "C" int trt_stat_replicas(void) { return TRT_STAT_REPLICAS; }
 // Programmatic dependent launch is a win for the inference chain (batch-1 forward: ~200 dependent kernels of a few
 // microseconds; measured 6.68 -> 6.28 ms for the 5-fold x 3-TTA ensemble) and a small loss inside the train step (11.66 ->
 // 11.98 ms: early-launched successors compete with the side-stream weight-gradient kernels for SM slots), so it is a mode
-// the host turns on around the eval forward (trt_set_pdl) rather than a process-wide default.  TEETHRT_PDL=0 forbids it.
+// the host turns on around the eval forward (trt_set_pdl) rather than a process-wide default.  TEETHRT_PDL=0 forbids it, =2 forces it everywhere (A/B switch).
 static int g_pdl = 0;
 bool trt_pdl_enabled() {
-  static const int allowed = [] { const char* e = getenv("TEETHRT_PDL"); return (e && *e) ? (*e != '0') : 1; }();
-  return allowed && g_pdl;
+  static const int mode = [] { const char* e = getenv("TEETHRT_PDL"); return (e && *e) ? (*e - '0') : 1; }();    // 0 never, 1 when the host asks, 2 always (A/B)
+  return mode == 2 || (mode == 1 && g_pdl);
 }
 extern "C" int trt_set_pdl(int on) {
   const int prev = g_pdl;
