@@ -372,6 +372,25 @@ class BatchTrainTransform:
                                     luts=u8(2 * B, 768), stats=torch.zeros(2 * B * 769, device=dev, dtype=torch.int64))}
         return self._bufs[key]
 
+    def _pinned(self, dev, B, blob_bytes):
+        """Page-locked staging for the job tables and the point-operation LUTs: a ring of four sets, each guarded by the event
+        recorded behind its upload.  (A fresh `pin_memory()` per call page-locks every step, and an upload from PAGEABLE memory
+        blocks the host until the stream has drained - the previous train step - so the GPU idled while the rest of the
+        transform and the step were still being enqueued: 13.7 instead of 12.0 ms per step end to end on a slow host.)"""
+        ring = self.__dict__.setdefault("_pin_ring", {})
+        key = (str(dev), B)
+        if key not in ring or ring[key]["cap"] < blob_bytes:
+            ring[key] = dict(cap=max(blob_bytes, B * (64 + 8 * _AUG_JOB.itemsize)), i=0, sets=[])
+            for _ in range(4):
+                ring[key]["sets"].append(dict(blob=torch.empty(ring[key]["cap"], dtype=torch.uint8).pin_memory(),
+                                              luts=torch.empty((2 * B, 768), dtype=torch.uint8).pin_memory(), ev=None))
+        r = ring[key]
+        st = r["sets"][r["i"] % 4]
+        r["i"] += 1
+        if st["ev"] is not None:
+            st["ev"].synchronize()
+        return st
+
     def apply(self, imgs, plan):
         from ._lib import lib, check, stream as cur_stream
         if isinstance(imgs, np.ndarray):
@@ -393,7 +412,8 @@ class BatchTrainTransform:
         crop = np.zeros((B, 8), np.int32)
         crop[:, :4] = plan.boxes
         crop[:, 4] = plan.flips
-        layer_jobs, luts_host, fallbacks = [], np.zeros((2 * B, 768), np.uint8), []
+        pin = self._pinned(dev, B, B * (crop.itemsize * 8 + len(plan.layers) * _AUG_JOB.itemsize + _FIN_JOB.itemsize))
+        layer_jobs, luts_host, fallbacks = [], pin["luts"].numpy(), []
         slot = 0
         for l, layer in enumerate(plan.layers):
             jobs, need_stats = [], False
@@ -448,7 +468,7 @@ class BatchTrainTransform:
         table = [crop.tobytes()] + [b"".join(j.tobytes() for _, j in jobs) for jobs, _ in layer_jobs]
         offs = np.cumsum([0] + [len(t) for t in table])
         fin_off = int(offs[-1])
-        blob = torch.empty(fin_off + B * _FIN_JOB.itemsize, dtype=torch.uint8).pin_memory()
+        blob = pin["blob"][:fin_off + B * _FIN_JOB.itemsize]
         host = blob.numpy()
         for t, o in zip(table, offs[:-1]):
             host[o:o + len(t)] = np.frombuffer(t, np.uint8)
@@ -463,7 +483,9 @@ class BatchTrainTransform:
         host[fin_off:] = np.frombuffer(fin.tobytes(), np.uint8)
         dblob = blob.to(dev, non_blocking=True)
         dluts = sc["luts"]
-        dluts.copy_(torch.from_numpy(luts_host), non_blocking=True)
+        dluts.copy_(pin["luts"], non_blocking=True)
+        pin["ev"] = torch.cuda.Event()
+        pin["ev"].record(torch.cuda.current_stream(dev))
         p0 = dblob.data_ptr()
         st = cur_stream()
         check(lib.trt_crop_resize_batch_u8(imgs.data_ptr(), B, H, W, p0, S, 1, kmax, hmax, sc["bounds"].data_ptr(),
