@@ -561,7 +561,10 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const _
       __syncthreads();
     }
     if (worker) {
-      for (int oy = sub; oy < TOH; oy += SUBS) {
+      // only the tile's rows inside the map: a bottom tile of 6 (14x14) or 4 (28x28) rows needs one pass of the K = 5 row
+      // lanes instead of two (the rows past the edge are zero-filled dD: correct, but a third of the kernel's time there)
+      const int rows_here = min(TOH, g.OH - q.ty * TOH);
+      for (int oy = sub; oy < rows_here; oy += SUBS) {
         const uint4* xrow = s_in + ((oy * S + kh) * IW) * CL + lane;
         const uint4* drow = s_d + (oy * TOW) * CL + lane;
         if (S == 1) {
