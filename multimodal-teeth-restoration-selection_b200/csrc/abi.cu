@@ -127,9 +127,5 @@ extern "C" int trt_init(int device) {
   if (n > 0) g_num_sms = n;          // one box holds identical GPUs; grids are sized for this count
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return trt_set_error(TRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if (const char* e = getenv("TEETHRT_CARVEOUT")) {      // bring-up probe (tools/launch_probe.py): device-wide carve-out preference
-    if (*e == '1') TRT_CUDA(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
-    if (*e == '2') TRT_CUDA(cudaDeviceSetCacheConfig(cudaFuncCachePreferL1));
-  }
   return TRT_OK;
 }

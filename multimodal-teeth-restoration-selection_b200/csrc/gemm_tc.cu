@@ -640,8 +640,7 @@ static int gemm_launch(const void* A, const void* B, void* C, int M, int N, int 
   p.tmem_cols = pow2_cols(p.nacc * p.acc_stride);
   SmemLayout L = make_layout(p.block_n, p.stages, p.ngroups, p.b_resident ? p.num_k_blocks : p.stages, nostage);
   size_t smem_bytes = (size_t)L.total + 1024;      // slack for the manual 1024B alignment
-  static const int smem_floor_kb = [] { const char* e = getenv("TEETHRT_GEMM_SMEM_FLOOR"); return e ? atoi(e) : 120; }();
-  if (smem_bytes < (size_t)smem_floor_kb * 1024) smem_bytes = (size_t)smem_floor_kb * 1024;   // > half an SM's smem: exactly one persistent CTA per SM
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // > half an SM's smem: exactly one persistent CTA per SM
   CUtensorMap ta, tb;
   int rc;
   const uint64_t a_cols = p.a_kblocks > 0 ? (uint64_t)p.a_kblocks * BK : (uint64_t)K;     // physical width of A

@@ -2,7 +2,9 @@
 """Fixed cost of a launch inside a CUDA graph: a tiny tcgen05 GEMM, a tiny depthwise convolution and a tiny elementwise
 kernel, each alone (R back-to-back launches in one graph) and interleaved.  If a pair costs more than the sum of its parts
 the kernels do not overlap each other's tail / the SM is reconfigured between them (shared-memory carve-out flips).
-Environment switches read by the library: TEETHRT_CARVEOUT=1/2, TEETHRT_GEMM_SMEM_FLOOR=<KB>, TEETHRT_PDL=1."""
+The carve-out / shared-memory-floor switches this probe was first run with (device-wide cudaFuncCachePreferShared / L1, the
+GEMM without its 120 KB floor) changed nothing and were removed from the library; PROBE_PDL=1 turns programmatic dependent
+launch on."""
 import json
 import os
 import sys
