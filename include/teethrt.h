@@ -288,10 +288,12 @@ int trt_pack_w1x1_batch(const long long* table_dev, int count, int total_tiles, 
 /* x: [N,H,W,C]; in_rec != NULL: input = silu(bn(x)) applied on load; out_rec != NULL (eval): out = silu(bn_out(conv)),
  * pooled_sum[n,c] (optional; zeroed here unless pooled_zeroed: one arena memset per forward instead of one per block)
  * += sum_hw out; stats != NULL (train): fp64 {sum, sum^2} of the raw output.
- * in_fin_host (optional): the INPUT's BatchNorm is lazy - in_rec is derived from in_fin_host->stats and published. */
+ * in_fin_host (optional): the INPUT's BatchNorm is lazy - in_rec is derived from in_fin_host->stats and published.
+ * act_out (optional, stride 1 with in_rec, [N,H,W,C] bf16): receives silu(bn(x)), the activated input the kernel forms in
+ * shared memory anyway; trt_dwconv_bwd's weight gradient then takes it as x_raw with x_rec = NULL and skips the activation. */
 int trt_dwconv_fwd(const void* x, const float* in_rec, const float* w, void* out, const float* out_rec, float* pooled_sum,
-                   int pooled_zeroed, double* stats, const trt_bn_fin_t* in_fin_host, int N, int H, int W, int C, int k, int s,
-                   trt_stream_t stream);
+                   int pooled_zeroed, double* stats, const trt_bn_fin_t* in_fin_host, void* act_out, int N, int H, int W, int C,
+                   int k, int s, trt_stream_t stream);
 /* gy = dD, the gradient w.r.t. the RAW depthwise output (the BN-backward affine of the following BatchNorm has already been
  * applied by trt_affine2).  g_out (NULL = skip) = convT(dD) * (x_rec ? silu'(bn(x_raw)) : 1), bstats += {sum g, sum g*xhat};
  * dw[C,1,k,k] (NULL = skip) += correlation of dD with act(x) (act = silu(bn) when x_rec).  The two halves are independent:

@@ -90,7 +90,7 @@ _SIGS = {
     "trt_scale_f32": (i32, [vp, sz, f32, vp]),
     "trt_pack_w1x1": (i32, [vp, vp, vp, i32, i32, vp]),
     "trt_pack_w1x1_batch": (i32, [vp, i32, i32, vp]),
-    "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "trt_dwconv_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "trt_stem_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "trt_stem_wgrad": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),

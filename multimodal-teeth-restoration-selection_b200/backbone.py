@@ -454,8 +454,13 @@ def forward_train(enc, x, save=True):
         oh, ow = ops.same_out(h, s), ops.same_out(w, s)
         d_raw = torch.empty((N * oh * ow, cm), device=dev, dtype=bf16)
         st = stats.take(ops.STAT_REPLICAS * 2 * cm)
+        # stride 1: the forward also writes its activated input once, and the weight-gradient kernel of the backward pass reads
+        # that instead of recomputing silu(bn(x)) over its halo'd tiles (TEETHRT_DW_SAVE_ACT=0: recompute, the round-1 path)
+        dw_act = None
+        if save and s == 1 and dw_rec is not None and os.environ.get("TEETHRT_DW_SAVE_ACT", "1") != "0":
+            dw_act = torch.empty_like(dw_in)
         ops.dwconv_fwd(dw_in, None if dw_rec is None else dw_rec.rec, blk.conv_dw.weight.detach(), d_raw, N, h, w, k, s, stats=st,
-                       in_fin=None if dw_rec is None else dw_rec.fin())
+                       in_fin=None if dw_rec is None else dw_rec.fin(), act_out=dw_act)
         rec_d = bn_stage(bn_dw, N * oh * ow, st)
         pooled = pool_arena.take(N * cm, (N, cm))
         ops.pool_act(d_raw, rec_d.rec, pooled, N, oh * ow, act=1, zeroed=True, fin=rec_d.fin())
@@ -468,7 +473,7 @@ def forward_train(enc, x, save=True):
         rec_o = bn_stage(bn_out, N * oh * ow, st)
         y = ops.bn_apply(p_raw, rec_o.rec, torch.empty_like(p_raw), residual=cur if has_skip else None, act=0, fin=rec_o.fin())
         sv.update(d_raw=d_raw, pooled=pooled, s1=s1, gate=gate, a=a, p_raw=p_raw, oh=oh, ow=ow, has_skip=has_skip,
-                  bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out)
+                  bn_dw=bn_dw, pw_name=pw_name, bn_out=bn_out, dw_act=dw_act)
         ctx["blocks"].append((blk, sv))
         cur, cur_rec, h, w = y, None, oh, ow
     st = stats.take(ops.STAT_REPLICAS * 2 * enc.num_features)
@@ -664,7 +669,10 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
             e_raw, rec1 = sv["e_raw"], REC[name + ".bn1"]
             bst = bstats.take(ops.STAT_REPLICAS * 2 * cm)
             g1 = torch.empty_like(e_raw)
-            sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), e_raw, rec1, dw_grad, N, h, w, k, s)
+            if sv.get("dw_act") is not None:       # the forward saved silu(bn1(e_raw)): no activation in the weight-gradient kernel
+                sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), sv["dw_act"], None, dw_grad, N, h, w, k, s)
+            else:
+                sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), e_raw, rec1, dw_grad, N, h, w, k, s)
             ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), e_raw, rec1, g1, bst, None, N, h, w, k, s)
             de = bn_dx(name + ".bn1", N * h * w, bst, g1, e_raw, g1)
             dx, dy_bst = dgrad(de, Wp[name + ".conv_pw"][1], bidx, residual=dy if sv["has_skip"] else None)
@@ -676,7 +684,10 @@ def backward_train_iter(enc, ctx, dfeat, grads, split_after=()):
             if in_rec is not None:                       # input was the (lazy) stem output: BN+SiLU applied on load
                 bst = bstats.take(ops.STAT_REPLICAS * 2 * c["cin"])
                 g_in = torch.empty_like(x_in)
-                sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), x_in, in_rec, dw_grad, N, h, w, k, s)
+                if sv.get("dw_act") is not None:
+                    sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), sv["dw_act"], None, dw_grad, N, h, w, k, s)
+                else:
+                    sq.dw_wgrad(dD, blk.conv_dw.weight.detach(), x_in, in_rec, dw_grad, N, h, w, k, s)
                 ops.dwconv_bwd(dD, blk.conv_dw.weight.detach(), x_in, in_rec, g_in, bst, None, N, h, w, k, s)
                 ds = bn_dx("bn1", N * h * w, bst, g_in, x_in, g_in)
                 _stem_wgrad(ctx, ds, grads, sq)

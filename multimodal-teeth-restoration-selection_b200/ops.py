@@ -200,10 +200,11 @@ def act_bwd(dA, gate, dmean, inv_hw, x, rec, g_out, bstats, N, HW, act=1):
 
 
 # ------------------------------------------------------------------------------------------------ spatial convs
-def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, in_fin=None, pooled_zeroed=False):
-    """in_fin: lazy BatchNorm record of the INPUT (in_rec is derived from its statistics and published by this launch)."""
+def dwconv_fwd(x, in_rec, w, out, N, H, W, k, s, out_rec=None, pooled=None, stats=None, in_fin=None, pooled_zeroed=False, act_out=None):
+    """in_fin: lazy BatchNorm record of the INPUT (in_rec is derived from its statistics and published by this launch).
+    act_out (stride 1, with in_rec): receives silu(bn(x)) for the weight-gradient kernel of the backward pass."""
     check(lib.trt_dwconv_fwd(ptr(x), ptr(in_rec), ptr(w), ptr(out), ptr(out_rec), ptr(pooled), int(pooled_zeroed), ptr(stats),
-                             _ref(in_fin), N, H, W, x.shape[-1], k, s, stream()))
+                             _ref(in_fin), ptr(act_out), N, H, W, x.shape[-1], k, s, stream()))
     return out
 
 

@@ -431,6 +431,18 @@ def test_dwconv_forward_backward(ops, k, s, N, H, W, C):
     xh = (x_raw.double().view(-1, C) - rec1[2].double()) * rec1[3].double()
     bt = ops.stats_total(bst)
     assert torch.allclose(bt[0], gd.sum(0), rtol=1e-3, atol=1e-2) and torch.allclose(bt[1], (gd * xh).sum(0), rtol=1e-3, atol=1e-2)
+    if s == 1:
+        # the forward can also emit its activated input; the weight gradient taken from that tensor (no activation in the
+        # kernel) equals the one that recomputes silu(bn(x)) from the raw input
+        act = torch.full_like(x_raw, float("nan"))
+        y_b = torch.empty_like(y)
+        ops.dwconv_fwd(x_raw, rec1, w, y_b, N, H, W, k, s, stats=ops.new_stats(C, "cuda"), act_out=act)
+        assert torch.equal(y_b, y)
+        want_act = ops.bn_apply(x_raw.view(-1, C), rec1, torch.empty_like(x_raw.view(-1, C)), act=1).view_as(x_raw)
+        assert torch.equal(act, want_act)
+        dw_b = torch.zeros_like(w)
+        ops.dwconv_bwd(dD_dev, w, act, None, None, None, dw_b, N, H, W, k, s)
+        assert rel_err(dw_b, dw) < 1e-3
     # no-transform / no-coef flavour (DS block whose input is already an activation)
     xt2 = x_raw.float().requires_grad_(True)
     y2 = F.conv2d(same_pad_t(xt2.permute(0, 3, 1, 2), k, s), w, stride=s, groups=C).permute(0, 2, 3, 1)
