@@ -14,3 +14,6 @@ timeout 200 python tools/prof_top.py > /dev/null 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${T}_top_kernels python tools/prof_top.py > gpurun_out/${T}_ncu_top.log 2>&1
 echo "ncu full exit=$?"; tail -1 gpurun_out/${T}_ncu_top.log
 timeout 300 python tools/knockout.py --out gpurun_out/${T}_knockout.jsonl 2>&1 | tail -18
+timeout 300 python tools/dw_probe.py 2>&1 | tail -15 > gpurun_out/${T}_dw_probe.jsonl; tail -1 gpurun_out/${T}_dw_probe.jsonl
+timeout 300 python tools/gemm_probe.py 2>&1 | tail -23 > gpurun_out/${T}_gemm_probe.jsonl; tail -1 gpurun_out/${T}_gemm_probe.jsonl
+timeout 300 python tools/knockout.py --infer 1 --out gpurun_out/${T}_knockout_infer1.jsonl 2>&1 | tail -9
