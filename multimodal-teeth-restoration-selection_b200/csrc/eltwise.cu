@@ -1171,13 +1171,17 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
 __global__ void pack_w_batch_kernel(const long long* __restrict__ table, int count) {
   __shared__ float tile[32][33];
   __shared__ int s_entry;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    int lo = 0, hi = count - 1;
-    while (lo < hi) {                               // last entry whose first tile is <= blockIdx.x
-      const int mid = (lo + hi + 1) >> 1;
-      if (table[mid * 6 + 5] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  if (threadIdx.y == 0) {
+    // last entry whose first tile is <= blockIdx.x (first tiles ascend, entry 0 starts at tile 0): one warp counts them
+    // with independent loads - ONE L2 round trip; the binary search this replaces was a chain of log2(count) dependent
+    // loads in front of a block that only moves 8 KB (17 k such blocks per step)
+    int n_le = 0;
+    for (int base = 0; base < count; base += 32) {
+      const int i = base + threadIdx.x;
+      const bool le = i < count && __ldg(table + i * 6 + 5) <= (long long)blockIdx.x;
+      n_le += __popc(__ballot_sync(0xffffffffu, le));
     }
-    s_entry = lo;
+    if (threadIdx.x == 0) s_entry = n_le - 1;
   }
   __syncthreads();
   const long long* e = table + s_entry * 6;

@@ -147,6 +147,26 @@ def test_pack_w1x1(ops):
     assert torch.equal(o, w.view(144, 24).to(bf16)) and torch.equal(ot, w.view(144, 24).t().contiguous().to(bf16))
 
 
+@pytest.mark.parametrize("count", [1, 5, 40, 70])
+def test_pack_w1x1_batch(ops, count):
+    """All 1x1 weights of a model in one launch: every block finds its table entry (first tiles ascending, more than one
+    warp's worth of entries at count = 40 / 70), ragged N / K, entries with and without the transposed copy."""
+    g = torch.Generator().manual_seed(count)
+    shapes = [(int(torch.randint(1, 150, (1,), generator=g)), int(torch.randint(1, 150, (1,), generator=g))) for _ in range(count)]
+    ws = [rnd(n, k, seed=100 + i) for i, (n, k) in enumerate(shapes)]
+    outs = [torch.zeros(n, k, device="cuda", dtype=bf16) for n, k in shapes]
+    outs_t = [torch.zeros(k, n, device="cuda", dtype=bf16) if i % 3 else None for i, (n, k) in enumerate(shapes)]
+    rows, tiles = [], 0
+    for w, o, ot, (n, k) in zip(ws, outs, outs_t, shapes):
+        rows.append([w.data_ptr(), o.data_ptr(), ot.data_ptr() if ot is not None else 0, n, k, tiles])
+        tiles += ((n + 31) // 32) * ((k + 31) // 32)
+    ops.pack_w1x1_batch(torch.tensor(rows, dtype=torch.int64).cuda(), tiles)
+    for w, o, ot in zip(ws, outs, outs_t):
+        assert torch.equal(o, w.to(bf16))
+        if ot is not None:
+            assert torch.equal(ot, w.t().contiguous().to(bf16))
+
+
 # ------------------------------------------------------------------------------------------------ BN + SE composite
 def make_rec(ops, xr, gamma, beta, eps=1e-3):
     """rec via trt_bn_finalize from fp64 sums of the stored (bf16) tensor; also returns the running stats it updated."""
