@@ -19,7 +19,8 @@ def dw_case(H, Cc, k, s):
     rec = torch.stack([torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1, torch.randn(Cc, device="cuda") * 0.1, torch.rand(Cc, device="cuda") + 0.5]).contiguous()
     w = torch.randn(Cc, 1, k, k, device="cuda") / k
     y = torch.empty(N, OH, OH, Cc, device="cuda", dtype=bf16); dD = torch.randn(N, OH, OH, Cc, device="cuda").to(bf16)
-    return dict(x=x, rec=rec, w=w, y=y, dD=dD, g=torch.empty_like(x), st=ops.new_stats(Cc, "cuda"), bst=ops.new_stats(Cc, "cuda"), dw=torch.zeros_like(w), H=H, k=k, s=s)
+    return dict(x=x, rec=rec, w=w, y=y, dD=dD, g=torch.empty_like(x), st=ops.new_stats(Cc, "cuda"), bst=ops.new_stats(Cc, "cuda"), dw=torch.zeros_like(w), H=H, k=k, s=s,
+                act=torch.empty_like(x) if s == 1 else None)
 c1, c2 = dw_case(56, 192, 3, 1), dw_case(112, 144, 3, 2)
 gate = torch.rand(N, 192, device="cuda"); dmean = torch.randn(N, 192, device="cuda")
 sums = torch.zeros(5, N, 192, device="cuda"); coef = torch.randn(3, 192, device="cuda") * 0.1; pooled = torch.zeros(N, 192, device="cuda")
@@ -28,8 +29,14 @@ def run():
     ops.gemm(C, Wt, 0, out=dA)
     ops.gemm_wgrad(C, A, dW)
     for c in (c1, c2):
-        ops.dwconv_fwd(c["x"], c["rec"], c["w"], c["y"], N, c["H"], c["H"], c["k"], c["s"], stats=c["st"])
-        ops.dwconv_bwd(c["dD"], c["w"], c["x"], c["rec"], c["g"], c["bst"], c["dw"], N, c["H"], c["H"], c["k"], c["s"])
+        # the shipped step: the stride-1 forward also stores its activated input (act_out); data gradient and weight gradient
+        # are separate launches, the stride-1 weight gradient reads the saved activation (no silu(bn(x)) recomputation)
+        ops.dwconv_fwd(c["x"], c["rec"], c["w"], c["y"], N, c["H"], c["H"], c["k"], c["s"], stats=c["st"], act_out=c["act"])
+        ops.dwconv_bwd(c["dD"], c["w"], c["x"], c["rec"], c["g"], c["bst"], None, N, c["H"], c["H"], c["k"], c["s"])
+        if c["act"] is not None:
+            ops.dwconv_bwd(c["dD"], c["w"], c["act"], None, None, None, c["dw"], N, c["H"], c["H"], c["k"], c["s"])
+        # "before" row (TEETHRT_DW_SAVE_ACT=0; still the stride-2 path): the weight gradient recomputes silu(bn(x)) per tile
+        ops.dwconv_bwd(c["dD"], c["w"], c["x"], c["rec"], None, None, c["dw"], N, c["H"], c["H"], c["k"], c["s"])
     # SE / BatchNorm backward of the depthwise output, merged path: five-sum pass, then the apply pass
     ops.se_bwd_reduce(c1["dD"].view(-1, 192), c1["y"].view(-1, 192), c1["rec"], sums, N, 3136, zeroed=False, full=True)
     ops.act_bwd_apply(c1["dD"].view(-1, 192), gate, dmean, 1.0 / 3136, c1["y"].view(-1, 192), c1["rec"], coef, c1["g"].view(-1, 192), N, 3136)
