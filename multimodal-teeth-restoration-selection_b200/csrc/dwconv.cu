@@ -11,6 +11,7 @@
 //
 // Replaces cuDNN/ATen depthwise conv launches inside `self.backbone(x_img)`
 // (experiments/multimodal_v1/train_mm_joint_dualtask.py:154) and their autograd backward (:248).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -377,20 +378,22 @@ template <int K> struct S2Tile {
   static constexpr int D_BYTES = DH * DW * PX_BYTES, X_BYTES = TI * TI * PX_BYTES, STAGE = D_BYTES + X_BYTES;
 };
 
-template <int K, int PY, int PX>
-__device__ __forceinline__ void s2_class_rows(const uint4* s_d, const uint4* s_w, int dy, int dx, int lane, float (&acc)[8][8]) {
+// NP = pixels per call: the thread's 8 same-parity pixels are computed as two halves of 4 (accumulators for all 8 at once
+// need 64 registers on top of the row window: the k5 kernel spilled 800 bytes per thread under the 128-register cap)
+template <int K, int PY, int PX, int NP>
+__device__ __forceinline__ void s2_class_rows(const uint4* s_d, const uint4* s_w, int dy, int dx, int lane, float (&acc)[NP][8]) {
   // taps of this class: kh = PY + 2a (a < NA), kw = PX + 2b (b < NB); dD row = dy - a, dD col = dx - b + p
   constexpr int NA = (K - PY + 1) / 2, NB = (K - PX + 1) / 2, DW = S2Tile<K>::DW;
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
-    uint4 row[8 + NB - 1];
+    uint4 row[NP + NB - 1];
 #pragma unroll
-    for (int j = 0; j < 8 + NB - 1; ++j) row[j] = s_d[((dy - a) * DW + dx - (NB - 1) + j) * CL + lane];
+    for (int j = 0; j < NP + NB - 1; ++j) row[j] = s_d[((dy - a) * DW + dx - (NB - 1) + j) * CL + lane];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const uint4 wv = s_w[((PY + 2 * a) * K + PX + 2 * b) * CL + lane];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) fma8(acc[p], row[p + (NB - 1) - b], wv);
+      for (int p = 0; p < NP; ++p) fma8(acc[p], row[p + (NB - 1) - b], wv);
     }
   }
 }
@@ -454,41 +457,47 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     // dD coordinates (tile-local) of tap (a = 0, b = 0) for this thread's first pixel
     const int dy = (iy0 + r + g.pad_t - py) / 2 - d_origin(iy0, g.pad_t);
     const int dx = (ix0 + rx + g.pad_l - px) / 2 - d_origin(ix0, g.pad_l);
-    float acc[8][8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
-    if (py == 0) {
-      if (px == 0) s2_class_rows<K, 0, 0>(s_d, s_w, dy, dx, lane, acc);
-      else s2_class_rows<K, 0, 1>(s_d, s_w, dy, dx, lane, acc);
-    } else {
-      if (px == 0) s2_class_rows<K, 1, 0>(s_d, s_w, dy, dx, lane, acc);
-      else s2_class_rows<K, 1, 1>(s_d, s_w, dy, dx, lane, acc);
-    }
     const int iy = iy0 + r;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      constexpr int NP = 4;
+      float acc[NP][8];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int ix = ix0 + rx + 2 * p;
-      if (cvalid && iy < g.H && ix < g.W) {
-        const size_t idx = ((size_t)(q.n * g.H + iy) * g.W + ix) * V + cv;
-        f8 o;
-        if (x_rec) {
-          const f8 xr = unpack8(s_x[(r * T::TI + rx + 2 * p) * CL + lane]);
+      for (int p = 0; p < NP; ++p)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i] * silu_gradf_(fmaf(xr.v[i], sc.v[i], sh.v[i]));
-          const uint4 qv = pack8(o);
-          g_out[idx] = qv;
-          const f8 rr = unpack8(qv);
+        for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
+      const int dxh = dx + NP * half;
+      if (py == 0) {
+        if (px == 0) s2_class_rows<K, 0, 0, NP>(s_d, s_w, dy, dxh, lane, acc);
+        else s2_class_rows<K, 0, 1, NP>(s_d, s_w, dy, dxh, lane, acc);
+      } else {
+        if (px == 0) s2_class_rows<K, 1, 0, NP>(s_d, s_w, dy, dxh, lane, acc);
+        else s2_class_rows<K, 1, 1, NP>(s_d, s_w, dy, dxh, lane, acc);
+      }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            red[0][i] += rr.v[i];
-            red[1][i] = fmaf(rr.v[i], xr.v[i], red[1][i]);     // sum g*x, fixed up after the loop
+      for (int p = 0; p < NP; ++p) {
+        const int pp = NP * half + p;
+        const int ix = ix0 + rx + 2 * pp;
+        if (cvalid && iy < g.H && ix < g.W) {
+          const size_t idx = ((size_t)(q.n * g.H + iy) * g.W + ix) * V + cv;
+          f8 o;
+          if (x_rec) {
+            const f8 xr = unpack8(s_x[(r * T::TI + rx + 2 * pp) * CL + lane]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i] * silu_gradf_(fmaf(xr.v[i], sc.v[i], sh.v[i]));
+            const uint4 qv = pack8(o);
+            g_out[idx] = qv;
+            const f8 rr = unpack8(qv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              red[0][i] += rr.v[i];
+              red[1][i] = fmaf(rr.v[i], xr.v[i], red[1][i]);     // sum g*x, fixed up after the loop
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i];
+            g_out[idx] = pack8(o);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] = acc[p][i];
-          g_out[idx] = pack8(o);
         }
       }
     }
@@ -512,14 +521,19 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
 // dW[c][kh][kw] += sum_{n,oy,ox} dD[n,oy,ox,c] * act(x)[n, oy*S-pad_t+kh, ox*S-pad_l+kw, c]
 // thread = (channel lane, filter row kh, output-row subset); the filter row slides over an input row kept in registers.
 // The gradient does not depend on the tile position, so the accumulators live in registers across ALL the block's items.
-template <int K, int S>
+// Tile height of the weight-gradient kernel: NPT / K row lanes share a tile's rows (K = 3: 10 lanes, K = 5: 6), so stride-1
+// tiles are 10 / 12 rows tall - every pass over the lanes is full (with the 8-row tile of the other kernels the K = 5 lanes ran
+// 6 + 2 and the K = 3 lanes 8 of 10).  Stride 2 keeps 8 rows: a taller input tile would not leave room for two blocks per SM.
+__host__ __device__ constexpr int wgrad_tile_h(int K, int S) { return S == 1 ? (K == 5 ? 12 : 10) : TOH; }
+
+template <int K, int S, int WH>
 __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                    const __grid_constant__ CUtensorMap tm_d,
                                                                    const float* __restrict__ in_rec, float* __restrict__ dw,
                                                                    const DwGeom g) {
   constexpr int TOW = 8;
-  constexpr int IH = (TOH - 1) * S + K, IW = (TOW - 1) * S + K;
-  constexpr int X_BYTES = IH * IW * PX_BYTES, D_BYTES = TOH * TOW * PX_BYTES, STAGE = X_BYTES + D_BYTES;
+  constexpr int IH = (WH - 1) * S + K, IW = (TOW - 1) * S + K;
+  constexpr int X_BYTES = IH * IW * PX_BYTES, D_BYTES = WH * TOW * PX_BYTES, STAGE = X_BYTES + D_BYTES;
   constexpr int SUBS = NPT / K;                 // row subsets per filter row (K=3: 10, K=5: 6)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
@@ -543,8 +557,8 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const _
   auto issue = [&](int it, int st) {
     const Item q = decode_item(it, tiles, g);
     ptx::mbar_expect_tx(&bar[st], STAGE);
-    ptx::tma_load_4d(smem + st * STAGE, &tm_x, &bar[st], cb * 64, q.tx * TOW * S - g.pad_l, q.ty * TOH * S - g.pad_t, q.n);
-    ptx::tma_load_4d(smem + st * STAGE + X_BYTES, &tm_d, &bar[st], cb * 64, q.tx * TOW, q.ty * TOH, q.n);
+    ptx::tma_load_4d(smem + st * STAGE, &tm_x, &bar[st], cb * 64, q.tx * TOW * S - g.pad_l, q.ty * WH * S - g.pad_t, q.n);
+    ptx::tma_load_4d(smem + st * STAGE + X_BYTES, &tm_d, &bar[st], cb * 64, q.tx * TOW, q.ty * WH, q.n);
   };
   f8 sc, sh;
   if (in_rec && cvalid) { sc = ldf8(in_rec + 8 * cv); sh = ldf8(in_rec + g.C + 8 * cv); }
@@ -567,13 +581,13 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const _
     ptx::mbar_wait(&bar[st], (phase >> st) & 1u);
     phase ^= 1u << st;
     if (in_rec) {
-      if (cvalid) activate_tile<IH, IW>(s_in, sc, sh, q.ty * TOH * S - g.pad_t, q.tx * TOW * S - g.pad_l, g.H, g.W, lane, pt);
+      if (cvalid) activate_tile<IH, IW>(s_in, sc, sh, q.ty * WH * S - g.pad_t, q.tx * TOW * S - g.pad_l, g.H, g.W, lane, pt);
       __syncthreads();
     }
     if (worker) {
-      // only the tile's rows inside the map: a bottom tile of 6 (14x14) or 4 (28x28) rows needs one pass of the K = 5 row
-      // lanes instead of two (the rows past the edge are zero-filled dD: correct, but a third of the kernel's time there)
-      const int rows_here = min(TOH, g.OH - q.ty * TOH);
+      // only the tile's rows inside the map: a short bottom tile needs fewer passes of the row lanes (the rows past the
+      // edge are zero-filled dD: correct, but up to a third of the kernel's time on the small maps)
+      const int rows_here = min(WH, g.OH - q.ty * WH);
       for (int oy = sub; oy < rows_here; oy += SUBS) {
         const uint4* xrow = s_in + ((oy * S + kh) * IW) * CL + lane;
         const uint4* drow = s_d + (oy * TOW) * CL + lane;
@@ -753,26 +767,36 @@ extern "C" int trt_dwconv_bwd(const void* gy, const float* w, const void* x_raw,
   }
   if (!dw) return TRT_OK;            // data gradient only (the weight gradient may run as its own call on another stream)
   {
+    // tall tiles only where they save passes (not on the 14x14 / 7x7 maps: same pass count, larger boxes);
+    // TEETHRT_DW_WGRAD_TALL=0: the 8-row tile everywhere (A/B)
+    static const int tall_on = [] { const char* e = getenv("TEETHRT_DW_WGRAD_TALL"); return (e && *e == '0') ? 0 : 1; }();
+    auto lane_passes = [&](int th) {          // passes of the NPT / k row lanes over one column of tiles
+      const int subs = NPT / k;
+      int n = 0;
+      for (int y = 0; y < g.OH; y += th) n += ((g.OH - y < th ? g.OH - y : th) + subs - 1) / subs;
+      return n;
+    };
+    const int wh = (tall_on && lane_passes(wgrad_tile_h(k, s)) < lane_passes(TOH)) ? wgrad_tile_h(k, s) : TOH;
     g.tiles_x = (g.OW + 7) / 8;
-    g.tiles_y = (g.OH + TOH - 1) / TOH;
+    g.tiles_y = (g.OH + wh - 1) / wh;
     set_magic(g);
     const int items = N * g.tiles_x * g.tiles_y;
     TRT_REQUIRE((long long)items * g.tiles_x * g.tiles_y < (1ll << 32), "trt_dwconv_bwd: too many tiles");
-#define LAUNCH_BW(KK, SS)                                                                                          \
+#define LAUNCH_BW(KK, SS, WH)                                                                                      \
   do {                                                                                                             \
-    const int IH = (TOH - 1) * SS + KK, IW = 7 * SS + KK;                                                          \
-    const size_t smem = 2 * ((size_t)IH * IW + TOH * 8) * PX_BYTES + 16 + 128;                                     \
+    const int IH = (WH - 1) * SS + KK, IW = 7 * SS + KK;                                                           \
+    const size_t smem = 2 * ((size_t)IH * IW + WH * 8) * PX_BYTES + 16 + 128;                                      \
     CUtensorMap tx, td;                                                                                            \
     if ((rc = trt_make_tmap_nhwc(&tx, x_raw, N, H, W, C, 64, IW, IH))) return rc;                                  \
-    if ((rc = trt_make_tmap_nhwc(&td, gy, N, g.OH, g.OW, C, 64, 8, TOH))) return rc;                               \
+    if ((rc = trt_make_tmap_nhwc(&td, gy, N, g.OH, g.OW, C, 64, 8, WH))) return rc;                                \
     int G;                                                                                                         \
-    if ((rc = persistent_blocks(dwconv_bwd_weight_kernel<KK, SS>, smem, cblocks, items, &G))) return rc;           \
-    dwconv_bwd_weight_kernel<KK, SS><<<dim3(G, cblocks), TPB, smem, stream>>>(tx, td, x_rec, dw, g);               \
+    if ((rc = persistent_blocks(dwconv_bwd_weight_kernel<KK, SS, WH>, smem, cblocks, items, &G))) return rc;       \
+    dwconv_bwd_weight_kernel<KK, SS, WH><<<dim3(G, cblocks), TPB, smem, stream>>>(tx, td, x_rec, dw, g);           \
   } while (0)
-    if (k == 3 && s == 1) LAUNCH_BW(3, 1);
-    else if (k == 3 && s == 2) LAUNCH_BW(3, 2);
-    else if (k == 5 && s == 1) LAUNCH_BW(5, 1);
-    else LAUNCH_BW(5, 2);
+    if (k == 3 && s == 1) { if (wh == TOH) LAUNCH_BW(3, 1, TOH); else LAUNCH_BW(3, 1, wgrad_tile_h(3, 1)); }
+    else if (k == 3 && s == 2) LAUNCH_BW(3, 2, TOH);
+    else if (k == 5 && s == 1) { if (wh == TOH) LAUNCH_BW(5, 1, TOH); else LAUNCH_BW(5, 1, wgrad_tile_h(5, 1)); }
+    else LAUNCH_BW(5, 2, TOH);
 #undef LAUNCH_BW
   }
   return trt_check_launch("trt_dwconv_bwd(weight)");
