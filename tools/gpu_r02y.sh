@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 late A/B: 1024-thread one-block tab MLP kernels + warp-parallel entry search in pack_w_batch_kernel (new library)
 # against the previous library (tools/ab/libteethrt_base.so, built from the previous commit), interleaved on one box.
+# The base library is the previous commit built the same way: git stash (or checkout) -> python -c "import __graft_entry__ as g; g.build()" -> cp the .so to tools/ab/libteethrt_base.so -> restore and rebuild.
 mkdir -p gpurun_out
 LIB=multimodal-teeth-restoration-selection_b200/libteethrt.so
 cp $LIB /tmp/new.so
