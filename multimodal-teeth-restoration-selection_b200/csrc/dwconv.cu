@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const _
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = TRT_ALIGNED_SMEM(smem_raw, 128);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
-  float* s_acc = reinterpret_cast<float*>(smem);                       // [K*K][64], overlays the tiles after the loop
+  float* s_acc = reinterpret_cast<float*>(smem);                       // [SUBS][K*K][64], overlays the tiles after the loop
   const int V = g.C / 8, cb = blockIdx.y;
   const int lane = threadIdx.x % CL, pt = threadIdx.x / CL;
   const int cv = cb * CL + lane;
@@ -616,18 +616,26 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_weight_kernel(const _
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < K * K * 64; i += TPB) s_acc[i] = 0.f;
-  __syncthreads();
+  // block reduction over the row lanes: every lane parks its K x 8 partials ([sub][tap][64 channels], over the tiles - all
+  // loads have landed), then thread i sums the SUBS entries of (tap, channel) i - consecutive threads read consecutive floats.
+  // (fp32 atomicAdd on shared memory compiles to an ATOMS.CAST.SPIN loop: 24 / 40 of them per thread, SUBS-way contended,
+  // were the tail of every block - a fixed cost that weighed most on the 7x7 / 14x14 layers with ~6 tiles per block.)
+  static_assert((size_t)SUBS * K * K * 64 * sizeof(float) <= 2 * (size_t)STAGE, "partials must fit over the tile buffers");
   if (worker) {
 #pragma unroll
-    for (int kw = 0; kw < K; ++kw)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(s_acc + (kh * K + kw) * 64 + lane * 8 + i, acc[kw][i]);
+    for (int kw = 0; kw < K; ++kw) {
+      float4* dst = reinterpret_cast<float4*>(s_acc + ((size_t)(sub * K + kh) * K + kw) * 64 + lane * 8);
+      dst[0] = make_float4(acc[kw][0], acc[kw][1], acc[kw][2], acc[kw][3]);
+      dst[1] = make_float4(acc[kw][4], acc[kw][5], acc[kw][6], acc[kw][7]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * K * 64; i += TPB) {
+    float total = 0.f;
+#pragma unroll
+    for (int sb = 0; sb < SUBS; ++sb) total += s_acc[sb * K * K * 64 + i];
     const int tap = i / 64, c = cb * 64 + (i % 64);
-    if (c < g.C) atomicAdd(dw + (size_t)c * K * K + tap, s_acc[i]);
+    if (c < g.C) atomicAdd(dw + (size_t)c * K * K + tap, total);
   }
 }
 
