@@ -165,14 +165,17 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
   }
   pdl_launch_dependents();
   pdl_wait();
-  load_weights<K>(s_w, w, cb, g.C, false);
-  __syncthreads();
   const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
   auto issue = [&](int it, int st) {
     const Item q = decode_item(it, tiles, g);
     ptx::mbar_expect_tx(&bar[st], T::IN_BYTES);
     ptx::tma_load_4d(smem + st * T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW * S - g.pad_l, q.ty * TOH * S - g.pad_t, q.n);
   };
+  // the first tile is requested BEFORE the prologue (filter staging, lazy BatchNorm record): its HBM round trip overlaps them
+  // (the issuing thread initialised the barriers itself; the other threads meet them after the __syncthreads below)
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, 0);
+  load_weights<K>(s_w, w, cb, g.C, false);
+  __syncthreads();
   f8 sc, sh, osc, osh;
   if (has_fin) {
     // lazy BatchNorm on the input: scale/shift of this block's 64 channels straight from the producer's statistics; the
@@ -188,7 +191,6 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_fwd_kernel(const __grid_c
   const int oy = pt / 4, oxb = (pt % 4) * P;
   int it = blockIdx.x, st = 0;
   uint32_t phase = 0;
-  if (threadIdx.x == 0 && it < items) issue(it, 0);
   for (; it < items; it += G, st ^= 1) {
     const Item q = decode_item(it, tiles, g);
     const int oy0 = q.ty * TOH, ox0 = q.tx * T::TOW;
@@ -316,8 +318,6 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
     ptx::mbar_init(&bar[1], 1);
     ptx::fence_barrier_init();
   }
-  load_weights<K>(s_w, w, cb, g.C, true);
-  __syncthreads();
   const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
   auto issue = [&](int it, int st) {
     const Item q = decode_item(it, tiles, g);
@@ -325,6 +325,9 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
     ptx::tma_load_4d(smem + st * STAGE, &tm_d, &bar[st], cb * 64, q.tx * T::TOW - PAD, q.ty * TOH - PAD, q.n);
     if (x_rec) ptx::tma_load_4d(smem + st * STAGE + T::IN_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TOW, q.ty * TOH, q.n);
   };
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, 0);      // first tile in flight during the filter staging
+  load_weights<K>(s_w, w, cb, g.C, true);
+  __syncthreads();
   f8 sc, sh;
   if (x_rec && cvalid) { sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv); }
   float red[2][8];
@@ -333,7 +336,6 @@ __global__ void __launch_bounds__(TPB, DW_MINB) dwconv_bwd_data_s1_kernel(const 
   const int oy = pt / 4, oxb = (pt % 4) * P;
   int it = blockIdx.x, st = 0;
   uint32_t phase = 0;
-  if (threadIdx.x == 0 && it < items) issue(it, 0);
   for (; it < items; it += G, st ^= 1) {
     const Item q = decode_item(it, tiles, g);
     if (threadIdx.x == 0 && it + G < items) issue(it + G, st ^ 1);
@@ -420,8 +422,6 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     ptx::mbar_init(&bar[1], 1);
     ptx::fence_barrier_init();
   }
-  load_weights<K>(s_w, w, cb, g.C, false);
-  __syncthreads();
   const int tiles = g.tiles_x * g.tiles_y, items = g.N * tiles, G = gridDim.x;
   // first dD row/col a tile can touch: floor((i0 + pad - (K-1)) / 2); i0 is a multiple of 16 and pad <= K-1, so the
   // numerator is >= -(K-1) and the floor is taken on a shifted non-negative value
@@ -432,6 +432,9 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
     ptx::tma_load_4d(smem + st * T::STAGE, &tm_d, &bar[st], cb * 64, d_origin(q.tx * T::TI, g.pad_l), d_origin(q.ty * T::TI, g.pad_t), q.n);
     if (x_rec) ptx::tma_load_4d(smem + st * T::STAGE + T::D_BYTES, &tm_x, &bar[st], cb * 64, q.tx * T::TI, q.ty * T::TI, q.n);
   };
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, 0);      // first tile in flight during the filter staging
+  load_weights<K>(s_w, w, cb, g.C, false);
+  __syncthreads();
   f8 sc, sh;
   if (x_rec && cvalid) { sc = ldf8(x_rec + 8 * cv); sh = ldf8(x_rec + g.C + 8 * cv); }
   float red[2][8];
@@ -445,7 +448,6 @@ __global__ void __launch_bounds__(TPB, 2) dwconv_bwd_data_s2_kernel(const __grid
   const int r = 2 * u + ry;                                       // tile-local input row; the thread's columns are rx + 2p
   int it = blockIdx.x, st = 0;
   uint32_t phase = 0;
-  if (threadIdx.x == 0 && it < items) issue(it, 0);
   for (; it < items; it += G, st ^= 1) {
     const Item q = decode_item(it, tiles, g);
     if (threadIdx.x == 0 && it + G < items) issue(it + G, st ^ 1);
