@@ -41,6 +41,16 @@ def test_sass_is_blackwell_native(built):
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "FHFMA.BF16"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass                                  # no legacy mma.sync path
+    # per-kernel properties found with ptxas / cuobjdump in round 2: no shared-memory fp32 atomics
+    # (ATOMS.CAST.SPIN = a CAS loop per atomicAdd) and no local-memory traffic in the depthwise kernels of the train step
+    fn, bad = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and "dwconv_" in fn and ("ATOMS.CAST" in line or " STL" in line or " LDL" in line):
+            bad[fn] = bad.get(fn, 0) + 1
+    # the k5 stride-2 data gradient keeps two 8-byte spill slots (16 bytes of spill stores): everything else must be clean
+    assert all("bwd_data_s2_kernelILi5E" in f and n <= 16 for f, n in bad.items()), bad
 
 
 def test_no_cpu_fallback_without_gpu(built):
